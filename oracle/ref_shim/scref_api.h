@@ -1,0 +1,97 @@
+/* scref — C driver around the UNMODIFIED reference sources (test infrastructure only).
+ *
+ * Built by oracle/Makefile into oracle/_ref/libscref.so from the sources where they lie under
+ * /root/reference (nothing is copied). Every entry point calls the reference's own symbols:
+ *   sc::TransformSystem            src/core/src/sc_ecs.cpp:118-211
+ *   sc::CameraSystem               src/core/src/sc_ecs.cpp:213-272
+ *   sc::CullingSystem              src/engine/world/sc_world_partition.cpp:1199-1284
+ *   sc::RenderPrepStreamingSystem  src/engine/world/sc_world_partition.cpp:1286-1359
+ *   sc::mat4_* / frustumFromViewProj / sphereInFrustum / computeWorldBoundsSphere
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+ */
+#ifndef SCREF_API_H
+#define SCREF_API_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ScRefWorld ScRefWorld;
+
+#define SCREF_HAS_BOUNDS 1u
+#define SCREF_HAS_MESH   2u
+#define SCREF_NO_PARENT  0xFFFFFFFFu
+
+/* jobWorkers==0 -> hardware_concurrency-1 like src/sandbox/src/main.cpp:52-54 */
+ScRefWorld* screfCreate(uint32_t jobWorkers);
+void screfDestroy(ScRefWorld* w);
+uint32_t screfJobWorkers(void);
+/* joins the reference job workers (src/core/src/sc_jobs.cpp:152-171); also registered with atexit */
+void screfShutdown(void);
+
+/* ECS mutation through the reference's World (sc_ecs.h:282-418) */
+void screfCreateEntities(ScRefWorld* w, uint32_t n, uint32_t* outEntity);
+void screfAddInstances(ScRefWorld* w, uint32_t n, const uint32_t* entity, const uint32_t* parent,
+                       const float* trs9, const float* aabb6, const uint32_t* meshMat2, const uint32_t* flags);
+void screfDestroyEntities(ScRefWorld* w, uint32_t n, const uint32_t* entity);
+void screfSetLocal(ScRefWorld* w, uint32_t n, const uint32_t* entity, const float* trs9);
+void screfSetParent(ScRefWorld* w, uint32_t n, const uint32_t* entity, const uint32_t* parent);
+void screfMarkDirty(ScRefWorld* w, uint32_t n, const uint32_t* entity);
+
+/* Systems (the plugin signature void(World&,float,void*), sc_scheduler.h:38) */
+void screfRunTransform(ScRefWorld* w);
+void screfSetViewProj(ScRefWorld* w, const float* viewProj16);
+void screfSetFreezeCulling(ScRefWorld* w, int freeze);
+void screfRunCulling(ScRefWorld* w);
+/* maxDraws: WorldStreamingBudgets::maxDrawsBudget (0 = unlimited) */
+void screfRunRenderPrep(ScRefWorld* w, uint32_t maxDraws);
+/* Camera: adds a camera entity (Transform+Camera active) and runs sc::CameraSystem to fill viewProj */
+uint32_t screfAddCamera(ScRefWorld* w, const float* trs9, float fovY, float nearZ, float farZ, float aspect);
+void screfRunCamera(ScRefWorld* w, float aspect);
+
+/* Read-back */
+uint32_t screfTransformCount(ScRefWorld* w);
+/* Transform-pool dense order (defines every output order, sc_ecs.h:199-277) */
+uint32_t screfDenseEntities(ScRefWorld* w, uint32_t cap, uint32_t* outEntity);
+void screfReadWorld(ScRefWorld* w, uint32_t n, const uint32_t* entity, float* out16);
+void screfReadTransform(ScRefWorld* w, uint32_t n, const uint32_t* entity, uint32_t* outParent, float* outTrs9,
+                        uint8_t* outDirty);
+void screfGetViewProj(ScRefWorld* w, float* out16);
+void screfGetPlanes(ScRefWorld* w, float* out24);
+void screfGetCullStats(ScRefWorld* w, uint32_t* total, uint32_t* visible, uint32_t* culled);
+uint32_t screfReadVisible(ScRefWorld* w, uint32_t cap, uint32_t* out);
+uint32_t screfReadCulled(ScRefWorld* w, uint32_t cap, uint32_t* out);
+uint32_t screfReadCandidates(ScRefWorld* w, uint32_t cap, uint32_t* out);
+void screfGetRenderPrepStats(ScRefWorld* w, uint32_t* emitted, uint32_t* dropped);
+/* 80-byte DrawItem records (sc_ecs.h:159-165) copied verbatim */
+uint32_t screfReadDraws(ScRefWorld* w, uint32_t cap, void* out80);
+uint32_t screfSizeofTransform(void);
+uint32_t screfSizeofDrawItem(void);
+
+/* Config 1: the sandbox's default streamed scene (src/sandbox/src/main.cpp:66-99,241-263) run through the
+ * reference Scheduler for `frames` frames. Returns number of active sectors. */
+uint32_t screfBuildDefaultScene(ScRefWorld* w, uint32_t frames);
+
+/* Frame timing of the reference path: runs Transform -> (Culling per view) -> RenderPrep `iters` times.
+ * Before every iteration all entities in dirtyEntity[0..nDirty) get markDirty. Returns seconds per stage. */
+void screfTimeFrame(ScRefWorld* w, uint32_t iters, uint32_t nViews, const float* viewProj16xV,
+                    uint32_t nDirty, const uint32_t* dirtyEntity, uint32_t maxDraws,
+                    double* outTransformS, double* outCullS, double* outPrepS);
+
+/* Raw math entry points for known-answer tests */
+void screfMat4Trs(const float* pos3, const float* rot3, const float* scale3, float* out16);
+void screfMat4Mul(const float* a16, const float* b16, float* out16);
+void screfMat4Inverse(const float* a16, float* out16);
+void screfMat4Perspective(float fovYRad, float aspect, float zn, float zf, int flipY, float* out16);
+void screfFrustumFromViewProj(const float* vp16, float* out24);
+int  screfSphereInFrustum(const float* planes24, const float* center3, float radius);
+void screfWorldBoundsSphere(const float* world16, const float* aabb6, float* outCenter3, float* outRadius);
+float screfSinf(float x);
+float screfCosf(float x);
+/* XOR-fold hash of sinf/cosf bits over float bit patterns [first, first+count) with stride */
+void screfSinCosSweep(uint32_t first, uint64_t count, uint32_t stride, uint64_t* outSinHash, uint64_t* outCosHash);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
