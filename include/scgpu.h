@@ -1,0 +1,175 @@
+/* scgpu.h — C ABI of libscgpu.so: the B200-native scene-update hot path for SandboxCityEngine.
+ *
+ * One call per frame, scgpuUpdate(), replaces the reference's RenderPrep chain
+ *     sc::TransformSystem            /root/reference/src/core/src/sc_ecs.cpp:118-211
+ *     sc::CullingSystem              /root/reference/src/engine/world/sc_world_partition.cpp:1199-1284
+ *     sc::RenderPrepStreamingSystem  /root/reference/src/engine/world/sc_world_partition.cpp:1286-1359
+ * (registered at src/sandbox/src/main.cpp:256-259) on an HBM-resident SoA mirror of the Transform pool.
+ * The adapter systems in sc-gameengine_b200/host/ keep the plugin signature void(World&, float, void*)
+ * (src/core/include/sc_scheduler.h:38) and call only the functions below.
+ *
+ * Conventions (style of src/engine/include/sc_engine_render.h:22-63,130-163): opaque context, POD structs,
+ * int 1 = ok / 0 = failure, null-tolerant, no exceptions or aborts across the boundary; the failure text is
+ * available from scgpuLastError(). The context owns every device buffer and its stream; the caller owns every
+ * host pointer it passes and may reuse it as soon as the call returns. One context is not re-entrant; calls
+ * may come from any thread (the device is selected on entry).
+ *
+ * There is no CPU fallback: without a CUDA device scgpuCreate() fails.
+ */
+#ifndef SCGPU_H
+#define SCGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SCGPU_API __declspec(dllexport)
+#else
+#define SCGPU_API __attribute__((visibility("default")))
+#endif
+
+#define SCGPU_API_VERSION 1u
+#define SCGPU_MAX_VIEWS 8u
+#define SCGPU_INVALID_ENTITY 0xFFFFFFFFu /* sc::kInvalidEntity, src/core/include/sc_ecs.h:36 */
+
+/* per-instance component flags (which ECS components the entity owns besides Transform) */
+#define SCGPU_HAS_BOUNDS 1u /* sc::Bounds     (sc_world_partition.h:298-301); absent => always visible (.cpp:1252-1256) */
+#define SCGPU_HAS_MESH   2u /* sc::RenderMesh (sc_ecs.h:113-117); absent => not a culling candidate (.cpp:1206-1210) */
+
+/* scgpuUpdate flags */
+#define SCGPU_UPDATE_FREEZE_CULLING 1u /* CullingState::freezeCulling (.cpp:1227-1233): every candidate visible */
+#define SCGPU_UPDATE_SKIP_TRANSFORM 2u /* cull/compact only (views changed, transforms did not) */
+#define SCGPU_UPDATE_CULLED_LISTS   4u /* also build CullingState::culled (.cpp:1273-1280) for every view */
+
+typedef struct ScGpuScene ScGpuScene;
+
+typedef struct ScGpuSceneDesc
+{
+  uint32_t struct_size;      /* sizeof(ScGpuSceneDesc) */
+  int32_t device;            /* CUDA device ordinal */
+  uint32_t max_instances;    /* Transform-pool capacity (slots) */
+  uint32_t max_entity_index; /* largest Entity::index()+1 that will be seen (<= 1<<24, sc_ecs.h:18-20); 0 => 1<<24 */
+  uint32_t max_views;        /* 1..SCGPU_MAX_VIEWS */
+  uint32_t flags;            /* reserved, 0 */
+  void* stream;              /* cudaStream_t to run on, or NULL for a context-owned stream */
+} ScGpuSceneDesc;
+
+/* sc::DrawItem, src/core/include/sc_ecs.h:159-165: entity@0 meshId@4 materialId@8 model@16, 80 bytes */
+typedef struct ScGpuDrawItem
+{
+  uint32_t entity;
+  uint32_t meshId;
+  uint32_t materialId;
+  uint32_t _pad;
+  float model[16];
+} ScGpuDrawItem;
+
+/* sc::CullingStats (sc_world_partition.h:334-339) per view + sc::RenderPrepStats (:353-357) */
+typedef struct ScGpuCounts
+{
+  uint32_t transforms;                   /* live Transform slots */
+  uint32_t renderablesTotal;             /* Transform && RenderMesh */
+  uint32_t visible[SCGPU_MAX_VIEWS];
+  uint32_t culled[SCGPU_MAX_VIEWS];
+  uint32_t recomputed;                   /* world matrices rewritten by the last update */
+} ScGpuCounts;
+
+/* ---- lifetime ------------------------------------------------------------------------------------- */
+SCGPU_API uint32_t scgpuGetApiVersion(void);
+SCGPU_API ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc);
+SCGPU_API void scgpuDestroy(ScGpuScene* ctx);
+/* never NULL; "" when the last call succeeded. ctx may be NULL (reports the last scgpuCreate failure). */
+SCGPU_API const char* scgpuLastError(const ScGpuScene* ctx);
+
+/* ---- ECS deltas (replace World::add / World::destroy / setLocal / setParent / markDirty,
+ *      src/core/include/sc_ecs.h:73-96,282-330, src/core/src/sc_ecs.cpp:80-90) ------------------------- */
+/* Appends n Transforms in pool order. parent: entity handles or SCGPU_INVALID_ENTITY (NULL => none).
+ * trs9: localPos, localRot (radians, XYZ Euler), localScale. aabb6: min.xyz,max.xyz (NULL => unit cube
+ * [-0.5,0.5]^3, sc_world_partition.cpp:27). meshMat2: meshId, materialId (NULL => 0,0). flags: SCGPU_HAS_*
+ * (NULL => BOUNDS|MESH). New instances are dirty with an identity world matrix (sc_ecs.h:63-71). */
+SCGPU_API int scgpuSpawn(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const uint32_t* parent,
+                         const float* trs9, const float* aabb6, const uint32_t* meshMat2, const uint32_t* flags);
+/* World::destroy for each handle in order, with ComponentPool::remove's swap-with-last (sc_ecs.h:240-262), so
+ * the pool order — and therefore every output order — stays identical to the reference's. Unknown or stale
+ * handles are skipped like the reference does. */
+SCGPU_API int scgpuDespawn(ScGpuScene* ctx, uint32_t n, const uint32_t* entity);
+SCGPU_API int scgpuSetLocal(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const float* trs9);
+SCGPU_API int scgpuSetParent(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const uint32_t* parent);
+SCGPU_API int scgpuMarkDirty(ScGpuScene* ctx, uint32_t n, const uint32_t* entity);
+/* Same as scgpuSetLocal but entity/trs9 are DEVICE pointers (producers that already live in HBM). */
+SCGPU_API int scgpuSetLocalDevice(ScGpuScene* ctx, uint32_t n, const uint32_t* d_entity, const float* d_trs9);
+/* Marks every live instance dirty (first frame / teleport). */
+SCGPU_API int scgpuMarkAllDirty(ScGpuScene* ctx);
+
+/* ---- views (replace RenderFrameData::viewProj + frustumFromViewProj, sc_world_partition.cpp:1071-1103) - */
+SCGPU_API int scgpuSetViews(ScGpuScene* ctx, uint32_t nViews, const float* viewProj16);
+/* planes24 per view: 6 x (nx, ny, nz, d) in the order left,right,bottom,top,near,far */
+SCGPU_API int scgpuSetViewPlanes(ScGpuScene* ctx, uint32_t nViews, const float* planes24);
+SCGPU_API int scgpuGetViewPlanes(ScGpuScene* ctx, uint32_t view, float* outPlanes24);
+
+/* ---- the frame ----------------------------------------------------------------------------------------- */
+/* Enqueues apply-deltas -> transform -> cull (all views, one pass) -> compact on the context stream and
+ * returns without waiting. */
+SCGPU_API int scgpuUpdate(ScGpuScene* ctx, uint32_t flags);
+SCGPU_API int scgpuSynchronize(ScGpuScene* ctx);
+
+/* ---- results (each waits for the last scgpuUpdate) ------------------------------------------------------ */
+SCGPU_API int scgpuGetCounts(ScGpuScene* ctx, ScGpuCounts* out);
+/* CullingState::visible / ::culled for one view: entity handles in Transform-pool order. cap is the capacity
+ * of out in entries; *outCount receives the full count even when it exceeds cap. */
+SCGPU_API int scgpuReadVisible(ScGpuScene* ctx, uint32_t view, uint32_t* outEntity, uint32_t cap, uint32_t* outCount);
+SCGPU_API int scgpuReadCulled(ScGpuScene* ctx, uint32_t view, uint32_t* outEntity, uint32_t cap, uint32_t* outCount);
+/* RenderFrameData::draws for one view; maxDraws = WorldStreamingBudgets::maxDrawsBudget (0 = unlimited). */
+SCGPU_API int scgpuReadDrawItems(ScGpuScene* ctx, uint32_t view, uint32_t maxDraws, ScGpuDrawItem* out, uint32_t cap,
+                                 uint32_t* outEmitted, uint32_t* outDropped);
+/* Transform::worldMatrix (column-major) of the given entities; unknown handles yield zeros and return 0. */
+SCGPU_API int scgpuReadWorld(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, float* out16);
+/* Transform-pool dense order (ComponentPool::denseEntities) */
+SCGPU_API int scgpuReadDenseEntities(ScGpuScene* ctx, uint32_t* outEntity, uint32_t cap, uint32_t* outCount);
+SCGPU_API int scgpuReadParents(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, uint32_t* outParent);
+
+/* ---- zero-copy access for device-side consumers ---------------------------------------------------------- */
+typedef struct ScGpuDeviceViews
+{
+  const uint32_t* visibleEntity[SCGPU_MAX_VIEWS]; /* device, compacted entity handles per view */
+  const uint32_t* visibleSlot[SCGPU_MAX_VIEWS];   /* device, the matching Transform-pool slots */
+  const uint32_t* visibleCount;                   /* device, [max_views+1]; last = renderablesTotal */
+  const float* worldCol[4];                       /* device, world matrix column planes (float4 per slot) */
+  const uint32_t* entity;                         /* device, slot -> entity handle */
+  uint32_t count;                                 /* live slots */
+} ScGpuDeviceViews;
+SCGPU_API int scgpuGetDeviceViews(ScGpuScene* ctx, ScGpuDeviceViews* out);
+SCGPU_API void* scgpuGetStream(ScGpuScene* ctx);
+/* Materialises draw items for one view into a context-owned device buffer and returns it. */
+SCGPU_API int scgpuBuildDrawItemsDevice(ScGpuScene* ctx, uint32_t view, uint32_t maxDraws,
+                                        const ScGpuDrawItem** outDevice, uint32_t* outEmitted, uint32_t* outDropped);
+
+/* ---- multi-GPU: one context per process per GPU, instance set sharded by world cell ------------------------
+ * The only exchange is the gather of the compacted per-view lists and counts to the submitting rank. */
+#define SCGPU_COMM_ID_BYTES 128
+SCGPU_API int scgpuCommGetUniqueId(void* outId128);
+SCGPU_API int scgpuCommInit(ScGpuScene* ctx, uint32_t nRanks, uint32_t rank, const void* id128);
+/* After scgpuUpdate: gathers every rank's counts to all ranks and every rank's visible lists to `root`,
+ * concatenated in rank order (shard-major stable order). Enqueued on the context stream. */
+SCGPU_API int scgpuGatherVisible(ScGpuScene* ctx, uint32_t root);
+/* counts[rank][view] for all ranks (valid on every rank after the gather) */
+SCGPU_API int scgpuGetGatheredCounts(ScGpuScene* ctx, uint32_t* outCounts, uint32_t capRanks);
+/* root only: concatenated list of one view; *outCount = sum over ranks */
+SCGPU_API int scgpuReadGatheredVisible(ScGpuScene* ctx, uint32_t view, uint32_t* outEntity, uint32_t cap,
+                                       uint32_t* outCount);
+
+/* ---- introspection used by bench.py ------------------------------------------------------------------------ */
+/* number of kernel launches this context has issued so far */
+SCGPU_API uint64_t scgpuKernelLaunchCount(ScGpuScene* ctx);
+/* device time of the main fused kernel and of the whole last update, from CUDA events on the context stream */
+SCGPU_API int scgpuLastUpdateTimings(ScGpuScene* ctx, float* outFusedKernelMs, float* outUpdateMs);
+SCGPU_API int scgpuEnableTimings(ScGpuScene* ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCGPU_H */

@@ -1,0 +1,1001 @@
+// scgpu_api.cu — the C ABI of include/scgpu.h over the kernels in scgpu_kernels.cuh.
+//
+// Host-side state is deliberately small: an entity mirror (dense handles + sparse index, the two arrays of the
+// reference's ComponentPool<Transform>, src/core/include/sc_ecs.h:199-277) so that despawns replay the
+// reference's swap-with-last order exactly, plus device buffer bookkeeping. All arithmetic runs on the GPU.
+#include "../../include/scgpu.h"
+#include "scgpu_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace scgpu;
+
+namespace
+{
+
+thread_local std::string g_createError;
+
+struct DeviceBuffer
+{
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+// ---- NCCL, loaded lazily so that libscgpu.so has no link-time dependency on it -------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclUint32 = 3 };  // ncclDataType_t: ncclInt8=0, ncclUint8=1, ncclInt32=2, ncclUint32=3
+struct NcclApi
+{
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool loadNccl(std::string& err)
+{
+  if (g_nccl.lib) return true;
+  // prefer a copy already in the process (torch's bundled NCCL), then the system library
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define SC_SYM(field, name) \
+  *(void**)(&g_nccl.field) = dlsym(lib, name); \
+  if (!g_nccl.field) { err = std::string("libnccl lacks ") + name; return false; }
+  SC_SYM(GetUniqueId, "ncclGetUniqueId")
+  SC_SYM(CommInitRank, "ncclCommInitRank")
+  SC_SYM(CommDestroy, "ncclCommDestroy")
+  SC_SYM(AllGather, "ncclAllGather")
+  SC_SYM(Send, "ncclSend")
+  SC_SYM(Recv, "ncclRecv")
+  SC_SYM(GroupStart, "ncclGroupStart")
+  SC_SYM(GroupEnd, "ncclGroupEnd")
+  SC_SYM(GetErrorString, "ncclGetErrorString")
+#undef SC_SYM
+  g_nccl.lib = lib;
+  return true;
+}
+
+}  // namespace
+
+struct ScGpuScene
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool ownStream = false;
+  uint32_t capacity = 0;     // slots
+  uint32_t capacityPad = 0;  // rounded up to kTile
+  uint32_t sparseSize = 0;
+  uint32_t maxViews = 1;
+  uint32_t nViews = 0;
+  uint32_t count = 0;
+  uint32_t frame = 1;        // id of the NEXT update; instances dirtied now carry this stamp
+  bool topologyDirty = false;
+  bool anyParentEver = false;
+  bool forceAllDirty = false;
+  bool updatedOnce = false;
+  uint32_t lastUpdateFlags = 0;
+  uint32_t lastNumTiles = 0;
+  bool culledListsValid = false;
+
+  SceneArrays a{};
+  uint8_t* vismask = nullptr;
+  uint32_t* tileCounts = nullptr;
+  uint32_t* tileOffsets = nullptr;
+  uint32_t* totals = nullptr;  // [maxViews+1] + recomputed at [maxViews+1]
+  uint32_t* visEntity[kMaxViews] = {};
+  uint32_t* visSlot[kMaxViews] = {};
+  uint32_t* culledEntity[kMaxViews] = {};
+  uint32_t maxTiles = 0;
+
+  ViewPlanes planes{};
+  uint32_t* hTotals = nullptr;  // pinned [maxViews+2]
+  cudaEvent_t evDone = nullptr;
+  cudaEvent_t evK0 = nullptr, evK1 = nullptr, evU0 = nullptr, evU1 = nullptr;
+  bool timings = false;
+
+  DeviceBuffer staging;   // uploads
+  DeviceBuffer scratch;   // read-back gathers / draw items
+  DeviceBuffer drawItems;
+
+  std::vector<uint32_t> hEntity;  // dense handles (ComponentPool::m_denseEntities)
+  std::vector<uint32_t> hSparse;  // index -> slot+1 (ComponentPool::m_sparse)
+  std::vector<uint32_t> hOrigin;  // scratch for despawn batches: slot -> slot its content came from
+
+  uint64_t launches = 0;
+  std::string err;
+
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  uint32_t nRanks = 1, rank = 0;
+  uint32_t* dAllCounts = nullptr;   // [nRanks][maxViews+1]
+  uint32_t* hAllCounts = nullptr;   // pinned
+  uint32_t* gathered[kMaxViews] = {};
+  size_t gatheredCap = 0;
+  bool gatheredValid = false;
+};
+
+namespace
+{
+
+bool fail(ScGpuScene* c, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else g_createError = buf;
+  return false;
+}
+
+#define SC_CUDA(c, call)                                                                         \
+  do                                                                                             \
+  {                                                                                              \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return (int)fail((c), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define SC_NCCL(c, call)                                                                          \
+  do                                                                                              \
+  {                                                                                               \
+    int e__ = (call);                                                                             \
+    if (e__ != ncclSuccess)                                                                       \
+      return (int)fail((c), "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(e__) : "?"); \
+  } while (0)
+
+bool enter(ScGpuScene* c)
+{
+  if (!c) return false;
+  c->err.clear();
+  if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, "cudaSetDevice(%d) failed", c->device);
+  return true;
+}
+
+int ensure(ScGpuScene* c, DeviceBuffer& b, size_t bytes)
+{
+  if (b.bytes >= bytes) return 1;
+  if (b.ptr)
+  {
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+    SC_CUDA(c, cudaFree(b.ptr));
+    b.ptr = nullptr;
+    b.bytes = 0;
+  }
+  size_t want = std::max(bytes, (size_t)1 << 20);
+  want = (want + 255) & ~(size_t)255;
+  SC_CUDA(c, cudaMalloc(&b.ptr, want));
+  b.bytes = want;
+  return 1;
+}
+
+inline uint32_t blocksFor(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
+
+template <typename T>
+int devAlloc(ScGpuScene* c, T** p, size_t n, bool zero)
+{
+  SC_CUDA(c, cudaMalloc((void**)p, std::max(n, (size_t)1) * sizeof(T)));
+  if (zero) SC_CUDA(c, cudaMemsetAsync(*p, 0, std::max(n, (size_t)1) * sizeof(T), c->stream));
+  return 1;
+}
+
+// frustumFromViewProj, src/engine/world/sc_world_partition.cpp:1071-1103. O(1) per view, computed on the host
+// in plain IEEE float (this file is compiled with -ffp-contract=off and without -mfma): rows of the column-major
+// matrix, planes r3 +- r0, r3 +- r1, r3 +- r2, each scaled by 1/sqrt(a^2+b^2+c^2) when that exceeds 1e-8.
+void planesFromViewProj(const float* m, float4* out)
+{
+  const float r0[4] = { m[0], m[4], m[8], m[12] };
+  const float r1[4] = { m[1], m[5], m[9], m[13] };
+  const float r2[4] = { m[2], m[6], m[10], m[14] };
+  const float r3[4] = { m[3], m[7], m[11], m[15] };
+  const float* rows[3] = { r0, r1, r2 };
+  for (int p = 0; p < 6; ++p)
+  {
+    const float* r = rows[p >> 1];
+    const bool plus = (p & 1) == 0;
+    volatile float a = plus ? r3[0] + r[0] : r3[0] - r[0];
+    volatile float b = plus ? r3[1] + r[1] : r3[1] - r[1];
+    volatile float cc = plus ? r3[2] + r[2] : r3[2] - r[2];
+    volatile float d = plus ? r3[3] + r[3] : r3[3] - r[3];
+    float4 pl = make_float4(0.f, 0.f, 0.f, 0.f);
+    volatile float aa = a * a, bb = b * b, c2 = cc * cc;
+    volatile float s1 = aa + bb;
+    volatile float lenSq = s1 + c2;
+    if (lenSq > 1e-8f)
+    {
+      volatile float invLen = 1.0f / sqrtf(lenSq);
+      pl.x = a * invLen; pl.y = b * invLen; pl.z = cc * invLen; pl.w = d * invLen;
+    }
+    out[p] = pl;
+  }
+}
+
+void freeAll(ScGpuScene* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
+  cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
+  cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
+  for (uint32_t v = 0; v < kMaxViews; ++v)
+  {
+    cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
+  }
+  cudaFree(c->staging.ptr); cudaFree(c->scratch.ptr); cudaFree(c->drawItems.ptr);
+  cudaFree(c->dAllCounts);
+  if (c->hTotals) cudaFreeHost(c->hTotals);
+  if (c->hAllCounts) cudaFreeHost(c->hAllCounts);
+  if (c->evDone) cudaEventDestroy(c->evDone);
+  if (c->evK0) cudaEventDestroy(c->evK0);
+  if (c->evK1) cudaEventDestroy(c->evK1);
+  if (c->evU0) cudaEventDestroy(c->evU0);
+  if (c->evU1) cudaEventDestroy(c->evU1);
+  if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
+{
+  int nDev = 0;
+  cudaError_t e = cudaGetDeviceCount(&nDev);
+  if (e != cudaSuccess || nDev == 0)
+    return (int)fail(c, "no CUDA device available (%s); scgpu has no CPU fallback", cudaGetErrorString(e));
+  if (d->device < 0 || d->device >= nDev) return (int)fail(c, "device ordinal %d out of range (0..%d)", d->device, nDev - 1);
+  c->device = d->device;
+  SC_CUDA(c, cudaSetDevice(c->device));
+  cudaDeviceProp prop{};
+  SC_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10)
+    return (int)fail(c, "device %d is sm_%d%d; libscgpu is built for sm_100a (B200) only", c->device, prop.major, prop.minor);
+  if (d->stream) { c->stream = (cudaStream_t)d->stream; c->ownStream = false; }
+  else { SC_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
+
+  c->capacity = d->max_instances;
+  c->capacityPad = ((d->max_instances + kTile - 1) / kTile) * kTile;
+  if (c->capacityPad == 0) c->capacityPad = kTile;
+  c->sparseSize = d->max_entity_index ? d->max_entity_index : (1u << 24);
+  if (c->sparseSize > (1u << 24)) c->sparseSize = 1u << 24;
+  c->maxViews = d->max_views;
+  c->maxTiles = c->capacityPad / kTile;
+
+  const size_t n = c->capacityPad;
+  for (int k = 0; k < 4; ++k)
+  {
+    if (!devAlloc(c, &c->a.rec[k], n, true)) return 0;
+    if (!devAlloc(c, &c->a.world[k], n, true)) return 0;
+  }
+  if (!devAlloc(c, &c->a.parent, n, false)) return 0;
+  if (!devAlloc(c, &c->a.parentSlot, n, false)) return 0;
+  if (!devAlloc(c, &c->a.entity, n, true)) return 0;
+  if (!devAlloc(c, &c->a.meshMat, n, true)) return 0;
+  if (!devAlloc(c, &c->a.sparse, (size_t)c->sparseSize, true)) return 0;
+  c->a.sparseSize = c->sparseSize;
+  if (!devAlloc(c, &c->vismask, n, true)) return 0;
+  if (!devAlloc(c, &c->tileCounts, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
+  if (!devAlloc(c, &c->tileOffsets, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
+  if (!devAlloc(c, &c->totals, (size_t)kMaxViews + 2, true)) return 0;
+  for (uint32_t v = 0; v < c->maxViews; ++v)
+  {
+    if (!devAlloc(c, &c->visEntity[v], n, false)) return 0;
+    if (!devAlloc(c, &c->visSlot[v], n, false)) return 0;
+  }
+  SC_CUDA(c, cudaMallocHost((void**)&c->hTotals, sizeof(uint32_t) * (kMaxViews + 2)));
+  memset(c->hTotals, 0, sizeof(uint32_t) * (kMaxViews + 2));
+  SC_CUDA(c, cudaEventCreateWithFlags(&c->evDone, cudaEventDisableTiming));
+  SC_CUDA(c, cudaEventCreate(&c->evK0));
+  SC_CUDA(c, cudaEventCreate(&c->evK1));
+  SC_CUDA(c, cudaEventCreate(&c->evU0));
+  SC_CUDA(c, cudaEventCreate(&c->evU1));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->hEntity.reserve(c->capacity);
+  return 1;
+}
+
+int uploadTo(ScGpuScene* c, void* dst, const void* src, size_t bytes)
+{
+  SC_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 1;
+}
+
+// stamps are 24 bits wide and 0 means "never"
+uint32_t stampOf(uint32_t frame) { return frame & 0xFFFFFFu; }
+
+int waitDone(ScGpuScene* c)
+{
+  if (!c->updatedOnce) return (int)fail(c, "no scgpuUpdate has been issued yet");
+  SC_CUDA(c, cudaEventSynchronize(c->evDone));
+  return 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t scgpuGetApiVersion(void) { return SCGPU_API_VERSION; }
+
+const char* scgpuLastError(const ScGpuScene* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc)
+{
+  g_createError.clear();
+  if (!desc) { fail(nullptr, "scgpuCreate: desc is NULL"); return nullptr; }
+  if (desc->struct_size != sizeof(ScGpuSceneDesc)) { fail(nullptr, "scgpuCreate: struct_size %u != %zu", desc->struct_size, sizeof(ScGpuSceneDesc)); return nullptr; }
+  if (desc->max_views == 0 || desc->max_views > SCGPU_MAX_VIEWS) { fail(nullptr, "scgpuCreate: max_views must be 1..%u", SCGPU_MAX_VIEWS); return nullptr; }
+  if (desc->max_instances == 0 || desc->max_instances > (1u << 24)) { fail(nullptr, "scgpuCreate: max_instances must be 1..%u (24-bit entity index, sc_ecs.h:18-20)", 1u << 24); return nullptr; }
+  ScGpuScene* c = new (std::nothrow) ScGpuScene();
+  if (!c) { fail(nullptr, "out of host memory"); return nullptr; }
+  if (!createImpl(c, desc))
+  {
+    g_createError = c->err;
+    freeAll(c);
+    return nullptr;
+  }
+  return c;
+}
+
+void scgpuDestroy(ScGpuScene* ctx) { freeAll(ctx); }
+
+void* scgpuGetStream(ScGpuScene* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+uint64_t scgpuKernelLaunchCount(ScGpuScene* ctx) { return ctx ? ctx->launches : 0; }
+
+int scgpuEnableTimings(ScGpuScene* ctx, int enable)
+{
+  if (!enter(ctx)) return 0;
+  ctx->timings = enable != 0;
+  return 1;
+}
+
+int scgpuSynchronize(ScGpuScene* ctx)
+{
+  if (!enter(ctx)) return 0;
+  SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 1;
+}
+
+// ---- deltas -------------------------------------------------------------------------------------------
+
+int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* parent, const float* trs9,
+               const float* aabb6, const uint32_t* meshMat2, const uint32_t* flags)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity || !trs9) return (int)fail(c, "scgpuSpawn: entity and trs9 are required");
+  if ((uint64_t)c->count + n > c->capacity) return (int)fail(c, "scgpuSpawn: %u + %u instances exceed max_instances %u", c->count, n, c->capacity);
+  // validate against the mirror first so a failed call leaves the scene untouched
+  if (c->hSparse.size() < c->sparseSize) c->hSparse.resize(c->sparseSize, 0u);
+  for (uint32_t j = 0; j < n; ++j)
+  {
+    const uint32_t idx = entity[j] & 0xFFFFFFu;
+    if (entity[j] == SCGPU_INVALID_ENTITY) return (int)fail(c, "scgpuSpawn: entity[%u] is the invalid handle", j);
+    if (idx >= c->sparseSize) return (int)fail(c, "scgpuSpawn: entity index %u >= max_entity_index %u", idx, c->sparseSize);
+    if (c->hSparse[idx] != 0u)
+    {
+      for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u;
+      return (int)fail(c, "scgpuSpawn: entity index %u already owns a Transform", idx);
+    }
+    c->hSparse[idx] = c->count + j + 1u;
+  }
+  c->hEntity.insert(c->hEntity.end(), entity, entity + n);
+
+  const uint32_t chunkMax = 1u << 20;
+  for (uint32_t off = 0; off < n; off += chunkMax)
+  {
+    const uint32_t m = std::min(chunkMax, n - off);
+    size_t bytes = 0;
+    const size_t oEntity = bytes; bytes += (size_t)m * 4;
+    const size_t oParent = bytes; bytes += parent ? (size_t)m * 4 : 0;
+    const size_t oTrs = bytes; bytes += (size_t)m * 36;
+    const size_t oAabb = bytes; bytes += aabb6 ? (size_t)m * 24 : 0;
+    const size_t oMm = bytes; bytes += meshMat2 ? (size_t)m * 8 : 0;
+    const size_t oFlags = bytes; bytes += flags ? (size_t)m * 4 : 0;
+    if (!ensure(c, c->staging, bytes)) return 0;
+    char* s = (char*)c->staging.ptr;
+    if (!uploadTo(c, s + oEntity, entity + off, (size_t)m * 4)) return 0;
+    if (parent && !uploadTo(c, s + oParent, parent + off, (size_t)m * 4)) return 0;
+    if (!uploadTo(c, s + oTrs, trs9 + (size_t)off * 9, (size_t)m * 36)) return 0;
+    if (aabb6 && !uploadTo(c, s + oAabb, aabb6 + (size_t)off * 6, (size_t)m * 24)) return 0;
+    if (meshMat2 && !uploadTo(c, s + oMm, meshMat2 + (size_t)off * 2, (size_t)m * 8)) return 0;
+    if (flags && !uploadTo(c, s + oFlags, flags + off, (size_t)m * 4)) return 0;
+    k_spawn<<<blocksFor(m), kBlock, 0, c->stream>>>(
+      c->a, c->count + off, m, (const uint32_t*)(s + oEntity), parent ? (const uint32_t*)(s + oParent) : nullptr,
+      (const float*)(s + oTrs), aabb6 ? (const float*)(s + oAabb) : nullptr,
+      meshMat2 ? (const uint32_t*)(s + oMm) : nullptr, flags ? (const uint32_t*)(s + oFlags) : nullptr, stampOf(c->frame));
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+  }
+  if (parent)
+  {
+    bool any = c->anyParentEver;
+    for (uint32_t j = 0; j < n && !any; ++j) any = parent[j] != SCGPU_INVALID_ENTITY;
+    if (any) { c->anyParentEver = true; c->topologyDirty = true; }
+  }
+  // a new Transform can turn a dangling parent handle valid (and shifts nothing else): re-resolve if any hierarchy exists
+  if (c->anyParentEver) c->topologyDirty = true;
+  c->count += n;
+  return 1;
+}
+
+int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity) return (int)fail(c, "scgpuDespawn: entity is NULL");
+  if (c->hOrigin.size() < c->count)
+  {
+    const size_t old = c->hOrigin.size();
+    c->hOrigin.resize(c->count);
+    for (size_t i = old; i < c->hOrigin.size(); ++i) c->hOrigin[i] = (uint32_t)i;
+  }
+  std::vector<uint32_t> touched;
+  std::vector<uint32_t> removedIdx;
+  touched.reserve(n);
+  removedIdx.reserve(n);
+  const uint32_t count0 = c->count;
+  uint32_t cnt = c->count;
+  for (uint32_t j = 0; j < n; ++j)
+  {
+    const uint32_t e = entity[j];
+    const uint32_t idx = e & 0xFFFFFFu;
+    if (e == SCGPU_INVALID_ENTITY || idx >= c->hSparse.size()) continue;
+    const uint32_t sp = c->hSparse[idx];
+    if (sp == 0u || c->hEntity[sp - 1u] != e) continue;  // stale or unknown handle: World::destroy returns false
+    const uint32_t s = sp - 1u, last = cnt - 1u;
+    if (s != last)
+    {
+      const uint32_t moved = c->hEntity[last];
+      c->hEntity[s] = moved;
+      c->hSparse[moved & 0xFFFFFFu] = s + 1u;
+      c->hOrigin[s] = c->hOrigin[last];
+      touched.push_back(s);
+    }
+    c->hSparse[idx] = 0u;
+    removedIdx.push_back(idx);
+    --cnt;
+  }
+  c->hEntity.resize(cnt);
+  // net moves: final content of every touched slot that survived
+  std::vector<uint2> moves;
+  moves.reserve(touched.size());
+  for (uint32_t s : touched)
+  {
+    if (s < cnt && c->hOrigin[s] != s)
+    {
+      moves.push_back(make_uint2(s, c->hOrigin[s]));
+      c->hOrigin[s] = s;  // also dedups slots touched more than once
+    }
+  }
+  for (uint32_t s : touched) if (s < c->hOrigin.size()) c->hOrigin[s] = s;
+  for (uint32_t s = cnt; s < count0; ++s) c->hOrigin[s] = s;
+  c->count = cnt;
+
+  const uint32_t nMoves = (uint32_t)moves.size(), nRem = (uint32_t)removedIdx.size();
+  if (nMoves + nRem > 0)
+  {
+    const size_t bytes = (size_t)nMoves * 8 + (size_t)nRem * 4;
+    if (!ensure(c, c->staging, bytes)) return 0;
+    char* s = (char*)c->staging.ptr;
+    if (nMoves && !uploadTo(c, s, moves.data(), (size_t)nMoves * 8)) return 0;
+    if (nRem && !uploadTo(c, s + (size_t)nMoves * 8, removedIdx.data(), (size_t)nRem * 4)) return 0;
+    // moves/removedIdx are pageable host vectors: the copies above are complete (staged) when the calls return
+    k_despawn_apply<<<blocksFor((uint64_t)nMoves + nRem), kBlock, 0, c->stream>>>(
+      c->a, nMoves, (const uint2*)s, nRem, (const uint32_t*)(s + (size_t)nMoves * 8));
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+    if (c->anyParentEver) c->topologyDirty = true;
+  }
+  return 1;
+}
+
+static int uploadEntityBatch(ScGpuScene* c, uint32_t n, const uint32_t* entity, const void* payload, size_t payloadBytesPer,
+                             const uint32_t** dEntity, const void** dPayload)
+{
+  const size_t bytes = (size_t)n * 4 + (size_t)n * payloadBytesPer;
+  if (!ensure(c, c->staging, bytes)) return 0;
+  char* s = (char*)c->staging.ptr;
+  if (!uploadTo(c, s, entity, (size_t)n * 4)) return 0;
+  if (payload && !uploadTo(c, s + (size_t)n * 4, payload, (size_t)n * payloadBytesPer)) return 0;
+  *dEntity = (const uint32_t*)s;
+  if (dPayload) *dPayload = s + (size_t)n * 4;
+  return 1;
+}
+
+int scgpuSetLocal(ScGpuScene* c, uint32_t n, const uint32_t* entity, const float* trs9)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity || !trs9) return (int)fail(c, "scgpuSetLocal: NULL argument");
+  const uint32_t* dE; const void* dT;
+  if (!uploadEntityBatch(c, n, entity, trs9, 36, &dE, &dT)) return 0;
+  k_set_local<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, (const float*)dT, stampOf(c->frame));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  return 1;
+}
+
+int scgpuSetLocalDevice(ScGpuScene* c, uint32_t n, const uint32_t* d_entity, const float* d_trs9)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!d_entity || !d_trs9) return (int)fail(c, "scgpuSetLocalDevice: NULL argument");
+  k_set_local<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, d_entity, d_trs9, stampOf(c->frame));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  return 1;
+}
+
+int scgpuSetParent(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* parent)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity || !parent) return (int)fail(c, "scgpuSetParent: NULL argument");
+  const uint32_t* dE; const void* dP;
+  if (!uploadEntityBatch(c, n, entity, parent, 4, &dE, &dP)) return 0;
+  k_set_parent<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, (const uint32_t*)dP, stampOf(c->frame));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  c->anyParentEver = true;
+  c->topologyDirty = true;
+  return 1;
+}
+
+int scgpuMarkDirty(ScGpuScene* c, uint32_t n, const uint32_t* entity)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity) return (int)fail(c, "scgpuMarkDirty: NULL argument");
+  const uint32_t* dE;
+  if (!uploadEntityBatch(c, n, entity, nullptr, 0, &dE, nullptr)) return 0;
+  k_mark_dirty<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, stampOf(c->frame));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  return 1;
+}
+
+int scgpuMarkAllDirty(ScGpuScene* c)
+{
+  if (!enter(c)) return 0;
+  c->forceAllDirty = true;
+  return 1;
+}
+
+// ---- views --------------------------------------------------------------------------------------------
+
+int scgpuSetViews(ScGpuScene* c, uint32_t nViews, const float* viewProj16)
+{
+  if (!enter(c)) return 0;
+  if (nViews == 0 || nViews > c->maxViews) return (int)fail(c, "scgpuSetViews: nViews %u not in 1..%u", nViews, c->maxViews);
+  if (!viewProj16) return (int)fail(c, "scgpuSetViews: NULL matrix");
+  for (uint32_t v = 0; v < nViews; ++v) planesFromViewProj(viewProj16 + (size_t)v * 16, c->planes.planes[v]);
+  c->nViews = nViews;
+  return 1;
+}
+
+int scgpuSetViewPlanes(ScGpuScene* c, uint32_t nViews, const float* planes24)
+{
+  if (!enter(c)) return 0;
+  if (nViews == 0 || nViews > c->maxViews) return (int)fail(c, "scgpuSetViewPlanes: nViews %u not in 1..%u", nViews, c->maxViews);
+  if (!planes24) return (int)fail(c, "scgpuSetViewPlanes: NULL planes");
+  for (uint32_t v = 0; v < nViews; ++v)
+    for (int p = 0; p < 6; ++p)
+    {
+      const float* s = planes24 + (size_t)v * 24 + p * 4;
+      c->planes.planes[v][p] = make_float4(s[0], s[1], s[2], s[3]);
+    }
+  c->nViews = nViews;
+  return 1;
+}
+
+int scgpuGetViewPlanes(ScGpuScene* c, uint32_t view, float* out)
+{
+  if (!enter(c)) return 0;
+  if (view >= c->nViews || !out) return (int)fail(c, "scgpuGetViewPlanes: bad view %u", view);
+  memcpy(out, c->planes.planes[view], sizeof(float) * 24);
+  return 1;
+}
+
+// ---- the frame ----------------------------------------------------------------------------------------
+
+int scgpuUpdate(ScGpuScene* c, uint32_t flags)
+{
+  if (!enter(c)) return 0;
+  if (c->nViews == 0) return (int)fail(c, "scgpuUpdate: no views set (scgpuSetViews)");
+  const uint32_t stamp = stampOf(c->frame);
+  const uint32_t numTiles = (c->count + kTile - 1) / kTile;
+  if (c->timings) SC_CUDA(c, cudaEventRecord(c->evU0, c->stream));
+
+  if (c->topologyDirty && c->count)
+  {
+    k_resolve_parents<<<blocksFor(c->count), kBlock, 0, c->stream>>>(c->a, c->count, stamp);
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+  }
+  c->topologyDirty = false;
+
+  SC_CUDA(c, cudaMemsetAsync(c->totals, 0, sizeof(uint32_t) * (kMaxViews + 2), c->stream));
+  if (numTiles)
+  {
+    UpdateParams p{};
+    p.rec0 = c->a.rec[0]; p.rec1 = c->a.rec[1]; p.rec2 = c->a.rec[2]; p.rec3 = c->a.rec[3];
+    p.w0 = c->a.world[0]; p.w1 = c->a.world[1]; p.w2 = c->a.world[2]; p.w3 = c->a.world[3];
+    p.parentSlot = c->a.parentSlot;
+    p.vismask = c->vismask;
+    p.tileCounts = c->tileCounts;
+    p.recomputed = c->totals + kMaxViews + 1;
+    p.count = c->count;
+    p.numTiles = numTiles;
+    p.stamp = stamp;
+    p.nViews = c->nViews;
+    p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
+              ((flags & SCGPU_UPDATE_SKIP_TRANSFORM) ? kUpdSkipTransform : 0u);
+    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0, c->stream));
+    if (c->anyParentEver) k_update<true><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);
+    else k_update<false><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK1, c->stream));
+
+    k_scan_tiles<<<c->nViews + 1, 1024, 0, c->stream>>>(c->tileCounts, c->tileOffsets, c->totals, numTiles);
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+
+    ScatterParams sp{};
+    sp.vismask = c->vismask; sp.entity = c->a.entity; sp.tileCounts = c->tileCounts; sp.tileOffsets = c->tileOffsets;
+    for (uint32_t v = 0; v < kMaxViews; ++v) { sp.outEntity[v] = c->visEntity[v]; sp.outSlot[v] = c->visSlot[v]; }
+    sp.count = c->count; sp.numTiles = numTiles; sp.nViews = c->nViews;
+    k_scatter_visible<<<numTiles, kBlock, 0, c->stream>>>(sp);
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+
+    if (flags & SCGPU_UPDATE_CULLED_LISTS)
+    {
+      for (uint32_t v = 0; v < c->nViews; ++v)
+        if (!c->culledEntity[v] && !devAlloc(c, &c->culledEntity[v], (size_t)c->capacityPad, false)) return 0;
+      CulledParams cp{};
+      cp.vismask = c->vismask; cp.rec3 = c->a.rec[3]; cp.entity = c->a.entity; cp.tileOffsets = c->tileOffsets;
+      for (uint32_t v = 0; v < kMaxViews; ++v) cp.outEntity[v] = c->culledEntity[v];
+      cp.count = c->count; cp.numTiles = numTiles; cp.nViews = c->nViews;
+      k_scatter_culled<<<numTiles, kBlock, 0, c->stream>>>(cp);
+      ++c->launches;
+      SC_CUDA(c, cudaGetLastError());
+    }
+  }
+  c->culledListsValid = (flags & SCGPU_UPDATE_CULLED_LISTS) != 0;
+  // totals layout: [0..nViews) visible per view, [nViews] candidates, [kMaxViews+1] recomputed
+  SC_CUDA(c, cudaMemcpyAsync(c->hTotals, c->totals, sizeof(uint32_t) * (kMaxViews + 2), cudaMemcpyDeviceToHost, c->stream));
+  if (c->timings) SC_CUDA(c, cudaEventRecord(c->evU1, c->stream));
+  SC_CUDA(c, cudaEventRecord(c->evDone, c->stream));
+
+  c->lastUpdateFlags = flags;
+  c->lastNumTiles = numTiles;
+  c->forceAllDirty = false;
+  c->updatedOnce = true;
+  c->gatheredValid = false;
+  ++c->frame;
+  if (stampOf(c->frame) == 0u) ++c->frame;  // stamp 0 is reserved for "never dirty"
+  return 1;
+}
+
+int scgpuLastUpdateTimings(ScGpuScene* c, float* outFusedKernelMs, float* outUpdateMs)
+{
+  if (!enter(c)) return 0;
+  if (!c->timings) return (int)fail(c, "timings are disabled (scgpuEnableTimings)");
+  if (!waitDone(c)) return 0;
+  float k = 0.f, u = 0.f;
+  if (c->lastNumTiles) SC_CUDA(c, cudaEventElapsedTime(&k, c->evK0, c->evK1));
+  SC_CUDA(c, cudaEventElapsedTime(&u, c->evU0, c->evU1));
+  if (outFusedKernelMs) *outFusedKernelMs = k;
+  if (outUpdateMs) *outUpdateMs = u;
+  return 1;
+}
+
+// ---- results ------------------------------------------------------------------------------------------
+
+int scgpuGetCounts(ScGpuScene* c, ScGpuCounts* out)
+{
+  if (!enter(c)) return 0;
+  if (!out) return (int)fail(c, "scgpuGetCounts: NULL out");
+  if (!waitDone(c)) return 0;
+  memset(out, 0, sizeof(*out));
+  out->transforms = c->count;
+  out->renderablesTotal = c->hTotals[c->nViews];
+  for (uint32_t v = 0; v < c->nViews; ++v)
+  {
+    out->visible[v] = c->hTotals[v];
+    out->culled[v] = out->renderablesTotal - c->hTotals[v];
+  }
+  out->recomputed = c->hTotals[kMaxViews + 1];
+  return 1;
+}
+
+int scgpuReadVisible(ScGpuScene* c, uint32_t view, uint32_t* outEntity, uint32_t cap, uint32_t* outCount)
+{
+  if (!enter(c)) return 0;
+  if (view >= c->nViews) return (int)fail(c, "scgpuReadVisible: view %u >= %u", view, c->nViews);
+  if (!waitDone(c)) return 0;
+  const uint32_t n = c->hTotals[view];
+  if (outCount) *outCount = n;
+  const uint32_t m = std::min(n, cap);
+  if (m && outEntity)
+  {
+    SC_CUDA(c, cudaMemcpyAsync(outEntity, c->visEntity[view], (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return 1;
+}
+
+int scgpuReadCulled(ScGpuScene* c, uint32_t view, uint32_t* outEntity, uint32_t cap, uint32_t* outCount)
+{
+  if (!enter(c)) return 0;
+  if (view >= c->nViews) return (int)fail(c, "scgpuReadCulled: view %u >= %u", view, c->nViews);
+  if (!waitDone(c)) return 0;
+  if (!c->culledListsValid) return (int)fail(c, "scgpuReadCulled: the last update did not pass SCGPU_UPDATE_CULLED_LISTS");
+  const uint32_t n = c->hTotals[c->nViews] - c->hTotals[view];
+  if (outCount) *outCount = n;
+  const uint32_t m = std::min(n, cap);
+  if (m && outEntity)
+  {
+    SC_CUDA(c, cudaMemcpyAsync(outEntity, c->culledEntity[view], (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return 1;
+}
+
+int scgpuBuildDrawItemsDevice(ScGpuScene* c, uint32_t view, uint32_t maxDraws, const ScGpuDrawItem** outDevice,
+                              uint32_t* outEmitted, uint32_t* outDropped)
+{
+  if (!enter(c)) return 0;
+  if (view >= c->nViews) return (int)fail(c, "scgpuBuildDrawItemsDevice: view %u >= %u", view, c->nViews);
+  if (!waitDone(c)) return 0;
+  // RenderPrepStreamingSystem (.cpp:1296,1315-1319): maxDraws == 0 means unlimited
+  const uint32_t vis = c->hTotals[view];
+  const uint32_t emitted = (maxDraws > 0 && vis > maxDraws) ? maxDraws : vis;
+  if (!ensure(c, c->drawItems, (size_t)emitted * sizeof(ScGpuDrawItem))) return 0;
+  if (emitted)
+  {
+    k_build_draw_items<<<blocksFor((uint64_t)emitted * 5ull), kBlock, 0, c->stream>>>(
+      c->visSlot[view], c->a.entity, c->a.meshMat, c->a.world[0], c->a.world[1], c->a.world[2], c->a.world[3], emitted,
+      (float4*)c->drawItems.ptr);
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+  }
+  if (outDevice) *outDevice = (const ScGpuDrawItem*)c->drawItems.ptr;
+  if (outEmitted) *outEmitted = emitted;
+  if (outDropped) *outDropped = vis - emitted;
+  return 1;
+}
+
+int scgpuReadDrawItems(ScGpuScene* c, uint32_t view, uint32_t maxDraws, ScGpuDrawItem* out, uint32_t cap,
+                       uint32_t* outEmitted, uint32_t* outDropped)
+{
+  const ScGpuDrawItem* d = nullptr;
+  uint32_t emitted = 0, dropped = 0;
+  if (!scgpuBuildDrawItemsDevice(c, view, maxDraws, &d, &emitted, &dropped)) return 0;
+  if (outEmitted) *outEmitted = emitted;
+  if (outDropped) *outDropped = dropped;
+  const uint32_t m = std::min(emitted, cap);
+  if (m && out)
+  {
+    SC_CUDA(c, cudaMemcpyAsync(out, d, (size_t)m * sizeof(ScGpuDrawItem), cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return 1;
+}
+
+int scgpuReadWorld(ScGpuScene* c, uint32_t n, const uint32_t* entity, float* out16)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity || !out16) return (int)fail(c, "scgpuReadWorld: NULL argument");
+  const size_t bytes = (size_t)n * 4 + 256 + (size_t)n * 64 + 16;
+  if (!ensure(c, c->scratch, bytes)) return 0;
+  char* s = (char*)c->scratch.ptr;
+  uint32_t* dE = (uint32_t*)s;
+  const size_t oOut = (((size_t)n * 4 + 255) & ~(size_t)255);
+  float4* dOut = (float4*)(s + oOut);
+  uint32_t* dMissing = (uint32_t*)(s + oOut + (size_t)n * 64);
+  SC_CUDA(c, cudaMemcpyAsync(dE, entity, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  SC_CUDA(c, cudaMemsetAsync(dMissing, 0, 4, c->stream));
+  k_gather_world<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, dOut, dMissing);
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  uint32_t missing = 0;
+  SC_CUDA(c, cudaMemcpyAsync(out16, dOut, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaMemcpyAsync(&missing, dMissing, 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (missing) return (int)fail(c, "scgpuReadWorld: %u of %u handles own no Transform (zeros returned for them)", missing, n);
+  return 1;
+}
+
+int scgpuReadParents(ScGpuScene* c, uint32_t n, const uint32_t* entity, uint32_t* outParent)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity || !outParent) return (int)fail(c, "scgpuReadParents: NULL argument");
+  if (!ensure(c, c->scratch, (size_t)n * 8)) return 0;
+  uint32_t* dE = (uint32_t*)c->scratch.ptr;
+  uint32_t* dO = dE + n;
+  SC_CUDA(c, cudaMemcpyAsync(dE, entity, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  k_gather_parent<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, dO);
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  SC_CUDA(c, cudaMemcpyAsync(outParent, dO, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+int scgpuReadDenseEntities(ScGpuScene* c, uint32_t* outEntity, uint32_t cap, uint32_t* outCount)
+{
+  if (!enter(c)) return 0;
+  if (outCount) *outCount = c->count;
+  const uint32_t m = std::min(c->count, cap);
+  if (m && outEntity)
+  {
+    // read from the device copy (not the host mirror) so tests can check that the two agree
+    SC_CUDA(c, cudaMemcpyAsync(outEntity, c->a.entity, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return 1;
+}
+
+int scgpuGetDeviceViews(ScGpuScene* c, ScGpuDeviceViews* out)
+{
+  if (!enter(c)) return 0;
+  if (!out) return (int)fail(c, "scgpuGetDeviceViews: NULL out");
+  memset(out, 0, sizeof(*out));
+  for (uint32_t v = 0; v < c->maxViews; ++v) { out->visibleEntity[v] = c->visEntity[v]; out->visibleSlot[v] = c->visSlot[v]; }
+  out->visibleCount = c->totals;
+  for (int k = 0; k < 4; ++k) out->worldCol[k] = (const float*)c->a.world[k];
+  out->entity = c->a.entity;
+  out->count = c->count;
+  return 1;
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------
+
+int scgpuCommGetUniqueId(void* outId128)
+{
+  std::string err;
+  if (!outId128 || !loadNccl(err)) { g_createError = err.empty() ? "scgpuCommGetUniqueId: NULL out" : err; return 0; }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_createError = "ncclGetUniqueId failed"; return 0; }
+  memcpy(outId128, &id, SCGPU_COMM_ID_BYTES);
+  return 1;
+}
+
+int scgpuCommInit(ScGpuScene* c, uint32_t nRanks, uint32_t rank, const void* id128)
+{
+  if (!enter(c)) return 0;
+  if (nRanks == 0 || rank >= nRanks || !id128) return (int)fail(c, "scgpuCommInit: bad arguments");
+  std::string err;
+  if (!loadNccl(err)) return (int)fail(c, "%s", err.c_str());
+  ncclUniqueId id;
+  memcpy(&id, id128, SCGPU_COMM_ID_BYTES);
+  SC_NCCL(c, g_nccl.CommInitRank(&c->comm, (int)nRanks, id, (int)rank));
+  c->nRanks = nRanks;
+  c->rank = rank;
+  const size_t n = (size_t)nRanks * (kMaxViews + 2);
+  SC_CUDA(c, cudaMalloc((void**)&c->dAllCounts, n * 4));
+  SC_CUDA(c, cudaMallocHost((void**)&c->hAllCounts, n * 4));
+  memset(c->hAllCounts, 0, n * 4);
+  return 1;
+}
+
+int scgpuGatherVisible(ScGpuScene* c, uint32_t root)
+{
+  if (!enter(c)) return 0;
+  if (!c->comm) return (int)fail(c, "scgpuGatherVisible: scgpuCommInit was not called");
+  if (root >= c->nRanks) return (int)fail(c, "scgpuGatherVisible: root %u >= %u ranks", root, c->nRanks);
+  if (!c->updatedOnce) return (int)fail(c, "scgpuGatherVisible: no update issued");
+  const size_t row = kMaxViews + 2;
+  // 1) counts of every rank to every rank (V*4 bytes each; one small allgather)
+  SC_NCCL(c, g_nccl.AllGather(c->totals, c->dAllCounts, row, ncclUint32, c->comm, c->stream));
+  ++c->launches;
+  SC_CUDA(c, cudaMemcpyAsync(c->hAllCounts, c->dAllCounts, (size_t)c->nRanks * row * 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));  // receive sizes must be known on the host
+  // 2) lists: exact-size send/recv to the submitting rank, concatenated in rank order
+  if (c->rank == root)
+  {
+    size_t need = 0;
+    for (uint32_t v = 0; v < c->nViews; ++v)
+    {
+      size_t tot = 0;
+      for (uint32_t r = 0; r < c->nRanks; ++r) tot += c->hAllCounts[r * row + v];
+      need = std::max(need, tot);
+    }
+    if (need > c->gatheredCap)
+    {
+      for (uint32_t v = 0; v < c->maxViews; ++v)
+      {
+        if (c->gathered[v]) SC_CUDA(c, cudaFree(c->gathered[v]));
+        c->gathered[v] = nullptr;
+        SC_CUDA(c, cudaMalloc((void**)&c->gathered[v], std::max(need, (size_t)1) * 4));
+      }
+      c->gatheredCap = need;
+    }
+  }
+  SC_NCCL(c, g_nccl.GroupStart());
+  for (uint32_t v = 0; v < c->nViews; ++v)
+  {
+    if (c->rank == root)
+    {
+      size_t off = 0;
+      for (uint32_t r = 0; r < c->nRanks; ++r)
+      {
+        const size_t cnt = c->hAllCounts[r * row + v];
+        if (r == root)
+        {
+          if (cnt) SC_CUDA(c, cudaMemcpyAsync(c->gathered[v] + off, c->visEntity[v], cnt * 4, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        else if (cnt)
+        {
+          SC_NCCL(c, g_nccl.Recv(c->gathered[v] + off, cnt, ncclUint32, (int)r, c->comm, c->stream));
+        }
+        off += cnt;
+      }
+    }
+    else
+    {
+      const size_t cnt = c->hAllCounts[c->rank * row + v];
+      if (cnt) SC_NCCL(c, g_nccl.Send(c->visEntity[v], cnt, ncclUint32, (int)root, c->comm, c->stream));
+    }
+  }
+  SC_NCCL(c, g_nccl.GroupEnd());
+  ++c->launches;
+  c->gatheredValid = true;
+  return 1;
+}
+
+int scgpuGetGatheredCounts(ScGpuScene* c, uint32_t* outCounts, uint32_t capRanks)
+{
+  if (!enter(c)) return 0;
+  if (!c->gatheredValid || !outCounts) return (int)fail(c, "scgpuGetGatheredCounts: no gather since the last update");
+  const size_t row = kMaxViews + 2;
+  for (uint32_t r = 0; r < c->nRanks && r < capRanks; ++r)
+    for (uint32_t v = 0; v < c->nViews; ++v) outCounts[r * c->nViews + v] = c->hAllCounts[r * row + v];
+  return 1;
+}
+
+int scgpuReadGatheredVisible(ScGpuScene* c, uint32_t view, uint32_t* outEntity, uint32_t cap, uint32_t* outCount)
+{
+  if (!enter(c)) return 0;
+  if (!c->gatheredValid) return (int)fail(c, "scgpuReadGatheredVisible: no gather since the last update");
+  if (view >= c->nViews) return (int)fail(c, "scgpuReadGatheredVisible: bad view");
+  const size_t row = kMaxViews + 2;
+  size_t tot = 0;
+  for (uint32_t r = 0; r < c->nRanks; ++r) tot += c->hAllCounts[r * row + view];
+  if (outCount) *outCount = (uint32_t)tot;
+  if (!c->gathered[view]) return (int)fail(c, "scgpuReadGatheredVisible: this rank was not the gather root");
+  const size_t m = std::min(tot, (size_t)cap);
+  if (m && outEntity)
+  {
+    SC_CUDA(c, cudaMemcpyAsync(outEntity, c->gathered[view], m * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+// scgpu_math.cuh — device arithmetic of the scene-update hot path, bit-matched to the reference's CPU code.
+//
+// Every parity-critical operation is written with the explicit round-to-nearest intrinsics
+// (__fmul_rn/__fadd_rn/__dmul_rn/__dadd_rn ...): nvcc never contracts those into FMA, so the results do not
+// depend on -fmad. Denormals are kept (no -ftz), sqrt and division are the IEEE variants.
+//
+// Reference (relative to /root/reference):
+//   mat4_mul           src/core/src/sc_math.cpp:52-68   ((a0*b0 + a1*b1) + a2*b2) + a3*b3, separate mul/add
+//   mat4_rotation_xyz  src/core/src/sc_math.cpp:100-128 R = (Rz*Ry)*Rx, dense products
+//   mat4_trs           src/core/src/sc_math.cpp:130-142 M = T*(R*S), dense products
+//   computeWorldBoundsSphere / sphereInFrustum  src/engine/world/sc_world_partition.cpp:1105-1144
+//   std::sin/std::cos(float) -> glibc 2.39 sinf/cosf generic variant (see oracle/scoracle.c header)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scgpu
+{
+
+struct Mat4
+{
+  float4 c0, c1, c2, c3;  // columns; element (row r, col c) = c<c>.<xyzw[r]>
+};
+
+// ---------------------------------------------------------------------------------------------------
+// glibc sinf/cosf (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, sincosf.h) in IEEE double, no contraction
+// ---------------------------------------------------------------------------------------------------
+
+__constant__ uint32_t kInvPio4[24] = {
+  0xa2,       0xa2f9,     0xa2f983,   0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529,
+  0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
+  0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041
+};
+
+// sine polynomial of sincosf.h:sinf_poly (n even): x + x^3*s1 + x^7*(s2 + x^2*s3)
+__device__ __forceinline__ float sin_poly(double x, double x2)
+{
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  const double x3 = __dmul_rn(x, x2);
+  const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+  const double x7 = __dmul_rn(x3, x2);
+  const double s = __dadd_rn(x, __dmul_rn(x3, S1));
+  return __double2float_rn(__dadd_rn(s, __dmul_rn(x7, s1)));
+}
+
+// cosine polynomial of sincosf.h:sinf_poly (n odd), table 0 coefficients. Table 1 holds the negated
+// coefficients; round-to-nearest is sign-symmetric, so its result is exactly the negation of this one.
+__device__ __forceinline__ float cos_poly(double x2)
+{
+  const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+               C4 = 0x1.99343027bf8c3p-16;
+  const double x4 = __dmul_rn(x2, x2);
+  const double c2 = __dadd_rn(C3, __dmul_rn(x2, C4));
+  const double c1 = __dadd_rn(C0, __dmul_rn(x2, C1));
+  const double x6 = __dmul_rn(x4, x2);
+  const double c = __dadd_rn(c1, __dmul_rn(x4, C2));
+  return __double2float_rn(__dadd_rn(c, __dmul_rn(x6, c2)));
+}
+
+// sincosf.h:reduce_large — |x| >= 120, 32x96 -> 128 bit fixed-point product with 4/pi
+__device__ __noinline__ double reduce_large(uint32_t xi, int* np)
+{
+  const uint32_t* arr = &kInvPio4[(xi >> 26) & 15];
+  const int shift = (xi >> 23) & 7;
+  uint64_t n, res0, res1, res2;
+  xi = (xi & 0xffffff) | 0x800000;
+  xi <<= shift;
+  res0 = (uint32_t)(xi * arr[0]);
+  res1 = (uint64_t)xi * arr[4];
+  res2 = (uint64_t)xi * arr[8];
+  res0 = (res2 >> 32) | (res0 << 32);
+  res0 += res1;
+  n = (res0 + (1ULL << 61)) >> 62;
+  res0 -= n << 62;
+  const double x = __ll2double_rn((long long)res0);
+  *np = (int)n;
+  return __dmul_rn(x, 0x1.921FB54442D18p-62);
+}
+
+// sinf(y) and cosf(y) of glibc 2.39 (generic variant) sharing one range reduction; bit-identical to the two
+// separate libm calls of sc_math.cpp:102-107.
+__device__ __forceinline__ void sincosf_glibc(float y, float& sn, float& cs)
+{
+  const uint32_t yi = __float_as_uint(y);
+  const uint32_t top = (yi >> 20) & 0x7ffu;
+  // abstop12 thresholds: pio4f = 0x3f490fdb, 2^-12 = 0x39800000, 120.0f = 0x42f00000, inf = 0x7f800000
+  const uint32_t kTopPio4 = 0x3f4u, kTopTiny = 0x398u, kTop120 = 0x42fu, kTopInf = 0x7f8u;
+  double x = (double)y;
+
+  if (top < kTopPio4)
+  {
+    if (top < kTopTiny)
+    {
+      sn = y;
+      cs = 1.0f;
+      return;
+    }
+    const double x2 = __dmul_rn(x, x);
+    sn = sin_poly(x, x2);
+    cs = cos_poly(x2);
+    return;
+  }
+
+  int n;
+  int q;  // quadrant used for the sign / table selection
+  if (top < kTop120)
+  {
+    // sincosf.h:reduce_fast, !TOINT_INTRINSICS: hpi_inv prescaled by 2^24
+    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    n = (__double2int_rz(r) + 0x800000) >> 24;
+    x = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
+    q = n;
+  }
+  else if (top < kTopInf)
+  {
+    x = reduce_large(yi, &n);
+    q = n + (int)(yi >> 31);
+  }
+  else
+  {
+    // __math_invalidf: (y - y) / (y - y)
+    const float d = __fsub_rn(y, y);
+    sn = cs = __fdiv_rn(d, d);
+    return;
+  }
+
+  // sign[q & 3] = {1, -1, -1, 1}; multiplication by +-1.0 is exact
+  const double xs = (((q + 1) & 2) != 0) ? -x : x;
+  const double x2 = __dmul_rn(x, x);
+  const float S = sin_poly(xs, x2);
+  float C = cos_poly(x2);
+  if (q & 2) C = -C;  // table 1
+  if (n & 1) { sn = C; cs = S; }
+  else       { sn = S; cs = C; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dense 4x4 products, reference operation order
+// ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float dot4_ref(float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3)
+{
+  float r = __fmul_rn(a0, b0);
+  r = __fadd_rn(r, __fmul_rn(a1, b1));
+  r = __fadd_rn(r, __fmul_rn(a2, b2));
+  r = __fadd_rn(r, __fmul_rn(a3, b3));
+  return r;
+}
+
+__device__ __forceinline__ float4 mul_col(const Mat4& a, float4 b)
+{
+  float4 r;
+  r.x = dot4_ref(a.c0.x, a.c1.x, a.c2.x, a.c3.x, b.x, b.y, b.z, b.w);
+  r.y = dot4_ref(a.c0.y, a.c1.y, a.c2.y, a.c3.y, b.x, b.y, b.z, b.w);
+  r.z = dot4_ref(a.c0.z, a.c1.z, a.c2.z, a.c3.z, b.x, b.y, b.z, b.w);
+  r.w = dot4_ref(a.c0.w, a.c1.w, a.c2.w, a.c3.w, b.x, b.y, b.z, b.w);
+  return r;
+}
+
+// mat4_mul, sc_math.cpp:52-68
+__device__ __forceinline__ Mat4 mat4_mul(const Mat4& a, const Mat4& b)
+{
+  Mat4 r;
+  r.c0 = mul_col(a, b.c0);
+  r.c1 = mul_col(a, b.c1);
+  r.c2 = mul_col(a, b.c2);
+  r.c3 = mul_col(a, b.c3);
+  return r;
+}
+
+__device__ __forceinline__ Mat4 mat4_identity()
+{
+  Mat4 m;
+  m.c0 = make_float4(1.f, 0.f, 0.f, 0.f);
+  m.c1 = make_float4(0.f, 1.f, 0.f, 0.f);
+  m.c2 = make_float4(0.f, 0.f, 1.f, 0.f);
+  m.c3 = make_float4(0.f, 0.f, 0.f, 1.f);
+  return m;
+}
+
+// mat4_trs, sc_math.cpp:130-142, all four products dense (zeros and ones take part), so that signed zeros,
+// NaN and Inf propagate exactly as on the CPU.
+__device__ __forceinline__ Mat4 mat4_trs_dense(float px, float py, float pz, float rx, float ry, float rz, float sx_,
+                                               float sy_, float sz_)
+{
+  float sx, cx, sy, cy, sz, cz;
+  sincosf_glibc(rx, sx, cx);
+  sincosf_glibc(ry, sy, cy);
+  sincosf_glibc(rz, sz, cz);
+
+  Mat4 rxm = mat4_identity();
+  rxm.c1.y = cx; rxm.c1.z = sx; rxm.c2.y = -sx; rxm.c2.z = cx;
+  Mat4 rym = mat4_identity();
+  rym.c0.x = cy; rym.c0.z = -sy; rym.c2.x = sy; rym.c2.z = cy;
+  Mat4 rzm = mat4_identity();
+  rzm.c0.x = cz; rzm.c0.y = sz; rzm.c1.x = -sz; rzm.c1.y = cz;
+
+  const Mat4 r = mat4_mul(mat4_mul(rzm, rym), rxm);
+
+  Mat4 s;
+  s.c0 = make_float4(sx_, 0.f, 0.f, 0.f);
+  s.c1 = make_float4(0.f, sy_, 0.f, 0.f);
+  s.c2 = make_float4(0.f, 0.f, sz_, 0.f);
+  s.c3 = make_float4(0.f, 0.f, 0.f, 1.f);
+
+  Mat4 t = mat4_identity();
+  t.c3 = make_float4(px, py, pz, 1.f);
+
+  return mat4_mul(t, mat4_mul(r, s));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bounds + plane tests, sc_world_partition.cpp:1105-1144
+// ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float sum3_ref(float a, float b, float c)
+{
+  return __fadd_rn(__fadd_rn(a, b), c);
+}
+
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }  // std::max
+
+// computeWorldBoundsSphere: center = M * aabb-centre (affine, left-to-right sum), radius = |extent| * max column norm
+__device__ __forceinline__ void world_bounds_sphere(const Mat4& m, float bminx, float bminy, float bminz, float bmaxx,
+                                                    float bmaxy, float bmaxz, float& ox, float& oy, float& oz,
+                                                    float& radius)
+{
+  const float cx = __fmul_rn(__fadd_rn(bminx, bmaxx), 0.5f);
+  const float cy = __fmul_rn(__fadd_rn(bminy, bmaxy), 0.5f);
+  const float cz = __fmul_rn(__fadd_rn(bminz, bmaxz), 0.5f);
+  const float ex = __fmul_rn(__fsub_rn(bmaxx, bminx), 0.5f);
+  const float ey = __fmul_rn(__fsub_rn(bmaxy, bminy), 0.5f);
+  const float ez = __fmul_rn(__fsub_rn(bmaxz, bminz), 0.5f);
+
+  ox = __fadd_rn(sum3_ref(__fmul_rn(m.c0.x, cx), __fmul_rn(m.c1.x, cy), __fmul_rn(m.c2.x, cz)), m.c3.x);
+  oy = __fadd_rn(sum3_ref(__fmul_rn(m.c0.y, cx), __fmul_rn(m.c1.y, cy), __fmul_rn(m.c2.y, cz)), m.c3.y);
+  oz = __fadd_rn(sum3_ref(__fmul_rn(m.c0.z, cx), __fmul_rn(m.c1.z, cy), __fmul_rn(m.c2.z, cz)), m.c3.z);
+
+  const float sx = __fsqrt_rn(sum3_ref(__fmul_rn(m.c0.x, m.c0.x), __fmul_rn(m.c0.y, m.c0.y), __fmul_rn(m.c0.z, m.c0.z)));
+  const float sy = __fsqrt_rn(sum3_ref(__fmul_rn(m.c1.x, m.c1.x), __fmul_rn(m.c1.y, m.c1.y), __fmul_rn(m.c1.z, m.c1.z)));
+  const float sz = __fsqrt_rn(sum3_ref(__fmul_rn(m.c2.x, m.c2.x), __fmul_rn(m.c2.y, m.c2.y), __fmul_rn(m.c2.z, m.c2.z)));
+  const float maxScale = std_max(sx, std_max(sy, sz));
+  const float localRadius = __fsqrt_rn(sum3_ref(__fmul_rn(ex, ex), __fmul_rn(ey, ey), __fmul_rn(ez, ez)));
+  radius = __fmul_rn(localRadius, maxScale);
+}
+
+// sphereInFrustum for one view: culled iff any plane has ((n0*c0 + n1*c1) + n2*c2) + d < -radius (NaN => kept)
+__device__ __forceinline__ bool sphere_in_frustum(const float4* __restrict__ planes, float cx, float cy, float cz,
+                                                  float radius)
+{
+  const float negR = -radius;
+  bool inside = true;
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+  {
+    const float4 pl = planes[p];
+    const float d = __fadd_rn(sum3_ref(__fmul_rn(pl.x, cx), __fmul_rn(pl.y, cy), __fmul_rn(pl.z, cz)), pl.w);
+    inside = inside && !(d < negR);
+  }
+  return inside;
+}
+
+}  // namespace scgpu

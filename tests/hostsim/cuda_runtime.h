@@ -1,0 +1,28 @@
+// Host stand-in for <cuda_runtime.h>: lets tests compile sc-gameengine_b200/csrc/scgpu_math.cuh with g++
+// (-O2 -ffp-contract=off) so the device arithmetic can be checked against the oracle without a GPU.
+// The _rn intrinsics map to plain IEEE operations, which is exactly what they are on the device.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __constant__ static const
+#define __restrict__
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline float __double2float_rn(double a) { return (float)a; }
+static inline int __double2int_rz(double a) { return (int)a; }
+static inline double __ll2double_rn(long long a) { return (double)a; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }

@@ -1,0 +1,200 @@
+"""GPU parity proper: the CUDA path through the C ABI (libscgpu.so) against the plain-C oracle, and against the
+compiled reference (oracle/_ref) when it travelled to the box. Bit-exact: ordered visible/culled lists, counts,
+draw items and world matrices (NaNs compare equal to NaNs)."""
+import numpy as np
+import pytest
+
+import oracle_bind
+from oracle_bind import PortScene, RefScene
+from scenarios import (INVALID, GpuAdapter, assert_same_bits, compare_draws, compare_frame, random_aabb,
+                       random_forest, random_trs)
+from scgpu import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _checkers():
+    out = [("port", PortScene())]
+    if oracle_bind.ref_available():
+        out.append(("ref", RefScene()))
+    return out
+
+
+def _entities(checkers, n):
+    for name, s in checkers:
+        if name == "ref":
+            return s.create_entities(n)
+    return np.arange(n, dtype=np.uint32)
+
+
+def test_create_reports_device():
+    import scgpu
+    s = scgpu.Scene(1024, max_views=2)
+    assert s.lib.scgpuGetApiVersion() == 1
+    s.close()
+
+
+@pytest.mark.parametrize("n,seed", [(1, 1), (255, 2), (1024, 3), (1025, 4), (50_000, 5)])
+def test_flat_city_matches_oracle(n, seed):
+    sc = scenes.city_flat(n, seed=seed)
+    chk = _checkers()
+    e = _entities(chk, n)
+    g = GpuAdapter(n + 8, max_views=5)
+    vps = scenes.standard_views(5)
+    for _, s in chk + [("gpu", g)]:
+        s.spawn(e, sc["trs9"], None, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+        s.update(vps)
+    for name, s in chk:
+        compare_frame(g, s, e, 5, f"flat n={n} vs {name}")
+        compare_draws(g, s, 0, f"flat n={n} vs {name}")
+        compare_draws(g, s, 5, f"flat n={n} budget vs {name}")
+    assert g.recomputed == n
+    # second frame, nothing dirty: nothing recomputed, same lists
+    g.update(vps)
+    assert g.recomputed == 0
+    compare_frame(g, chk[0][1], e, 5, "flat clean frame")
+    g.close()
+
+
+@pytest.mark.parametrize("n,seed", [(10, 1), (3000, 2), (40_000, 3)])
+def test_depth4_city_matches_oracle(n, seed):
+    sc = scenes.city_hier(n, seed=seed)
+    chk = _checkers()
+    e = _entities(chk, n)
+    par = scenes.parent_handles(sc["parent"], e)
+    g = GpuAdapter(n, max_views=5)
+    vps = scenes.standard_views(5)
+    rng = np.random.default_rng(seed)
+    for _, s in chk + [("gpu", g)]:
+        s.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+        s.update(vps)
+    for name, s in chk:
+        compare_frame(g, s, e, 5, f"hier n={n} frame0 vs {name}")
+    # 30 % dirty
+    idx = rng.choice(n, max(1, n * 3 // 10), replace=False)
+    t2 = sc["trs9"][idx].copy()
+    t2[:, 0:3] += rng.normal(size=(len(idx), 3)).astype(np.float32)
+    t2[:, 4] += np.float32(0.1)
+    for _, s in chk + [("gpu", g)]:
+        s.set_local(e[idx], t2)
+        s.update(vps)
+    for name, s in chk:
+        compare_frame(g, s, e, 5, f"hier n={n} frame1 vs {name}")
+        compare_draws(g, s, 0, f"hier n={n} vs {name}")
+        assert g.recomputed == s.recomputed if name == "port" else True
+    g.close()
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_random_forest_edge_cases(seed):
+    rng = np.random.default_rng(seed)
+    chk = _checkers()
+    n = 1500
+    e = _entities(chk, n)
+    g = GpuAdapter(4096, max_views=3)
+    parent_idx = random_forest(rng, n, max_back=600 if seed % 2 else 40)  # long jumps cross sub-tiles
+    trs = random_trs(rng, n, spread=60.0)
+    flags = rng.choice([0, 1, 2, 3], size=n, p=[0.05, 0.1, 0.15, 0.7]).astype(np.uint32)
+    trs[5, 6:9] = 0.0
+    trs[6, 6:8] = 0.0
+    trs[7, 0] = np.nan
+    trs[8, 4] = np.inf
+    trs[9, 3:6] = [1e6, -3e9, 1e-30]
+    trs[10, 3:6] = [120.0, -119.99, 0.78539819]
+    trs[11, 6] = -2.0
+    par = scenes.parent_handles(parent_idx, e)
+    par[20] = e[20]
+    par[21] = 0x00ABCDEF
+    par[30], par[31] = e[31], e[30]
+    par[40], par[41], par[42] = e[41], e[42], e[40]
+    par[43] = e[40]
+    par[300], par[900] = e[900], e[300]   # cycle across sub-tiles
+    par[901] = e[300]
+    aabb = random_aabb(rng, n)
+    mm = rng.integers(0, 50, size=(n, 2)).astype(np.uint32)
+    everyone = chk + [("gpu", g)]
+    vps = scenes.standard_views(3, center=(0.0, 10.0, 80.0))
+    for _, s in everyone:
+        s.spawn(e, trs, par, aabb, mm, flags)
+        s.update(vps)
+    for name, s in chk:
+        compare_frame(g, s, e, 3, f"frame0 vs {name}")
+    assert np.array_equal(g.s.read_parents(e), chk[0][1].parent), "parent fix-ups differ"
+
+    idx = rng.choice(n, 200, replace=False)
+    t2 = random_trs(rng, 200, spread=60.0)
+    for _, s in everyone:
+        s.set_local(e[idx], t2)
+        s.set_parent(e[[40, 50, 51]], np.array([INVALID, e[52], e[20]], np.uint32))
+        s.update(vps)
+    for name, s in chk:
+        compare_frame(g, s, e, 3, f"frame1 vs {name}")
+
+    dead = rng.choice(n, 300, replace=False)
+    dead_handles = np.concatenate([e[dead], np.array([0x00FFFFF0, e[dead[0]]], np.uint32)])
+    for _, s in everyone:
+        s.despawn(dead_handles)
+    live = np.setdiff1d(np.arange(n), dead)
+    if len(chk) > 1:
+        e2 = chk[1][1].create_entities(100)
+    else:
+        e2 = np.arange(n, n + 100, dtype=np.uint32)
+    trs3 = random_trs(rng, 100, spread=60.0)
+    par3 = e[rng.choice(live, 100)]
+    bb3 = random_aabb(rng, 100)
+    for _, s in everyone:
+        s.spawn(e2, trs3, par3, bb3, None, None)
+        s.update(vps)
+    assert np.array_equal(g.dense_entities(), chk[0][1].entity), "pool order after swap-remove differs"
+    alive = np.concatenate([e[live], e2])
+    for name, s in chk:
+        compare_frame(g, s, alive, 3, f"frame2 vs {name}")
+        compare_draws(g, s, 0, f"frame2 vs {name}")
+        compare_draws(g, s, 13, f"frame2 budget vs {name}")
+    for _, s in everyone:
+        s.update(vps, freeze=True)
+    for name, s in chk:
+        compare_frame(g, s, alive, 3, f"freeze vs {name}")
+    # mark-all-dirty must reproduce the same matrices (idempotence)
+    before = g.read_world(alive)
+    g.mark_all_dirty()
+    g.update(vps)
+    assert_same_bits(before, g.read_world(alive), "idempotent recompute")
+    g.close()
+
+
+def test_views_zero_and_identity_matrix():
+    """Zero VP => zero planes => everything visible; identity VP => unit cube planes"""
+    n = 2000
+    sc = scenes.city_flat(n, seed=9)
+    chk = _checkers()
+    e = _entities(chk, n)
+    g = GpuAdapter(n, max_views=2)
+    vps = np.stack([np.zeros(16, np.float32), np.eye(4, dtype=np.float32).ravel()])
+    for _, s in chk + [("gpu", g)]:
+        s.spawn(e, sc["trs9"], None, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+        s.update(vps)
+    assert len(g.visible[0]) == n
+    for name, s in chk:
+        compare_frame(g, s, e, 2, f"special views vs {name}")
+    pl = g.s.get_view_planes(1)
+    assert np.array_equal(pl, np.array([[1, 0, 0, 1], [-1, 0, 0, 1], [0, 1, 0, 1], [0, -1, 0, 1], [0, 0, 1, 1], [0, 0, -1, 1]], np.float32))
+    g.close()
+
+
+def test_empty_scene_and_errors():
+    import scgpu
+    s = scgpu.Scene(16, max_views=1)
+    with pytest.raises(scgpu.ScGpuError):
+        s.update()  # no views
+    s.set_views(np.eye(4, dtype=np.float32).ravel())
+    s.update()
+    c = s.counts()
+    assert (c.transforms, c.renderablesTotal, c.visible[0]) == (0, 0, 0)
+    assert len(s.read_visible(0)) == 0
+    with pytest.raises(scgpu.ScGpuError):
+        s.spawn(np.arange(17, dtype=np.uint32), np.zeros((17, 9), np.float32))  # over capacity
+    s.spawn(np.array([3], np.uint32), np.array([[0, 0, 0, 0, 0, 0, 1, 1, 1]], np.float32))
+    with pytest.raises(scgpu.ScGpuError):
+        s.spawn(np.array([3], np.uint32), np.zeros((1, 9), np.float32))  # duplicate Transform
+    s.close()
