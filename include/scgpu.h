@@ -168,6 +168,9 @@ SCGPU_API uint64_t scgpuKernelLaunchCount(ScGpuScene* ctx);
 /* device time of the main fused kernel and of the whole last update, from CUDA events on the context stream */
 SCGPU_API int scgpuLastUpdateTimings(ScGpuScene* ctx, float* outFusedKernelMs, float* outUpdateMs);
 SCGPU_API int scgpuEnableTimings(ScGpuScene* ctx, int enable);
+/* per-launch device times (ms) of up to the last 256 updates since timings were enabled, oldest first */
+SCGPU_API int scgpuReadUpdateTimings(ScGpuScene* ctx, float* outFusedKernelMs, float* outUpdateMs, uint32_t cap,
+                                     uint32_t* outCount);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,7 @@ struct ScGpuScene
   bool culledListsValid = false;
 
   SceneArrays a{};
+  uint16_t* tileMap = nullptr;  // per sub-tile level-sorted thread -> slot map (hierarchical scenes)
   uint8_t* vismask = nullptr;
   uint32_t* tileCounts = nullptr;
   uint32_t* tileOffsets = nullptr;
@@ -110,7 +111,11 @@ struct ScGpuScene
   ViewPlanes planes{};
   uint32_t* hTotals = nullptr;  // pinned [maxViews+2]
   cudaEvent_t evDone = nullptr;
-  cudaEvent_t evK0 = nullptr, evK1 = nullptr, evU0 = nullptr, evU1 = nullptr;
+  // ring of CUDA event pairs around the fused kernel / the whole update, so that a benchmark can read the
+  // per-launch device times of many asynchronous updates after a single synchronise
+  static constexpr uint32_t kTimingRing = 256;
+  cudaEvent_t evK0[kTimingRing] = {}, evK1[kTimingRing] = {}, evU0[kTimingRing] = {}, evU1[kTimingRing] = {};
+  uint32_t timedUpdates = 0;
   bool timings = false;
 
   DeviceBuffer staging;   // uploads
@@ -239,7 +244,7 @@ void freeAll(ScGpuScene* c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
-  cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
+  cudaFree(c->tileMap); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
@@ -249,10 +254,13 @@ void freeAll(ScGpuScene* c)
   if (c->hTotals) cudaFreeHost(c->hTotals);
   if (c->hAllCounts) cudaFreeHost(c->hAllCounts);
   if (c->evDone) cudaEventDestroy(c->evDone);
-  if (c->evK0) cudaEventDestroy(c->evK0);
-  if (c->evK1) cudaEventDestroy(c->evK1);
-  if (c->evU0) cudaEventDestroy(c->evU0);
-  if (c->evU1) cudaEventDestroy(c->evU1);
+  for (uint32_t i = 0; i < ScGpuScene::kTimingRing; ++i)
+  {
+    if (c->evK0[i]) cudaEventDestroy(c->evK0[i]);
+    if (c->evK1[i]) cudaEventDestroy(c->evK1[i]);
+    if (c->evU0[i]) cudaEventDestroy(c->evU0[i]);
+    if (c->evU1[i]) cudaEventDestroy(c->evU1[i]);
+  }
   if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -294,6 +302,7 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   if (!devAlloc(c, &c->a.sparse, (size_t)c->sparseSize, true)) return 0;
   c->a.sparseSize = c->sparseSize;
   if (!devAlloc(c, &c->vismask, n, true)) return 0;
+  if (!devAlloc(c, &c->tileMap, n, true)) return 0;
   if (!devAlloc(c, &c->tileCounts, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->tileOffsets, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->totals, (size_t)kMaxViews + 2, true)) return 0;
@@ -305,10 +314,6 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   SC_CUDA(c, cudaMallocHost((void**)&c->hTotals, sizeof(uint32_t) * (kMaxViews + 2)));
   memset(c->hTotals, 0, sizeof(uint32_t) * (kMaxViews + 2));
   SC_CUDA(c, cudaEventCreateWithFlags(&c->evDone, cudaEventDisableTiming));
-  SC_CUDA(c, cudaEventCreate(&c->evK0));
-  SC_CUDA(c, cudaEventCreate(&c->evK1));
-  SC_CUDA(c, cudaEventCreate(&c->evU0));
-  SC_CUDA(c, cudaEventCreate(&c->evU1));
   SC_CUDA(c, cudaStreamSynchronize(c->stream));
   c->hEntity.reserve(c->capacity);
   return 1;
@@ -365,7 +370,18 @@ uint64_t scgpuKernelLaunchCount(ScGpuScene* ctx) { return ctx ? ctx->launches : 
 int scgpuEnableTimings(ScGpuScene* ctx, int enable)
 {
   if (!enter(ctx)) return 0;
+  if (enable && !ctx->evK0[0])
+  {
+    for (uint32_t i = 0; i < ScGpuScene::kTimingRing; ++i)
+    {
+      SC_CUDA(ctx, cudaEventCreate(&ctx->evK0[i]));
+      SC_CUDA(ctx, cudaEventCreate(&ctx->evK1[i]));
+      SC_CUDA(ctx, cudaEventCreate(&ctx->evU0[i]));
+      SC_CUDA(ctx, cudaEventCreate(&ctx->evU1[i]));
+    }
+  }
   ctx->timings = enable != 0;
+  ctx->timedUpdates = 0;
   return 1;
 }
 
@@ -625,13 +641,20 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
   if (c->nViews == 0) return (int)fail(c, "scgpuUpdate: no views set (scgpuSetViews)");
   const uint32_t stamp = stampOf(c->frame);
   const uint32_t numTiles = (c->count + kTile - 1) / kTile;
-  if (c->timings) SC_CUDA(c, cudaEventRecord(c->evU0, c->stream));
+  const uint32_t tslot = c->timedUpdates % ScGpuScene::kTimingRing;
+  if (c->timings) SC_CUDA(c, cudaEventRecord(c->evU0[tslot], c->stream));
 
   if (c->topologyDirty && c->count)
   {
     k_resolve_parents<<<blocksFor(c->count), kBlock, 0, c->stream>>>(c->a, c->count, stamp);
     ++c->launches;
     SC_CUDA(c, cudaGetLastError());
+    if (c->anyParentEver)
+    {
+      k_build_tile_map<<<blocksFor(c->count), kBlock, 0, c->stream>>>(c->a.parentSlot, c->tileMap, c->count);
+      ++c->launches;
+      SC_CUDA(c, cudaGetLastError());
+    }
   }
   c->topologyDirty = false;
 
@@ -642,6 +665,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.rec0 = c->a.rec[0]; p.rec1 = c->a.rec[1]; p.rec2 = c->a.rec[2]; p.rec3 = c->a.rec[3];
     p.w0 = c->a.world[0]; p.w1 = c->a.world[1]; p.w2 = c->a.world[2]; p.w3 = c->a.world[3];
     p.parentSlot = c->a.parentSlot;
+    p.tileMap = c->tileMap;
     p.vismask = c->vismask;
     p.tileCounts = c->tileCounts;
     p.recomputed = c->totals + kMaxViews + 1;
@@ -651,12 +675,22 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.nViews = c->nViews;
     p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
               ((flags & SCGPU_UPDATE_SKIP_TRANSFORM) ? kUpdSkipTransform : 0u);
-    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0, c->stream));
-    if (c->anyParentEver) k_update<true><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);
-    else k_update<false><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);
+    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
+#define SC_LAUNCH_UPDATE(V)                                                                 \
+  case V:                                                                                   \
+    if (c->anyParentEver) k_update<true, V><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);  \
+    else k_update<false, V><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);                  \
+    break;
+    switch (c->nViews)
+    {
+      SC_LAUNCH_UPDATE(1) SC_LAUNCH_UPDATE(2) SC_LAUNCH_UPDATE(3) SC_LAUNCH_UPDATE(4)
+      SC_LAUNCH_UPDATE(5) SC_LAUNCH_UPDATE(6) SC_LAUNCH_UPDATE(7) SC_LAUNCH_UPDATE(8)
+      default: return (int)fail(c, "scgpuUpdate: unsupported view count %u", c->nViews);
+    }
+#undef SC_LAUNCH_UPDATE
     ++c->launches;
     SC_CUDA(c, cudaGetLastError());
-    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK1, c->stream));
+    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK1[tslot], c->stream));
 
     k_scan_tiles<<<c->nViews + 1, 1024, 0, c->stream>>>(c->tileCounts, c->tileOffsets, c->totals, numTiles);
     ++c->launches;
@@ -686,7 +720,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
   c->culledListsValid = (flags & SCGPU_UPDATE_CULLED_LISTS) != 0;
   // totals layout: [0..nViews) visible per view, [nViews] candidates, [kMaxViews+1] recomputed
   SC_CUDA(c, cudaMemcpyAsync(c->hTotals, c->totals, sizeof(uint32_t) * (kMaxViews + 2), cudaMemcpyDeviceToHost, c->stream));
-  if (c->timings) SC_CUDA(c, cudaEventRecord(c->evU1, c->stream));
+  if (c->timings) { SC_CUDA(c, cudaEventRecord(c->evU1[tslot], c->stream)); ++c->timedUpdates; }
   SC_CUDA(c, cudaEventRecord(c->evDone, c->stream));
 
   c->lastUpdateFlags = flags;
@@ -701,14 +735,28 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
 
 int scgpuLastUpdateTimings(ScGpuScene* c, float* outFusedKernelMs, float* outUpdateMs)
 {
+  uint32_t n = 0;
+  return scgpuReadUpdateTimings(c, outFusedKernelMs, outUpdateMs, 1, &n);
+}
+
+int scgpuReadUpdateTimings(ScGpuScene* c, float* outFusedKernelMs, float* outUpdateMs, uint32_t cap, uint32_t* outCount)
+{
   if (!enter(c)) return 0;
   if (!c->timings) return (int)fail(c, "timings are disabled (scgpuEnableTimings)");
   if (!waitDone(c)) return 0;
-  float k = 0.f, u = 0.f;
-  if (c->lastNumTiles) SC_CUDA(c, cudaEventElapsedTime(&k, c->evK0, c->evK1));
-  SC_CUDA(c, cudaEventElapsedTime(&u, c->evU0, c->evU1));
-  if (outFusedKernelMs) *outFusedKernelMs = k;
-  if (outUpdateMs) *outUpdateMs = u;
+  const uint32_t have = std::min(c->timedUpdates, ScGpuScene::kTimingRing);
+  const uint32_t n = std::min(have, cap);
+  // newest last: entries [timedUpdates-n, timedUpdates)
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    const uint32_t slot = (c->timedUpdates - n + i) % ScGpuScene::kTimingRing;
+    float k = 0.f, u = 0.f;
+    if (c->lastNumTiles) SC_CUDA(c, cudaEventElapsedTime(&k, c->evK0[slot], c->evK1[slot]));
+    SC_CUDA(c, cudaEventElapsedTime(&u, c->evU0[slot], c->evU1[slot]));
+    if (outFusedKernelMs) outFusedKernelMs[i] = k;
+    if (outUpdateMs) outUpdateMs[i] = u;
+  }
+  if (outCount) *outCount = n;
   return 1;
 }
 

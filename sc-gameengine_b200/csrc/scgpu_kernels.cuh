@@ -8,6 +8,9 @@
 //   rec3[slot] = { aabbMax.x, aabbMax.y, aabbMax.z, flags }     exactly SURVEY.md §8(d)'s read set.
 //   world0..3[slot] = world matrix columns (float4 planes, coalesced 128-bit stores)
 //   parentSlot[slot] = resolved parent slot or kNone (maintained by k_resolve_parents on topology changes)
+//   tileMap[slot]    = (level << 8) | local index: thread t of a 256-slot sub-tile works on slot base+local.
+//                      The map sorts each sub-tile by hierarchy level, so warps are level-homogeneous and the
+//                      per-level resolve loop never runs the transform code with a fraction of its lanes.
 //   flags: bit0 HAS_BOUNDS, bit1 HAS_MESH, bits 8..31 = dirty stamp (id of the update that must recompute
 //          the instance). A stamp instead of a dirty bit means the frame kernel never writes the records.
 //
@@ -27,6 +30,13 @@ constexpr uint32_t kSubTiles = 4;      // sub-tiles of kBlock slots per CTA
 constexpr uint32_t kTile = kBlock * kSubTiles;
 constexpr uint32_t kFlagBounds = 1u, kFlagMesh = 2u;
 constexpr uint32_t kStampShift = 8;
+// hierarchy levels kept in tileMap: 0..kMaxTileLevel resolved through shared memory, deeper chains through
+// walk_up(), unreachable nodes (cycles) never visited
+constexpr uint32_t kMaxTileLevel = 14, kLevelDeep = 254, kLevelUnreachable = 255;
+
+#ifndef SCGPU_HIER_MIN_BLOCKS
+#define SCGPU_HIER_MIN_BLOCKS 3
+#endif
 
 constexpr uint32_t kUpdForceDirty = 1u, kUpdFreeze = 2u, kUpdSkipTransform = 4u;
 
@@ -46,6 +56,7 @@ struct UpdateParams
   float4* w2;
   float4* w3;
   const uint32_t* parentSlot;
+  const uint16_t* tileMap;
   uint8_t* vismask;
   uint32_t* tileCounts;  // [(nViews+1)][numTiles]; row nViews = culling candidates
   uint32_t* recomputed;  // single counter
@@ -80,13 +91,55 @@ __device__ __forceinline__ void store_world(const UpdateParams& p, uint32_t s, c
   p.w0[s] = m.c0; p.w1[s] = m.c1; p.w2[s] = m.c2; p.w3[s] = m.c3;
 }
 
-// local TRS matrix of a slot (mat4_trs, sc_math.cpp:130-142)
-__device__ __forceinline__ Mat4 local_of(const UpdateParams& p, uint32_t s)
+// ---- out-of-line slow paths --------------------------------------------------------------------------------
+// The rare paths (dense fallbacks for non-finite input, ancestor walks) are real function calls. They exchange
+// matrices with the caller through a per-thread shared-memory slot (4 float4, stride kBlock) instead of through
+// reference parameters, so that no matrix of the hot path ever has its address taken (which would pin it to
+// local memory).
+__device__ __forceinline__ Mat4 xs_load(const float4* x)
 {
-  const float4 a = p.rec0[s];
-  const float4 b = p.rec1[s];
-  const float sz = p.rec2[s].x;
-  return mat4_trs_dense(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, sz);
+  Mat4 m;
+  m.c0 = x[0]; m.c1 = x[kBlock]; m.c2 = x[2 * kBlock]; m.c3 = x[3 * kBlock];
+  return m;
+}
+
+__device__ __forceinline__ void xs_store(float4* x, const Mat4& m)
+{
+  x[0] = m.c0; x[kBlock] = m.c1; x[2 * kBlock] = m.c2; x[3 * kBlock] = m.c3;
+}
+
+__device__ __noinline__ void trs_dense_to(float px, float py, float pz, float rx, float ry, float rz, float sx, float sy,
+                                          float sz, float4* out)
+{
+  xs_store(out, mat4_trs_dense(px, py, pz, rx, ry, rz, sx, sy, sz));
+}
+
+// out = a * b, dense (sc_math.cpp:52-68); out may alias a or b
+__device__ __noinline__ void mul_dense_to(const float4* a, const float4* b, float4* out)
+{
+  const Mat4 A = xs_load(a), B = xs_load(b);
+  xs_store(out, mat4_mul(A, B));
+}
+
+// mat4_trs (sc_math.cpp:130-142): structured fast path where it is value-exact, dense call otherwise
+__device__ __forceinline__ Mat4 trs_any(float4 a, float4 b, float sz, bool& affine, float4* scratch)
+{
+  affine = trs_inputs_tame(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, sz);
+  if (affine) return mat4_trs_fast(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, sz);
+  trs_dense_to(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, sz, scratch);
+  return xs_load(scratch);
+}
+
+// parent.world * local (sc_ecs.cpp:191-195). scratchA/scratchB: two exchange slots owned by this thread.
+__device__ __forceinline__ Mat4 compose_any(const Mat4& pw, const Mat4& l, bool localAffine, float4* scratchA,
+                                            float4* scratchB)
+{
+  const float mag = fabsf(pw.c3.x) + fabsf(pw.c3.y) + fabsf(pw.c3.z) + fabsf(pw.c3.w);
+  if (localAffine && mag < __int_as_float(0x7f800000)) return mat4_mul_affine(pw, l);
+  xs_store(scratchA, pw);
+  xs_store(scratchB, l);
+  mul_dense_to(scratchA, scratchB, scratchA);
+  return xs_load(scratchA);
 }
 
 __device__ __forceinline__ bool slot_dirty(const UpdateParams& p, uint32_t s)
@@ -100,8 +153,9 @@ __device__ __forceinline__ bool slot_dirty(const UpdateParams& p, uint32_t s)
 // Reproduces what the reference's DFS (sc_ecs.cpp:167-210) would have produced for slot `ps` this frame without
 // depending on any other thread: finds the ancestor closest to the root that is dirty, starts from the stored
 // world matrix of ITS parent (clean with clean ancestors => not written by anyone this frame) and multiplies
-// down. Returns false when the chain never reaches a root (cycle): such nodes are never visited by the DFS.
-__device__ __noinline__ bool walk_up(const UpdateParams& p, uint32_t ps, bool needWorld, Mat4& outW, bool& outDirty)
+// down. The parent's world matrix is left in the exchange slot `out`.
+// Returns bit0 = a root is reachable (false: cycle, such nodes are never visited by the DFS), bit1 = parent dirty.
+__device__ __noinline__ uint32_t walk_up(const UpdateParams& p, uint32_t ps, bool needWorld, float4* out, float4* tmp)
 {
   // pass 1: Brent cycle detection + index of the dirty ancestor closest to the root
   int lastDirty = -1;
@@ -116,241 +170,314 @@ __device__ __noinline__ bool walk_up(const UpdateParams& p, uint32_t ps, bool ne
       cur = nxt;
       ++steps;
       ++lam;
-      if (cur == tortoise) return false;
+      if (cur == tortoise) return 0u;
       if (lam == power) { tortoise = cur; power <<= 1; lam = 0; }
     }
   }
-  outDirty = lastDirty >= 0;
-  if (!needWorld && !outDirty) return true;
-  if (!outDirty)
+  const bool dirty = lastDirty >= 0;
+  if (!dirty)
   {
-    outW = load_world(p, ps);
-    return true;
+    if (needWorld) { out[0] = p.w0[ps]; out[kBlock] = p.w1[ps]; out[2 * kBlock] = p.w2[ps]; out[3 * kBlock] = p.w3[ps]; }
+    return 1u;
   }
   // pass 2: recompute ps's world from the topmost dirty ancestor down
-  Mat4 W;
+  Mat4 W = mat4_identity();
   for (int d = lastDirty; d >= 0; --d)
   {
     uint32_t node = ps;
     for (int k = 0; k < d; ++k) node = p.parentSlot[node];
-    const Mat4 L = local_of(p, node);
+    bool affine;
+    const Mat4 L = trs_any(p.rec0[node], p.rec1[node], p.rec2[node].x, affine, tmp);
     if (d == lastDirty)
     {
       const uint32_t up = p.parentSlot[node];
-      W = (up == kNone) ? L : mat4_mul(load_world(p, up), L);
+      if (up == kNone) W = L;
+      else
+      {
+        Mat4 U;
+        U.c0 = p.w0[up]; U.c1 = p.w1[up]; U.c2 = p.w2[up]; U.c3 = p.w3[up];
+        W = compose_any(U, L, affine, out, tmp);
+      }
     }
     else
     {
-      W = mat4_mul(W, L);
+      W = compose_any(W, L, affine, out, tmp);
     }
   }
-  outW = W;
-  return true;
+  xs_store(out, W);
+  return 3u;
+}
+
+// signed plane distance in the reference's order: ((n0*c0 + n1*c1) + n2*c2) + d
+__device__ __forceinline__ float plane_dist(const float4 pl, float cx, float cy, float cz)
+{
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pl.x, cx), __fmul_rn(pl.y, cy)), __fmul_rn(pl.z, cz)), pl.w);
 }
 
 // ---- K1+K2: fused transform + cull, all views in one pass ------------------------------------------------
 // One thread per slot, kSubTiles sub-tiles of kBlock consecutive slots per CTA.
-// kHier=false: no instance has a parent (flat scene): pure streaming.
-// kHier=true : parents inside the sub-tile are resolved level by level through shared memory (the parent's
-//              fresh world matrix is staged there by its own thread); parents outside it by walk_up().
-template <bool kHier>
-__global__ void __launch_bounds__(kBlock) k_update(const __grid_constant__ UpdateParams p,
-                                                   const __grid_constant__ ViewPlanes vp)
+// kHier=false: no instance has a parent (flat scene): pure streaming, thread t <-> slot base+t.
+// kHier=true : thread t <-> slot base + tileMap.local (level-sorted). Levels are resolved one per iteration:
+//              a node's thread publishes its fresh world matrix in shared memory, one barrier, then the next
+//              level multiplies. Parents outside the sub-tile (or deeper than kMaxTileLevel) go through walk_up().
+// kViews    : compile-time view count, so the 6*V plane tests read their planes straight from the constant bank.
+template <bool kHier, int kViews>
+__global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_update(const __grid_constant__ UpdateParams p,
+                                                                  const __grid_constant__ ViewPlanes vp)
 {
   __shared__ uint32_t sCounts[kMaxViews + 2];
+  __shared__ uint32_t sLvlMask[kSubTiles];
   __shared__ float4 sW[kHier ? 4 : 1][kHier ? kBlock : 1];
-  __shared__ uint8_t sState[kHier ? kBlock : 1];
+  __shared__ float4 sX[4][kBlock];  // per-thread exchange slots of the out-of-line slow paths
+  __shared__ uint8_t sDirty[kHier ? kBlock : 1];
 
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
   if (tid < kMaxViews + 2) sCounts[tid] = 0;
+  if (tid < kSubTiles) sLvlMask[tid] = 0;
   __syncthreads();
 
-  const uint32_t allMask = (1u << p.nViews) - 1u;
-  uint32_t nRecomputed = 0;
+  constexpr uint32_t allMask = (1u << kViews) - 1u;
+  const bool skip = (p.flags & kUpdSkipTransform) != 0;
+  const bool force = (p.flags & kUpdForceDirty) != 0;
+  const bool freeze = (p.flags & kUpdFreeze) != 0;
+  uint32_t nRecomputed = 0, nCand = 0;
+  uint32_t nVis[kViews];
+#pragma unroll
+  for (int v = 0; v < kViews; ++v) nVis[v] = 0;
 
+#pragma unroll 1
   for (uint32_t sub = 0; sub < kSubTiles; ++sub)
   {
     const uint32_t base = blockIdx.x * kTile + sub * kBlock;
     if (base >= p.count) break;  // block-uniform
-    const uint32_t i = base + tid;
-    const bool live = i < p.count;
 
-    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f), r3 = r2;
+    uint32_t local = tid, lvl = 0;
+    if constexpr (kHier)
+    {
+      const uint32_t m = p.tileMap[base + tid];
+      local = m & 0xFFu;
+      lvl = m >> 8;
+    }
+    const uint32_t s = base + local;
+    const bool live = s < p.count;
+
+    float4 r0, r1, r2, r3;
+    r0 = r1 = r2 = r3 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t fl = 0;
-    if (live)
-    {
-      r3 = ld_stream(p.rec3 + i);
-      r2 = ld_stream(p.rec2 + i);
-      fl = __float_as_uint(r3.w);
-    }
-    bool ownDirty = false;
-    if (live && !(p.flags & kUpdSkipTransform))
-      ownDirty = (p.flags & kUpdForceDirty) || ((fl >> kStampShift) == p.stamp);
-
     Mat4 W = mat4_identity();
-    uint32_t ps = kNone;
-    bool hier = false;
-    if (kHier)
-    {
-      if (live) ps = p.parentSlot[i];
-      hier = __syncthreads_or(ps != kNone) != 0;
-    }
 
-    if (!hier)
+    if constexpr (!kHier)
     {
+      if (live)
+      {
+        r3 = ld_stream(p.rec3 + s);
+        r2 = ld_stream(p.rec2 + s);
+        fl = __float_as_uint(r3.w);
+      }
+      const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
       if (live)
       {
         if (ownDirty)
         {
-          const float4 a = ld_stream(p.rec0 + i);
-          const float4 b = ld_stream(p.rec1 + i);
-          W = mat4_trs_dense(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, r2.x);
-          store_world(p, i, W);
+          r0 = ld_stream(p.rec0 + s);
+          r1 = ld_stream(p.rec1 + s);
+          bool affine;
+          W = trs_any(r0, r1, r2.x, affine, &sX[0][tid]);
+          store_world(p, s, W);
           ++nRecomputed;
         }
         else
         {
-          W = load_world(p, i);
+          W = load_world(p, s);
         }
       }
     }
-    else if constexpr (kHier)
+    else
     {
-      // sState: 0 pending, 1 done & clean, 2 done & recomputed, 3 dead (unreachable from any root)
-      enum { PENDING = 0, DONE_CLEAN = 1, DONE_DIRTY = 2, DEAD = 3 };
-      enum { SRC_ROOT = 0, SRC_WALKED = 1, SRC_TILE = 2 };
-      int state = live ? PENDING : DEAD;
-      int src = SRC_ROOT;
-      Mat4 PW = mat4_identity();
-      bool pDirtyWalked = false;
-      if (live && ps != kNone)
+      const bool reachable = live && lvl != kLevelUnreachable;
+      const bool deep = lvl == kLevelDeep;
+      const uint32_t effLvl = deep ? 0u : lvl;
+      // ---- phase A: every global load of the sub-tile is issued here, before any dependent work ----
+      uint32_t ps = kNone;
+      if (live)
       {
-        if (ps - base < kBlock)
-        {
-          src = SRC_TILE;  // parent's thread is in this CTA: wait for it to publish through shared memory
-        }
-        else
-        {
-          src = SRC_WALKED;  // parent lives in another sub-tile: resolve it from global memory alone
-          if (!walk_up(p, ps, ownDirty, PW, pDirtyWalked)) state = DEAD;
-        }
+        // permuted inside the sub-tile: the other half of every sector is wanted by a sibling warp -> keep in L1
+        r3 = __ldg(p.rec3 + s); r2 = __ldg(p.rec2 + s);
+        r0 = __ldg(p.rec0 + s); r1 = __ldg(p.rec1 + s);
+        if (reachable && lvl != 0) ps = p.parentSlot[s];
       }
-      sState[tid] = (uint8_t)state;
-      for (;;)
+      fl = __float_as_uint(r3.w);
+      const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+      // clean nodes and nodes the DFS never visits keep their stored matrix: fetch it with the other loads
+      const bool keepStored = live && (!ownDirty || !reachable);
+      Mat4 stored = mat4_identity();
+      if (keepStored) stored = load_world(p, s);
+
+      // levels present in this sub-tile (block-wide OR of one bit per thread)
       {
-        __syncthreads();
-        bool progressed = false;
-        if (state == PENDING)
+        const uint32_t bit = (reachable && !deep) ? (1u << lvl) : 0u;
+        const uint32_t w = __reduce_or_sync(0xffffffffu, bit);
+        if (lane == 0 && w) atomicOr(&sLvlMask[sub], w);
+      }
+      __syncthreads();  // sLvlMask complete; also orders the previous sub-tile's shared reads before our writes
+      const uint32_t lvlMask = sLvlMask[sub];
+      const int maxLvl = lvlMask ? (31 - __clz(lvlMask)) : 0;
+
+      // ---- phase B: no dependency on other threads (warps are level-homogeneous, so no lane idles here).
+      // Matrices cross the barriers of phase C in shared memory only: sX[.][tid] = local matrix (private),
+      // sW[.][local] = world matrix (provisional for clean nodes, parent's for walked ones, then published).
+      const bool hasParent = ps != kNone;
+      const bool inTile = hasParent && !deep && (ps - base < kBlock);
+      const bool walked = hasParent && !inTile;
+      if (keepStored && !walked) xs_store(&sW[0][local], stored);  // provisional; `stored` dies here
+      bool pDirty = false;
+      if (walked) pDirty = (walk_up(p, ps, true, &sW[0][local], &sX[0][tid]) & 2u) != 0;  // reachable => finds a root
+      bool haveL = false, affine = true;
+      if (reachable && (ownDirty || pDirty))
+      {
+        const Mat4 L = trs_any(r0, r1, r2.x, affine, &sX[0][tid]);
+        xs_store(&sX[0][tid], L);
+        haveL = true;
+      }
+
+      // ---- phase C: one iteration per level, only parent.world * local is serialized ----
+      bool nodeDirty = false;
+#pragma unroll 1
+      for (int l = 0; l <= maxLvl; ++l)
+      {
+        if (reachable && effLvl == (uint32_t)l)
         {
-          bool go = false, pDirty = false, hasParent = false;
-          if (src == SRC_ROOT)
+          if (inTile) pDirty = sDirty[ps - base] != 0;
+          nodeDirty = ownDirty || pDirty;
+          if (nodeDirty)
           {
-            go = true;
-          }
-          else if (src == SRC_WALKED)
-          {
-            go = true; pDirty = pDirtyWalked; hasParent = true;
-          }
-          else
-          {
-            const uint32_t pt = ps - base;
-            const int pst = sState[pt];
-            if (pst == DONE_CLEAN || pst == DONE_DIRTY)
+            Mat4 L;
+            if (haveL) L = xs_load(&sX[0][tid]);
+            else L = trs_any(__ldg(p.rec0 + s), __ldg(p.rec1 + s), r2.x, affine, &sX[0][tid]);
+            if (hasParent)
             {
-              go = true; pDirty = (pst == DONE_DIRTY); hasParent = true;
-              if (ownDirty || pDirty)
-              {
-                PW.c0 = sW[0][pt]; PW.c1 = sW[1][pt]; PW.c2 = sW[2][pt]; PW.c3 = sW[3][pt];
-              }
-            }
-            else if (pst == DEAD)
-            {
-              state = DEAD;
-              progressed = true;
-            }
-          }
-          if (go)
-          {
-            const bool nodeDirty = ownDirty || pDirty;
-            if (nodeDirty)
-            {
-              const Mat4 L = local_of(p, i);
-              W = hasParent ? mat4_mul(PW, L) : L;
+              const Mat4 PW = xs_load(inTile ? &sW[0][ps - base] : &sW[0][local]);
+              xs_store(&sW[0][local], compose_any(PW, L, affine, &sX[0][tid], &sW[0][local]));
             }
             else
             {
-              W = load_world(p, i);
+              xs_store(&sW[0][local], L);
             }
-            state = nodeDirty ? DONE_DIRTY : DONE_CLEAN;
-            progressed = true;
           }
-        }
-        const int any = __syncthreads_or(progressed);
-        if (progressed)
-        {
-          sState[tid] = (uint8_t)state;
-          if (state != DEAD)
+          else if (walked)
           {
-            sW[0][tid] = W.c0; sW[1][tid] = W.c1; sW[2][tid] = W.c2; sW[3][tid] = W.c3;
+            xs_store(&sW[0][local], load_world(p, s));  // the slot held the walked parent matrix
           }
+          sDirty[local] = nodeDirty ? 1 : 0;
         }
-        if (!any) break;
+        if (l < maxLvl) __syncthreads();
       }
-      if (state == DONE_DIRTY)
+      // every live node's matrix is now in its slot (cycle members and their descendants, which the DFS never
+      // visits, still hold the provisional stored one)
+      if (live) W = xs_load(&sW[0][local]);
+      if (nodeDirty)
       {
-        store_world(p, i, W);
+        store_world(p, s, W);
         ++nRecomputed;
-      }
-      else if (live && state != DONE_CLEAN)
-      {
-        W = load_world(p, i);  // cycle members and their descendants: never visited by the DFS, world stays
       }
     }
 
     // ---- bounding sphere + 6*V plane tests in registers (CullingSystem, .cpp:1240-1270) ----
-    uint32_t mask = 0;
     const bool cand = live && (fl & kFlagMesh);
-    if (cand)
+    const bool test = cand && !freeze && (fl & kFlagBounds);
+    uint32_t mask = 0;
+    if (__any_sync(0xffffffffu, test))
     {
-      if ((p.flags & kUpdFreeze) || !(fl & kFlagBounds))
+      float cx, cy, cz, radius;
+      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, cx, cy, cz, radius);
+      const float negR = -radius;
+#pragma unroll
+      for (int v = 0; v < kViews; ++v)
       {
-        mask = allMask;
-      }
-      else
-      {
-        float cx, cy, cz, radius;
-        world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, cx, cy, cz, radius);
-#pragma unroll 1
-        for (uint32_t v = 0; v < p.nViews; ++v)
-          if (sphere_in_frustum(vp.planes[v], cx, cy, cz, radius)) mask |= 1u << v;
+        bool alive = test;
+        // plane pairs (left,right) (bottom,top) (near,far); stop as soon as the whole warp is outside
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp)
+        {
+          if (!__any_sync(0xffffffffu, alive)) break;
+          const float d0 = plane_dist(vp.planes[v][2 * pp], cx, cy, cz);
+          const float d1 = plane_dist(vp.planes[v][2 * pp + 1], cx, cy, cz);
+          alive = alive && !(d0 < negR) && !(d1 < negR);  // NaN compares false => stays visible
+        }
+        if (alive) mask |= 1u << v;
       }
     }
-    if (live) p.vismask[i] = (uint8_t)mask;
+    if (cand && !test) mask = allMask;  // frozen culling or no Bounds component: always visible
+    if (live) p.vismask[s] = (uint8_t)mask;
 
-    // per-view visible counts of this tile (warp ballot + popc, one shared atomic per warp and view)
-#pragma unroll 1
-    for (uint32_t v = 0; v < p.nViews; ++v)
-    {
-      const uint32_t b = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
-      if (lane == 0 && b) atomicAdd(&sCounts[v], __popc(b));
-    }
-    {
-      const uint32_t b = __ballot_sync(0xffffffffu, cand);
-      if (lane == 0 && b) atomicAdd(&sCounts[p.nViews], __popc(b));
-    }
+#pragma unroll
+    for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
+    nCand += cand ? 1u : 0u;
   }
 
-  // recomputed counter: warp reduce, one shared atomic per warp
-  {
-    uint32_t r = nRecomputed;
+  // per-tile counts: one warp reduction (REDUX) per counter, one shared atomic per warp
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-    if (lane == 0 && r) atomicAdd(&sCounts[kMaxViews + 1], r);
+  for (int v = 0; v < kViews; ++v)
+  {
+    const uint32_t r = __reduce_add_sync(0xffffffffu, nVis[v]);
+    if (lane == 0 && r) atomicAdd(&sCounts[v], r);
+  }
+  {
+    const uint32_t r = __reduce_add_sync(0xffffffffu, nCand);
+    if (lane == 0 && r) atomicAdd(&sCounts[kViews], r);
+    const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
+    if (lane == 0 && q) atomicAdd(&sCounts[kMaxViews + 1], q);
   }
   __syncthreads();
-  if (tid <= p.nViews) p.tileCounts[tid * p.numTiles + blockIdx.x] = sCounts[tid];
+  if (tid <= (uint32_t)kViews) p.tileCounts[tid * p.numTiles + blockIdx.x] = sCounts[tid];
   if (tid == 0 && sCounts[kMaxViews + 1]) atomicAdd(p.recomputed, sCounts[kMaxViews + 1]);
+}
+
+// ---- tile map: per sub-tile, sort the slots by hierarchy level ----------------------------------------------
+// Runs only when the topology changed (spawn / despawn / setParent). level = number of ancestors (walk with
+// Brent's cycle detection); > kMaxTileLevel => kLevelDeep; no root reachable => kLevelUnreachable.
+__global__ void __launch_bounds__(kBlock) k_build_tile_map(const uint32_t* __restrict__ parentSlot,
+                                                           uint16_t* __restrict__ tileMap, uint32_t count)
+{
+  constexpr uint32_t kBins = kMaxTileLevel + 4;  // levels 0..14, deep, unreachable, beyond count
+  __shared__ uint32_t sWarpCnt[kBlock / 32][kBins];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t base = blockIdx.x * kBlock;
+  const uint32_t s = base + tid;
+  for (uint32_t k = tid; k < (kBlock / 32) * kBins; k += kBlock) (&sWarpCnt[0][0])[k] = 0;
+
+  uint32_t level = kLevelUnreachable, bin = kBins - 1;
+  if (s < count)
+  {
+    uint32_t cur = s, tortoise = s, steps = 0, power = 1, lam = 0;
+    bool cycle = false;
+    for (;;)
+    {
+      const uint32_t nxt = parentSlot[cur];
+      if (nxt == kNone) break;
+      cur = nxt;
+      ++steps;
+      ++lam;
+      if (cur == tortoise) { cycle = true; break; }
+      if (lam == power) { tortoise = cur; power <<= 1; lam = 0; }
+    }
+    if (cycle) { level = kLevelUnreachable; bin = kMaxTileLevel + 2; }
+    else if (steps > kMaxTileLevel) { level = kLevelDeep; bin = kMaxTileLevel + 1; }
+    else { level = steps; bin = steps; }
+  }
+  __syncthreads();
+  // stable counting sort by bin: rank inside the warp by match, across warps through shared counters
+  const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+  const uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
+  if (rankInWarp == 0) sWarpCnt[warp][bin] = __popc(peers);
+  __syncthreads();
+  uint32_t offset = 0;
+  for (uint32_t b = 0; b < bin; ++b)
+    for (uint32_t w = 0; w < kBlock / 32; ++w) offset += sWarpCnt[w][b];
+  for (uint32_t w = 0; w < warp; ++w) offset += sWarpCnt[w][bin];
+  const uint32_t rank = offset + rankInWarp;
+  tileMap[base + rank] = (uint16_t)((level << 8) | tid);
 }
 
 // ---- K3a: exclusive scan of the per-tile counts, one CTA per row (view) -----------------------------------

@@ -210,6 +210,101 @@ __device__ __forceinline__ Mat4 mat4_trs_dense(float px, float py, float pz, flo
 }
 
 // ---------------------------------------------------------------------------------------------------
+// structured products: same values as the dense reference products, without the zero/one terms
+//
+// For FINITE operands every skipped term is x*(+-0) = +-0 or x*1 = x, and adding +-0 to a sum never changes
+// its value; the kept terms are evaluated in the reference's order with the same roundings. The results are
+// therefore equal to the dense ones as real numbers - the only representable difference is the SIGN OF A ZERO
+// entry, which no consumer can observe (every later use multiplies, adds or compares with <). Non-finite
+// operands (where 0*inf = NaN would contaminate the dense result) take the dense path.
+// ---------------------------------------------------------------------------------------------------
+
+// true when mat4_trs_fast() is valid: all nine inputs finite and small enough that rotation*scale cannot
+// overflow (|R| <= 2, so |scale| < 2^120 keeps |R*s| finite). One comparison on the sum of magnitudes.
+__device__ __forceinline__ bool trs_inputs_tame(float px, float py, float pz, float rx, float ry, float rz, float sx,
+                                                float sy, float sz)
+{
+  const float sum = fabsf(px) + fabsf(py) + fabsf(pz) + fabsf(rx) + fabsf(ry) + fabsf(rz) + fabsf(sx) + fabsf(sy) +
+                    fabsf(sz);
+  return sum < 0x1p120f;  // false for NaN
+}
+
+// mat4_trs for tame inputs: R = (Rz*Ry)*Rx, M = T*(R*S) with the structural zeros and ones removed.
+__device__ __forceinline__ Mat4 mat4_trs_fast(float px, float py, float pz, float rx, float ry, float rz, float sx_,
+                                              float sy_, float sz_)
+{
+  float sx, cx, sy, cy, sz, cz;
+  sincosf_glibc(rx, sx, cx);
+  sincosf_glibc(ry, sy, cy);
+  sincosf_glibc(rz, sz, cz);
+  // A = Rz*Ry
+  const float a00 = __fmul_rn(cz, cy), a10 = __fmul_rn(sz, cy), a20 = -sy;
+  const float a01 = -sz, a11 = cz;  // a21 = 0
+  const float a02 = __fmul_rn(cz, sy), a12 = __fmul_rn(sz, sy), a22 = cy;
+  // R = A*Rx : col0 = A.col0 ; col1 = A.col1*cx + A.col2*sx ; col2 = A.col1*(-sx) + A.col2*cx
+  const float nsx = -sx;
+  const float r01 = __fadd_rn(__fmul_rn(a01, cx), __fmul_rn(a02, sx));
+  const float r11 = __fadd_rn(__fmul_rn(a11, cx), __fmul_rn(a12, sx));
+  const float r21 = __fmul_rn(a22, sx);
+  const float r02 = __fadd_rn(__fmul_rn(a01, nsx), __fmul_rn(a02, cx));
+  const float r12 = __fadd_rn(__fmul_rn(a11, nsx), __fmul_rn(a12, cx));
+  const float r22 = __fmul_rn(a22, cx);
+  Mat4 m;
+  m.c0 = make_float4(__fmul_rn(a00, sx_), __fmul_rn(a10, sx_), __fmul_rn(a20, sx_), 0.f);
+  m.c1 = make_float4(__fmul_rn(r01, sy_), __fmul_rn(r11, sy_), __fmul_rn(r21, sy_), 0.f);
+  m.c2 = make_float4(__fmul_rn(r02, sz_), __fmul_rn(r12, sz_), __fmul_rn(r22, sz_), 0.f);
+  m.c3 = make_float4(px, py, pz, 1.f);
+  return m;
+}
+
+__device__ __noinline__ Mat4 mat4_trs_dense_call(float px, float py, float pz, float rx, float ry, float rz, float sx,
+                                                 float sy, float sz)
+{
+  return mat4_trs_dense(px, py, pz, rx, ry, rz, sx, sy, sz);
+}
+
+// mat4_trs with the fast path where it is exact; `affine` reports that the bottom row is exactly (0,0,0,1)
+__device__ __forceinline__ Mat4 mat4_trs(float px, float py, float pz, float rx, float ry, float rz, float sx, float sy,
+                                         float sz, bool& affine)
+{
+  affine = trs_inputs_tame(px, py, pz, rx, ry, rz, sx, sy, sz);
+  if (affine) return mat4_trs_fast(px, py, pz, rx, ry, rz, sx, sy, sz);
+  return mat4_trs_dense_call(px, py, pz, rx, ry, rz, sx, sy, sz);
+}
+
+__device__ __noinline__ Mat4 mat4_mul_dense_call(const Mat4& a, const Mat4& b) { return mat4_mul(a, b); }
+
+// parent.world * local where local's bottom row is exactly (0,0,0,1): the term p[r][3]*0 is dropped for the
+// first three columns and p[r][3]*1 = p[r][3] for the last. Requires the parent's last column to be finite.
+__device__ __forceinline__ Mat4 mat4_mul_affine(const Mat4& p, const Mat4& l)
+{
+  Mat4 r;
+#define SC_COL3(dst, L)                                                                                      \
+  dst.x = __fadd_rn(__fadd_rn(__fmul_rn(p.c0.x, L.x), __fmul_rn(p.c1.x, L.y)), __fmul_rn(p.c2.x, L.z));     \
+  dst.y = __fadd_rn(__fadd_rn(__fmul_rn(p.c0.y, L.x), __fmul_rn(p.c1.y, L.y)), __fmul_rn(p.c2.y, L.z));     \
+  dst.z = __fadd_rn(__fadd_rn(__fmul_rn(p.c0.z, L.x), __fmul_rn(p.c1.z, L.y)), __fmul_rn(p.c2.z, L.z));     \
+  dst.w = __fadd_rn(__fadd_rn(__fmul_rn(p.c0.w, L.x), __fmul_rn(p.c1.w, L.y)), __fmul_rn(p.c2.w, L.z));
+  SC_COL3(r.c0, l.c0)
+  SC_COL3(r.c1, l.c1)
+  SC_COL3(r.c2, l.c2)
+  SC_COL3(r.c3, l.c3)
+#undef SC_COL3
+  r.c3.x = __fadd_rn(r.c3.x, p.c3.x);
+  r.c3.y = __fadd_rn(r.c3.y, p.c3.y);
+  r.c3.z = __fadd_rn(r.c3.z, p.c3.z);
+  r.c3.w = __fadd_rn(r.c3.w, p.c3.w);
+  return r;
+}
+
+// world = parent.world * local (sc_ecs.cpp:191-195)
+__device__ __forceinline__ Mat4 compose(const Mat4& parentWorld, const Mat4& local, bool localAffine)
+{
+  const float mag = fabsf(parentWorld.c3.x) + fabsf(parentWorld.c3.y) + fabsf(parentWorld.c3.z) + fabsf(parentWorld.c3.w);
+  if (localAffine && mag < __int_as_float(0x7f800000)) return mat4_mul_affine(parentWorld, local);
+  return mat4_mul_dense_call(parentWorld, local);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // bounds + plane tests, sc_world_partition.cpp:1105-1144
 // ---------------------------------------------------------------------------------------------------
 

@@ -107,6 +107,7 @@ SYMBOLS = {
     "scgpuKernelLaunchCount": (C.c_uint64, [_vp]),
     "scgpuLastUpdateTimings": (C.c_int, [_vp, _f32p, _f32p]),
     "scgpuEnableTimings": (C.c_int, [_vp, C.c_int]),
+    "scgpuReadUpdateTimings": (C.c_int, [_vp, _vp, _vp, C.c_uint32, _u32p]),
 }
 
 
@@ -115,7 +116,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = Path(path) if path else LIB_PATH
+    # SCGPU_LIB: A/B-testing hook for kernel build variants (bench only)
+    p = Path(path) if path else Path(os.environ.get("SCGPU_LIB", LIB_PATH))
     if not p.exists():
         raise ScGpuError(f"{p} not found: build it with `make -C sc-gameengine_b200` (there is no CPU fallback)")
     lib = C.CDLL(str(p))
@@ -314,6 +316,13 @@ class Scene:
         u = C.c_float(0)
         self._ck(self.lib.scgpuLastUpdateTimings(self.ctx, C.byref(k), C.byref(u)), "scgpuLastUpdateTimings")
         return k.value, u.value
+
+    def read_timings(self, cap=256):
+        k = np.zeros(cap, np.float32)
+        u = np.zeros(cap, np.float32)
+        n = C.c_uint32(0)
+        self._ck(self.lib.scgpuReadUpdateTimings(self.ctx, _ptr(k), _ptr(u), cap, C.byref(n)), "scgpuReadUpdateTimings")
+        return k[: n.value], u[: n.value]
 
     # -- multi-GPU
     @staticmethod

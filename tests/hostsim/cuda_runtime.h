@@ -24,5 +24,6 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline float __double2float_rn(double a) { return (float)a; }
 static inline int __double2int_rz(double a) { return (int)a; }
 static inline double __ll2double_rn(long long a) { return (double)a; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }

@@ -9,6 +9,19 @@ void hs_trs(const float* t, float* out16)
   Mat4 m = mat4_trs_dense(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
   std::memcpy(out16, &m, 64);
 }
+int hs_trs_fast(const float* t, float* out16)
+{
+  bool affine = false;
+  Mat4 m = mat4_trs(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], affine);
+  std::memcpy(out16, &m, 64);
+  return affine ? 1 : 0;
+}
+void hs_compose(const float* a, const float* b, int localAffine, float* out16)
+{
+  Mat4 A, B; std::memcpy(&A, a, 64); std::memcpy(&B, b, 64);
+  Mat4 m = compose(A, B, localAffine != 0);
+  std::memcpy(out16, &m, 64);
+}
 void hs_mul(const float* a, const float* b, float* out16)
 {
   Mat4 A, B; std::memcpy(&A, a, 64); std::memcpy(&B, b, 64);

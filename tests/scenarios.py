@@ -72,10 +72,13 @@ def same_bits(a, b):
 
 
 def assert_same_bits(a, b, what=""):
+    """Same IEEE value in every float: identical bits, except that NaN matches any NaN (payloads differ between
+    libm and the GPU) and +0 matches -0 (the structured products of scgpu_math.cuh drop x*0 terms, which can
+    only change the sign of a zero entry; see DESIGN.md "Parity definition")."""
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
     assert a.shape == b.shape, (what, a.shape, b.shape)
-    eq = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    eq = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
     if not eq.all():
         idx = np.argwhere(~eq)
         i = tuple(idx[0])
