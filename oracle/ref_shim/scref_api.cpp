@@ -226,6 +226,28 @@ void screfReadTransform(ScRefWorld* w, uint32_t n, const uint32_t* entity, uint3
   }
 }
 
+void screfReadComponents(ScRefWorld* w, uint32_t n, const uint32_t* entity, uint32_t* outFlags, float* outAabb6,
+                         uint32_t* outMeshMat2)
+{
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    const sc::Entity e = ent(entity[i]);
+    uint32_t f = 0;
+    if (const sc::Bounds* b = w->world.get<sc::Bounds>(e))
+    {
+      f |= SCREF_HAS_BOUNDS;
+      outAabb6[i * 6 + 0] = b->localAabb.min.x; outAabb6[i * 6 + 1] = b->localAabb.min.y; outAabb6[i * 6 + 2] = b->localAabb.min.z;
+      outAabb6[i * 6 + 3] = b->localAabb.max.x; outAabb6[i * 6 + 4] = b->localAabb.max.y; outAabb6[i * 6 + 5] = b->localAabb.max.z;
+    }
+    if (const sc::RenderMesh* rm = w->world.get<sc::RenderMesh>(e))
+    {
+      f |= SCREF_HAS_MESH;
+      outMeshMat2[i * 2 + 0] = rm->meshId; outMeshMat2[i * 2 + 1] = rm->materialId;
+    }
+    outFlags[i] = f;
+  }
+}
+
 void screfGetViewProj(ScRefWorld* w, float* out16) { std::memcpy(out16, w->world.renderFrame().viewProj.m, 64); }
 
 void screfGetPlanes(ScRefWorld* w, float* out24)

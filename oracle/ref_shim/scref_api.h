@@ -56,6 +56,9 @@ uint32_t screfDenseEntities(ScRefWorld* w, uint32_t cap, uint32_t* outEntity);
 void screfReadWorld(ScRefWorld* w, uint32_t n, const uint32_t* entity, float* out16);
 void screfReadTransform(ScRefWorld* w, uint32_t n, const uint32_t* entity, uint32_t* outParent, float* outTrs9,
                         uint8_t* outDirty);
+/* which of Bounds / RenderMesh each entity owns, with their contents */
+void screfReadComponents(ScRefWorld* w, uint32_t n, const uint32_t* entity, uint32_t* outFlags, float* outAabb6,
+                         uint32_t* outMeshMat2);
 void screfGetViewProj(ScRefWorld* w, float* out16);
 void screfGetPlanes(ScRefWorld* w, float* out24);
 void screfGetCullStats(ScRefWorld* w, uint32_t* total, uint32_t* visible, uint32_t* culled);

@@ -134,10 +134,11 @@ _PED = [  # ped root -> torso -> limb -> prop  (depth 4, 4 nodes)
 def city_hier(n, seed=424242):
     """Config 3: n instances in depth-4 groups (vehicles + wheels, peds + attachments), spawned group by group.
     Group roots are placed like city props; children carry small local offsets and rotations about X/Y."""
-    n_groups_est = int(np.ceil(n / 6.0)) + 16
+    n_groups_est = int(np.ceil(n / (4.0 + 6.0 * float(__import__('os').environ.get('SCGPU_VEHICLE_FRACTION', '0.5'))) * 1.2)) + 16
     roots = city_props(n_groups_est, seed)
     rng = np.random.default_rng(seed)
-    is_vehicle = rng.random(n_groups_est) < 0.5
+    import os as _os
+    is_vehicle = rng.random(n_groups_est) < float(_os.environ.get('SCGPU_VEHICLE_FRACTION', '0.5'))
     sizes = np.where(is_vehicle, len(_VEHICLE), len(_PED))
     starts = np.concatenate([[0], np.cumsum(sizes)])
     total = int(starts[-1])

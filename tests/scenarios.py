@@ -144,3 +144,52 @@ def random_aabb(rng, n):
     c = rng.normal(size=(n, 3)) * 0.5
     e = rng.uniform(0.1, 2.0, size=(n, 3))
     return np.concatenate([c - e, c + e], axis=1).astype(np.float32)
+
+
+# ---- golden fixtures (tests/golden/*.npz, produced by the reference itself; see tests/golden/make_golden.py) ----
+
+def load_golden(name):
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / name)
+
+
+def check_snapshot(scene, g, prefix, n_views, what):
+    """scene: after update(); g: golden npz; compares everything the reference produced for that frame"""
+    e = g[prefix + "entity"]
+    for v in range(n_views):
+        assert np.array_equal(scene.visible[v], g[f"{prefix}visible_{v}"]), f"{what}: visible list, view {v}"
+        assert np.array_equal(scene.culled[v], g[f"{prefix}culled_{v}"]), f"{what}: culled list, view {v}"
+    assert_same_bits(scene.read_world(e), g[prefix + "world"], what + " world")
+    for key in g.files:
+        if key.startswith(prefix + "draws_") and key.endswith("_stats"):
+            md = int(key[len(prefix + "draws_"):-len("_stats")])
+            items, em, dr = scene.read_draw_items(0, md)
+            assert [em, dr] == list(g[key]), f"{what}: draw stats budget {md}"
+            assert np.array_equal(items["entity"], g[f"{prefix}draws_{md}_entity"]), what
+            assert np.array_equal(items["meshId"], g[f"{prefix}draws_{md}_mesh"]), what
+            assert np.array_equal(items["materialId"], g[f"{prefix}draws_{md}_mat"]), what
+            assert_same_bits(items["model"], g[f"{prefix}draws_{md}_model"], what + " draw models")
+
+
+def replay_default_scene(scene, g):
+    """Config 1: the sandbox's default scene. The golden holds the settled state; re-marking everything dirty
+    must reproduce the reference's matrices, lists and draws."""
+    scene.spawn(g["entity"], g["trs_after"], g["parent_after"], g["aabb"], g["mesh_mat"], g["flags"])
+    scene.update(g["view_proj"])
+    check_snapshot(scene, g, "", 1, "default scene")
+    assert len(scene.visible[0]) == 166 and len(scene.culled[0]) == 553
+
+
+def replay_forest_scene(scene, g):
+    vps = g["view_proj"]
+    scene.spawn(g["in_entity"], g["in_trs"], g["in_parent"], g["in_aabb"], g["in_mesh_mat"], g["in_flags"])
+    scene.update(vps)
+    check_snapshot(scene, g, "f0_", 3, "forest frame 0")
+    scene.set_local(g["f1_set_entity"], g["f1_set_trs"])
+    scene.set_parent(g["f1_setparent_entity"], g["f1_setparent_parent"])
+    scene.update(vps)
+    check_snapshot(scene, g, "f1_", 3, "forest frame 1")
+    scene.despawn(g["f2_despawn"])
+    scene.spawn(g["f2_spawn_entity"], g["f2_spawn_trs"], g["f2_spawn_parent"], g["f2_spawn_aabb"], None, None)
+    scene.update(vps)
+    check_snapshot(scene, g, "f2_", 3, "forest frame 2")

@@ -1,0 +1,99 @@
+"""The CUDA math header (sc-gameengine_b200/csrc/scgpu_math.cuh) compiled for the HOST through tests/hostsim's
+intrinsic shim, checked against the oracle. This is the same source the kernels inline, so the arithmetic order
+and the structured fast paths are verified without a GPU (the GPU tests then verify the kernels around it)."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from scenarios import assert_same_bits
+
+HS_DIR = Path(__file__).resolve().parent / "hostsim"
+f = lambda a: a.ctypes.data_as(C.c_void_p)
+
+SPECIAL = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 1.0, -1.0, 0.5, 3.1415927, 1.5707964, 6.2831855, 1e10, -1e10,
+                    1e36, 2.0 ** 119, 1e37, 3e38, np.inf, -np.inf, np.nan], np.float32)
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.run(["make", "-C", str(HS_DIR)], check=True, capture_output=True)
+    L = C.CDLL(str(HS_DIR / "libhostsim.so"))
+    L.hs_sincos_sweep.restype = C.c_uint64
+    L.hs_sincos_sweep.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+    return L
+
+
+def test_sincos_strided_sweep_is_bit_exact(hs, port):
+    """every 1021st float bit pattern (4.2 M inputs incl. NaN/Inf/denormals): device sincos == oracle sinf/cosf.
+    The full 2^32 sweep (0 mismatches) was run once in the build container; it takes ~100 s."""
+    sf = C.cast(port.sco_sinf, C.c_void_p)
+    cf = C.cast(port.sco_cosf, C.c_void_p)
+    assert hs.hs_sincos_sweep(0, (1 << 32) // 1021 + 1, 1021, sf, cf) == 0
+    # dense around the range-reduction thresholds pi/4, 2^-12, 120
+    for centre in (0x3f490fdb, 0x39800000, 0x42f00000, 0x7f800000, 0x00800000):
+        assert hs.hs_sincos_sweep(centre - 50000, 100000, 1, sf, cf) == 0
+        assert hs.hs_sincos_sweep((centre | 0x80000000) - 50000, 100000, 1, sf, cf) == 0
+
+
+def test_dense_trs_and_mul_are_bit_exact(hs, port):
+    rng = np.random.default_rng(5)
+    a, b = np.zeros(16, np.float32), np.zeros(16, np.float32)
+    for i in range(3000):
+        t = (rng.normal(size=9) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+        for _ in range(rng.integers(0, 3)):
+            t[rng.integers(0, 9)] = SPECIAL[rng.integers(0, len(SPECIAL))]
+        hs.hs_trs(f(t), f(a))
+        port.sco_mat4_trs(f(t[0:3].copy()), f(t[3:6].copy()), f(t[6:9].copy()), f(b))
+        eq = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+        assert eq.all(), (t, a, b)
+        x, y = rng.normal(size=16).astype(np.float32), rng.normal(size=16).astype(np.float32)
+        hs.hs_mul(f(x), f(y), f(a))
+        port.sco_mat4_mul(f(x), f(y), f(b))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_structured_fast_paths_equal_dense_values(hs, port):
+    """mat4_trs (fast path + dense fallback) and compose (affine + dense fallback) give the oracle's VALUES for
+    tame and for hostile inputs alike; only the sign of a zero may differ (Parity definition)."""
+    rng = np.random.default_rng(3)
+    nfast = 0
+    a, b, c, d = (np.zeros(16, np.float32) for _ in range(4))
+    for i in range(20000):
+        t = (rng.normal(size=9) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+        for _ in range(rng.integers(0, 4)):
+            t[rng.integers(0, 9)] = SPECIAL[rng.integers(0, len(SPECIAL))]
+        fast = hs.hs_trs_fast(f(t), f(a))
+        nfast += fast
+        port.sco_mat4_trs(f(t[0:3].copy()), f(t[3:6].copy()), f(t[6:9].copy()), f(b))
+        assert_same_bits(a, b, f"trs {t}")
+        p = (rng.normal(size=16) * 10.0 ** rng.integers(-2, 3)).astype(np.float32)
+        if i % 3 == 0:
+            p[3], p[7], p[11], p[15] = 0, 0, 0, 1
+        for _ in range(rng.integers(0, 3)):
+            p[rng.integers(0, 16)] = SPECIAL[rng.integers(0, len(SPECIAL))]
+        hs.hs_compose(f(p), f(a), int(fast), f(c))
+        port.sco_mat4_mul(f(p), f(b), f(d))
+        assert_same_bits(c, d, f"compose {p} {t}")
+    assert 0.3 < nfast / 20000 < 0.95  # both paths exercised
+
+
+def test_sphere_and_plane_tests_are_bit_exact(hs, port):
+    rng = np.random.default_rng(9)
+    s1, s2 = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    pl = np.zeros(24, np.float32)
+    for i in range(3000):
+        w = (rng.normal(size=16) * 10.0 ** rng.integers(-2, 3)).astype(np.float32)
+        bb = np.sort(rng.normal(size=(2, 3)).astype(np.float32), axis=0).ravel()
+        if i % 50 == 0:
+            w[rng.integers(0, 16)] = SPECIAL[rng.integers(0, len(SPECIAL))]
+        hs.hs_sphere(f(w), f(bb), f(s1))
+        port.sco_world_bounds_sphere(f(w), f(bb), f(s2), f(s2[3:]))
+        eq = (s1.view(np.uint32) == s2.view(np.uint32)) | (np.isnan(s1) & np.isnan(s2))
+        assert eq.all()
+        port.sco_frustum_from_viewproj(f(rng.normal(size=16).astype(np.float32)), f(pl))
+        c = (rng.normal(size=3) * 3).astype(np.float32)
+        r = np.float32(abs(rng.normal()))
+        assert hs.hs_in_frustum(f(pl), f(c), C.c_float(float(r))) == port.sco_sphere_in_frustum(f(pl), f(c), C.c_float(float(r)))
