@@ -16,15 +16,7 @@
 #include <thread>
 #include <vector>
 
-struct ScRefWorld
-{
-  sc::World world;
-  sc::CullingState culling{};
-  sc::RenderPrepStreamingState renderPrep{};
-  sc::WorldStreamingState* streaming = nullptr;  // heap: holds a WorldPartition
-  sc::CameraSystemState camera{};
-  sc::SpawnerState spawner{};
-};
+#include "scref_internal.h"
 
 namespace
 {

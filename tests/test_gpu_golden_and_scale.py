@@ -110,3 +110,18 @@ def test_nccl_gather_across_gpus():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU OK" in r.stdout
+
+
+def test_dropin_adapter_systems_against_reference_systems():
+    """The C++ adapter systems (sc-gameengine_b200/host) and the reference's own CPU systems run on ONE sc::World
+    (the sandbox's default streamed scene + scripted edits, churn, freeze, draw budget) and must produce the same
+    CullingState, RenderFrameData and world matrices every frame. The binary holds the reference's compiled code, so
+    it is prebuilt in the build container (oracle/Makefile `dropin`) and travels in oracle/_ref/."""
+    exe = ROOT / "oracle" / "_ref" / "sc_dropin_test"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/sc_dropin_test not built (needs /root/reference)")
+    env = dict(os.environ, GLIBC_TUNABLES="glibc.cpu.hwcaps=-FMA,-AVX2")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300, env=env)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "DROPIN OK" in r.stdout
