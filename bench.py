@@ -35,6 +35,9 @@ REF_SAMPLE = 2_000_000  # instances per step of the CPU reference arm (bounded s
 
 def build_scene(n, rank, seed=424242):
     from scgpu import scenes
+    if os.environ.get("SCGPU_BENCH_WORKLOAD", "hier") == "flat":  # diagnostic only; the reported workload is "hier"
+        sc = scenes.city_flat(n, seed=seed + 7919 * rank)
+        return sc
     sc = scenes.city_hier(n, seed=seed + 7919 * rank)
     # rank r owns the block of world cells shifted by r grid sides along +x: contiguous cell blocks of one world
     shift = np.float32(rank * sc["side"] * scenes.SECTOR_SIZE)

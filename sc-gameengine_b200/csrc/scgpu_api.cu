@@ -265,6 +265,15 @@ void freeAll(ScGpuScene* c)
   delete c;
 }
 
+// k_update stages its planes in more than the default 48 KB of shared memory: opt in once per instantiation
+template <int V>
+cudaError_t optInSmem()
+{
+  cudaError_t e = cudaFuncSetAttribute(k_update<true, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemHier);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_update<false, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemFlat);
+}
+
 int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
 {
   int nDev = 0;
@@ -278,6 +287,8 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   SC_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
   if (prop.major < 10)
     return (int)fail(c, "device %d is sm_%d%d; libscgpu is built for sm_100a (B200) only", c->device, prop.major, prop.minor);
+  SC_CUDA(c, optInSmem<1>()); SC_CUDA(c, optInSmem<2>()); SC_CUDA(c, optInSmem<3>()); SC_CUDA(c, optInSmem<4>());
+  SC_CUDA(c, optInSmem<5>()); SC_CUDA(c, optInSmem<6>()); SC_CUDA(c, optInSmem<7>()); SC_CUDA(c, optInSmem<8>());
   if (d->stream) { c->stream = (cudaStream_t)d->stream; c->ownStream = false; }
   else { SC_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
 
@@ -676,10 +687,10 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
               ((flags & SCGPU_UPDATE_SKIP_TRANSFORM) ? kUpdSkipTransform : 0u);
     if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
-#define SC_LAUNCH_UPDATE(V)                                                                 \
-  case V:                                                                                   \
-    if (c->anyParentEver) k_update<true, V><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);  \
-    else k_update<false, V><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes);                  \
+#define SC_LAUNCH_UPDATE(V)                                                                               \
+  case V:                                                                                                 \
+    if (c->anyParentEver) k_update<true, V><<<numTiles, kBlock, kUpdateSmemHier, c->stream>>>(p, c->planes); \
+    else k_update<false, V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                 \
     break;
     switch (c->nViews)
     {

@@ -38,6 +38,7 @@ constexpr uint32_t kMaxTileLevel = 14, kLevelDeep = 254, kLevelUnreachable = 255
 #define SCGPU_HIER_MIN_BLOCKS 3
 #endif
 
+constexpr uint32_t kUpdateSmemFlat = 3 * 4 * kBlock * 16, kUpdateSmemHier = 4 * 4 * kBlock * 16;  // dynamic smem of k_update
 constexpr uint32_t kUpdForceDirty = 1u, kUpdFreeze = 2u, kUpdSkipTransform = 4u;
 
 struct ViewPlanes
@@ -208,6 +209,41 @@ __device__ __noinline__ uint32_t walk_up(const UpdateParams& p, uint32_t ps, boo
   return 3u;
 }
 
+// ---- TMA bulk copies (cp.async.bulk + mbarrier): stage a sub-tile's planes in shared memory ahead of use ------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  uint32_t done;
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  } while (!done);
+}
+
 // signed plane distance in the reference's order: ((n0*c0 + n1*c1) + n2*c2) + d
 __device__ __forceinline__ float plane_dist(const float4 pl, float cx, float cy, float cz)
 {
@@ -227,15 +263,54 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
 {
   __shared__ uint32_t sCounts[kMaxViews + 2];
   __shared__ uint32_t sLvlMask[kSubTiles];
-  __shared__ float4 sW[kHier ? 4 : 1][kHier ? kBlock : 1];
-  __shared__ float4 sX[4][kBlock];  // per-thread exchange slots of the out-of-line slow paths
+  // dynamic shared memory (kUpdateSmemFlat / kUpdateSmemHier bytes, opted in by the host):
+  //   sRec[2][4][kBlock]  TMA staging, double buffered: the record planes (and parentSlot / tileMap) of a sub-tile
+  //                       are bulk-copied two sub-tiles ahead, so the DRAM round trip overlaps the arithmetic
+  //   sX[4][kBlock]       per-thread exchange slots (local matrix; scratch of the out-of-line slow paths)
+  //   sW[4][kBlock]       published world matrices (hierarchical scenes only)
+  extern __shared__ __align__(128) unsigned char sDyn[];
+  float4(*sRec)[4][kBlock] = reinterpret_cast<float4(*)[4][kBlock]>(sDyn);
+  float4(*sX)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(sDyn + 2 * 4 * kBlock * sizeof(float4));
+  float4(*sW)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(sDyn + 3 * 4 * kBlock * sizeof(float4));
   __shared__ uint8_t sDirty[kHier ? kBlock : 1];
+  __shared__ __align__(16) uint32_t sPs[kHier ? 2 : 1][kHier ? kBlock : 4];
+  __shared__ __align__(16) uint16_t sMap[kHier ? 2 : 1][kHier ? kBlock : 8];
+  __shared__ __align__(8) uint64_t sFull[2];
 
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
   if (tid < kMaxViews + 2) sCounts[tid] = 0;
   if (tid < kSubTiles) sLvlMask[tid] = 0;
+  const uint32_t tileBase = blockIdx.x * kTile;
+  const uint32_t nSub = min(kSubTiles, (p.count - tileBase + kBlock - 1) / kBlock);
+  // the arrays are padded to a multiple of kTile, so a partial last sub-tile is still copied whole
+  auto stage = [&](uint32_t sub)
+  {
+    const uint32_t b = sub & 1u, base = tileBase + sub * kBlock;
+    constexpr uint32_t kPlane = kBlock * sizeof(float4);
+    mbar_expect_tx(&sFull[b], 4u * kPlane + (kHier ? kBlock * 6u : 0u));
+    bulk_g2s(&sRec[b][0][0], p.rec0 + base, kPlane, &sFull[b]);
+    bulk_g2s(&sRec[b][1][0], p.rec1 + base, kPlane, &sFull[b]);
+    bulk_g2s(&sRec[b][2][0], p.rec2 + base, kPlane, &sFull[b]);
+    bulk_g2s(&sRec[b][3][0], p.rec3 + base, kPlane, &sFull[b]);
+    if constexpr (kHier)
+    {
+      bulk_g2s(&sPs[b][0], p.parentSlot + base, kBlock * 4u, &sFull[b]);
+      bulk_g2s(&sMap[b][0], p.tileMap + base, kBlock * 2u, &sFull[b]);
+    }
+  };
+  if (tid == 0)
+  {
+    mbar_init(&sFull[0], 1);
+    mbar_init(&sFull[1], 1);
+    mbar_fence_init();
+  }
   __syncthreads();
+  if (tid == 0)
+  {
+    stage(0);
+    if (nSub > 1) stage(1);
+  }
 
   constexpr uint32_t allMask = (1u << kViews) - 1u;
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
@@ -247,15 +322,16 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
   for (int v = 0; v < kViews; ++v) nVis[v] = 0;
 
 #pragma unroll 1
-  for (uint32_t sub = 0; sub < kSubTiles; ++sub)
+  for (uint32_t sub = 0; sub < nSub; ++sub)
   {
-    const uint32_t base = blockIdx.x * kTile + sub * kBlock;
-    if (base >= p.count) break;  // block-uniform
+    const uint32_t base = tileBase + sub * kBlock;
+    const uint32_t buf = sub & 1u;
+    mbar_wait(&sFull[buf], (sub >> 1) & 1u);  // this sub-tile's planes have landed in shared memory
 
     uint32_t local = tid, lvl = 0;
     if constexpr (kHier)
     {
-      const uint32_t m = p.tileMap[base + tid];
+      const uint32_t m = sMap[buf][tid];
       local = m & 0xFFu;
       lvl = m >> 8;
     }
@@ -271,17 +347,19 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
     {
       if (live)
       {
-        r3 = ld_stream(p.rec3 + s);
-        r2 = ld_stream(p.rec2 + s);
+        r3 = sRec[buf][3][local];
+        r2 = sRec[buf][2][local];
+        r0 = sRec[buf][0][local];
+        r1 = sRec[buf][1][local];
         fl = __float_as_uint(r3.w);
       }
+      __syncthreads();  // everybody has copied its record out of the staging buffer: refill it
+      if (tid == 0 && sub + 2 < nSub) stage(sub + 2);
       const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
       if (live)
       {
         if (ownDirty)
         {
-          r0 = ld_stream(p.rec0 + s);
-          r1 = ld_stream(p.rec1 + s);
           bool affine;
           W = trs_any(r0, r1, r2.x, affine, &sX[0][tid]);
           store_world(p, s, W);
@@ -302,10 +380,9 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
       uint32_t ps = kNone;
       if (live)
       {
-        // permuted inside the sub-tile: the other half of every sector is wanted by a sibling warp -> keep in L1
-        r3 = __ldg(p.rec3 + s); r2 = __ldg(p.rec2 + s);
-        r0 = __ldg(p.rec0 + s); r1 = __ldg(p.rec1 + s);
-        if (reachable && lvl != 0) ps = p.parentSlot[s];
+        r3 = sRec[buf][3][local]; r2 = sRec[buf][2][local];
+        r0 = sRec[buf][0][local]; r1 = sRec[buf][1][local];
+        if (reachable && lvl != 0) ps = sPs[buf][local];
       }
       fl = __float_as_uint(r3.w);
       const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
@@ -321,6 +398,7 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
         if (lane == 0 && w) atomicOr(&sLvlMask[sub], w);
       }
       __syncthreads();  // sLvlMask complete; also orders the previous sub-tile's shared reads before our writes
+      if (tid == 0 && sub + 2 < nSub) stage(sub + 2);  // everybody has copied its record out of the staging buffer
       const uint32_t lvlMask = sLvlMask[sub];
       const int maxLvl = lvlMask ? (31 - __clz(lvlMask)) : 0;
 
