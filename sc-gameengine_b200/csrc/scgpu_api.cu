@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -98,7 +99,10 @@ struct ScGpuScene
   bool culledListsValid = false;
 
   SceneArrays a{};
-  uint16_t* tileMap = nullptr;  // per sub-tile level-sorted thread -> slot map (hierarchical scenes)
+  uint16_t* tileMap = nullptr;  // per sub-tile level-sorted thread -> slot map (level-loop kernel)
+  uint8_t* slotInfo = nullptr;  // depth of every slot inside its hierarchy window (window kernel)
+  uint16_t* winStart = nullptr; // [tiles][kMaxWin+2] window starts per tile, last entry = window count
+  bool windowKernel = true;     // hierarchical scenes: warp-window kernel (false: level-loop kernel, for A/B runs)
   uint8_t* vismask = nullptr;
   uint32_t* tileCounts = nullptr;
   uint32_t* tileOffsets = nullptr;
@@ -244,7 +248,7 @@ void freeAll(ScGpuScene* c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
-  cudaFree(c->tileMap); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
+  cudaFree(c->tileMap); cudaFree(c->slotInfo); cudaFree(c->winStart); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
@@ -292,6 +296,7 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   if (d->stream) { c->stream = (cudaStream_t)d->stream; c->ownStream = false; }
   else { SC_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
 
+  if (const char* e = getenv("SCGPU_HIER_KERNEL")) c->windowKernel = strcmp(e, "level") != 0;
   c->capacity = d->max_instances;
   c->capacityPad = ((d->max_instances + kTile - 1) / kTile) * kTile;
   if (c->capacityPad == 0) c->capacityPad = kTile;
@@ -314,6 +319,8 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   c->a.sparseSize = c->sparseSize;
   if (!devAlloc(c, &c->vismask, n, true)) return 0;
   if (!devAlloc(c, &c->tileMap, n, true)) return 0;
+  if (!devAlloc(c, &c->slotInfo, n, true)) return 0;
+  if (!devAlloc(c, &c->winStart, (size_t)c->maxTiles * (kMaxWin + 2), true)) return 0;
   if (!devAlloc(c, &c->tileCounts, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->tileOffsets, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->totals, (size_t)kMaxViews + 2, true)) return 0;
@@ -662,7 +669,10 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     SC_CUDA(c, cudaGetLastError());
     if (c->anyParentEver)
     {
-      k_build_tile_map<<<blocksFor(c->count), kBlock, 0, c->stream>>>(c->a.parentSlot, c->tileMap, c->count);
+      if (c->windowKernel)
+        k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winStart, c->count);
+      else
+        k_build_tile_map<<<blocksFor(c->count), kBlock, 0, c->stream>>>(c->a.parentSlot, c->tileMap, c->count);
       ++c->launches;
       SC_CUDA(c, cudaGetLastError());
     }
@@ -689,7 +699,8 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
 #define SC_LAUNCH_UPDATE(V)                                                                               \
   case V:                                                                                                 \
-    if (c->anyParentEver) k_update<true, V><<<numTiles, kBlock, kUpdateSmemHier, c->stream>>>(p, c->planes); \
+    if (c->anyParentEver && c->windowKernel) k_update_win<V><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->winStart); \
+    else if (c->anyParentEver) k_update<true, V><<<numTiles, kBlock, kUpdateSmemHier, c->stream>>>(p, c->planes); \
     else k_update<false, V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                 \
     break;
     switch (c->nViews)

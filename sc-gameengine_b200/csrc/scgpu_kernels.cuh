@@ -512,6 +512,270 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
   if (tid == 0 && sCounts[kMaxViews + 1]) atomicAdd(p.recomputed, sCounts[kMaxViews + 1]);
 }
 
+// ---- hierarchy windows ------------------------------------------------------------------------------------------
+// A window is a run of <= 32 consecutive slots owned by one warp. k_build_windows (topology changes only) cuts every
+// kTile-slot tile into windows at positions that NO parent link crosses, so a hierarchy group never straddles two
+// warps and k_update_win resolves it with shuffles alone. Per slot it records the depth inside the window
+// (0 = root or parent outside the window), per tile the window starts.
+constexpr uint32_t kMaxWin = 128;          // windows per tile (greedy cuts give ~36; forced 32-slot cuts bound it)
+constexpr uint32_t kWinUnreachable = 0x40; // slotInfo: node on / below a cycle closed inside its window
+constexpr uint32_t kWinExternal = 0x20;    // slotInfo: parent lives outside the window (resolved by walk_up)
+
+__global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __restrict__ parentSlot, uint8_t* __restrict__ slotInfo,
+                                                          uint16_t* __restrict__ winStart, uint32_t count)
+{
+  __shared__ int sCross[kTile + 2];
+  __shared__ uint16_t sStart[kMaxWin + 1];
+  __shared__ uint16_t sWinOf[kTile];  // window start (tile-relative) of every slot
+  __shared__ uint32_t sWarpSum[kBlock / 32];
+  __shared__ uint32_t sNumWin;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t tileBase = blockIdx.x * kTile;
+  const uint32_t n = min(kTile, count - tileBase);
+
+  for (uint32_t k = tid; k < kTile + 2; k += kBlock) sCross[k] = 0;
+  __syncthreads();
+  // a link between slots lo < hi (both in this tile) crosses every cut position c with lo < c <= hi
+  for (uint32_t k = tid; k < n; k += kBlock)
+  {
+    const uint32_t ps = parentSlot[tileBase + k];
+    if (ps != kNone && ps >= tileBase && ps < tileBase + n && ps != tileBase + k)
+    {
+      const uint32_t q = ps - tileBase, lo = min(k, q), hi = max(k, q);
+      atomicAdd(&sCross[lo + 1], 1);
+      atomicAdd(&sCross[hi + 1], -1);
+    }
+  }
+  __syncthreads();
+  // inclusive prefix sum over kTile+1 positions: thread t owns positions 4t..4t+3 (+ the last one)
+  {
+    int v[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sum += sCross[tid * 4 + j]; v[j] = sum; }
+    int x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((int)lane >= o) x += y;
+    }
+    if (lane == 31) sWarpSum[warp] = (uint32_t)x;
+    __syncthreads();
+    int off = x - sum;
+    for (uint32_t w = 0; w < warp; ++w) off += (int)sWarpSum[w];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sCross[tid * 4 + j] = v[j] + off;
+    if (tid == kBlock - 1) sCross[kTile] += v[3] + off;
+  }
+  __syncthreads();
+  // greedy cuts by warp 0: the next window ends at the LARGEST uncrossed position within 32 slots (forced at 32)
+  if (warp == 0)
+  {
+    uint32_t start = 0, nw = 0;
+    while (start < n)
+    {
+      if (lane == 0) sStart[nw] = (uint16_t)start;
+      ++nw;
+      const uint32_t c = start + 1 + lane;  // candidate end
+      const bool ok = c <= n && (c == n || sCross[c] == 0);
+      uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (nw >= kMaxWin - 32) m = 0;  // too many small windows: finish with forced cuts so that nw <= kMaxWin
+      start = m ? start + 32u - __clz(m) : min(start + 32u, n);
+    }
+    if (lane == 0) { sStart[nw] = (uint16_t)n; sNumWin = nw; }
+  }
+  __syncthreads();
+  const uint32_t nw = sNumWin;
+  for (uint32_t k = tid; k < kMaxWin + 2; k += kBlock)
+    winStart[(size_t)blockIdx.x * (kMaxWin + 2) + k] = (k == kMaxWin + 1) ? (uint16_t)nw : (k <= nw ? sStart[k] : (uint16_t)0xFFFF);
+  for (uint32_t w = warp; w < nw; w += kBlock / 32)
+    for (uint32_t k = sStart[w] + lane; k < sStart[w + 1]; k += 32) sWinOf[k] = sStart[w];
+  __syncthreads();
+  // depth inside the window (0: root, or parent outside the window => kWinExternal)
+  for (uint32_t k = tid; k < n; k += kBlock)
+  {
+    uint32_t cur = k, depth = 0, info = 0;
+    for (;;)
+    {
+      const uint32_t ps = parentSlot[tileBase + cur];
+      if (ps == kNone) break;
+      const bool inside = ps >= tileBase && (ps - tileBase) < n && sWinOf[ps - tileBase] == sWinOf[k];
+      if (!inside)
+      {
+        if (depth == 0) info = kWinExternal;  // deeper nodes hang off an ancestor that carries the flag itself
+        break;
+      }
+      cur = ps - tileBase;
+      if (++depth > 32u) { info = kWinUnreachable; depth = 0; break; }  // a cycle closed inside the window
+    }
+    slotInfo[tileBase + k] = (uint8_t)(info | (depth & 31u));
+  }
+}
+
+// ---- K1+K2, hierarchical scenes: one window per warp, levels resolved with shuffles ----------------------------
+// Loads and stores are the flat kernel's (coalesced 128-bit planes, slot = window start + lane). Inside the warp:
+//   1. dirty / never-visited bits are propagated parent -> child level by level (one shuffle per level),
+//   2. every lane that must be recomputed builds its local matrix (all lanes busy, FP64 sincos in parallel),
+//   3. for level 1..max, the lanes of that level fetch their parent's world matrix from the parent's lane and
+//      multiply: parent-before-child, parent matrices staged in registers of the same warp.
+// No shared memory traffic, no CTA barrier, no dependency between warps: they free-run like in the flat kernel.
+template <int kViews>
+__global__ void __launch_bounds__(kBlock, 3) k_update_win(const __grid_constant__ UpdateParams p,
+                                                          const __grid_constant__ ViewPlanes vp,
+                                                          const uint8_t* __restrict__ slotInfo,
+                                                          const uint16_t* __restrict__ winStart)
+{
+  __shared__ uint32_t sCounts[kMaxViews + 2];
+  __shared__ uint16_t sStart[kMaxWin + 2];
+  __shared__ float4 sX[8][kBlock];  // two private exchange slots per thread for the out-of-line slow paths
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t tileBase = blockIdx.x * kTile;
+  if (tid < kMaxViews + 2) sCounts[tid] = 0;
+  if (tid < kMaxWin + 2) sStart[tid] = winStart[(size_t)blockIdx.x * (kMaxWin + 2) + tid];
+  __syncthreads();
+  const uint32_t nWin = sStart[kMaxWin + 1];
+
+  constexpr uint32_t allMask = (1u << kViews) - 1u;
+  const bool skip = (p.flags & kUpdSkipTransform) != 0;
+  const bool force = (p.flags & kUpdForceDirty) != 0;
+  const bool freeze = (p.flags & kUpdFreeze) != 0;
+  float4* const xa = &sX[0][tid];
+  float4* const xb = &sX[4][tid];
+  uint32_t nRecomputed = 0, nCand = 0;
+  uint32_t nVis[kViews];
+#pragma unroll
+  for (int v = 0; v < kViews; ++v) nVis[v] = 0;
+
+#pragma unroll 1
+  for (uint32_t w = warp; w < nWin; w += kBlock / 32)
+  {
+    const uint32_t a = tileBase + sStart[w];
+    const uint32_t len = sStart[w + 1] - sStart[w];
+    const bool live = lane < len;
+    const uint32_t s = a + lane;
+
+    float4 r0, r1, r2, r3;
+    r0 = r1 = r2 = r3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t info = kWinUnreachable, ps = kNone;
+    if (live)
+    {
+      r3 = ld_stream(p.rec3 + s); r2 = ld_stream(p.rec2 + s);
+      r0 = ld_stream(p.rec0 + s); r1 = ld_stream(p.rec1 + s);
+      info = slotInfo[s];
+      ps = p.parentSlot[s];
+    }
+    const uint32_t fl = __float_as_uint(r3.w);
+    const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+    const uint32_t wl = info & 31u;
+    const bool external = (info & kWinExternal) != 0;
+    bool dead = !live || (info & kWinUnreachable);  // never visited by the DFS: world matrix stays as stored
+    const uint32_t parentLane = (wl != 0) ? (ps - a) & 31u : lane;
+    const uint32_t maxL = __reduce_max_sync(0xffffffffu, live ? wl : 0u);
+
+    // ---- parents outside the window: resolved from global memory alone (walk_up leaves the matrix in xa) ----
+    bool nodeDirty = ownDirty;
+    if (live && external)
+    {
+      const uint32_t walk = walk_up(p, ps, true, xa, xb);
+      if (!(walk & 1u)) dead = true;
+      nodeDirty = ownDirty || (walk & 2u) != 0;
+    }
+    // ---- 1. inherit dirtiness / deadness down the levels ----
+    for (uint32_t l = 1; l <= maxL; ++l)
+    {
+      const bool pd = __shfl_sync(0xffffffffu, nodeDirty ? 1 : 0, parentLane) != 0;
+      const bool pdead = __shfl_sync(0xffffffffu, dead ? 1 : 0, parentLane) != 0;
+      if (live && wl == l)
+      {
+        nodeDirty = nodeDirty || pd;
+        dead = dead || pdead;
+      }
+    }
+    if (dead) nodeDirty = false;
+
+    // ---- 2. local matrices of everything that is recomputed; stored world matrices of the rest ----
+    Mat4 W = mat4_identity();
+    bool affine = true;
+    if (nodeDirty)
+    {
+      W = trs_any(r0, r1, r2.x, affine, xb);  // roots: world == local
+      if (external) W = compose_any(xs_load(xa), W, affine, xa, xb);
+    }
+    else if (live)
+    {
+      W = load_world(p, s);
+    }
+
+    // ---- 3. parent.world * local, one level at a time, parents read from their lanes ----
+    for (uint32_t l = 1; l <= maxL; ++l)
+    {
+      Mat4 PW;
+      PW.c0.x = __shfl_sync(0xffffffffu, W.c0.x, parentLane); PW.c0.y = __shfl_sync(0xffffffffu, W.c0.y, parentLane);
+      PW.c0.z = __shfl_sync(0xffffffffu, W.c0.z, parentLane); PW.c0.w = __shfl_sync(0xffffffffu, W.c0.w, parentLane);
+      PW.c1.x = __shfl_sync(0xffffffffu, W.c1.x, parentLane); PW.c1.y = __shfl_sync(0xffffffffu, W.c1.y, parentLane);
+      PW.c1.z = __shfl_sync(0xffffffffu, W.c1.z, parentLane); PW.c1.w = __shfl_sync(0xffffffffu, W.c1.w, parentLane);
+      PW.c2.x = __shfl_sync(0xffffffffu, W.c2.x, parentLane); PW.c2.y = __shfl_sync(0xffffffffu, W.c2.y, parentLane);
+      PW.c2.z = __shfl_sync(0xffffffffu, W.c2.z, parentLane); PW.c2.w = __shfl_sync(0xffffffffu, W.c2.w, parentLane);
+      PW.c3.x = __shfl_sync(0xffffffffu, W.c3.x, parentLane); PW.c3.y = __shfl_sync(0xffffffffu, W.c3.y, parentLane);
+      PW.c3.z = __shfl_sync(0xffffffffu, W.c3.z, parentLane); PW.c3.w = __shfl_sync(0xffffffffu, W.c3.w, parentLane);
+      if (nodeDirty && wl == l) W = compose_any(PW, W, affine, xa, xb);
+    }
+    if (nodeDirty)
+    {
+      store_world(p, s, W);
+      ++nRecomputed;
+    }
+
+    // ---- bounding sphere + 6*V plane tests in registers (CullingSystem, .cpp:1240-1270) ----
+    const bool cand = live && (fl & kFlagMesh);
+    const bool test = cand && !freeze && (fl & kFlagBounds);
+    uint32_t mask = 0;
+    if (__any_sync(0xffffffffu, test))
+    {
+      float cx, cy, cz, radius;
+      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, cx, cy, cz, radius);
+      const float negR = -radius;
+#pragma unroll
+      for (int v = 0; v < kViews; ++v)
+      {
+        bool alive = test;
+#pragma unroll
+        for (int pp = 0; pp < 3; ++pp)
+        {
+          if (!__any_sync(0xffffffffu, alive)) break;
+          const float d0 = plane_dist(vp.planes[v][2 * pp], cx, cy, cz);
+          const float d1 = plane_dist(vp.planes[v][2 * pp + 1], cx, cy, cz);
+          alive = alive && !(d0 < negR) && !(d1 < negR);  // NaN compares false => stays visible
+        }
+        if (alive) mask |= 1u << v;
+      }
+    }
+    if (cand && !test) mask = allMask;
+    if (live) p.vismask[s] = (uint8_t)mask;
+#pragma unroll
+    for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
+    nCand += cand ? 1u : 0u;
+  }
+
+#pragma unroll
+  for (int v = 0; v < kViews; ++v)
+  {
+    const uint32_t r = __reduce_add_sync(0xffffffffu, nVis[v]);
+    if (lane == 0 && r) atomicAdd(&sCounts[v], r);
+  }
+  {
+    const uint32_t r = __reduce_add_sync(0xffffffffu, nCand);
+    if (lane == 0 && r) atomicAdd(&sCounts[kViews], r);
+    const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
+    if (lane == 0 && q) atomicAdd(&sCounts[kMaxViews + 1], q);
+  }
+  __syncthreads();
+  if (tid <= (uint32_t)kViews) p.tileCounts[tid * p.numTiles + blockIdx.x] = sCounts[tid];
+  if (tid == 0 && sCounts[kMaxViews + 1]) atomicAdd(p.recomputed, sCounts[kMaxViews + 1]);
+}
+
 // ---- tile map: per sub-tile, sort the slots by hierarchy level ----------------------------------------------
 // Runs only when the topology changed (spawn / despawn / setParent). level = number of ancestors (walk with
 // Brent's cycle detection); > kMaxTileLevel => kLevelDeep; no root reachable => kLevelUnreachable.
