@@ -1,9 +1,10 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 show() { python - "$1" <<'PY'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print(sys.argv[1], "ms/step %.3f"%d["ms_per_step"], "kernel ms %.3f"%d["roofline"]["kernel_ms_avg"], "frac %.3f"%d["roofline"]["frac"])
 PY
 }
-timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/h_win.json 2>> gpurun_out/b.err; show gpurun_out/h_win.json
+B="timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
+$B > gpurun_out/w4t.json 2>> gpurun_out/b.err; show gpurun_out/w4t.json
 tail -3 gpurun_out/b.err

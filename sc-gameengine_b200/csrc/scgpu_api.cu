@@ -696,10 +696,12 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.nViews = c->nViews;
     p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
               ((flags & SCGPU_UPDATE_SKIP_TRANSFORM) ? kUpdSkipTransform : 0u);
+    if (c->anyParentEver && c->windowKernel)  // the window kernel accumulates its per-tile counts with atomics
+      SC_CUDA(c, cudaMemsetAsync(c->tileCounts, 0, sizeof(uint32_t) * (size_t)(c->nViews + 1) * numTiles, c->stream));
     if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
 #define SC_LAUNCH_UPDATE(V)                                                                               \
   case V:                                                                                                 \
-    if (c->anyParentEver && c->windowKernel) k_update_win<V><<<numTiles, kBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->winStart); \
+    if (c->anyParentEver && c->windowKernel) k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->winStart); \
     else if (c->anyParentEver) k_update<true, V><<<numTiles, kBlock, kUpdateSmemHier, c->stream>>>(p, c->planes); \
     else k_update<false, V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                 \
     break;

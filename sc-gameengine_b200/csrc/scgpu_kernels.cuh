@@ -620,22 +620,25 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
 //   3. for level 1..max, the lanes of that level fetch their parent's world matrix from the parent's lane and
 //      multiply: parent-before-child, parent matrices staged in registers of the same warp.
 // No shared memory traffic, no CTA barrier, no dependency between warps: they free-run like in the flat kernel.
+constexpr uint32_t kWinTilesPerCta = 4;  // tiles per CTA of k_update_win: ~146 windows shared by 8 warps
+
 template <int kViews>
 __global__ void __launch_bounds__(kBlock, 3) k_update_win(const __grid_constant__ UpdateParams p,
                                                           const __grid_constant__ ViewPlanes vp,
                                                           const uint8_t* __restrict__ slotInfo,
                                                           const uint16_t* __restrict__ winStart)
 {
-  __shared__ uint32_t sCounts[kMaxViews + 2];
-  __shared__ uint16_t sStart[kMaxWin + 2];
+  __shared__ uint16_t sStart[kWinTilesPerCta][kMaxWin + 2];
+  __shared__ uint32_t sNext;        // next unclaimed (tile, window) of this CTA: warps pull work dynamically
   __shared__ float4 sX[8][kBlock];  // two private exchange slots per thread for the out-of-line slow paths
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t tileBase = blockIdx.x * kTile;
-  if (tid < kMaxViews + 2) sCounts[tid] = 0;
-  if (tid < kMaxWin + 2) sStart[tid] = winStart[(size_t)blockIdx.x * (kMaxWin + 2) + tid];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t firstTile = blockIdx.x * kWinTilesPerCta;
+  const uint32_t nTiles = min(kWinTilesPerCta, p.numTiles - firstTile);
+  for (uint32_t k = tid; k < nTiles * (kMaxWin + 2); k += kBlock)
+    (&sStart[0][0])[k] = winStart[(size_t)firstTile * (kMaxWin + 2) + k];
+  if (tid == 0) sNext = 0;
   __syncthreads();
-  const uint32_t nWin = sStart[kMaxWin + 1];
 
   constexpr uint32_t allMask = (1u << kViews) - 1u;
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
@@ -643,16 +646,29 @@ __global__ void __launch_bounds__(kBlock, 3) k_update_win(const __grid_constant_
   const bool freeze = (p.flags & kUpdFreeze) != 0;
   float4* const xa = &sX[0][tid];
   float4* const xb = &sX[4][tid];
-  uint32_t nRecomputed = 0, nCand = 0;
-  uint32_t nVis[kViews];
-#pragma unroll
-  for (int v = 0; v < kViews; ++v) nVis[v] = 0;
+  uint32_t nRecomputed = 0;
 
+  // No barrier below this line: a warp that finishes a window claims the next one, whichever tile it belongs to.
+  uint32_t t = 0, wBase = 0;  // claimed indices only grow, so the tile cursor moves forward
 #pragma unroll 1
-  for (uint32_t w = warp; w < nWin; w += kBlock / 32)
+  for (;;)
   {
-    const uint32_t a = tileBase + sStart[w];
-    const uint32_t len = sStart[w + 1] - sStart[w];
+    uint32_t claim = 0;
+    if (lane == 0) claim = atomicAdd(&sNext, 1u);
+    claim = __shfl_sync(0xffffffffu, claim, 0);
+    while (t < nTiles && claim >= wBase + sStart[t][kMaxWin + 1]) { wBase += sStart[t][kMaxWin + 1]; ++t; }
+    if (t >= nTiles) break;
+    const uint32_t w = claim - wBase;
+    const uint32_t tile = firstTile + t;
+    const uint32_t tileBase = tile * kTile;
+    const uint16_t* sStartT = sStart[t];
+    uint32_t nCand = 0;
+    uint32_t nVis[kViews];
+#pragma unroll
+    for (int v = 0; v < kViews; ++v) nVis[v] = 0;
+  {
+    const uint32_t a = tileBase + sStartT[w];
+    const uint32_t len = sStartT[w + 1] - sStartT[w];
     const bool live = lane < len;
     const uint32_t s = a + lane;
 
@@ -758,22 +774,20 @@ __global__ void __launch_bounds__(kBlock, 3) k_update_win(const __grid_constant_
     for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
     nCand += cand ? 1u : 0u;
   }
-
+    // per-tile counts (zeroed by the host before the launch): ballots, one global atomic per warp and counter
 #pragma unroll
-  for (int v = 0; v < kViews; ++v)
-  {
-    const uint32_t r = __reduce_add_sync(0xffffffffu, nVis[v]);
-    if (lane == 0 && r) atomicAdd(&sCounts[v], r);
+    for (int v = 0; v < kViews; ++v)
+    {
+      const uint32_t c = __reduce_add_sync(0xffffffffu, nVis[v]);
+      if (lane == 0 && c) atomicAdd(&p.tileCounts[v * p.numTiles + tile], c);
+    }
+    {
+      const uint32_t c = __reduce_add_sync(0xffffffffu, nCand);
+      if (lane == 0 && c) atomicAdd(&p.tileCounts[kViews * p.numTiles + tile], c);
+    }
   }
-  {
-    const uint32_t r = __reduce_add_sync(0xffffffffu, nCand);
-    if (lane == 0 && r) atomicAdd(&sCounts[kViews], r);
-    const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
-    if (lane == 0 && q) atomicAdd(&sCounts[kMaxViews + 1], q);
-  }
-  __syncthreads();
-  if (tid <= (uint32_t)kViews) p.tileCounts[tid * p.numTiles + blockIdx.x] = sCounts[tid];
-  if (tid == 0 && sCounts[kMaxViews + 1]) atomicAdd(p.recomputed, sCounts[kMaxViews + 1]);
+  const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
+  if (lane == 0 && q) atomicAdd(p.recomputed, q);
 }
 
 // ---- tile map: per sub-tile, sort the slots by hierarchy level ----------------------------------------------
