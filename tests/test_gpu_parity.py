@@ -198,3 +198,49 @@ def test_empty_scene_and_errors():
     with pytest.raises(scgpu.ScGpuError):
         s.spawn(np.array([3], np.uint32), np.zeros((1, 9), np.float32))  # duplicate Transform
     s.close()
+
+
+@pytest.mark.parametrize("hier", [False, True])
+def test_frustum_boundary_shell(hier):
+    """Whole warps of instances whose bounding spheres graze a frustum plane (signed distance + radius within a few
+    1e-6 of zero, relative): the conservative warp prefilter and the early-outs must never change a single decision."""
+    rng = np.random.default_rng(77)
+    vps = scenes.standard_views(5)
+    chk = _checkers()[:1]
+    port = chk[0][1]
+    planes = np.zeros(24, np.float32)
+    n = 64 * 512
+    trs = np.zeros((n, 9), np.float32)
+    trs[:, 6:9] = 1.0
+    half_diag = np.float32(np.sqrt(0.75))  # unit cube: |extent| = sqrt(3)/2, scale 1
+    for blk in range(n // 64):
+        v, pl = blk % 5, (blk // 5) % 6
+        oracle_bind.port_lib().sco_frustum_from_viewproj(vps[v].ctypes.data_as(oracle_bind.C.c_void_p),
+                                                         planes.ctypes.data_as(oracle_bind.C.c_void_p))
+        nrm, d = planes[pl * 4: pl * 4 + 3].astype(np.float64), float(planes[pl * 4 + 3])
+        if not np.any(nrm):
+            continue
+        # a point on the plane shifted to signed distance -(radius) * (1 + eps), eps in +-3e-6, jittered along the plane
+        base = -nrm * d / np.dot(nrm, nrm)
+        t1 = np.cross(nrm, [0.3, 0.9, 0.1]); t1 /= np.linalg.norm(t1)
+        for k in range(64):
+            eps = rng.uniform(-3e-6, 3e-6)
+            c = base - nrm * half_diag * (1.0 + eps) + t1 * rng.uniform(-0.5, 0.5)
+            trs[blk * 64 + k, 0:3] = c.astype(np.float32)
+    e = _entities(chk, n)
+    par = None
+    if hier:  # pairs: odd slots are children of the even slot before them, with a tiny local offset
+        parent_idx = np.full(n, -1, np.int64)
+        parent_idx[1::2] = np.arange(0, n, 2)
+        child = trs[1::2].copy()
+        trs[1::2, 0:3] = rng.uniform(-1e-3, 1e-3, size=(n // 2, 3)).astype(np.float32)
+        trs[1::2, 3:9] = child[:, 3:9]
+        par = scenes.parent_handles(parent_idx, e)
+    g = GpuAdapter(n, max_views=5)
+    for s in (port, g):
+        s.spawn(e, trs, par, None, None, None)
+        s.update(vps)
+    compare_frame(g, port, e, 5, "boundary shell")
+    tot = sum(len(v) for v in port.visible)
+    assert 0 < tot < 5 * n, "the shell must straddle the planes"
+    g.close()
