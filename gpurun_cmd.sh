@@ -1,1 +1,11 @@
-for i in 1 2 3; do timeout 600 python -m pytest tests/test_gpu_golden_and_scale.py -m gpu -x -q > gpurun_out/flaky_$i.log 2>&1; tail -3 gpurun_out/flaky_$i.log; grep -n "^E " gpurun_out/flaky_$i.log | head -8; done
+show() { python - "$1" <<'PY'
+import json,sys
+d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], "ms/step %.3f"%d["ms_per_step"], "kernel ms %.3f"%d["roofline"]["kernel_ms_avg"], "frac %.3f"%d["roofline"]["frac"])
+PY
+}
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; tail -3 gpurun_out/tests_full.log
+B="timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
+$B > gpurun_out/wc.json 2>> gpurun_out/b.err; show gpurun_out/wc.json
+SCGPU_LIB=variants/win4.so $B > gpurun_out/wc4.json 2>> gpurun_out/b.err; show gpurun_out/wc4.json
+SCGPU_BENCH_WORKLOAD=flat $B > gpurun_out/fc.json 2>> gpurun_out/b.err; show gpurun_out/fc.json

@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
 constexpr uint32_t kWinTilesPerCta = 4;  // tiles per CTA of k_update_win: ~146 windows shared by 8 warps
 
 template <int kViews>
-__global__ void __launch_bounds__(kBlock, 3) k_update_win(const __grid_constant__ UpdateParams p,
+__global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant__ UpdateParams p,
                                                           const __grid_constant__ ViewPlanes vp,
                                                           const uint8_t* __restrict__ slotInfo,
                                                           const uint16_t* __restrict__ winStart)

@@ -32,10 +32,18 @@ __constant__ uint32_t kInvPio4[24] = {
   0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041
 };
 
+// s_sincosf_data.c coefficients, kept in constant memory so that the FP64 instructions take them as constant-bank
+// operands instead of re-materialising 64-bit immediates through uniform registers at every use
+__constant__ double kSinCosCoef[11] = {
+  -0x1.555545995a603p-3, 0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13,                                  // S1 S2 S3
+  0x1p0, -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10, 0x1.99343027bf8c3p-16,    // C0..C4
+  0x1.45F306DC9C883p+23, 0x1.921FB54442D18p0, 0x1.921FB54442D18p-62                                     // 2/pi*2^24, pi/2, pi*2^-63
+};
+
 // sine polynomial of sincosf.h:sinf_poly (n even): x + x^3*s1 + x^7*(s2 + x^2*s3)
 __device__ __forceinline__ float sin_poly(double x, double x2)
 {
-  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  const double S1 = kSinCosCoef[0], S2 = kSinCosCoef[1], S3 = kSinCosCoef[2];
   const double x3 = __dmul_rn(x, x2);
   const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
   const double x7 = __dmul_rn(x3, x2);
@@ -47,8 +55,7 @@ __device__ __forceinline__ float sin_poly(double x, double x2)
 // coefficients; round-to-nearest is sign-symmetric, so its result is exactly the negation of this one.
 __device__ __forceinline__ float cos_poly(double x2)
 {
-  const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
-               C4 = 0x1.99343027bf8c3p-16;
+  const double C0 = kSinCosCoef[3], C1 = kSinCosCoef[4], C2 = kSinCosCoef[5], C3 = kSinCosCoef[6], C4 = kSinCosCoef[7];
   const double x4 = __dmul_rn(x2, x2);
   const double c2 = __dadd_rn(C3, __dmul_rn(x2, C4));
   const double c1 = __dadd_rn(C0, __dmul_rn(x2, C1));
@@ -74,7 +81,7 @@ __device__ __noinline__ double reduce_large(uint32_t xi, int* np)
   res0 -= n << 62;
   const double x = __ll2double_rn((long long)res0);
   *np = (int)n;
-  return __dmul_rn(x, 0x1.921FB54442D18p-62);
+  return __dmul_rn(x, kSinCosCoef[10]);
 }
 
 // sinf(y) and cosf(y) of glibc 2.39 (generic variant) sharing one range reduction; bit-identical to the two
@@ -106,9 +113,9 @@ __device__ __forceinline__ void sincosf_glibc(float y, float& sn, float& cs)
   if (top < kTop120)
   {
     // sincosf.h:reduce_fast, !TOINT_INTRINSICS: hpi_inv prescaled by 2^24
-    const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+    const double r = __dmul_rn(x, kSinCosCoef[8]);
     n = (__double2int_rz(r) + 0x800000) >> 24;
-    x = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
+    x = __dsub_rn(x, __dmul_rn((double)n, kSinCosCoef[9]));
     q = n;
   }
   else if (top < kTopInf)
