@@ -6,6 +6,4 @@ PY
 }
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; tail -3 gpurun_out/tests_full.log
 B="timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
-$B > gpurun_out/wc.json 2>> gpurun_out/b.err; show gpurun_out/wc.json
-SCGPU_LIB=variants/win4.so $B > gpurun_out/wc4.json 2>> gpurun_out/b.err; show gpurun_out/wc4.json
-SCGPU_BENCH_WORKLOAD=flat $B > gpurun_out/fc.json 2>> gpurun_out/b.err; show gpurun_out/fc.json
+$B > gpurun_out/wB.json 2>> gpurun_out/b.err; show gpurun_out/wB.json

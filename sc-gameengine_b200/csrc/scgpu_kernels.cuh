@@ -725,18 +725,38 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
     }
 
     // ---- 3. parent.world * local, one level at a time, parents read from their lanes ----
+    // Common case: every matrix involved is affine (bottom row (0,0,0,1)) with a finite translation, so only the
+    // upper 3x4 travels through the shuffles and the product skips the bottom row. Anything else: full 4x4.
+    bool wAff = live && (nodeDirty ? (affine && !external) : mat4_is_affine(W));
+    if (nodeDirty && external) wAff = mat4_is_affine(W);
     for (uint32_t l = 1; l <= maxL; ++l)
     {
+      const bool mine = nodeDirty && wl == l;
+      const float mag = fabsf(W.c3.x) + fabsf(W.c3.y) + fabsf(W.c3.z);
+      const bool parentOk = __shfl_sync(0xffffffffu, (wAff && mag < __int_as_float(0x7f800000)) ? 1 : 0, parentLane) != 0;
       Mat4 PW;
       PW.c0.x = __shfl_sync(0xffffffffu, W.c0.x, parentLane); PW.c0.y = __shfl_sync(0xffffffffu, W.c0.y, parentLane);
-      PW.c0.z = __shfl_sync(0xffffffffu, W.c0.z, parentLane); PW.c0.w = __shfl_sync(0xffffffffu, W.c0.w, parentLane);
+      PW.c0.z = __shfl_sync(0xffffffffu, W.c0.z, parentLane);
       PW.c1.x = __shfl_sync(0xffffffffu, W.c1.x, parentLane); PW.c1.y = __shfl_sync(0xffffffffu, W.c1.y, parentLane);
-      PW.c1.z = __shfl_sync(0xffffffffu, W.c1.z, parentLane); PW.c1.w = __shfl_sync(0xffffffffu, W.c1.w, parentLane);
+      PW.c1.z = __shfl_sync(0xffffffffu, W.c1.z, parentLane);
       PW.c2.x = __shfl_sync(0xffffffffu, W.c2.x, parentLane); PW.c2.y = __shfl_sync(0xffffffffu, W.c2.y, parentLane);
-      PW.c2.z = __shfl_sync(0xffffffffu, W.c2.z, parentLane); PW.c2.w = __shfl_sync(0xffffffffu, W.c2.w, parentLane);
+      PW.c2.z = __shfl_sync(0xffffffffu, W.c2.z, parentLane);
       PW.c3.x = __shfl_sync(0xffffffffu, W.c3.x, parentLane); PW.c3.y = __shfl_sync(0xffffffffu, W.c3.y, parentLane);
-      PW.c3.z = __shfl_sync(0xffffffffu, W.c3.z, parentLane); PW.c3.w = __shfl_sync(0xffffffffu, W.c3.w, parentLane);
-      if (nodeDirty && wl == l) W = compose_any(PW, W, affine, xa, xb);
+      PW.c3.z = __shfl_sync(0xffffffffu, W.c3.z, parentLane);
+      if (__all_sync(0xffffffffu, !mine || (parentOk && affine)))
+      {
+        if (mine) W = mat4_mul_affine3(PW, W);  // wAff stays true
+      }
+      else
+      {
+        PW.c0.w = __shfl_sync(0xffffffffu, W.c0.w, parentLane); PW.c1.w = __shfl_sync(0xffffffffu, W.c1.w, parentLane);
+        PW.c2.w = __shfl_sync(0xffffffffu, W.c2.w, parentLane); PW.c3.w = __shfl_sync(0xffffffffu, W.c3.w, parentLane);
+        if (mine)
+        {
+          W = compose_any(PW, W, affine, xa, xb);
+          wAff = mat4_is_affine(W);
+        }
+      }
     }
     if (nodeDirty)
     {

@@ -303,6 +303,32 @@ __device__ __forceinline__ Mat4 mat4_mul_affine(const Mat4& p, const Mat4& l)
   return r;
 }
 
+// the same with an affine parent too (bottom row (0,0,0,1)): the bottom row of the product is (0,0,0,1) again
+__device__ __forceinline__ Mat4 mat4_mul_affine3(const Mat4& p, const Mat4& l)
+{
+  Mat4 r;
+#define SC_COL3R(dst, L)                                                                                   \
+  dst.x = __fadd_rn(__fadd_rn(__fmul_rn(p.c0.x, L.x), __fmul_rn(p.c1.x, L.y)), __fmul_rn(p.c2.x, L.z));     \
+  dst.y = __fadd_rn(__fadd_rn(__fmul_rn(p.c0.y, L.x), __fmul_rn(p.c1.y, L.y)), __fmul_rn(p.c2.y, L.z));     \
+  dst.z = __fadd_rn(__fadd_rn(__fmul_rn(p.c0.z, L.x), __fmul_rn(p.c1.z, L.y)), __fmul_rn(p.c2.z, L.z));     \
+  dst.w = 0.0f;
+  SC_COL3R(r.c0, l.c0)
+  SC_COL3R(r.c1, l.c1)
+  SC_COL3R(r.c2, l.c2)
+  SC_COL3R(r.c3, l.c3)
+#undef SC_COL3R
+  r.c3.x = __fadd_rn(r.c3.x, p.c3.x);
+  r.c3.y = __fadd_rn(r.c3.y, p.c3.y);
+  r.c3.z = __fadd_rn(r.c3.z, p.c3.z);
+  r.c3.w = 1.0f;
+  return r;
+}
+
+__device__ __forceinline__ bool mat4_is_affine(const Mat4& m)
+{
+  return m.c0.w == 0.0f && m.c1.w == 0.0f && m.c2.w == 0.0f && m.c3.w == 1.0f;
+}
+
 // world = parent.world * local (sc_ecs.cpp:191-195)
 __device__ __forceinline__ Mat4 compose(const Mat4& parentWorld, const Mat4& local, bool localAffine)
 {
