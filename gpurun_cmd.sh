@@ -6,4 +6,5 @@ PY
 }
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; tail -3 gpurun_out/tests_full.log
 B="timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
-$B > gpurun_out/wB.json 2>> gpurun_out/b.err; show gpurun_out/wB.json
+$B > gpurun_out/h.json 2>> gpurun_out/b.err; show gpurun_out/h.json
+SCGPU_BENCH_WORKLOAD=flat $B > gpurun_out/f.json 2>> gpurun_out/b.err; show gpurun_out/f.json

@@ -99,10 +99,8 @@ struct ScGpuScene
   bool culledListsValid = false;
 
   SceneArrays a{};
-  uint16_t* tileMap = nullptr;  // per sub-tile level-sorted thread -> slot map (level-loop kernel)
   uint8_t* slotInfo = nullptr;  // depth of every slot inside its hierarchy window (window kernel)
   uint16_t* winStart = nullptr; // [tiles][kMaxWin+2] window starts per tile, last entry = window count
-  bool windowKernel = true;     // hierarchical scenes: warp-window kernel (false: level-loop kernel, for A/B runs)
   uint8_t* vismask = nullptr;
   uint32_t* tileCounts = nullptr;
   uint32_t* tileOffsets = nullptr;
@@ -248,7 +246,7 @@ void freeAll(ScGpuScene* c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
-  cudaFree(c->tileMap); cudaFree(c->slotInfo); cudaFree(c->winStart); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
+  cudaFree(c->slotInfo); cudaFree(c->winStart); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
@@ -273,9 +271,7 @@ void freeAll(ScGpuScene* c)
 template <int V>
 cudaError_t optInSmem()
 {
-  cudaError_t e = cudaFuncSetAttribute(k_update<true, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemHier);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_update<false, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemFlat);
+  return cudaFuncSetAttribute(k_update_flat<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemFlat);
 }
 
 int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
@@ -296,7 +292,6 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   if (d->stream) { c->stream = (cudaStream_t)d->stream; c->ownStream = false; }
   else { SC_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
 
-  if (const char* e = getenv("SCGPU_HIER_KERNEL")) c->windowKernel = strcmp(e, "level") != 0;
   c->capacity = d->max_instances;
   c->capacityPad = ((d->max_instances + kTile - 1) / kTile) * kTile;
   if (c->capacityPad == 0) c->capacityPad = kTile;
@@ -318,7 +313,6 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   if (!devAlloc(c, &c->a.sparse, (size_t)c->sparseSize, true)) return 0;
   c->a.sparseSize = c->sparseSize;
   if (!devAlloc(c, &c->vismask, n, true)) return 0;
-  if (!devAlloc(c, &c->tileMap, n, true)) return 0;
   if (!devAlloc(c, &c->slotInfo, n, true)) return 0;
   if (!devAlloc(c, &c->winStart, (size_t)c->maxTiles * (kMaxWin + 2), true)) return 0;
   if (!devAlloc(c, &c->tileCounts, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
@@ -669,10 +663,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     SC_CUDA(c, cudaGetLastError());
     if (c->anyParentEver)
     {
-      if (c->windowKernel)
-        k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winStart, c->count);
-      else
-        k_build_tile_map<<<blocksFor(c->count), kBlock, 0, c->stream>>>(c->a.parentSlot, c->tileMap, c->count);
+      k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winStart, c->count);
       ++c->launches;
       SC_CUDA(c, cudaGetLastError());
     }
@@ -686,7 +677,6 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.rec0 = c->a.rec[0]; p.rec1 = c->a.rec[1]; p.rec2 = c->a.rec[2]; p.rec3 = c->a.rec[3];
     p.w0 = c->a.world[0]; p.w1 = c->a.world[1]; p.w2 = c->a.world[2]; p.w3 = c->a.world[3];
     p.parentSlot = c->a.parentSlot;
-    p.tileMap = c->tileMap;
     p.vismask = c->vismask;
     p.tileCounts = c->tileCounts;
     p.recomputed = c->totals + kMaxViews + 1;
@@ -696,14 +686,16 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.nViews = c->nViews;
     p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
               ((flags & SCGPU_UPDATE_SKIP_TRANSFORM) ? kUpdSkipTransform : 0u);
-    if (c->anyParentEver && c->windowKernel)  // the window kernel accumulates its per-tile counts with atomics
+    if (c->anyParentEver)  // the window kernel accumulates its per-tile counts with atomics
       SC_CUDA(c, cudaMemsetAsync(c->tileCounts, 0, sizeof(uint32_t) * (size_t)(c->nViews + 1) * numTiles, c->stream));
     if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
-#define SC_LAUNCH_UPDATE(V)                                                                               \
-  case V:                                                                                                 \
-    if (c->anyParentEver && c->windowKernel) k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->winStart); \
-    else if (c->anyParentEver) k_update<true, V><<<numTiles, kBlock, kUpdateSmemHier, c->stream>>>(p, c->planes); \
-    else k_update<false, V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                 \
+#define SC_LAUNCH_UPDATE(V)                                                                                              \
+  case V:                                                                                                                \
+    if (c->anyParentEver)                                                                                                \
+      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, \
+                                                                                                     c->winStart);      \
+    else                                                                                                                 \
+      k_update_flat<V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                                   \
     break;
     switch (c->nViews)
     {

@@ -8,13 +8,13 @@
 //   rec3[slot] = { aabbMax.x, aabbMax.y, aabbMax.z, flags }     exactly SURVEY.md §8(d)'s read set.
 //   world0..3[slot] = world matrix columns (float4 planes, coalesced 128-bit stores)
 //   parentSlot[slot] = resolved parent slot or kNone (maintained by k_resolve_parents on topology changes)
-//   tileMap[slot]    = (level << 8) | local index: thread t of a 256-slot sub-tile works on slot base+local.
-//                      The map sorts each sub-tile by hierarchy level, so warps are level-homogeneous and the
-//                      per-level resolve loop never runs the transform code with a fraction of its lanes.
+//   slotInfo[slot]   = depth of the slot inside its hierarchy window (+ flags), winStart[tile][..] = window starts:
+//                      hierarchical scenes are cut into windows of <= 32 consecutive slots that no parent link
+//                      crosses; one warp resolves one window with shuffles (k_build_windows / k_update_win).
 //   flags: bit0 HAS_BOUNDS, bit1 HAS_MESH, bits 8..31 = dirty stamp (id of the update that must recompute
 //          the instance). A stamp instead of a dirty bit means the frame kernel never writes the records.
 //
-// Frame = k_update (transform + sphere + V-view plane tests + per-tile counts, one pass over the records)
+// Frame = k_update_flat | k_update_win (transform + sphere + V-view plane tests + per-tile counts, one pass)
 //         -> k_scan_tiles (exclusive scan of the per-tile counts, V+1 rows)
 //         -> k_scatter_visible (stable per-view compaction of entity handles / slots)
 #pragma once
@@ -30,15 +30,7 @@ constexpr uint32_t kSubTiles = 4;      // sub-tiles of kBlock slots per CTA
 constexpr uint32_t kTile = kBlock * kSubTiles;
 constexpr uint32_t kFlagBounds = 1u, kFlagMesh = 2u;
 constexpr uint32_t kStampShift = 8;
-// hierarchy levels kept in tileMap: 0..kMaxTileLevel resolved through shared memory, deeper chains through
-// walk_up(), unreachable nodes (cycles) never visited
-constexpr uint32_t kMaxTileLevel = 14, kLevelDeep = 254, kLevelUnreachable = 255;
-
-#ifndef SCGPU_HIER_MIN_BLOCKS
-#define SCGPU_HIER_MIN_BLOCKS 3
-#endif
-
-constexpr uint32_t kUpdateSmemFlat = 3 * 4 * kBlock * 16, kUpdateSmemHier = 4 * 4 * kBlock * 16;  // dynamic smem of k_update
+constexpr uint32_t kUpdateSmemFlat = 3 * 4 * kBlock * 16;  // dynamic shared memory of k_update_flat
 constexpr uint32_t kUpdForceDirty = 1u, kUpdFreeze = 2u, kUpdSkipTransform = 4u;
 
 struct ViewPlanes
@@ -57,7 +49,6 @@ struct UpdateParams
   float4* w2;
   float4* w3;
   const uint32_t* parentSlot;
-  const uint16_t* tileMap;
   uint8_t* vismask;
   uint32_t* tileCounts;  // [(nViews+1)][numTiles]; row nViews = culling candidates
   uint32_t* recomputed;  // single counter
@@ -250,37 +241,27 @@ __device__ __forceinline__ float plane_dist(const float4 pl, float cx, float cy,
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pl.x, cx), __fmul_rn(pl.y, cy)), __fmul_rn(pl.z, cz)), pl.w);
 }
 
-// ---- K1+K2: fused transform + cull, all views in one pass ------------------------------------------------
-// One thread per slot, kSubTiles sub-tiles of kBlock consecutive slots per CTA.
-// kHier=false: no instance has a parent (flat scene): pure streaming, thread t <-> slot base+t.
-// kHier=true : thread t <-> slot base + tileMap.local (level-sorted). Levels are resolved one per iteration:
-//              a node's thread publishes its fresh world matrix in shared memory, one barrier, then the next
-//              level multiplies. Parents outside the sub-tile (or deeper than kMaxTileLevel) go through walk_up().
-// kViews    : compile-time view count, so the 6*V plane tests read their planes straight from the constant bank.
-template <bool kHier, int kViews>
-__global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_update(const __grid_constant__ UpdateParams p,
-                                                                  const __grid_constant__ ViewPlanes vp)
+// ---- K1+K2, flat scenes: fused transform + cull, all views in one pass ------------------------------------------------
+// No instance has a parent: pure streaming. One thread per slot, kSubTiles sub-tiles of kBlock consecutive slots per
+// CTA; the four record planes of a sub-tile are staged in shared memory by TMA bulk copies two sub-tiles ahead, so the
+// DRAM round trip overlaps the arithmetic. kViews is a compile-time view count, so the 6*V plane tests read their
+// planes straight from the constant bank; views are tested in plane pairs with a warp-uniform early-out.
+template <int kViews>
+__global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant__ UpdateParams p,
+                                                           const __grid_constant__ ViewPlanes vp)
 {
   __shared__ uint32_t sCounts[kMaxViews + 2];
-  __shared__ uint32_t sLvlMask[kSubTiles];
-  // dynamic shared memory (kUpdateSmemFlat / kUpdateSmemHier bytes, opted in by the host):
-  //   sRec[2][4][kBlock]  TMA staging, double buffered: the record planes (and parentSlot / tileMap) of a sub-tile
-  //                       are bulk-copied two sub-tiles ahead, so the DRAM round trip overlaps the arithmetic
-  //   sX[4][kBlock]       per-thread exchange slots (local matrix; scratch of the out-of-line slow paths)
-  //   sW[4][kBlock]       published world matrices (hierarchical scenes only)
+  __shared__ __align__(8) uint64_t sFull[2];
+  // dynamic shared memory (kUpdateSmemFlat bytes, opted in by the host):
+  //   sRec[2][4][kBlock]  TMA staging, double buffered
+  //   sX[4][kBlock]       per-thread exchange slot of the out-of-line dense fallback
   extern __shared__ __align__(128) unsigned char sDyn[];
   float4(*sRec)[4][kBlock] = reinterpret_cast<float4(*)[4][kBlock]>(sDyn);
   float4(*sX)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(sDyn + 2 * 4 * kBlock * sizeof(float4));
-  float4(*sW)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(sDyn + 3 * 4 * kBlock * sizeof(float4));
-  __shared__ uint8_t sDirty[kHier ? kBlock : 1];
-  __shared__ __align__(16) uint32_t sPs[kHier ? 2 : 1][kHier ? kBlock : 4];
-  __shared__ __align__(16) uint16_t sMap[kHier ? 2 : 1][kHier ? kBlock : 8];
-  __shared__ __align__(8) uint64_t sFull[2];
 
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
   if (tid < kMaxViews + 2) sCounts[tid] = 0;
-  if (tid < kSubTiles) sLvlMask[tid] = 0;
   const uint32_t tileBase = blockIdx.x * kTile;
   const uint32_t nSub = min(kSubTiles, (p.count - tileBase + kBlock - 1) / kBlock);
   // the arrays are padded to a multiple of kTile, so a partial last sub-tile is still copied whole
@@ -288,16 +269,11 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
   {
     const uint32_t b = sub & 1u, base = tileBase + sub * kBlock;
     constexpr uint32_t kPlane = kBlock * sizeof(float4);
-    mbar_expect_tx(&sFull[b], 4u * kPlane + (kHier ? kBlock * 6u : 0u));
+    mbar_expect_tx(&sFull[b], 4u * kPlane);
     bulk_g2s(&sRec[b][0][0], p.rec0 + base, kPlane, &sFull[b]);
     bulk_g2s(&sRec[b][1][0], p.rec1 + base, kPlane, &sFull[b]);
     bulk_g2s(&sRec[b][2][0], p.rec2 + base, kPlane, &sFull[b]);
     bulk_g2s(&sRec[b][3][0], p.rec3 + base, kPlane, &sFull[b]);
-    if constexpr (kHier)
-    {
-      bulk_g2s(&sPs[b][0], p.parentSlot + base, kBlock * 4u, &sFull[b]);
-      bulk_g2s(&sMap[b][0], p.tileMap + base, kBlock * 2u, &sFull[b]);
-    }
   };
   if (tid == 0)
   {
@@ -324,141 +300,34 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
 #pragma unroll 1
   for (uint32_t sub = 0; sub < nSub; ++sub)
   {
-    const uint32_t base = tileBase + sub * kBlock;
     const uint32_t buf = sub & 1u;
-    mbar_wait(&sFull[buf], (sub >> 1) & 1u);  // this sub-tile's planes have landed in shared memory
-
-    uint32_t local = tid, lvl = 0;
-    if constexpr (kHier)
-    {
-      const uint32_t m = sMap[buf][tid];
-      local = m & 0xFFu;
-      lvl = m >> 8;
-    }
-    const uint32_t s = base + local;
+    const uint32_t s = tileBase + sub * kBlock + tid;
     const bool live = s < p.count;
+    mbar_wait(&sFull[buf], (sub >> 1) & 1u);  // this sub-tile's planes have landed in shared memory
 
     float4 r0, r1, r2, r3;
     r0 = r1 = r2 = r3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t fl = 0;
-    Mat4 W = mat4_identity();
-
-    if constexpr (!kHier)
+    if (live)
     {
-      if (live)
-      {
-        r3 = sRec[buf][3][local];
-        r2 = sRec[buf][2][local];
-        r0 = sRec[buf][0][local];
-        r1 = sRec[buf][1][local];
-        fl = __float_as_uint(r3.w);
-      }
-      __syncthreads();  // everybody has copied its record out of the staging buffer: refill it
-      if (tid == 0 && sub + 2 < nSub) stage(sub + 2);
-      const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
-      if (live)
-      {
-        if (ownDirty)
-        {
-          bool affine;
-          W = trs_any(r0, r1, r2.x, affine, &sX[0][tid]);
-          store_world(p, s, W);
-          ++nRecomputed;
-        }
-        else
-        {
-          W = load_world(p, s);
-        }
-      }
+      r3 = sRec[buf][3][tid]; r2 = sRec[buf][2][tid];
+      r0 = sRec[buf][0][tid]; r1 = sRec[buf][1][tid];
     }
-    else
+    __syncthreads();  // everybody has copied its record out of the staging buffer: refill it
+    if (tid == 0 && sub + 2 < nSub) stage(sub + 2);
+
+    const uint32_t fl = __float_as_uint(r3.w);
+    const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+    Mat4 W = mat4_identity();
+    if (ownDirty)
     {
-      const bool reachable = live && lvl != kLevelUnreachable;
-      const bool deep = lvl == kLevelDeep;
-      const uint32_t effLvl = deep ? 0u : lvl;
-      // ---- phase A: every global load of the sub-tile is issued here, before any dependent work ----
-      uint32_t ps = kNone;
-      if (live)
-      {
-        r3 = sRec[buf][3][local]; r2 = sRec[buf][2][local];
-        r0 = sRec[buf][0][local]; r1 = sRec[buf][1][local];
-        if (reachable && lvl != 0) ps = sPs[buf][local];
-      }
-      fl = __float_as_uint(r3.w);
-      const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
-      // clean nodes and nodes the DFS never visits keep their stored matrix: fetch it with the other loads
-      const bool keepStored = live && (!ownDirty || !reachable);
-      Mat4 stored = mat4_identity();
-      if (keepStored) stored = load_world(p, s);
-
-      // levels present in this sub-tile (block-wide OR of one bit per thread)
-      {
-        const uint32_t bit = (reachable && !deep) ? (1u << lvl) : 0u;
-        const uint32_t w = __reduce_or_sync(0xffffffffu, bit);
-        if (lane == 0 && w) atomicOr(&sLvlMask[sub], w);
-      }
-      __syncthreads();  // sLvlMask complete; also orders the previous sub-tile's shared reads before our writes
-      if (tid == 0 && sub + 2 < nSub) stage(sub + 2);  // everybody has copied its record out of the staging buffer
-      const uint32_t lvlMask = sLvlMask[sub];
-      const int maxLvl = lvlMask ? (31 - __clz(lvlMask)) : 0;
-
-      // ---- phase B: no dependency on other threads (warps are level-homogeneous, so no lane idles here).
-      // Matrices cross the barriers of phase C in shared memory only: sX[.][tid] = local matrix (private),
-      // sW[.][local] = world matrix (provisional for clean nodes, parent's for walked ones, then published).
-      const bool hasParent = ps != kNone;
-      const bool inTile = hasParent && !deep && (ps - base < kBlock);
-      const bool walked = hasParent && !inTile;
-      if (keepStored && !walked) xs_store(&sW[0][local], stored);  // provisional; `stored` dies here
-      bool pDirty = false;
-      if (walked) pDirty = (walk_up(p, ps, true, &sW[0][local], &sX[0][tid]) & 2u) != 0;  // reachable => finds a root
-      bool haveL = false, affine = true;
-      if (reachable && (ownDirty || pDirty))
-      {
-        const Mat4 L = trs_any(r0, r1, r2.x, affine, &sX[0][tid]);
-        xs_store(&sX[0][tid], L);
-        haveL = true;
-      }
-
-      // ---- phase C: one iteration per level, only parent.world * local is serialized ----
-      bool nodeDirty = false;
-#pragma unroll 1
-      for (int l = 0; l <= maxLvl; ++l)
-      {
-        if (reachable && effLvl == (uint32_t)l)
-        {
-          if (inTile) pDirty = sDirty[ps - base] != 0;
-          nodeDirty = ownDirty || pDirty;
-          if (nodeDirty)
-          {
-            Mat4 L;
-            if (haveL) L = xs_load(&sX[0][tid]);
-            else L = trs_any(__ldg(p.rec0 + s), __ldg(p.rec1 + s), r2.x, affine, &sX[0][tid]);
-            if (hasParent)
-            {
-              const Mat4 PW = xs_load(inTile ? &sW[0][ps - base] : &sW[0][local]);
-              xs_store(&sW[0][local], compose_any(PW, L, affine, &sX[0][tid], &sW[0][local]));
-            }
-            else
-            {
-              xs_store(&sW[0][local], L);
-            }
-          }
-          else if (walked)
-          {
-            xs_store(&sW[0][local], load_world(p, s));  // the slot held the walked parent matrix
-          }
-          sDirty[local] = nodeDirty ? 1 : 0;
-        }
-        if (l < maxLvl) __syncthreads();
-      }
-      // every live node's matrix is now in its slot (cycle members and their descendants, which the DFS never
-      // visits, still hold the provisional stored one)
-      if (live) W = xs_load(&sW[0][local]);
-      if (nodeDirty)
-      {
-        store_world(p, s, W);
-        ++nRecomputed;
-      }
+      bool affine;
+      W = trs_any(r0, r1, r2.x, affine, &sX[0][tid]);
+      store_world(p, s, W);
+      ++nRecomputed;
+    }
+    else if (live)
+    {
+      W = load_world(p, s);
     }
 
     // ---- bounding sphere + 6*V plane tests in registers (CullingSystem, .cpp:1240-1270) ----
@@ -488,7 +357,6 @@ __global__ void __launch_bounds__(kBlock, kHier ? SCGPU_HIER_MIN_BLOCKS : 4) k_u
     }
     if (cand && !test) mask = allMask;  // frozen culling or no Bounds component: always visible
     if (live) p.vismask[s] = (uint8_t)mask;
-
 #pragma unroll
     for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
     nCand += cand ? 1u : 0u;
@@ -808,52 +676,6 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
   }
   const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
   if (lane == 0 && q) atomicAdd(p.recomputed, q);
-}
-
-// ---- tile map: per sub-tile, sort the slots by hierarchy level ----------------------------------------------
-// Runs only when the topology changed (spawn / despawn / setParent). level = number of ancestors (walk with
-// Brent's cycle detection); > kMaxTileLevel => kLevelDeep; no root reachable => kLevelUnreachable.
-__global__ void __launch_bounds__(kBlock) k_build_tile_map(const uint32_t* __restrict__ parentSlot,
-                                                           uint16_t* __restrict__ tileMap, uint32_t count)
-{
-  constexpr uint32_t kBins = kMaxTileLevel + 4;  // levels 0..14, deep, unreachable, beyond count
-  __shared__ uint32_t sWarpCnt[kBlock / 32][kBins];
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t base = blockIdx.x * kBlock;
-  const uint32_t s = base + tid;
-  for (uint32_t k = tid; k < (kBlock / 32) * kBins; k += kBlock) (&sWarpCnt[0][0])[k] = 0;
-
-  uint32_t level = kLevelUnreachable, bin = kBins - 1;
-  if (s < count)
-  {
-    uint32_t cur = s, tortoise = s, steps = 0, power = 1, lam = 0;
-    bool cycle = false;
-    for (;;)
-    {
-      const uint32_t nxt = parentSlot[cur];
-      if (nxt == kNone) break;
-      cur = nxt;
-      ++steps;
-      ++lam;
-      if (cur == tortoise) { cycle = true; break; }
-      if (lam == power) { tortoise = cur; power <<= 1; lam = 0; }
-    }
-    if (cycle) { level = kLevelUnreachable; bin = kMaxTileLevel + 2; }
-    else if (steps > kMaxTileLevel) { level = kLevelDeep; bin = kMaxTileLevel + 1; }
-    else { level = steps; bin = steps; }
-  }
-  __syncthreads();
-  // stable counting sort by bin: rank inside the warp by match, across warps through shared counters
-  const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-  const uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
-  if (rankInWarp == 0) sWarpCnt[warp][bin] = __popc(peers);
-  __syncthreads();
-  uint32_t offset = 0;
-  for (uint32_t b = 0; b < bin; ++b)
-    for (uint32_t w = 0; w < kBlock / 32; ++w) offset += sWarpCnt[w][b];
-  for (uint32_t w = 0; w < warp; ++w) offset += sWarpCnt[w][bin];
-  const uint32_t rank = offset + rankInWarp;
-  tileMap[base + rank] = (uint16_t)((level << 8) | tid);
 }
 
 // ---- K3a: exclusive scan of the per-tile counts, one CTA per row (view) -----------------------------------
