@@ -85,19 +85,19 @@ __device__ __forceinline__ void store_world(const UpdateParams& p, uint32_t s, c
 
 // ---- out-of-line slow paths --------------------------------------------------------------------------------
 // The rare paths (dense fallbacks for non-finite input, ancestor walks) are real function calls. They exchange
-// matrices with the caller through a per-thread shared-memory slot (4 float4, stride kBlock) instead of through
+// matrices with the caller through a per-thread exchange slot (4 consecutive float4) instead of through
 // reference parameters, so that no matrix of the hot path ever has its address taken (which would pin it to
 // local memory).
 __device__ __forceinline__ Mat4 xs_load(const float4* x)
 {
   Mat4 m;
-  m.c0 = x[0]; m.c1 = x[kBlock]; m.c2 = x[2 * kBlock]; m.c3 = x[3 * kBlock];
+  m.c0 = x[0]; m.c1 = x[1]; m.c2 = x[2]; m.c3 = x[3];
   return m;
 }
 
 __device__ __forceinline__ void xs_store(float4* x, const Mat4& m)
 {
-  x[0] = m.c0; x[kBlock] = m.c1; x[2 * kBlock] = m.c2; x[3 * kBlock] = m.c3;
+  x[0] = m.c0; x[1] = m.c1; x[2] = m.c2; x[3] = m.c3;
 }
 
 __device__ __noinline__ void trs_dense_to(float px, float py, float pz, float rx, float ry, float rz, float sx, float sy,
@@ -169,7 +169,7 @@ __device__ __noinline__ uint32_t walk_up(const UpdateParams& p, uint32_t ps, boo
   const bool dirty = lastDirty >= 0;
   if (!dirty)
   {
-    if (needWorld) { out[0] = p.w0[ps]; out[kBlock] = p.w1[ps]; out[2 * kBlock] = p.w2[ps]; out[3 * kBlock] = p.w3[ps]; }
+    if (needWorld) { out[0] = p.w0[ps]; out[1] = p.w1[ps]; out[2] = p.w2[ps]; out[3] = p.w3[ps]; }
     return 1u;
   }
   // pass 2: recompute ps's world from the topmost dirty ancestor down
@@ -235,6 +235,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
   } while (!done);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // signed plane distance in the reference's order: ((n0*c0 + n1*c1) + n2*c2) + d
 __device__ __forceinline__ float plane_dist(const float4 pl, float cx, float cy, float cz)
 {
@@ -254,10 +265,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
   __shared__ __align__(8) uint64_t sFull[2];
   // dynamic shared memory (kUpdateSmemFlat bytes, opted in by the host):
   //   sRec[2][4][kBlock]  TMA staging, double buffered
-  //   sX[4][kBlock]       per-thread exchange slot of the out-of-line dense fallback
+  //   sX[kBlock][4]       per-thread exchange slot of the out-of-line dense fallback
   extern __shared__ __align__(128) unsigned char sDyn[];
   float4(*sRec)[4][kBlock] = reinterpret_cast<float4(*)[4][kBlock]>(sDyn);
-  float4(*sX)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(sDyn + 2 * 4 * kBlock * sizeof(float4));
+  float4(*sX)[4] = reinterpret_cast<float4(*)[4]>(sDyn + 2 * 4 * kBlock * sizeof(float4));
 
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
     if (ownDirty)
     {
       bool affine;
-      W = trs_any(r0, r1, r2.x, affine, &sX[0][tid]);
+      W = trs_any(r0, r1, r2.x, affine, &sX[tid][0]);
       store_world(p, s, W);
       ++nRecomputed;
     }
@@ -497,10 +508,12 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
                                                           const uint16_t* __restrict__ winStart)
 {
   __shared__ uint16_t sStart[kWinTilesPerCta][kMaxWin + 2];
-  __shared__ uint32_t sNext;        // next unclaimed (tile, window) of this CTA: warps pull work dynamically
-  __shared__ float4 sX[8][kBlock];  // two private exchange slots per thread for the out-of-line slow paths
+  __shared__ uint32_t sNext;  // next unclaimed (tile, window) of this CTA: warps pull work dynamically
+  // per-warp double buffer: the record planes of the NEXT claimed window are fetched with cp.async while the
+  // current window is being computed
+  __shared__ __align__(16) float4 sPre[kBlock / 32][2][4][32];
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t firstTile = blockIdx.x * kWinTilesPerCta;
   const uint32_t nTiles = min(kWinTilesPerCta, p.numTiles - firstTile);
   for (uint32_t k = tid; k < nTiles * (kMaxWin + 2); k += kBlock)
@@ -512,43 +525,69 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
-  float4* const xa = &sX[0][tid];
-  float4* const xb = &sX[4][tid];
+  // exchange slots of the out-of-line slow paths: thread-local, touched only when a slow path runs
+  float4 xaBuf[4], xbBuf[4];
+  float4* const xa = xaBuf;
+  float4* const xb = xbBuf;
   uint32_t nRecomputed = 0;
 
-  // No barrier below this line: a warp that finishes a window claims the next one, whichever tile it belongs to.
+  // No barrier below this line: a warp that finishes a window claims another one, whichever tile it belongs to.
   uint32_t t = 0, wBase = 0;  // claimed indices only grow, so the tile cursor moves forward
-#pragma unroll 1
-  for (;;)
+  // claim + locate + start fetching one window; returns false when the CTA's windows are exhausted
+  struct Win { uint32_t tile, a, len, info, ps; };
+  auto claim_and_fetch = [&](uint32_t buf, Win& o) -> bool
   {
     uint32_t claim = 0;
     if (lane == 0) claim = atomicAdd(&sNext, 1u);
     claim = __shfl_sync(0xffffffffu, claim, 0);
     while (t < nTiles && claim >= wBase + sStart[t][kMaxWin + 1]) { wBase += sStart[t][kMaxWin + 1]; ++t; }
-    if (t >= nTiles) break;
+    if (t >= nTiles) return false;
     const uint32_t w = claim - wBase;
-    const uint32_t tile = firstTile + t;
-    const uint32_t tileBase = tile * kTile;
-    const uint16_t* sStartT = sStart[t];
+    o.tile = firstTile + t;
+    o.a = o.tile * kTile + sStart[t][w];
+    o.len = sStart[t][w + 1] - sStart[t][w];
+    o.info = kWinUnreachable;
+    o.ps = kNone;
+    if (lane < o.len)
+    {
+      const uint32_t q = o.a + lane;
+      cp_async16(&sPre[warp][buf][0][lane], p.rec0 + q);
+      cp_async16(&sPre[warp][buf][1][lane], p.rec1 + q);
+      cp_async16(&sPre[warp][buf][2][lane], p.rec2 + q);
+      cp_async16(&sPre[warp][buf][3][lane], p.rec3 + q);
+      o.info = slotInfo[q];
+      o.ps = p.parentSlot[q];
+    }
+    cp_async_commit();
+    return true;
+  };
+  Win cur, nxt;
+  uint32_t buf = 0;
+  bool have = claim_and_fetch(0, cur);
+#pragma unroll 1
+  while (have)
+  {
+    const bool haveNext = claim_and_fetch(buf ^ 1u, nxt);  // in flight while this window is computed
+    if (haveNext) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    const uint32_t tile = cur.tile;
     uint32_t nCand = 0;
     uint32_t nVis[kViews];
 #pragma unroll
     for (int v = 0; v < kViews; ++v) nVis[v] = 0;
   {
-    const uint32_t a = tileBase + sStartT[w];
-    const uint32_t len = sStartT[w + 1] - sStartT[w];
+    const uint32_t a = cur.a;
+    const uint32_t len = cur.len;
     const bool live = lane < len;
     const uint32_t s = a + lane;
 
     float4 r0, r1, r2, r3;
     r0 = r1 = r2 = r3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t info = kWinUnreachable, ps = kNone;
+    const uint32_t info = cur.info, ps = cur.ps;
     if (live)
     {
-      r3 = ld_stream(p.rec3 + s); r2 = ld_stream(p.rec2 + s);
-      r0 = ld_stream(p.rec0 + s); r1 = ld_stream(p.rec1 + s);
-      info = slotInfo[s];
-      ps = p.parentSlot[s];
+      r3 = sPre[warp][buf][3][lane]; r2 = sPre[warp][buf][2][lane];
+      r0 = sPre[warp][buf][0][lane]; r1 = sPre[warp][buf][1][lane];
     }
     const uint32_t fl = __float_as_uint(r3.w);
     const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
@@ -673,6 +712,9 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
       const uint32_t c = __reduce_add_sync(0xffffffffu, nCand);
       if (lane == 0 && c) atomicAdd(&p.tileCounts[kViews * p.numTiles + tile], c);
     }
+    have = haveNext;
+    cur = nxt;
+    buf ^= 1u;
   }
   const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
   if (lane == 0 && q) atomicAdd(p.recomputed, q);
