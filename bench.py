@@ -372,7 +372,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {
-                "bound": "hbm", "kernel": "k_update<hier> (fused transform + sphere + 5-view cull + tile counts)",
+                "bound": "hbm", "kernel": "k_update_win<V> (fused transform + sphere + V-view cull + tile counts; hierarchy windows per warp)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_instance": ALG_BYTES_DIRTY, "kernel_ms_avg": k_avg_ms,

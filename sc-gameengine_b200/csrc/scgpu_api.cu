@@ -99,8 +99,12 @@ struct ScGpuScene
   bool culledListsValid = false;
 
   SceneArrays a{};
-  uint8_t* slotInfo = nullptr;  // depth of every slot inside its hierarchy window (window kernel)
-  uint16_t* winStart = nullptr; // [tiles][kMaxWin+2] window starts per tile, last entry = window count
+  // hierarchy windows (k_build_windows -> k_scan_tiles -> k_flatten_windows, on topology changes only)
+  uint16_t* slotInfo = nullptr;      // per slot: depth + parent lane inside its window, external / unreachable flags
+  uint16_t* winLocal = nullptr;      // [tiles][kMaxWin+1] window starts relative to the tile
+  uint32_t* tileWinCount = nullptr;  // [tiles]
+  uint32_t* tileWinBase = nullptr;   // [tiles+1] exclusive scan of tileWinCount, total at the end
+  uint32_t* winList = nullptr;       // [total+1] absolute start slot of every window (bit 31: generic path)
   uint8_t* vismask = nullptr;
   uint32_t* tileCounts = nullptr;
   uint32_t* tileOffsets = nullptr;
@@ -246,7 +250,7 @@ void freeAll(ScGpuScene* c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
-  cudaFree(c->slotInfo); cudaFree(c->winStart); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
+  cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
@@ -314,7 +318,10 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   c->a.sparseSize = c->sparseSize;
   if (!devAlloc(c, &c->vismask, n, true)) return 0;
   if (!devAlloc(c, &c->slotInfo, n, true)) return 0;
-  if (!devAlloc(c, &c->winStart, (size_t)c->maxTiles * (kMaxWin + 2), true)) return 0;
+  if (!devAlloc(c, &c->winLocal, (size_t)c->maxTiles * (kMaxWin + 1), true)) return 0;
+  if (!devAlloc(c, &c->tileWinCount, (size_t)c->maxTiles, true)) return 0;
+  if (!devAlloc(c, &c->tileWinBase, (size_t)c->maxTiles + 1, true)) return 0;
+  if (!devAlloc(c, &c->winList, (size_t)c->maxTiles * kMaxWin + 1, true)) return 0;
   if (!devAlloc(c, &c->tileCounts, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->tileOffsets, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->totals, (size_t)kMaxViews + 2, true)) return 0;
@@ -663,8 +670,10 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     SC_CUDA(c, cudaGetLastError());
     if (c->anyParentEver)
     {
-      k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winStart, c->count);
-      ++c->launches;
+      k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winLocal, c->tileWinCount, c->count);
+      k_scan_tiles<<<1, 1024, 0, c->stream>>>(c->tileWinCount, c->tileWinBase, c->tileWinBase + numTiles, numTiles);
+      k_flatten_windows<<<numTiles, 128, 0, c->stream>>>(c->winLocal, c->tileWinCount, c->tileWinBase, c->winList, numTiles, c->count);
+      c->launches += 3;
       SC_CUDA(c, cudaGetLastError());
     }
   }
@@ -693,7 +702,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
   case V:                                                                                                                \
     if (c->anyParentEver)                                                                                                \
       k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, \
-                                                                                                     c->winStart);      \
+                                                                                                     c->winList, c->tileWinBase); \
     else                                                                                                                 \
       k_update_flat<V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                                   \
     break;

@@ -223,6 +223,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
   uint32_t done;
@@ -252,11 +254,84 @@ __device__ __forceinline__ float plane_dist(const float4 pl, float cx, float cy,
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pl.x, cx), __fmul_rn(pl.y, cy)), __fmul_rn(pl.z, cz)), pl.w);
 }
 
+// ---- warp-cooperative pieces shared by the two frame kernels --------------------------------------------------------
+
+// Sines and cosines of the three Euler angles of every lane. Angles below 2^-12 (zero above all) cost nothing in libm
+// and nothing here; the others are worked off one PER ITERATION, each lane taking its next non-trivial angle
+// whichever axis it belongs to. A warp whose lanes rotate about different single axes (wheels about X, props about Y,
+// roots about Y) therefore evaluates one range reduction + two polynomials, not one per axis.
+__device__ __forceinline__ void sincos3_warp(bool active, float rx, float ry, float rz, float& sx, float& cx, float& sy,
+                                             float& cy, float& sz, float& cz)
+{
+  sx = rx; cx = 1.0f; sy = ry; cy = 1.0f; sz = rz; cz = 1.0f;
+  uint32_t need = 0;
+  if (active)
+    need = (sincos_is_trivial(rx) ? 0u : 1u) | (sincos_is_trivial(ry) ? 0u : 2u) | (sincos_is_trivial(rz) ? 0u : 4u);
+  while (__any_sync(0xffffffffu, need != 0u))
+  {
+    if (need)
+    {
+      const float y = (need & 1u) ? rx : ((need & 2u) ? ry : rz);
+      float sn, cs;
+      sincosf_glibc_nt(y, sn, cs);
+      if (need & 1u) { sx = sn; cx = cs; }
+      else if (need & 2u) { sy = sn; cy = cs; }
+      else { sz = sn; cz = cs; }
+      need &= need - 1u;
+    }
+  }
+}
+
+// sphereInFrustum for all views of one warp (CullingSystem, .cpp:1240-1270; cull iff d < -radius on any plane, NaN
+// keeps). The six tests of a view are independent, so their ORDER is free: `order` remembers, per view (3 bits
+// each), the plane that culled this warp's previous instances. That plane is tested first for all views; if it
+// culls every lane of the warp again - the normal case in an open world, where whole neighbourhoods lie on the same
+// side of a frustum - the view is finished after one plane. Only when some lane survives are the other planes
+// tested, one at a time with a warp-uniform early-out, and the plane that finished the job becomes the new favourite.
+// The predicate evaluated per (instance, plane) is exactly the reference's; no instance is ever decided by a
+// neighbour's result.
+template <int kViews>
+__device__ __forceinline__ uint32_t cull_views_warp(const ViewPlanes& vp, bool test, float cx, float cy, float cz,
+                                                    float negR, uint32_t& order)
+{
+  uint32_t alive = 0;
+#pragma unroll
+  for (int v = 0; v < kViews; ++v)
+  {
+    const uint32_t k0 = (order >> (3 * v)) & 7u;
+    const float d = plane_dist(vp.planes[v][k0], cx, cy, cz);
+    alive |= (d < negR) ? 0u : (1u << v);
+  }
+  alive = test ? alive : 0u;
+  if (__any_sync(0xffffffffu, alive != 0u))
+  {
+#pragma unroll 1
+    for (uint32_t v = 0; v < (uint32_t)kViews; ++v)
+    {
+      if (!__any_sync(0xffffffffu, (alive >> v) & 1u)) continue;
+      const uint32_t k0 = (order >> (3u * v)) & 7u;
+#pragma unroll 1
+      for (uint32_t k = 0; k < 6u; ++k)
+      {
+        if (k == k0) continue;
+        const float d = plane_dist(vp.planes[v][k], cx, cy, cz);
+        if (d < negR) alive &= ~(1u << v);
+        if (!__any_sync(0xffffffffu, (alive >> v) & 1u))
+        {
+          order = (order & ~(7u << (3u * v))) | (k << (3u * v));
+          break;
+        }
+      }
+    }
+  }
+  return alive;
+}
+
 // ---- K1+K2, flat scenes: fused transform + cull, all views in one pass ------------------------------------------------
 // No instance has a parent: pure streaming. One thread per slot, kSubTiles sub-tiles of kBlock consecutive slots per
 // CTA; the four record planes of a sub-tile are staged in shared memory by TMA bulk copies two sub-tiles ahead, so the
-// DRAM round trip overlaps the arithmetic. kViews is a compile-time view count, so the 6*V plane tests read their
-// planes straight from the constant bank; views are tested in plane pairs with a warp-uniform early-out.
+// DRAM round trip overlaps the arithmetic. kViews is a compile-time view count, so the plane tests read their planes
+// straight from the constant bank.
 template <int kViews>
 __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant__ UpdateParams p,
                                                            const __grid_constant__ ViewPlanes vp)
@@ -304,6 +379,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
   const bool force = (p.flags & kUpdForceDirty) != 0;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
   uint32_t nRecomputed = 0, nCand = 0;
+  uint32_t order = 0;  // favourite plane per view, see cull_views_warp
   uint32_t nVis[kViews];
 #pragma unroll
   for (int v = 0; v < kViews; ++v) nVis[v] = 0;
@@ -323,16 +399,28 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
       r3 = sRec[buf][3][tid]; r2 = sRec[buf][2][tid];
       r0 = sRec[buf][0][tid]; r1 = sRec[buf][1][tid];
     }
+    // WAR across proxies: the reads above go through the generic proxy, the refill below through the async proxy
+    // (TMA). A CTA barrier alone does not order the two - a queued ld.shared was observed to return the NEXT
+    // stage's bytes (tests: rows of sub-tile 0 carrying sub-tile 2's TRS). The proxy fence orders this thread's
+    // reads before every async-proxy access that follows the barrier.
+    fence_proxy_async_shared();
     __syncthreads();  // everybody has copied its record out of the staging buffer: refill it
     if (tid == 0 && sub + 2 < nSub) stage(sub + 2);
 
     const uint32_t fl = __float_as_uint(r3.w);
     const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+    const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x);
+    float sx, cx, sy, cy, sz, cz;
+    sincos3_warp(ownDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
     Mat4 W = mat4_identity();
     if (ownDirty)
     {
-      bool affine;
-      W = trs_any(r0, r1, r2.x, affine, &sX[tid][0]);
+      if (tame) W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, r2.x);
+      else
+      {
+        trs_dense_to(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, &sX[tid][0]);
+        W = xs_load(&sX[tid][0]);
+      }
       store_world(p, s, W);
       ++nRecomputed;
     }
@@ -341,35 +429,23 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
       W = load_world(p, s);
     }
 
-    // ---- bounding sphere + 6*V plane tests in registers (CullingSystem, .cpp:1240-1270) ----
+    // ---- bounding sphere + plane tests in registers ----
     const bool cand = live && (fl & kFlagMesh);
     const bool test = cand && !freeze && (fl & kFlagBounds);
     uint32_t mask = 0;
     if (__any_sync(0xffffffffu, test))
     {
-      float cx, cy, cz, radius;
-      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, cx, cy, cz, radius);
-      const float negR = -radius;
-#pragma unroll
-      for (int v = 0; v < kViews; ++v)
-      {
-        bool alive = test;
-        // plane pairs (left,right) (bottom,top) (near,far); stop as soon as the whole warp is outside
-#pragma unroll
-        for (int pp = 0; pp < 3; ++pp)
-        {
-          if (!__any_sync(0xffffffffu, alive)) break;
-          const float d0 = plane_dist(vp.planes[v][2 * pp], cx, cy, cz);
-          const float d1 = plane_dist(vp.planes[v][2 * pp + 1], cx, cy, cz);
-          alive = alive && !(d0 < negR) && !(d1 < negR);  // NaN compares false => stays visible
-        }
-        if (alive) mask |= 1u << v;
-      }
+      float ox, oy, oz, radius;
+      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, radius);
+      mask = cull_views_warp<kViews>(vp, test, ox, oy, oz, -radius, order);
     }
     if (cand && !test) mask = allMask;  // frozen culling or no Bounds component: always visible
     if (live) p.vismask[s] = (uint8_t)mask;
+    if (__any_sync(0xffffffffu, mask != 0u))
+    {
 #pragma unroll
-    for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
+      for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
+    }
     nCand += cand ? 1u : 0u;
   }
 
@@ -392,45 +468,78 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
 }
 
 // ---- hierarchy windows ------------------------------------------------------------------------------------------
-// A window is a run of <= 32 consecutive slots owned by one warp. k_build_windows (topology changes only) cuts every
-// kTile-slot tile into windows at positions that NO parent link crosses, so a hierarchy group never straddles two
-// warps and k_update_win resolves it with shuffles alone. Per slot it records the depth inside the window
-// (0 = root or parent outside the window), per tile the window starts.
-constexpr uint32_t kMaxWin = 128;          // windows per tile (greedy cuts give ~36; forced 32-slot cuts bound it)
-constexpr uint32_t kWinUnreachable = 0x40; // slotInfo: node on / below a cycle closed inside its window
-constexpr uint32_t kWinExternal = 0x20;    // slotInfo: parent lives outside the window (resolved by walk_up)
+// A window is a run of <= 32 consecutive slots owned by one warp. k_build_windows (topology changes only) cuts the
+// slot range into windows at positions that NO parent link crosses, so a hierarchy group never straddles two warps
+// and k_update_win resolves it inside the warp. Tile boundaries are not special: a window may run up to 31 slots
+// into the next tile when a group straddles the boundary (the tile where a window STARTS owns it). Per slot the
+// build records depth and parent lane inside the window, per window the start slot; links longer than a window
+// (or chains deeper than 32) are flagged and resolved from global memory by the generic path (window_slow).
+constexpr uint32_t kMaxWin = 96;              // windows per tile: two consecutive greedy windows span > 32 slots => <= 66
+constexpr uint32_t kHalo = 32;                // slots looked at on either side of a tile
+constexpr uint32_t kInfoDepthMask = 31u;      // slotInfo bits 0..4: depth inside the window
+constexpr uint32_t kInfoParentShift = 5;      // bits 5..9: lane of the parent (depth > 0)
+constexpr uint32_t kInfoExternal = 1u << 10;  // parent lives outside the window (resolved by walk_up)
+constexpr uint32_t kInfoUnreachable = 1u << 11;  // node on / below a cycle closed inside its window
+constexpr uint32_t kWinSlow = 0x80000000u;    // window list entry: some lane is external / unreachable
+constexpr uint32_t kWinSlotMask = 0x7FFFFFFFu;
 
-__global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __restrict__ parentSlot, uint8_t* __restrict__ slotInfo,
-                                                          uint16_t* __restrict__ winStart, uint32_t count)
+// first position in [from, from+kHalo) (and <= count) that no short link crosses; `from` itself when there is none
+// (forced cut through a chain longer than a window). sCross is indexed relative to `origin`.
+__device__ __forceinline__ uint32_t first_uncrossed(const int* sCross, uint32_t origin, uint32_t from, uint32_t count)
 {
-  __shared__ int sCross[kTile + 2];
-  __shared__ uint16_t sStart[kMaxWin + 1];
-  __shared__ uint16_t sWinOf[kTile];  // window start (tile-relative) of every slot
+  if (from >= count) return count;
+  for (uint32_t c = from; c < from + kHalo && c <= count; ++c)
+    if (c == count || sCross[c - origin] == 0) return c;
+  return from;
+}
+
+__global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __restrict__ parentSlot, uint16_t* __restrict__ slotInfo,
+                                                          uint16_t* __restrict__ winLocal, uint32_t* __restrict__ tileWinCount,
+                                                          uint32_t count)
+{
+  constexpr uint32_t kSpan = kTile + 3 * kHalo;  // slots [tileBase - kHalo, tileBase + kTile + 2*kHalo)
+  __shared__ int sCross[kSpan + 8];              // sCross[c - origin]: number of short links crossing position c
+  __shared__ uint16_t sStart[kMaxWin + 1];       // window starts relative to tileBase (<= kTile + kHalo)
+  __shared__ uint16_t sWinOf[kTile + kHalo];     // window index of every owned slot (relative to tileBase)
+  __shared__ uint32_t sWinFlag[kMaxWin];
   __shared__ uint32_t sWarpSum[kBlock / 32];
-  __shared__ uint32_t sNumWin;
+  __shared__ uint32_t sNumWin, sBeg, sEnd;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t tileBase = blockIdx.x * kTile;
-  const uint32_t n = min(kTile, count - tileBase);
+  const uint32_t origin = tileBase >= kHalo ? tileBase - kHalo : 0u;  // slot / position of sCross[0]
+  const uint32_t spanEnd = min(count, tileBase + kTile + 2 * kHalo);  // slots [origin, spanEnd)
 
-  for (uint32_t k = tid; k < kTile + 2; k += kBlock) sCross[k] = 0;
+  for (uint32_t k = tid; k < kSpan + 8; k += kBlock) sCross[k] = 0;
+  for (uint32_t k = tid; k < kMaxWin; k += kBlock) sWinFlag[k] = 0;
   __syncthreads();
-  // a link between slots lo < hi (both in this tile) crosses every cut position c with lo < c <= hi
-  for (uint32_t k = tid; k < n; k += kBlock)
+  // a link between slots lo < hi shorter than a window crosses every cut position c with lo < c <= hi
+  for (uint32_t k = origin + tid; k < spanEnd; k += kBlock)
   {
-    const uint32_t ps = parentSlot[tileBase + k];
-    if (ps != kNone && ps >= tileBase && ps < tileBase + n && ps != tileBase + k)
+    const uint32_t ps = parentSlot[k];
+    if (ps == kNone || ps == k || ps >= count) continue;
+    const uint32_t lo = min(k, ps), hi = max(k, ps);
+    if (hi - lo >= 32u) continue;  // can never sit inside one window: the child is flagged external below
+    // positions lo+1 .. hi, clipped to the span (difference array, summed below)
+    const uint32_t from = max(lo + 1u, origin), to = min(hi + 1u, origin + kSpan + 4u);
+    if (from < to)
     {
-      const uint32_t q = ps - tileBase, lo = min(k, q), hi = max(k, q);
-      atomicAdd(&sCross[lo + 1], 1);
-      atomicAdd(&sCross[hi + 1], -1);
+      atomicAdd(&sCross[from - origin], 1);
+      atomicAdd(&sCross[to - origin], -1);
     }
   }
   __syncthreads();
-  // inclusive prefix sum over kTile+1 positions: thread t owns positions 4t..4t+3 (+ the last one)
+  // inclusive prefix sum over the span: thread t owns 5 consecutive positions (256 * 5 >= kSpan + 8)
   {
-    int v[4], sum = 0;
+    constexpr int kPer = 5;
+    static_assert(kBlock * kPer >= kSpan + 8, "prefix sum coverage");
+    int v[kPer], sum = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { sum += sCross[tid * 4 + j]; v[j] = sum; }
+    for (int j = 0; j < kPer; ++j)
+    {
+      const uint32_t idx = tid * kPer + j;
+      sum += (idx < kSpan + 8) ? sCross[idx] : 0;
+      v[j] = sum;
+    }
     int x = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -442,82 +551,190 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
     __syncthreads();
     int off = x - sum;
     for (uint32_t w = 0; w < warp; ++w) off += (int)sWarpSum[w];
-    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sCross[tid * 4 + j] = v[j] + off;
-    if (tid == kBlock - 1) sCross[kTile] += v[3] + off;
+    for (int j = 0; j < kPer; ++j)
+    {
+      const uint32_t idx = tid * kPer + j;
+      if (idx < kSpan + 8) sCross[idx] = v[j] + off;
+    }
   }
   __syncthreads();
+  // this tile owns the windows that start in [beg, end): beg / end = first uncrossed position at or after the tile's
+  // first slot / the next tile's first slot. Both neighbours derive the shared boundary from the same data.
+  if (tid == 0)
+  {
+    sBeg = first_uncrossed(sCross, origin, tileBase, count);
+    sEnd = first_uncrossed(sCross, origin, tileBase + kTile, count);
+  }
+  __syncthreads();
+  const uint32_t beg = sBeg, end = sEnd;
   // greedy cuts by warp 0: the next window ends at the LARGEST uncrossed position within 32 slots (forced at 32)
   if (warp == 0)
   {
-    uint32_t start = 0, nw = 0;
-    while (start < n)
+    uint32_t start = beg, nw = 0;
+    while (start < end && nw < kMaxWin)
     {
-      if (lane == 0) sStart[nw] = (uint16_t)start;
+      if (lane == 0) sStart[nw] = (uint16_t)(start - tileBase);
       ++nw;
       const uint32_t c = start + 1 + lane;  // candidate end
-      const bool ok = c <= n && (c == n || sCross[c] == 0);
-      uint32_t m = __ballot_sync(0xffffffffu, ok);
-      if (nw >= kMaxWin - 32) m = 0;  // too many small windows: finish with forced cuts so that nw <= kMaxWin
-      start = m ? start + 32u - __clz(m) : min(start + 32u, n);
+      const bool ok = c <= end && (c == end || sCross[c - origin] == 0);
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      start = m ? start + 32u - __clz(m) : min(start + 32u, end);
     }
-    if (lane == 0) { sStart[nw] = (uint16_t)n; sNumWin = nw; }
+    if (lane == 0) { sStart[nw] = (uint16_t)(end - tileBase); sNumWin = nw; }
   }
   __syncthreads();
   const uint32_t nw = sNumWin;
-  for (uint32_t k = tid; k < kMaxWin + 2; k += kBlock)
-    winStart[(size_t)blockIdx.x * (kMaxWin + 2) + k] = (k == kMaxWin + 1) ? (uint16_t)nw : (k <= nw ? sStart[k] : (uint16_t)0xFFFF);
   for (uint32_t w = warp; w < nw; w += kBlock / 32)
-    for (uint32_t k = sStart[w] + lane; k < sStart[w + 1]; k += 32) sWinOf[k] = sStart[w];
+    for (uint32_t k = sStart[w] + lane; k < sStart[w + 1]; k += 32) sWinOf[k] = (uint16_t)w;
   __syncthreads();
-  // depth inside the window (0: root, or parent outside the window => kWinExternal)
-  for (uint32_t k = tid; k < n; k += kBlock)
+  // per owned slot: depth and parent lane inside the window
+  for (uint32_t k = (beg - tileBase) + tid; k < end - tileBase; k += kBlock)
   {
+    const uint32_t w = sWinOf[k], wa = sStart[w], wb = sStart[w + 1];
     uint32_t cur = k, depth = 0, info = 0;
     for (;;)
     {
       const uint32_t ps = parentSlot[tileBase + cur];
       if (ps == kNone) break;
-      const bool inside = ps >= tileBase && (ps - tileBase) < n && sWinOf[ps - tileBase] == sWinOf[k];
+      const bool inside = ps >= tileBase + wa && ps < tileBase + wb;
       if (!inside)
       {
-        if (depth == 0) info = kWinExternal;  // deeper nodes hang off an ancestor that carries the flag itself
+        if (depth == 0) info = kInfoExternal;  // deeper nodes hang off an ancestor that carries the flag itself
         break;
       }
+      if (depth == 0) info |= (ps - tileBase - wa) << kInfoParentShift;
       cur = ps - tileBase;
-      if (++depth > 32u) { info = kWinUnreachable; depth = 0; break; }  // a cycle closed inside the window
+      if (++depth > 32u) { info = kInfoUnreachable; depth = 0; break; }  // a cycle closed inside the window
     }
-    slotInfo[tileBase + k] = (uint8_t)(info | (depth & 31u));
+    if (info & (kInfoExternal | kInfoUnreachable)) sWinFlag[w] = 1u;
+    slotInfo[tileBase + k] = (uint16_t)(info | (depth & kInfoDepthMask));
   }
+  __syncthreads();
+  for (uint32_t k = tid; k <= nw; k += kBlock)
+    winLocal[(size_t)blockIdx.x * (kMaxWin + 1) + k] = (uint16_t)(sStart[k] | ((k < nw && sWinFlag[k]) ? 0x8000u : 0u));
+  if (tid == 0) tileWinCount[blockIdx.x] = nw;
 }
 
-// ---- K1+K2, hierarchical scenes: one window per warp, levels resolved with shuffles ----------------------------
+// per-tile window lists -> one list of absolute start slots (bit 31: generic path), winList[total] = count
+__global__ void __launch_bounds__(128) k_flatten_windows(const uint16_t* __restrict__ winLocal, const uint32_t* __restrict__ tileWinCount,
+                                                         const uint32_t* __restrict__ tileWinBase, uint32_t* __restrict__ winList,
+                                                         uint32_t numTiles, uint32_t count)
+{
+  const uint32_t tile = blockIdx.x, nw = tileWinCount[tile], base = tileWinBase[tile];
+  for (uint32_t k = threadIdx.x; k < nw; k += 128)
+  {
+    const uint32_t e = winLocal[(size_t)tile * (kMaxWin + 1) + k];
+    winList[base + k] = (tile * kTile + (e & 0x7FFFu)) | ((e & 0x8000u) ? kWinSlow : 0u);
+  }
+  if (tile == numTiles - 1 && threadIdx.x == 0) winList[base + nw] = count;
+}
+
+// ---- generic window resolution (rare) ------------------------------------------------------------------------------
+// Exact for ANY input: full 4x4 matrices, dense products where the structured ones are not value-exact, parents
+// outside the window resolved from global memory (walk_up), cycles left untouched. Called by all lanes of the warp.
+// Leaves this lane's world matrix in out[0..3]; returns 1 if the node was recomputed this frame.
+__device__ __noinline__ uint32_t window_slow(const UpdateParams& p, uint32_t a, uint32_t len, uint32_t info, float4* out)
+{
+  float4 xa[4], xb[4];
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool live = lane < len;
+  const uint32_t s = a + lane;
+  const bool skip = (p.flags & kUpdSkipTransform) != 0;
+  const bool force = (p.flags & kUpdForceDirty) != 0;
+  float4 r0, r1, r2, r3;
+  r0 = r1 = r2 = r3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) { r0 = p.rec0[s]; r1 = p.rec1[s]; r2 = p.rec2[s]; r3 = p.rec3[s]; }
+  const uint32_t fl = __float_as_uint(r3.w);
+  const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+  const uint32_t wl = info & kInfoDepthMask;
+  const bool external = (info & kInfoExternal) != 0;
+  bool dead = !live || (info & kInfoUnreachable);  // never visited by the DFS: world matrix stays as stored
+  const uint32_t parentLane = (wl != 0) ? ((info >> kInfoParentShift) & 31u) : lane;
+  const uint32_t maxL = __reduce_max_sync(0xffffffffu, live ? wl : 0u);
+
+  bool nodeDirty = ownDirty;
+  if (live && external)
+  {
+    const uint32_t walk = walk_up(p, p.parentSlot[s], true, xa, xb);
+    if (!(walk & 1u)) dead = true;
+    nodeDirty = ownDirty || (walk & 2u) != 0;
+  }
+  for (uint32_t l = 1; l <= maxL; ++l)
+  {
+    const bool pd = __shfl_sync(0xffffffffu, nodeDirty ? 1 : 0, parentLane) != 0;
+    const bool pdead = __shfl_sync(0xffffffffu, dead ? 1 : 0, parentLane) != 0;
+    if (live && wl == l)
+    {
+      nodeDirty = nodeDirty || pd;
+      dead = dead || pdead;
+    }
+  }
+  if (dead) nodeDirty = false;
+
+  Mat4 W = mat4_identity();
+  bool affine = true;
+  if (nodeDirty)
+  {
+    W = trs_any(r0, r1, r2.x, affine, xb);  // roots: world == local
+    if (external) W = compose_any(xs_load(xa), W, affine, xa, xb);
+  }
+  else if (live)
+  {
+    W = load_world(p, s);
+  }
+  for (uint32_t l = 1; l <= maxL; ++l)
+  {
+    Mat4 PW;
+    PW.c0.x = __shfl_sync(0xffffffffu, W.c0.x, parentLane); PW.c0.y = __shfl_sync(0xffffffffu, W.c0.y, parentLane);
+    PW.c0.z = __shfl_sync(0xffffffffu, W.c0.z, parentLane); PW.c0.w = __shfl_sync(0xffffffffu, W.c0.w, parentLane);
+    PW.c1.x = __shfl_sync(0xffffffffu, W.c1.x, parentLane); PW.c1.y = __shfl_sync(0xffffffffu, W.c1.y, parentLane);
+    PW.c1.z = __shfl_sync(0xffffffffu, W.c1.z, parentLane); PW.c1.w = __shfl_sync(0xffffffffu, W.c1.w, parentLane);
+    PW.c2.x = __shfl_sync(0xffffffffu, W.c2.x, parentLane); PW.c2.y = __shfl_sync(0xffffffffu, W.c2.y, parentLane);
+    PW.c2.z = __shfl_sync(0xffffffffu, W.c2.z, parentLane); PW.c2.w = __shfl_sync(0xffffffffu, W.c2.w, parentLane);
+    PW.c3.x = __shfl_sync(0xffffffffu, W.c3.x, parentLane); PW.c3.y = __shfl_sync(0xffffffffu, W.c3.y, parentLane);
+    PW.c3.z = __shfl_sync(0xffffffffu, W.c3.z, parentLane); PW.c3.w = __shfl_sync(0xffffffffu, W.c3.w, parentLane);
+    if (nodeDirty && wl == l) W = compose_any(PW, W, affine, xa, xb);
+  }
+  xs_store(out, W);
+  return nodeDirty ? 1u : 0u;
+}
+
+// ---- K1+K2, hierarchical scenes: one window per warp -----------------------------------------------------------------
 // Loads and stores are the flat kernel's (coalesced 128-bit planes, slot = window start + lane). Inside the warp:
-//   1. dirty / never-visited bits are propagated parent -> child level by level (one shuffle per level),
+//   1. dirty bits are propagated parent -> child with ballots (skipped when everything is dirty anyway),
 //   2. every lane that must be recomputed builds its local matrix (all lanes busy, FP64 sincos in parallel),
-//   3. for level 1..max, the lanes of that level fetch their parent's world matrix from the parent's lane and
-//      multiply: parent-before-child, parent matrices staged in registers of the same warp.
-// No shared memory traffic, no CTA barrier, no dependency between warps: they free-run like in the flat kernel.
+//   3. for level 1..max, the lanes of that level read their parent's world matrix (upper 3x4) from a per-warp
+//      shared-memory exchange area and multiply: parent-before-child, parent matrices staged in shared memory.
+// The fast path assumes what holds for every sane scene - tame TRS values, affine stored matrices, finite
+// translations, parents inside the window - and VERIFIES it per window (two warp votes); a window that fails the
+// check is redone by window_slow(), which is exact for any input. No CTA barrier inside the loop, no dependency
+// between warps: a warp that finishes a window claims the next unclaimed one of its CTA.
 constexpr uint32_t kWinTilesPerCta = 4;  // tiles per CTA of k_update_win: ~146 windows shared by 8 warps
 
 template <int kViews>
 __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant__ UpdateParams p,
                                                           const __grid_constant__ ViewPlanes vp,
-                                                          const uint8_t* __restrict__ slotInfo,
-                                                          const uint16_t* __restrict__ winStart)
+                                                          const uint16_t* __restrict__ slotInfo,
+                                                          const uint32_t* __restrict__ winList,
+                                                          const uint32_t* __restrict__ tileWinBase)
 {
-  __shared__ uint16_t sStart[kWinTilesPerCta][kMaxWin + 2];
-  __shared__ uint32_t sNext;  // next unclaimed (tile, window) of this CTA: warps pull work dynamically
+  __shared__ uint32_t sWin[kWinTilesPerCta * kMaxWin + 1];  // this CTA's slice of the window list
+  __shared__ uint32_t sNext;                                // next unclaimed window: warps pull work dynamically
+  __shared__ uint32_t sCnt[kWinTilesPerCta + 1][kMaxViews + 2];  // per-tile counts (+1 row: windows may spill over)
   // per-warp double buffer: the record planes of the NEXT claimed window are fetched with cp.async while the
   // current window is being computed
   __shared__ __align__(16) float4 sPre[kBlock / 32][2][4][32];
+  // per-warp exchange area of the level loop: upper 3x4 of every lane's world matrix as three float4 planes
+  __shared__ __align__(16) float4 sX[kBlock / 32][3][32];
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t firstTile = blockIdx.x * kWinTilesPerCta;
   const uint32_t nTiles = min(kWinTilesPerCta, p.numTiles - firstTile);
-  for (uint32_t k = tid; k < nTiles * (kMaxWin + 2); k += kBlock)
-    (&sStart[0][0])[k] = winStart[(size_t)firstTile * (kMaxWin + 2) + k];
+  const uint32_t wBeg = tileWinBase[firstTile];
+  const uint32_t nWin = tileWinBase[firstTile + nTiles] - wBeg;
+  for (uint32_t k = tid; k <= nWin; k += kBlock) sWin[k] = winList[wBeg + k];
+  for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kMaxViews + 2); k += kBlock) (&sCnt[0][0])[k] = 0;
   if (tid == 0) sNext = 0;
   __syncthreads();
 
@@ -525,38 +742,30 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
-  // exchange slots of the out-of-line slow paths: thread-local, touched only when a slow path runs
-  float4 xaBuf[4], xbBuf[4];
-  float4* const xa = xaBuf;
-  float4* const xb = xbBuf;
   uint32_t nRecomputed = 0;
+  uint32_t order = 0;  // favourite plane per view, see cull_views_warp
+  float4* const xw = &sX[warp][0][0];
 
-  // No barrier below this line: a warp that finishes a window claims another one, whichever tile it belongs to.
-  uint32_t t = 0, wBase = 0;  // claimed indices only grow, so the tile cursor moves forward
-  // claim + locate + start fetching one window; returns false when the CTA's windows are exhausted
-  struct Win { uint32_t tile, a, len, info, ps; };
-  auto claim_and_fetch = [&](uint32_t buf, Win& o) -> bool
+  // claim + start fetching one window; returns false when the CTA's windows are exhausted
+  struct Win { uint32_t a, len, info; };
+  auto claim_and_fetch = [&](uint32_t b, Win& o) -> bool
   {
-    uint32_t claim = 0;
-    if (lane == 0) claim = atomicAdd(&sNext, 1u);
-    claim = __shfl_sync(0xffffffffu, claim, 0);
-    while (t < nTiles && claim >= wBase + sStart[t][kMaxWin + 1]) { wBase += sStart[t][kMaxWin + 1]; ++t; }
-    if (t >= nTiles) return false;
-    const uint32_t w = claim - wBase;
-    o.tile = firstTile + t;
-    o.a = o.tile * kTile + sStart[t][w];
-    o.len = sStart[t][w + 1] - sStart[t][w];
-    o.info = kWinUnreachable;
-    o.ps = kNone;
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&sNext, 1u);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= nWin) return false;
+    const uint32_t e0 = sWin[w];
+    o.a = e0;
+    o.len = (sWin[w + 1] & kWinSlotMask) - (e0 & kWinSlotMask);
+    o.info = 0;
     if (lane < o.len)
     {
-      const uint32_t q = o.a + lane;
-      cp_async16(&sPre[warp][buf][0][lane], p.rec0 + q);
-      cp_async16(&sPre[warp][buf][1][lane], p.rec1 + q);
-      cp_async16(&sPre[warp][buf][2][lane], p.rec2 + q);
-      cp_async16(&sPre[warp][buf][3][lane], p.rec3 + q);
+      const uint32_t q = (e0 & kWinSlotMask) + lane;
+      cp_async16(&sPre[warp][b][0][lane], p.rec0 + q);
+      cp_async16(&sPre[warp][b][1][lane], p.rec1 + q);
+      cp_async16(&sPre[warp][b][2][lane], p.rec2 + q);
+      cp_async16(&sPre[warp][b][3][lane], p.rec3 + q);
       o.info = slotInfo[q];
-      o.ps = p.parentSlot[q];
     }
     cp_async_commit();
     return true;
@@ -570,100 +779,91 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
     const bool haveNext = claim_and_fetch(buf ^ 1u, nxt);  // in flight while this window is computed
     if (haveNext) cp_async_wait<1>();
     else cp_async_wait<0>();
-    const uint32_t tile = cur.tile;
-    uint32_t nCand = 0;
-    uint32_t nVis[kViews];
-#pragma unroll
-    for (int v = 0; v < kViews; ++v) nVis[v] = 0;
-  {
-    const uint32_t a = cur.a;
-    const uint32_t len = cur.len;
+    const uint32_t a = cur.a & kWinSlotMask, len = cur.len, info = cur.info;
     const bool live = lane < len;
     const uint32_t s = a + lane;
+    const uint32_t liveMask = 0xffffffffu >> (32u - len);
+    const uint32_t wl = info & kInfoDepthMask;
+    const uint32_t maxL = __reduce_max_sync(0xffffffffu, wl);
 
-    float4 r0, r1, r2, r3;
-    r0 = r1 = r2 = r3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t info = cur.info, ps = cur.ps;
-    if (live)
-    {
-      r3 = sPre[warp][buf][3][lane]; r2 = sPre[warp][buf][2][lane];
-      r0 = sPre[warp][buf][0][lane]; r1 = sPre[warp][buf][1][lane];
-    }
-    const uint32_t fl = __float_as_uint(r3.w);
-    const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
-    const uint32_t wl = info & 31u;
-    const bool external = (info & kWinExternal) != 0;
-    bool dead = !live || (info & kWinUnreachable);  // never visited by the DFS: world matrix stays as stored
-    const uint32_t parentLane = (wl != 0) ? (ps - a) & 31u : lane;
-    const uint32_t maxL = __reduce_max_sync(0xffffffffu, live ? wl : 0u);
-
-    // ---- parents outside the window: resolved from global memory alone (walk_up leaves the matrix in xa) ----
-    bool nodeDirty = ownDirty;
-    if (live && external)
-    {
-      const uint32_t walk = walk_up(p, ps, true, xa, xb);
-      if (!(walk & 1u)) dead = true;
-      nodeDirty = ownDirty || (walk & 2u) != 0;
-    }
-    // ---- 1. inherit dirtiness / deadness down the levels ----
-    for (uint32_t l = 1; l <= maxL; ++l)
-    {
-      const bool pd = __shfl_sync(0xffffffffu, nodeDirty ? 1 : 0, parentLane) != 0;
-      const bool pdead = __shfl_sync(0xffffffffu, dead ? 1 : 0, parentLane) != 0;
-      if (live && wl == l)
-      {
-        nodeDirty = nodeDirty || pd;
-        dead = dead || pdead;
-      }
-    }
-    if (dead) nodeDirty = false;
-
-    // ---- 2. local matrices of everything that is recomputed; stored world matrices of the rest ----
     Mat4 W = mat4_identity();
-    bool affine = true;
-    if (nodeDirty)
+    bool nodeDirty = false;
+    bool fast = (cur.a & kWinSlow) == 0u;
+    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f), r3 = r2;
+    if (live) r3 = sPre[warp][buf][3][lane];
+    const uint32_t fl = __float_as_uint(r3.w);
+    if (fast)
     {
-      W = trs_any(r0, r1, r2.x, affine, xb);  // roots: world == local
-      if (external) W = compose_any(xs_load(xa), W, affine, xa, xb);
-    }
-    else if (live)
-    {
-      W = load_world(p, s);
-    }
-
-    // ---- 3. parent.world * local, one level at a time, parents read from their lanes ----
-    // Common case: every matrix involved is affine (bottom row (0,0,0,1)) with a finite translation, so only the
-    // upper 3x4 travels through the shuffles and the product skips the bottom row. Anything else: full 4x4.
-    bool wAff = live && (nodeDirty ? (affine && !external) : mat4_is_affine(W));
-    if (nodeDirty && external) wAff = mat4_is_affine(W);
-    for (uint32_t l = 1; l <= maxL; ++l)
-    {
-      const bool mine = nodeDirty && wl == l;
-      const float mag = fabsf(W.c3.x) + fabsf(W.c3.y) + fabsf(W.c3.z);
-      const bool parentOk = __shfl_sync(0xffffffffu, (wAff && mag < __int_as_float(0x7f800000)) ? 1 : 0, parentLane) != 0;
-      Mat4 PW;
-      PW.c0.x = __shfl_sync(0xffffffffu, W.c0.x, parentLane); PW.c0.y = __shfl_sync(0xffffffffu, W.c0.y, parentLane);
-      PW.c0.z = __shfl_sync(0xffffffffu, W.c0.z, parentLane);
-      PW.c1.x = __shfl_sync(0xffffffffu, W.c1.x, parentLane); PW.c1.y = __shfl_sync(0xffffffffu, W.c1.y, parentLane);
-      PW.c1.z = __shfl_sync(0xffffffffu, W.c1.z, parentLane);
-      PW.c2.x = __shfl_sync(0xffffffffu, W.c2.x, parentLane); PW.c2.y = __shfl_sync(0xffffffffu, W.c2.y, parentLane);
-      PW.c2.z = __shfl_sync(0xffffffffu, W.c2.z, parentLane);
-      PW.c3.x = __shfl_sync(0xffffffffu, W.c3.x, parentLane); PW.c3.y = __shfl_sync(0xffffffffu, W.c3.y, parentLane);
-      PW.c3.z = __shfl_sync(0xffffffffu, W.c3.z, parentLane);
-      if (__all_sync(0xffffffffu, !mine || (parentOk && affine)))
+      float4 r0 = r2, r1 = r2;
+      if (live) { r0 = sPre[warp][buf][0][lane]; r1 = sPre[warp][buf][1][lane]; r2 = sPre[warp][buf][2][lane]; }
+      nodeDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+      const uint32_t pl16 = ((info >> kInfoParentShift) & 31u) * 16u;
+      // ---- 1. children inherit dirtiness level by level ----
+      uint32_t dirtyM = __ballot_sync(0xffffffffu, nodeDirty);
+      if (dirtyM != liveMask && dirtyM != 0u)
       {
-        if (mine) W = mat4_mul_affine3(PW, W);  // wAff stays true
-      }
-      else
-      {
-        PW.c0.w = __shfl_sync(0xffffffffu, W.c0.w, parentLane); PW.c1.w = __shfl_sync(0xffffffffu, W.c1.w, parentLane);
-        PW.c2.w = __shfl_sync(0xffffffffu, W.c2.w, parentLane); PW.c3.w = __shfl_sync(0xffffffffu, W.c3.w, parentLane);
-        if (mine)
+        for (uint32_t l = 1; l <= maxL; ++l)
         {
-          W = compose_any(PW, W, affine, xa, xb);
-          wAff = mat4_is_affine(W);
+          if (wl == l && ((dirtyM >> (pl16 >> 4)) & 1u)) nodeDirty = true;
+          dirtyM = __ballot_sync(0xffffffffu, nodeDirty);
         }
       }
+      // ---- 2. local matrices of everything that is recomputed; stored world matrices of the rest ----
+      const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x);
+      float sx, cx, sy, cy, sz, cz;
+      sincos3_warp(nodeDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
+      bool ok = true;
+      if (nodeDirty)
+      {
+        W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, r2.x);  // roots: world == local
+        ok = tame;
+      }
+      else if (live)
+      {
+        W = load_world(p, s);
+        ok = mat4_is_affine(W);
+      }
+      fast = __all_sync(0xffffffffu, ok);
+      // ---- 3. parent.world * local, one level at a time, parents read from the exchange area ----
+      if (fast && maxL != 0u && dirtyM != 0u)
+      {
+        xw[lane] = make_float4(W.c0.x, W.c0.y, W.c0.z, W.c1.x);
+        xw[32 + lane] = make_float4(W.c1.y, W.c1.z, W.c2.x, W.c2.y);
+        xw[64 + lane] = make_float4(W.c2.z, W.c3.x, W.c3.y, W.c3.z);
+        __syncwarp();
+        const float4* const xp = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(xw) + pl16);
+        for (uint32_t l = 1; l <= maxL; ++l)
+        {
+          if (nodeDirty && wl == l)
+          {
+            const float4 q0 = xp[0], q1 = xp[32], q2 = xp[64];
+            Mat4 P;
+            P.c0 = make_float4(q0.x, q0.y, q0.z, 0.f);
+            P.c1 = make_float4(q0.w, q1.x, q1.y, 0.f);
+            P.c2 = make_float4(q1.z, q1.w, q2.x, 0.f);
+            P.c3 = make_float4(q2.y, q2.z, q2.w, 1.f);
+            W = mat4_mul_affine3(P, W);
+            if (l < maxL)
+            {
+              xw[lane] = make_float4(W.c0.x, W.c0.y, W.c0.z, W.c1.x);
+              xw[32 + lane] = make_float4(W.c1.y, W.c1.z, W.c2.x, W.c2.y);
+              xw[64 + lane] = make_float4(W.c2.z, W.c3.x, W.c3.y, W.c3.z);
+            }
+          }
+          __syncwarp();
+        }
+        // the structured products are value-exact iff every parent translation was finite; a non-finite one
+        // propagates into the translation of all its descendants, so one test of the results covers all levels
+        const float mag = fabsf(W.c3.x) + fabsf(W.c3.y) + fabsf(W.c3.z);
+        fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
+      }
+    }
+    if (!fast)
+    {
+      float4 wb[4];
+      nodeDirty = window_slow(p, a, len, info, wb) != 0u;
+      W = xs_load(wb);
+      if (live) r2 = sPre[warp][buf][2][lane];
     }
     if (nodeDirty)
     {
@@ -671,53 +871,65 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant_
       ++nRecomputed;
     }
 
-    // ---- bounding sphere + 6*V plane tests in registers (CullingSystem, .cpp:1240-1270) ----
+    // ---- bounding sphere + plane tests in registers ----
     const bool cand = live && (fl & kFlagMesh);
     const bool test = cand && !freeze && (fl & kFlagBounds);
     uint32_t mask = 0;
     if (__any_sync(0xffffffffu, test))
     {
-      float cx, cy, cz, radius;
-      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, cx, cy, cz, radius);
-      const float negR = -radius;
-#pragma unroll
-      for (int v = 0; v < kViews; ++v)
-      {
-        bool alive = test;
-#pragma unroll
-        for (int pp = 0; pp < 3; ++pp)
-        {
-          if (!__any_sync(0xffffffffu, alive)) break;
-          const float d0 = plane_dist(vp.planes[v][2 * pp], cx, cy, cz);
-          const float d1 = plane_dist(vp.planes[v][2 * pp + 1], cx, cy, cz);
-          alive = alive && !(d0 < negR) && !(d1 < negR);  // NaN compares false => stays visible
-        }
-        if (alive) mask |= 1u << v;
-      }
+      float ox, oy, oz, radius;
+      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, radius);
+      mask = cull_views_warp<kViews>(vp, test, ox, oy, oz, -radius, order);
     }
     if (cand && !test) mask = allMask;
     if (live) p.vismask[s] = (uint8_t)mask;
-#pragma unroll
-    for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
-    nCand += cand ? 1u : 0u;
-  }
-    // per-tile counts (zeroed by the host before the launch): ballots, one global atomic per warp and counter
-#pragma unroll
-    for (int v = 0; v < kViews; ++v)
+
+    // ---- per-tile counts: ballots, shared-memory atomics by lane 0; a window may straddle a tile boundary ----
     {
-      const uint32_t c = __reduce_add_sync(0xffffffffu, nVis[v]);
-      if (lane == 0 && c) atomicAdd(&p.tileCounts[v * p.numTiles + tile], c);
-    }
-    {
-      const uint32_t c = __reduce_add_sync(0xffffffffu, nCand);
-      if (lane == 0 && c) atomicAdd(&p.tileCounts[kViews * p.numTiles + tile], c);
+      const uint32_t tl = (a / kTile) - firstTile;
+      const uint32_t room = (a / kTile + 1u) * kTile - a;                    // slots left in the window's first tile
+      const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
+      const uint32_t candM = __ballot_sync(0xffffffffu, cand);
+      const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
+      if (candM)
+      {
+        if (lane == 0)
+        {
+          atomicAdd(&sCnt[tl][kViews], __popc(candM & lowMask));
+          if (candM & ~lowMask) atomicAdd(&sCnt[tl + 1][kViews], __popc(candM & ~lowMask));
+        }
+        if (anyVis)
+        {
+#pragma unroll
+          for (int v = 0; v < kViews; ++v)
+          {
+            const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
+            if (lane == 0 && m)
+            {
+              atomicAdd(&sCnt[tl][v], __popc(m & lowMask));
+              if (m & ~lowMask) atomicAdd(&sCnt[tl + 1][v], __popc(m & ~lowMask));
+            }
+          }
+        }
+      }
     }
     have = haveNext;
     cur = nxt;
     buf ^= 1u;
   }
-  const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
-  if (lane == 0 && q) atomicAdd(p.recomputed, q);
+  {
+    const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
+    if (lane == 0 && q) atomicAdd(&sCnt[0][kMaxViews + 1], q);
+  }
+  __syncthreads();
+  // flush: the first tile of this CTA may also receive counts from the previous CTA's last window => atomics
+  for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kViews + 1); k += kBlock)
+  {
+    const uint32_t tl = k / (kViews + 1), v = k % (kViews + 1);
+    const uint32_t c = sCnt[tl][v];
+    if (c && firstTile + tl < p.numTiles) atomicAdd(&p.tileCounts[v * p.numTiles + firstTile + tl], c);
+  }
+  if (tid == 0 && sCnt[0][kMaxViews + 1]) atomicAdd(p.recomputed, sCnt[0][kMaxViews + 1]);
 }
 
 // ---- K3a: exclusive scan of the per-tile counts, one CTA per row (view) -----------------------------------

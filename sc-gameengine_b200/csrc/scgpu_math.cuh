@@ -84,30 +84,23 @@ __device__ __noinline__ double reduce_large(uint32_t xi, int* np)
   return __dmul_rn(x, kSinCosCoef[10]);
 }
 
-// sinf(y) and cosf(y) of glibc 2.39 (generic variant) sharing one range reduction; bit-identical to the two
-// separate libm calls of sc_math.cpp:102-107.
-__device__ __forceinline__ void sincosf_glibc(float y, float& sn, float& cs)
+// abstop12-style classes of sincosf.h: pio4f = 0x3f490fdb, 2^-12 = 0x39800000, 120.0f = 0x42f00000, inf = 0x7f800000
+constexpr uint32_t kTopTiny = 0x398u, kTop120 = 0x42fu, kTopInf = 0x7f8u;
+
+// |y| < 2^-12 (zero and denormals included): sinf returns y and cosf returns 1.0f without any arithmetic
+__device__ __forceinline__ bool sincos_is_trivial(float y) { return ((__float_as_uint(y) >> 20) & 0x7ffu) < kTopTiny; }
+
+// sinf(y) and cosf(y) of glibc 2.39 (generic variant) for |y| >= 2^-12, sharing one range reduction; bit-identical
+// to the two separate libm calls of sc_math.cpp:102-107.
+// glibc evaluates |y| < pi/4 without a reduction. Here that class goes through reduce_fast as well: for |y| < 0.75
+// it yields n = 0 exactly (|y * 2/pi * 2^24| < 2^23) and x - 0*pi/2 = x exactly, after which both routes evaluate
+// the same two polynomials with sign +1 and table 0. One route instead of two keeps a warp whose angles straddle
+// pi/4 from evaluating the polynomials twice.
+__device__ __forceinline__ void sincosf_glibc_nt(float y, float& sn, float& cs)
 {
   const uint32_t yi = __float_as_uint(y);
   const uint32_t top = (yi >> 20) & 0x7ffu;
-  // abstop12 thresholds: pio4f = 0x3f490fdb, 2^-12 = 0x39800000, 120.0f = 0x42f00000, inf = 0x7f800000
-  const uint32_t kTopPio4 = 0x3f4u, kTopTiny = 0x398u, kTop120 = 0x42fu, kTopInf = 0x7f8u;
   double x = (double)y;
-
-  if (top < kTopPio4)
-  {
-    if (top < kTopTiny)
-    {
-      sn = y;
-      cs = 1.0f;
-      return;
-    }
-    const double x2 = __dmul_rn(x, x);
-    sn = sin_poly(x, x2);
-    cs = cos_poly(x2);
-    return;
-  }
-
   int n;
   int q;  // quadrant used for the sign / table selection
   if (top < kTop120)
@@ -139,6 +132,17 @@ __device__ __forceinline__ void sincosf_glibc(float y, float& sn, float& cs)
   if (q & 2) C = -C;  // table 1
   if (n & 1) { sn = C; cs = S; }
   else       { sn = S; cs = C; }
+}
+
+__device__ __forceinline__ void sincosf_glibc(float y, float& sn, float& cs)
+{
+  if (sincos_is_trivial(y))
+  {
+    sn = y;
+    cs = 1.0f;
+    return;
+  }
+  sincosf_glibc_nt(y, sn, cs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -236,14 +240,11 @@ __device__ __forceinline__ bool trs_inputs_tame(float px, float py, float pz, fl
   return sum < 0x1p120f;  // false for NaN
 }
 
-// mat4_trs for tame inputs: R = (Rz*Ry)*Rx, M = T*(R*S) with the structural zeros and ones removed.
-__device__ __forceinline__ Mat4 mat4_trs_fast(float px, float py, float pz, float rx, float ry, float rz, float sx_,
-                                              float sy_, float sz_)
+// mat4_trs for tame inputs, given the six sines / cosines: R = (Rz*Ry)*Rx, M = T*(R*S) with the structural zeros
+// and ones removed.
+__device__ __forceinline__ Mat4 mat4_trs_from_sincos(float px, float py, float pz, float sx, float cx, float sy, float cy,
+                                                     float sz, float cz, float sx_, float sy_, float sz_)
 {
-  float sx, cx, sy, cy, sz, cz;
-  sincosf_glibc(rx, sx, cx);
-  sincosf_glibc(ry, sy, cy);
-  sincosf_glibc(rz, sz, cz);
   // A = Rz*Ry
   const float a00 = __fmul_rn(cz, cy), a10 = __fmul_rn(sz, cy), a20 = -sy;
   const float a01 = -sz, a11 = cz;  // a21 = 0
@@ -262,6 +263,16 @@ __device__ __forceinline__ Mat4 mat4_trs_fast(float px, float py, float pz, floa
   m.c2 = make_float4(__fmul_rn(r02, sz_), __fmul_rn(r12, sz_), __fmul_rn(r22, sz_), 0.f);
   m.c3 = make_float4(px, py, pz, 1.f);
   return m;
+}
+
+__device__ __forceinline__ Mat4 mat4_trs_fast(float px, float py, float pz, float rx, float ry, float rz, float sx_,
+                                              float sy_, float sz_)
+{
+  float sx, cx, sy, cy, sz, cz;
+  sincosf_glibc(rx, sx, cx);
+  sincosf_glibc(ry, sy, cy);
+  sincosf_glibc(rz, sz, cz);
+  return mat4_trs_from_sincos(px, py, pz, sx, cx, sy, cy, sz, cz, sx_, sy_, sz_);
 }
 
 __device__ __noinline__ Mat4 mat4_trs_dense_call(float px, float py, float pz, float rx, float ry, float rz, float sx,
@@ -364,10 +375,13 @@ __device__ __forceinline__ void world_bounds_sphere(const Mat4& m, float bminx, 
   oy = __fadd_rn(sum3_ref(__fmul_rn(m.c0.y, cx), __fmul_rn(m.c1.y, cy), __fmul_rn(m.c2.y, cz)), m.c3.y);
   oz = __fadd_rn(sum3_ref(__fmul_rn(m.c0.z, cx), __fmul_rn(m.c1.z, cy), __fmul_rn(m.c2.z, cz)), m.c3.z);
 
-  const float sx = __fsqrt_rn(sum3_ref(__fmul_rn(m.c0.x, m.c0.x), __fmul_rn(m.c0.y, m.c0.y), __fmul_rn(m.c0.z, m.c0.z)));
-  const float sy = __fsqrt_rn(sum3_ref(__fmul_rn(m.c1.x, m.c1.x), __fmul_rn(m.c1.y, m.c1.y), __fmul_rn(m.c1.z, m.c1.z)));
-  const float sz = __fsqrt_rn(sum3_ref(__fmul_rn(m.c2.x, m.c2.x), __fmul_rn(m.c2.y, m.c2.y), __fmul_rn(m.c2.z, m.c2.z)));
-  const float maxScale = std_max(sx, std_max(sy, sz));
+  // std::max(sx, std::max(sy, sz)) of the three column norms. sqrt is monotonic and correctly rounded, so the
+  // maximum of the square roots is the square root of the maximum of the squares (same comparison structure:
+  // NaN operands and ties select the same side in both domains): one sqrt instead of three.
+  const float qx = sum3_ref(__fmul_rn(m.c0.x, m.c0.x), __fmul_rn(m.c0.y, m.c0.y), __fmul_rn(m.c0.z, m.c0.z));
+  const float qy = sum3_ref(__fmul_rn(m.c1.x, m.c1.x), __fmul_rn(m.c1.y, m.c1.y), __fmul_rn(m.c1.z, m.c1.z));
+  const float qz = sum3_ref(__fmul_rn(m.c2.x, m.c2.x), __fmul_rn(m.c2.y, m.c2.y), __fmul_rn(m.c2.z, m.c2.z));
+  const float maxScale = __fsqrt_rn(std_max(qx, std_max(qy, qz)));
   const float localRadius = __fsqrt_rn(sum3_ref(__fmul_rn(ex, ex), __fmul_rn(ey, ey), __fmul_rn(ez, ez)));
   radius = __fmul_rn(localRadius, maxScale);
 }
