@@ -100,7 +100,7 @@ struct ScGpuScene
 
   SceneArrays a{};
   // hierarchy windows (k_build_windows -> k_scan_tiles -> k_flatten_windows, on topology changes only)
-  uint16_t* slotInfo = nullptr;      // per slot: depth + parent lane inside its window, external / unreachable flags
+  uint32_t* slotInfo = nullptr;      // per slot: depth + parent lane inside its window, external / unreachable flags
   uint16_t* winLocal = nullptr;      // [tiles][kMaxWin+1] window starts relative to the tile
   uint32_t* tileWinCount = nullptr;  // [tiles]
   uint32_t* tileWinBase = nullptr;   // [tiles+1] exclusive scan of tileWinCount, total at the end
@@ -275,7 +275,9 @@ void freeAll(ScGpuScene* c)
 template <int V>
 cudaError_t optInSmem()
 {
-  return cudaFuncSetAttribute(k_update_flat<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemFlat);
+  cudaError_t e = cudaFuncSetAttribute(k_update_flat<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemFlat);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_update_win<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemWin);
 }
 
 int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
@@ -701,7 +703,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
 #define SC_LAUNCH_UPDATE(V)                                                                                              \
   case V:                                                                                                                \
     if (c->anyParentEver)                                                                                                \
-      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, \
+      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kBlock, kUpdateSmemWin, c->stream>>>(p, c->planes, c->slotInfo, \
                                                                                                      c->winList, c->tileWinBase); \
     else                                                                                                                 \
       k_update_flat<V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                                   \

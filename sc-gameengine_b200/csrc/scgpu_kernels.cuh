@@ -493,7 +493,7 @@ __device__ __forceinline__ uint32_t first_uncrossed(const int* sCross, uint32_t 
   return from;
 }
 
-__global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __restrict__ parentSlot, uint16_t* __restrict__ slotInfo,
+__global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __restrict__ parentSlot, uint32_t* __restrict__ slotInfo,
                                                           uint16_t* __restrict__ winLocal, uint32_t* __restrict__ tileWinCount,
                                                           uint32_t count)
 {
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
       if (++depth > 32u) { info = kInfoUnreachable; depth = 0; break; }  // a cycle closed inside the window
     }
     if (info & (kInfoExternal | kInfoUnreachable)) sWinFlag[w] = 1u;
-    slotInfo[tileBase + k] = (uint16_t)(info | (depth & kInfoDepthMask));
+    slotInfo[tileBase + k] = info | (depth & kInfoDepthMask);
   }
   __syncthreads();
   for (uint32_t k = tid; k <= nw; k += kBlock)
@@ -700,236 +700,331 @@ __device__ __noinline__ uint32_t window_slow(const UpdateParams& p, uint32_t a, 
   return nodeDirty ? 1u : 0u;
 }
 
+// ---- shared-memory access by 32-bit shared address ------------------------------------------------------------------
+// The window kernel addresses its shared memory through plain 32-bit shared-window addresses computed once per
+// warp; going through generic pointers makes the compiler rebuild the address (S2R CgaCtaId, LEA ...) at every use.
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v)
+{
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a)
+{
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v)
+{
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+// One elected lane of the (converged) warp does the atomic. Written with elect.sync so that ptxas emits a bare
+// ATOMS: behind an `if (lane == 0)` it wraps every shared atomic in its warp-aggregation sequence (VOTE, FLO, two
+// POPC, S2R LTMASK, SHFL), ~15 instructions that are pure overhead when one lane is active by construction.
+__device__ __forceinline__ uint32_t warp_atoms_add(uint32_t a, uint32_t v)
+{
+  uint32_t old = 0, leader;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared.add.u32 %0, [%2], %3;\n\t}"
+               : "+r"(old), "=r"(leader)
+               : "r"(a), "r"(v)
+               : "memory");
+  return __shfl_sync(0xffffffffu, old, leader);
+}
+__device__ __forceinline__ void warp_reds_add(uint32_t a, uint32_t v)
+{
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async4s(uint32_t smem, const void* gmem)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16s(uint32_t smem, const void* gmem)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem), "l"(gmem) : "memory");
+}
+
 // ---- K1+K2, hierarchical scenes: one window per warp -----------------------------------------------------------------
 // Loads and stores are the flat kernel's (coalesced 128-bit planes, slot = window start + lane). Inside the warp:
 //   1. dirty bits are propagated parent -> child with ballots (skipped when everything is dirty anyway),
 //   2. every lane that must be recomputed builds its local matrix (all lanes busy, FP64 sincos in parallel),
-//   3. for level 1..max, the lanes of that level read their parent's world matrix (upper 3x4) from a per-warp
-//      shared-memory exchange area and multiply: parent-before-child, parent matrices staged in shared memory.
+//   3. the matrices go to a per-warp shared-memory area; for level 1..max the products parent.world * local of that
+//      level are computed by lane PAIRS (one lane columns 0-1, the other columns 2-3 + translation), 16 children per
+//      round, whichever lanes the children themselves occupy: parent-before-child, parent matrices staged in shared
+//      memory, and the lanes stay busy although a level holds only a fraction of the window's nodes.
 // The fast path assumes what holds for every sane scene - tame TRS values, affine stored matrices, finite
 // translations, parents inside the window - and VERIFIES it per window (two warp votes); a window that fails the
 // check is redone by window_slow(), which is exact for any input. No CTA barrier inside the loop, no dependency
 // between warps: a warp that finishes a window claims the next unclaimed one of its CTA.
+#ifndef SCGPU_WIN_MINBLOCKS
+#define SCGPU_WIN_MINBLOCKS 4
+#endif
 constexpr uint32_t kWinTilesPerCta = 4;  // tiles per CTA of k_update_win: ~146 windows shared by 8 warps
+constexpr uint32_t kWinWarps = kBlock / 32;
+// dynamic shared memory of k_update_win (byte offsets). Everything a warp touches in the loop sits in ONE per-warp
+// block, so that every address is "lane base + constant" and folds into the instruction's immediate offset.
+constexpr uint32_t kWsBuf = 4 * 512 + 128;              // one prefetch buffer: 4 record planes + 32 slotInfo words
+constexpr uint32_t kWwMat = 2 * kWsBuf;                 // [4][32] float4: matrix columns of the level loop
+constexpr uint32_t kWwSched = kWwMat + 4 * 512;         // [32] u16: children of the current level
+constexpr uint32_t kWwSize = kWwSched + 64;             // per-warp block
+constexpr uint32_t kWsWin = kWinWarps * kWwSize;        // [4*kMaxWin+1] u32: this CTA's slice of the window list
+constexpr uint32_t kWsCnt = kWsWin + ((kWinTilesPerCta * kMaxWin + 1) * 4 + 15) / 16 * 16;  // [tiles+1][kMaxViews+2] u32
+constexpr uint32_t kWsNext = kWsCnt + ((kWinTilesPerCta + 1) * (kMaxViews + 2) * 4 + 15) / 16 * 16;
+constexpr uint32_t kUpdateSmemWin = kWsNext + 16;
 
 template <int kViews>
-__global__ void __launch_bounds__(kBlock, 4) k_update_win(const __grid_constant__ UpdateParams p,
+__global__ void __launch_bounds__(kBlock, SCGPU_WIN_MINBLOCKS) k_update_win(const __grid_constant__ UpdateParams p,
                                                           const __grid_constant__ ViewPlanes vp,
-                                                          const uint16_t* __restrict__ slotInfo,
+                                                          const uint32_t* __restrict__ slotInfo,
                                                           const uint32_t* __restrict__ winList,
                                                           const uint32_t* __restrict__ tileWinBase)
 {
-  __shared__ uint32_t sWin[kWinTilesPerCta * kMaxWin + 1];  // this CTA's slice of the window list
-  __shared__ uint32_t sNext;                                // next unclaimed window: warps pull work dynamically
-  __shared__ uint32_t sCnt[kWinTilesPerCta + 1][kMaxViews + 2];  // per-tile counts (+1 row: windows may spill over)
-  // per-warp double buffer: the record planes of the NEXT claimed window are fetched with cp.async while the
-  // current window is being computed
-  __shared__ __align__(16) float4 sPre[kBlock / 32][2][4][32];
-  // per-warp exchange area of the level loop: upper 3x4 of every lane's world matrix as three float4 planes
-  __shared__ __align__(16) float4 sX[kBlock / 32][3][32];
-
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  extern __shared__ __align__(128) unsigned char sDynW[];
+  const uint32_t sBase = smem_u32(sDynW);
+  const uint32_t tid = threadIdx.x;
+  // lane / warp ids through volatile asm: the compiler then keeps them in registers instead of re-reading the
+  // special register (S2R, ~20 cycles each) wherever register pressure makes rematerialisation look cheap
+  uint32_t lane, warp;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+  asm volatile("shr.u32 %0, %1, 5;" : "=r"(warp) : "r"(tid));
   const uint32_t firstTile = blockIdx.x * kWinTilesPerCta;
   const uint32_t nTiles = min(kWinTilesPerCta, p.numTiles - firstTile);
   const uint32_t wBeg = tileWinBase[firstTile];
   const uint32_t nWin = tileWinBase[firstTile + nTiles] - wBeg;
-  for (uint32_t k = tid; k <= nWin; k += kBlock) sWin[k] = winList[wBeg + k];
-  for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kMaxViews + 2); k += kBlock) (&sCnt[0][0])[k] = 0;
-  if (tid == 0) sNext = 0;
+  {
+    uint32_t* sWin = reinterpret_cast<uint32_t*>(sDynW + kWsWin);
+    uint32_t* sCnt = reinterpret_cast<uint32_t*>(sDynW + kWsCnt);
+    for (uint32_t k = tid; k <= nWin; k += kBlock) sWin[k] = winList[wBeg + k];
+    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kMaxViews + 2); k += kBlock) sCnt[k] = 0;
+    if (tid == 0) *reinterpret_cast<uint32_t*>(sDynW + kWsNext) = 0;
+  }
   __syncthreads();
 
   constexpr uint32_t allMask = (1u << kViews) - 1u;
+  constexpr uint32_t kCntRow = (kMaxViews + 2) * 4;  // bytes per tile row of the count table
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
-  uint32_t nRecomputed = 0;
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
-  float4* const xw = &sX[warp][0][0];
+  const uint32_t warpBase = sBase + warp * kWwSize;
+  const uint32_t laneBase = warpBase + lane * 16;  // this lane's float4 of plane 0, buffer 0
 
-  // claim + start fetching one window; returns false when the CTA's windows are exhausted
-  struct Win { uint32_t a, len, info; };
-  auto claim_and_fetch = [&](uint32_t b, Win& o) -> bool
+  // A warp that finishes a window claims the next unclaimed one of its CTA (one shared atomic by an elected lane);
+  // the record planes and the slotInfo words of the claimed window are fetched with cp.async while the current
+  // window is being computed, so nothing of the next window occupies a register meanwhile. For the same reason
+  // the window geometry and the flag word are RE-READ from shared memory in each phase instead of being carried
+  // across the level loop in registers (the kernel lives at 64 registers / 4 CTAs per SM).
+  auto fetch = [&](uint32_t w, uint32_t off)
   {
-    uint32_t w = 0;
-    if (lane == 0) w = atomicAdd(&sNext, 1u);
-    w = __shfl_sync(0xffffffffu, w, 0);
-    if (w >= nWin) return false;
-    const uint32_t e0 = sWin[w];
-    o.a = e0;
-    o.len = (sWin[w + 1] & kWinSlotMask) - (e0 & kWinSlotMask);
-    o.info = 0;
-    if (lane < o.len)
+    const uint32_t e0 = lds32(sBase + kWsWin + w * 4) & kWinSlotMask, e1 = lds32(sBase + kWsWin + w * 4 + 4) & kWinSlotMask;
+    if (lane < e1 - e0)
     {
-      const uint32_t q = (e0 & kWinSlotMask) + lane;
-      cp_async16(&sPre[warp][b][0][lane], p.rec0 + q);
-      cp_async16(&sPre[warp][b][1][lane], p.rec1 + q);
-      cp_async16(&sPre[warp][b][2][lane], p.rec2 + q);
-      cp_async16(&sPre[warp][b][3][lane], p.rec3 + q);
-      o.info = slotInfo[q];
+      const uint32_t q = e0 + lane;
+      const uint32_t d = laneBase + off;
+      cp_async16s(d, p.rec0 + q);
+      cp_async16s(d + 512, p.rec1 + q);
+      cp_async16s(d + 1024, p.rec2 + q);
+      cp_async16s(d + 1536, p.rec3 + q);
+      cp_async4s(d + 2048 - lane * 12, slotInfo + q);
     }
-    cp_async_commit();
-    return true;
   };
-  Win cur, nxt;
-  uint32_t buf = 0;
-  bool have = claim_and_fetch(0, cur);
+  uint32_t w = warp_atoms_add(sBase + kWsNext, 1u), bufOff = 0;
+  if (w < nWin) fetch(w, 0);
+  cp_async_commit();
 #pragma unroll 1
-  while (have)
+  while (w < nWin)
   {
-    const bool haveNext = claim_and_fetch(buf ^ 1u, nxt);  // in flight while this window is computed
-    if (haveNext) cp_async_wait<1>();
-    else cp_async_wait<0>();
-    const uint32_t a = cur.a & kWinSlotMask, len = cur.len, info = cur.info;
-    const bool live = lane < len;
-    const uint32_t s = a + lane;
-    const uint32_t liveMask = 0xffffffffu >> (32u - len);
+    const uint32_t wNext = warp_atoms_add(sBase + kWsNext, 1u);
+    if (wNext < nWin) fetch(wNext, bufOff ^ kWsBuf);  // in flight while this window is computed
+    cp_async_commit();
+    cp_async_wait<1>();
+    const uint32_t recAddr = laneBase + bufOff;
+    const uint32_t winAddr = sBase + kWsWin + w * 4;
+    bool live, nodeDirty = false, fast;
+    uint32_t info;
+    Mat4 W = mat4_identity();
+    {
+      const uint32_t e0 = lds32(winAddr);
+      const uint32_t len = (lds32(winAddr + 4) & kWinSlotMask) - (e0 & kWinSlotMask);
+      live = lane < len;
+      fast = (e0 & kWinSlow) == 0u;
+      info = live ? lds32(recAddr + 2048 - lane * 12) : 0u;
+    }
     const uint32_t wl = info & kInfoDepthMask;
     const uint32_t maxL = __reduce_max_sync(0xffffffffu, wl);
-
-    Mat4 W = mat4_identity();
-    bool nodeDirty = false;
-    bool fast = (cur.a & kWinSlow) == 0u;
-    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f), r3 = r2;
-    if (live) r3 = sPre[warp][buf][3][lane];
-    const uint32_t fl = __float_as_uint(r3.w);
     if (fast)
     {
-      float4 r0 = r2, r1 = r2;
-      if (live) { r0 = sPre[warp][buf][0][lane]; r1 = sPre[warp][buf][1][lane]; r2 = sPre[warp][buf][2][lane]; }
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+      float sclZ = 0.f;
+      uint32_t fl = 0;
+      if (live)
+      {
+        r0 = lds128(recAddr); r1 = lds128(recAddr + 512); sclZ = __uint_as_float(lds32(recAddr + 1024));
+        fl = lds32(recAddr + 1536 + 12);
+      }
       nodeDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
-      const uint32_t pl16 = ((info >> kInfoParentShift) & 31u) * 16u;
+      const uint32_t parentLane = (info >> kInfoParentShift) & 31u;
       // ---- 1. children inherit dirtiness level by level ----
+      const uint32_t liveMask = __ballot_sync(0xffffffffu, live);
       uint32_t dirtyM = __ballot_sync(0xffffffffu, nodeDirty);
       if (dirtyM != liveMask && dirtyM != 0u)
       {
         for (uint32_t l = 1; l <= maxL; ++l)
         {
-          if (wl == l && ((dirtyM >> (pl16 >> 4)) & 1u)) nodeDirty = true;
+          if (wl == l && ((dirtyM >> parentLane) & 1u)) nodeDirty = true;
           dirtyM = __ballot_sync(0xffffffffu, nodeDirty);
         }
       }
       // ---- 2. local matrices of everything that is recomputed; stored world matrices of the rest ----
-      const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x);
+      const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, sclZ);
       float sx, cx, sy, cy, sz, cz;
       sincos3_warp(nodeDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
       bool ok = true;
       if (nodeDirty)
       {
-        W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, r2.x);  // roots: world == local
+        W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);  // roots: world == local
         ok = tame;
       }
       else if (live)
       {
-        W = load_world(p, s);
+        W = load_world(p, (lds32(winAddr) & kWinSlotMask) + lane);
         ok = mat4_is_affine(W);
       }
       fast = __all_sync(0xffffffffu, ok);
-      // ---- 3. parent.world * local, one level at a time, parents read from the exchange area ----
+      // ---- 3. parent.world * local level by level, 16 children per round, one lane PAIR per child ----
       if (fast && maxL != 0u && dirtyM != 0u)
       {
-        xw[lane] = make_float4(W.c0.x, W.c0.y, W.c0.z, W.c1.x);
-        xw[32 + lane] = make_float4(W.c1.y, W.c1.z, W.c2.x, W.c2.y);
-        xw[64 + lane] = make_float4(W.c2.z, W.c3.x, W.c3.y, W.c3.z);
+        const uint32_t own = laneBase + kWwMat;
+        sts128(own, W.c0); sts128(own + 512, W.c1); sts128(own + 1024, W.c2); sts128(own + 1536, W.c3);
         __syncwarp();
-        const float4* const xp = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(xw) + pl16);
         for (uint32_t l = 1; l <= maxL; ++l)
         {
-          if (nodeDirty && wl == l)
-          {
-            const float4 q0 = xp[0], q1 = xp[32], q2 = xp[64];
-            Mat4 P;
-            P.c0 = make_float4(q0.x, q0.y, q0.z, 0.f);
-            P.c1 = make_float4(q0.w, q1.x, q1.y, 0.f);
-            P.c2 = make_float4(q1.z, q1.w, q2.x, 0.f);
-            P.c3 = make_float4(q2.y, q2.z, q2.w, 1.f);
-            W = mat4_mul_affine3(P, W);
-            if (l < maxL)
-            {
-              xw[lane] = make_float4(W.c0.x, W.c0.y, W.c0.z, W.c1.x);
-              xw[32 + lane] = make_float4(W.c1.y, W.c1.z, W.c2.x, W.c2.y);
-              xw[64 + lane] = make_float4(W.c2.z, W.c3.x, W.c3.y, W.c3.z);
-            }
-          }
+          const bool mine = nodeDirty && wl == l;
+          const uint32_t m = __ballot_sync(0xffffffffu, mine);
+          if (m == 0u) continue;
+          const uint32_t cnt = __popc(m);
+          if (mine) sts16(warpBase + kWwSched + __popc(m & ((1u << lane) - 1u)) * 2u, lane | (parentLane << 8));
           __syncwarp();
+          for (uint32_t r = 0; r < cnt; r += 16u)
+          {
+            const uint32_t idx = r + (lane >> 1);
+            if (idx < cnt)
+            {
+              const uint32_t e = lds16(warpBase + kWwSched + idx * 2u);
+              const uint32_t cAddr = warpBase + (e & 31u) * 16u + (lane & 1u) * 1024u;  // child's columns 2h, 2h+1
+              const uint32_t pAddr = warpBase + (e >> 8) * 16u;
+              const float4 P0 = lds128(pAddr + kWwMat), P1 = lds128(pAddr + kWwMat + 512), P2 = lds128(pAddr + kWwMat + 1024);
+              const float4 La = lds128(cAddr + kWwMat), Lb = lds128(cAddr + kWwMat + 512);
+              float4 oa, ob;
+              oa.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, La.x), __fmul_rn(P1.x, La.y)), __fmul_rn(P2.x, La.z));
+              oa.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, La.x), __fmul_rn(P1.y, La.y)), __fmul_rn(P2.y, La.z));
+              oa.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, La.x), __fmul_rn(P1.z, La.y)), __fmul_rn(P2.z, La.z));
+              oa.w = La.w;
+              ob.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, Lb.x), __fmul_rn(P1.x, Lb.y)), __fmul_rn(P2.x, Lb.z));
+              ob.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, Lb.x), __fmul_rn(P1.y, Lb.y)), __fmul_rn(P2.y, Lb.z));
+              ob.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, Lb.x), __fmul_rn(P1.z, Lb.y)), __fmul_rn(P2.z, Lb.z));
+              ob.w = Lb.w;
+              if (lane & 1u)
+              {
+                const float4 P3 = lds128(pAddr + kWwMat + 1536);  // column 3: + parent translation (p[r][3] * 1)
+                ob.x = __fadd_rn(ob.x, P3.x); ob.y = __fadd_rn(ob.y, P3.y); ob.z = __fadd_rn(ob.z, P3.z);
+              }
+              sts128(cAddr + kWwMat, oa);
+              sts128(cAddr + kWwMat + 512, ob);
+            }
+            __syncwarp();
+          }
         }
+        W.c0 = lds128(own); W.c1 = lds128(own + 512); W.c2 = lds128(own + 1024); W.c3 = lds128(own + 1536);
         // the structured products are value-exact iff every parent translation was finite; a non-finite one
         // propagates into the translation of all its descendants, so one test of the results covers all levels
         const float mag = fabsf(W.c3.x) + fabsf(W.c3.y) + fabsf(W.c3.z);
         fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
       }
     }
+    const uint32_t a = lds32(winAddr) & kWinSlotMask;
     if (!fast)
     {
       float4 wb[4];
-      nodeDirty = window_slow(p, a, len, info, wb) != 0u;
+      nodeDirty = window_slow(p, a, (lds32(winAddr + 4) & kWinSlotMask) - a, info, wb) != 0u;
       W = xs_load(wb);
-      if (live) r2 = sPre[warp][buf][2][lane];
     }
-    if (nodeDirty)
+    if (nodeDirty) store_world(p, a + lane, W);
     {
-      store_world(p, s, W);
-      ++nRecomputed;
+      const uint32_t nd = __ballot_sync(0xffffffffu, nodeDirty);
+      if (nd) warp_reds_add(sBase + kWsCnt + (kMaxViews + 1) * 4, __popc(nd));
     }
 
     // ---- bounding sphere + plane tests in registers ----
+    float4 r3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) r3 = lds128(recAddr + 1536);
+    const uint32_t fl = __float_as_uint(r3.w);
     const bool cand = live && (fl & kFlagMesh);
     const bool test = cand && !freeze && (fl & kFlagBounds);
     uint32_t mask = 0;
     if (__any_sync(0xffffffffu, test))
     {
+      float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) r2 = lds128(recAddr + 1024);
       float ox, oy, oz, radius;
       world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, radius);
       mask = cull_views_warp<kViews>(vp, test, ox, oy, oz, -radius, order);
     }
     if (cand && !test) mask = allMask;
-    if (live) p.vismask[s] = (uint8_t)mask;
+    if (live) p.vismask[a + lane] = (uint8_t)mask;
 
-    // ---- per-tile counts: ballots, shared-memory atomics by lane 0; a window may straddle a tile boundary ----
+    // ---- per-tile counts: ballots, one shared-memory reduction per counter; a window may straddle a tile boundary ----
     {
-      const uint32_t tl = (a / kTile) - firstTile;
-      const uint32_t room = (a / kTile + 1u) * kTile - a;                    // slots left in the window's first tile
-      const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
       const uint32_t candM = __ballot_sync(0xffffffffu, cand);
-      const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
       if (candM)
       {
-        if (lane == 0)
-        {
-          atomicAdd(&sCnt[tl][kViews], __popc(candM & lowMask));
-          if (candM & ~lowMask) atomicAdd(&sCnt[tl + 1][kViews], __popc(candM & ~lowMask));
-        }
+        const uint32_t tl = (a / kTile) - firstTile;
+        const uint32_t room = (a / kTile + 1u) * kTile - a;  // slots left in the window's first tile
+        const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
+        const uint32_t cntAddr = sBase + kWsCnt + tl * kCntRow;
+        const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
+        warp_reds_add(cntAddr + kViews * 4, __popc(candM & lowMask));
+        if (candM & ~lowMask) warp_reds_add(cntAddr + kCntRow + kViews * 4, __popc(candM & ~lowMask));
         if (anyVis)
         {
 #pragma unroll
           for (int v = 0; v < kViews; ++v)
           {
             const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
-            if (lane == 0 && m)
+            if (m)
             {
-              atomicAdd(&sCnt[tl][v], __popc(m & lowMask));
-              if (m & ~lowMask) atomicAdd(&sCnt[tl + 1][v], __popc(m & ~lowMask));
+              warp_reds_add(cntAddr + v * 4, __popc(m & lowMask));
+              if (m & ~lowMask) warp_reds_add(cntAddr + kCntRow + v * 4, __popc(m & ~lowMask));
             }
           }
         }
       }
     }
-    have = haveNext;
-    cur = nxt;
-    buf ^= 1u;
-  }
-  {
-    const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
-    if (lane == 0 && q) atomicAdd(&sCnt[0][kMaxViews + 1], q);
+    w = wNext;
+    bufOff ^= kWsBuf;
   }
   __syncthreads();
   // flush: the first tile of this CTA may also receive counts from the previous CTA's last window => atomics
-  for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kViews + 1); k += kBlock)
   {
-    const uint32_t tl = k / (kViews + 1), v = k % (kViews + 1);
-    const uint32_t c = sCnt[tl][v];
-    if (c && firstTile + tl < p.numTiles) atomicAdd(&p.tileCounts[v * p.numTiles + firstTile + tl], c);
+    const uint32_t* sCnt = reinterpret_cast<const uint32_t*>(sDynW + kWsCnt);
+    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kViews + 1); k += kBlock)
+    {
+      const uint32_t tl = k / (kViews + 1), v = k % (kViews + 1);
+      const uint32_t c = sCnt[tl * (kMaxViews + 2) + v];
+      if (c && firstTile + tl < p.numTiles) atomicAdd(&p.tileCounts[v * p.numTiles + firstTile + tl], c);
+    }
+    if (tid == 0 && sCnt[kMaxViews + 1]) atomicAdd(p.recomputed, sCnt[kMaxViews + 1]);
   }
-  if (tid == 0 && sCnt[0][kMaxViews + 1]) atomicAdd(p.recomputed, sCnt[0][kMaxViews + 1]);
 }
 
 // ---- K3a: exclusive scan of the per-tile counts, one CTA per row (view) -----------------------------------
