@@ -703,7 +703,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
 #define SC_LAUNCH_UPDATE(V)                                                                                              \
   case V:                                                                                                                \
     if (c->anyParentEver)                                                                                                \
-      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kBlock, kUpdateSmemWin, c->stream>>>(p, c->planes, c->slotInfo, \
+      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kWinBlock, kUpdateSmemWin, c->stream>>>(p, c->planes, c->slotInfo, \
                                                                                                      c->winList, c->tileWinBase); \
     else                                                                                                                 \
       k_update_flat<V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                                   \

@@ -745,6 +745,8 @@ __device__ __forceinline__ void warp_reds_add(uint32_t a, uint32_t v)
 {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(a), "r"(v) : "memory");
 }
+// next free entry of the deferred-window list (single caller lane)
+__device__ __forceinline__ uint32_t warp_slow_slot(uint32_t sBase);
 __device__ __forceinline__ void cp_async4s(uint32_t smem, const void* gmem)
 {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem), "l"(gmem) : "memory");
@@ -766,11 +768,14 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem, const void* gmem)
 // translations, parents inside the window - and VERIFIES it per window (two warp votes); a window that fails the
 // check is redone by window_slow(), which is exact for any input. No CTA barrier inside the loop, no dependency
 // between warps: a warp that finishes a window claims the next unclaimed one of its CTA.
-#ifndef SCGPU_WIN_MINBLOCKS
-#define SCGPU_WIN_MINBLOCKS 4
+#ifndef SCGPU_WIN_BLOCK
+#define SCGPU_WIN_BLOCK 128
+#define SCGPU_WIN_MINBLOCKS 8
+#define SCGPU_WIN_TILES 2
 #endif
-constexpr uint32_t kWinTilesPerCta = 4;  // tiles per CTA of k_update_win: ~146 windows shared by 8 warps
-constexpr uint32_t kWinWarps = kBlock / 32;
+constexpr uint32_t kWinBlock = SCGPU_WIN_BLOCK;          // threads per CTA of k_update_win
+constexpr uint32_t kWinTilesPerCta = SCGPU_WIN_TILES;    // tiles per CTA: ~18 windows per warp
+constexpr uint32_t kWinWarps = kWinBlock / 32;
 // dynamic shared memory of k_update_win (byte offsets). Everything a warp touches in the loop sits in ONE per-warp
 // block, so that every address is "lane base + constant" and folds into the instruction's immediate offset.
 constexpr uint32_t kWsBuf = 4 * 512 + 128;              // one prefetch buffer: 4 record planes + 32 slotInfo words
@@ -780,10 +785,18 @@ constexpr uint32_t kWwSize = kWwSched + 64;             // per-warp block
 constexpr uint32_t kWsWin = kWinWarps * kWwSize;        // [4*kMaxWin+1] u32: this CTA's slice of the window list
 constexpr uint32_t kWsCnt = kWsWin + ((kWinTilesPerCta * kMaxWin + 1) * 4 + 15) / 16 * 16;  // [tiles+1][kMaxViews+2] u32
 constexpr uint32_t kWsNext = kWsCnt + ((kWinTilesPerCta + 1) * (kMaxViews + 2) * 4 + 15) / 16 * 16;
-constexpr uint32_t kUpdateSmemWin = kWsNext + 16;
+constexpr uint32_t kWsSlow = kWsNext + 16;            // [tiles*kMaxWin] u16: windows deferred to the generic path (count at kWsNext+4)
+constexpr uint32_t kUpdateSmemWin = kWsSlow + (kWinTilesPerCta * kMaxWin * 2 + 15) / 16 * 16;
+
+__device__ __forceinline__ uint32_t warp_slow_slot(uint32_t sBase)
+{
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(sBase + kWsNext + 4) : "memory");
+  return old;
+}
 
 template <int kViews>
-__global__ void __launch_bounds__(kBlock, SCGPU_WIN_MINBLOCKS) k_update_win(const __grid_constant__ UpdateParams p,
+__global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(const __grid_constant__ UpdateParams p,
                                                           const __grid_constant__ ViewPlanes vp,
                                                           const uint32_t* __restrict__ slotInfo,
                                                           const uint32_t* __restrict__ winList,
@@ -804,9 +817,9 @@ __global__ void __launch_bounds__(kBlock, SCGPU_WIN_MINBLOCKS) k_update_win(cons
   {
     uint32_t* sWin = reinterpret_cast<uint32_t*>(sDynW + kWsWin);
     uint32_t* sCnt = reinterpret_cast<uint32_t*>(sDynW + kWsCnt);
-    for (uint32_t k = tid; k <= nWin; k += kBlock) sWin[k] = winList[wBeg + k];
-    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kMaxViews + 2); k += kBlock) sCnt[k] = 0;
-    if (tid == 0) *reinterpret_cast<uint32_t*>(sDynW + kWsNext) = 0;
+    for (uint32_t k = tid; k <= nWin; k += kWinBlock) sWin[k] = winList[wBeg + k];
+    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kMaxViews + 2); k += kWinBlock) sCnt[k] = 0;
+    if (tid < 2) reinterpret_cast<uint32_t*>(sDynW + kWsNext)[tid] = 0;  // next unclaimed window, deferred count
   }
   __syncthreads();
 
@@ -818,6 +831,59 @@ __global__ void __launch_bounds__(kBlock, SCGPU_WIN_MINBLOCKS) k_update_win(cons
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
   const uint32_t warpBase = sBase + warp * kWwSize;
   const uint32_t laneBase = warpBase + lane * 16;  // this lane's float4 of plane 0, buffer 0
+
+  // store + bounding sphere + plane tests + per-tile counts of one resolved window
+  auto finish = [&](uint32_t w, uint32_t recAddr, bool live, bool nodeDirty, const Mat4& W)
+  {
+    const uint32_t a = lds32(sBase + kWsWin + w * 4) & kWinSlotMask;
+    if (nodeDirty) store_world(p, a + lane, W);
+    {
+      const uint32_t nd = __ballot_sync(0xffffffffu, nodeDirty);
+      if (nd) warp_reds_add(sBase + kWsCnt + (kMaxViews + 1) * 4, __popc(nd));
+    }
+    // ---- bounding sphere + plane tests in registers ----
+    float4 r3 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) r3 = lds128(recAddr + 1536);
+    const uint32_t fl = __float_as_uint(r3.w);
+    const bool cand = live && (fl & kFlagMesh);
+    const bool test = cand && !freeze && (fl & kFlagBounds);
+    uint32_t mask = 0;
+    if (__any_sync(0xffffffffu, test))
+    {
+      float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) r2 = lds128(recAddr + 1024);
+      float ox, oy, oz, radius;
+      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, radius);
+      mask = cull_views_warp<kViews>(vp, test, ox, oy, oz, -radius, order);
+    }
+    if (cand && !test) mask = allMask;
+    if (live) p.vismask[a + lane] = (uint8_t)mask;
+    // ---- per-tile counts: ballots, one shared-memory reduction per counter; a window may straddle a tile boundary ----
+    const uint32_t candM = __ballot_sync(0xffffffffu, cand);
+    if (candM)
+    {
+      const uint32_t tl = (a / kTile) - firstTile;
+      const uint32_t room = (a / kTile + 1u) * kTile - a;  // slots left in the window's first tile
+      const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
+      const uint32_t cntAddr = sBase + kWsCnt + tl * kCntRow;
+      const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
+      warp_reds_add(cntAddr + kViews * 4, __popc(candM & lowMask));
+      if (candM & ~lowMask) warp_reds_add(cntAddr + kCntRow + kViews * 4, __popc(candM & ~lowMask));
+      if (anyVis)
+      {
+#pragma unroll
+        for (int v = 0; v < kViews; ++v)
+        {
+          const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
+          if (m)
+          {
+            warp_reds_add(cntAddr + v * 4, __popc(m & lowMask));
+            if (m & ~lowMask) warp_reds_add(cntAddr + kCntRow + v * 4, __popc(m & ~lowMask));
+          }
+        }
+      }
+    }
+  };
 
   // A warp that finishes a window claims the next unclaimed one of its CTA (one shared atomic by an elected lane);
   // the record planes and the slotInfo words of the claimed window are fetched with cp.async while the current
@@ -952,72 +1018,40 @@ __global__ void __launch_bounds__(kBlock, SCGPU_WIN_MINBLOCKS) k_update_win(cons
         fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
       }
     }
-    const uint32_t a = lds32(winAddr) & kWinSlotMask;
-    if (!fast)
-    {
-      float4 wb[4];
-      nodeDirty = window_slow(p, a, (lds32(winAddr + 4) & kWinSlotMask) - a, info, wb) != 0u;
-      W = xs_load(wb);
-    }
-    if (nodeDirty) store_world(p, a + lane, W);
-    {
-      const uint32_t nd = __ballot_sync(0xffffffffu, nodeDirty);
-      if (nd) warp_reds_add(sBase + kWsCnt + (kMaxViews + 1) * 4, __popc(nd));
-    }
-
-    // ---- bounding sphere + plane tests in registers ----
-    float4 r3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) r3 = lds128(recAddr + 1536);
-    const uint32_t fl = __float_as_uint(r3.w);
-    const bool cand = live && (fl & kFlagMesh);
-    const bool test = cand && !freeze && (fl & kFlagBounds);
-    uint32_t mask = 0;
-    if (__any_sync(0xffffffffu, test))
-    {
-      float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) r2 = lds128(recAddr + 1024);
-      float ox, oy, oz, radius;
-      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, radius);
-      mask = cull_views_warp<kViews>(vp, test, ox, oy, oz, -radius, order);
-    }
-    if (cand && !test) mask = allMask;
-    if (live) p.vismask[a + lane] = (uint8_t)mask;
-
-    // ---- per-tile counts: ballots, one shared-memory reduction per counter; a window may straddle a tile boundary ----
-    {
-      const uint32_t candM = __ballot_sync(0xffffffffu, cand);
-      if (candM)
-      {
-        const uint32_t tl = (a / kTile) - firstTile;
-        const uint32_t room = (a / kTile + 1u) * kTile - a;  // slots left in the window's first tile
-        const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
-        const uint32_t cntAddr = sBase + kWsCnt + tl * kCntRow;
-        const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
-        warp_reds_add(cntAddr + kViews * 4, __popc(candM & lowMask));
-        if (candM & ~lowMask) warp_reds_add(cntAddr + kCntRow + kViews * 4, __popc(candM & ~lowMask));
-        if (anyVis)
-        {
-#pragma unroll
-          for (int v = 0; v < kViews; ++v)
-          {
-            const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
-            if (m)
-            {
-              warp_reds_add(cntAddr + v * 4, __popc(m & lowMask));
-              if (m & ~lowMask) warp_reds_add(cntAddr + kCntRow + v * 4, __popc(m & ~lowMask));
-            }
-          }
-        }
-      }
-    }
+    if (fast) finish(w, recAddr, live, nodeDirty, W);
+    else if (lane == 0) sts16(sBase + kWsSlow + warp_slow_slot(sBase) * 2u, w);  // redone by the generic path below
     w = wNext;
     bufOff ^= kWsBuf;
+  }
+  __syncthreads();
+  // ---- deferred windows: the generic path, kept OUT of the loop above so that the out-of-line call does not force
+  // the loop-carried values of the hot path into local memory ----
+  {
+    const uint32_t nSlow = lds32(sBase + kWsNext + 4);
+#pragma unroll 1
+    for (uint32_t k = warp; k < nSlow; k += kWinWarps)
+    {
+      const uint32_t w = lds16(sBase + kWsSlow + k * 2u);
+      const uint32_t a = lds32(sBase + kWsWin + w * 4) & kWinSlotMask;
+      const uint32_t len = (lds32(sBase + kWsWin + w * 4 + 4) & kWinSlotMask) - a;
+      const bool live = lane < len;
+      // the prefetch buffers are free now: stage this window's records once more for finish()
+      if (live)
+      {
+        sts128(laneBase, p.rec0[a + lane]); sts128(laneBase + 512, p.rec1[a + lane]);
+        sts128(laneBase + 1024, p.rec2[a + lane]); sts128(laneBase + 1536, p.rec3[a + lane]);
+      }
+      const uint32_t info = live ? slotInfo[a + lane] : 0u;
+      float4 wb[4];
+      const bool nodeDirty = window_slow(p, a, len, info, wb) != 0u;
+      finish(w, laneBase, live, nodeDirty, xs_load(wb));
+    }
   }
   __syncthreads();
   // flush: the first tile of this CTA may also receive counts from the previous CTA's last window => atomics
   {
     const uint32_t* sCnt = reinterpret_cast<const uint32_t*>(sDynW + kWsCnt);
-    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kViews + 1); k += kBlock)
+    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kViews + 1); k += kWinBlock)
     {
       const uint32_t tl = k / (kViews + 1), v = k % (kViews + 1);
       const uint32_t c = sCnt[tl * (kMaxViews + 2) + v];

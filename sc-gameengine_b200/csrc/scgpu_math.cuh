@@ -65,7 +65,7 @@ __device__ __forceinline__ float cos_poly(double x2)
 }
 
 // sincosf.h:reduce_large — |x| >= 120, 32x96 -> 128 bit fixed-point product with 4/pi
-__device__ __noinline__ double reduce_large(uint32_t xi, int* np)
+__device__ __forceinline__ double reduce_large(uint32_t xi, int* np)
 {
   const uint32_t* arr = &kInvPio4[(xi >> 26) & 15];
   const int shift = (xi >> 23) & 7;
