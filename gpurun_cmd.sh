@@ -6,6 +6,4 @@ PY
 }
 B="timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
 $B > gpurun_out/h.json 2>> gpurun_out/b.err; show gpurun_out/h.json
-SCGPU_LIB=scratch/libscgpu_b256x4.so $B > gpurun_out/h2.json 2>> gpurun_out/b.err; show gpurun_out/h2.json
-SCGPU_LIB=scratch/libscgpu_b128x8.so $B > gpurun_out/h3.json 2>> gpurun_out/b.err; show gpurun_out/h3.json
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; tail -5 gpurun_out/tests_full.log

@@ -480,8 +480,13 @@ constexpr uint32_t kInfoDepthMask = 31u;      // slotInfo bits 0..4: depth insid
 constexpr uint32_t kInfoParentShift = 5;      // bits 5..9: lane of the parent (depth > 0)
 constexpr uint32_t kInfoExternal = 1u << 10;  // parent lives outside the window (resolved by walk_up)
 constexpr uint32_t kInfoUnreachable = 1u << 11;  // node on / below a cycle closed inside its window
+constexpr uint32_t kInfoSchedShift = 12;      // bits 12..29: static schedule of the level loop, 6 bits per level 1..3:
+                                              //   bit 5 = this lane works in that level, bits 0..4 = lane of the child it
+                                              //   helps with (lanes 2j, 2j+1 take the j-th node of the level)
 constexpr uint32_t kWinSlow = 0x80000000u;    // window list entry: some lane is external / unreachable
-constexpr uint32_t kWinSlotMask = 0x7FFFFFFFu;
+constexpr uint32_t kWinNoStatic = 0x40000000u;  // window list entry: no static schedule (deeper than 3 levels, or a
+                                                // level with more nodes than half the window's lanes)
+constexpr uint32_t kWinSlotMask = 0x3FFFFFFFu;
 
 // first position in [from, from+kHalo) (and <= count) that no short link crosses; `from` itself when there is none
 // (forced cut through a chain longer than a window). sCross is indexed relative to `origin`.
@@ -501,7 +506,9 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
   __shared__ int sCross[kSpan + 8];              // sCross[c - origin]: number of short links crossing position c
   __shared__ uint16_t sStart[kMaxWin + 1];       // window starts relative to tileBase (<= kTile + kHalo)
   __shared__ uint16_t sWinOf[kTile + kHalo];     // window index of every owned slot (relative to tileBase)
-  __shared__ uint32_t sWinFlag[kMaxWin];
+  __shared__ uint32_t sWinFlag[kMaxWin];         // bit 0: generic path, bit 1: no static schedule
+  __shared__ uint32_t sLvl[kMaxWin][3];          // lanes of the window at depth 1, 2, 3
+  __shared__ uint32_t sInfo[kTile + kHalo];
   __shared__ uint32_t sWarpSum[kBlock / 32];
   __shared__ uint32_t sNumWin, sBeg, sEnd;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -510,7 +517,7 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
   const uint32_t spanEnd = min(count, tileBase + kTile + 2 * kHalo);  // slots [origin, spanEnd)
 
   for (uint32_t k = tid; k < kSpan + 8; k += kBlock) sCross[k] = 0;
-  for (uint32_t k = tid; k < kMaxWin; k += kBlock) sWinFlag[k] = 0;
+  for (uint32_t k = tid; k < kMaxWin; k += kBlock) { sWinFlag[k] = 0; sLvl[k][0] = sLvl[k][1] = sLvl[k][2] = 0; }
   __syncthreads();
   // a link between slots lo < hi shorter than a window crosses every cut position c with lo < c <= hi
   for (uint32_t k = origin + tid; k < spanEnd; k += kBlock)
@@ -607,12 +614,34 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
       cur = ps - tileBase;
       if (++depth > 32u) { info = kInfoUnreachable; depth = 0; break; }  // a cycle closed inside the window
     }
-    if (info & (kInfoExternal | kInfoUnreachable)) sWinFlag[w] = 1u;
-    slotInfo[tileBase + k] = info | (depth & kInfoDepthMask);
+    if (info & (kInfoExternal | kInfoUnreachable)) atomicOr(&sWinFlag[w], 1u);
+    if (depth > 3u) atomicOr(&sWinFlag[w], 2u);
+    else if (depth != 0u) atomicOr(&sLvl[w][depth - 1u], 1u << (k - wa));
+    sInfo[k] = info | (depth & kInfoDepthMask);
+  }
+  __syncthreads();
+  // static schedule of the level loop (used by k_update_win when every node of the window is recomputed): in
+  // level l, lanes 2j and 2j+1 of the window take the j-th node of that level
+  for (uint32_t k = (beg - tileBase) + tid; k < end - tileBase; k += kBlock)
+  {
+    const uint32_t w = sWinOf[k], wa = sStart[w], len = sStart[w + 1] - wa, h = k - wa;
+    uint32_t info = sInfo[k];
+#pragma unroll
+    for (uint32_t l = 0; l < 3u; ++l)
+    {
+      uint32_t m = sLvl[w][l];
+      const uint32_t cnt = __popc(m);
+      if (2u * cnt > len) { if (h == 0u) atomicOr(&sWinFlag[w], 2u); continue; }
+      const uint32_t j = h >> 1;
+      if (j >= cnt) continue;
+      for (uint32_t q = 0; q < j; ++q) m &= m - 1u;
+      info |= (32u | (uint32_t)(__ffs(m) - 1)) << (kInfoSchedShift + 6u * l);
+    }
+    slotInfo[tileBase + k] = info;
   }
   __syncthreads();
   for (uint32_t k = tid; k <= nw; k += kBlock)
-    winLocal[(size_t)blockIdx.x * (kMaxWin + 1) + k] = (uint16_t)(sStart[k] | ((k < nw && sWinFlag[k]) ? 0x8000u : 0u));
+    winLocal[(size_t)blockIdx.x * (kMaxWin + 1) + k] = (uint16_t)(sStart[k] | ((k < nw) ? (sWinFlag[k] & 3u) << 14 : 0u));
   if (tid == 0) tileWinCount[blockIdx.x] = nw;
 }
 
@@ -625,7 +654,7 @@ __global__ void __launch_bounds__(128) k_flatten_windows(const uint16_t* __restr
   for (uint32_t k = threadIdx.x; k < nw; k += 128)
   {
     const uint32_t e = winLocal[(size_t)tile * (kMaxWin + 1) + k];
-    winList[base + k] = (tile * kTile + (e & 0x7FFFu)) | ((e & 0x8000u) ? kWinSlow : 0u);
+    winList[base + k] = (tile * kTile + (e & 0x3FFFu)) | ((e & 0x4000u) ? kWinSlow : 0u) | ((e & 0x8000u) ? kWinNoStatic : 0u);
   }
   if (tile == numTiles - 1 && threadIdx.x == 0) winList[base + nw] = count;
 }
@@ -967,48 +996,78 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         ok = mat4_is_affine(W);
       }
       fast = __all_sync(0xffffffffu, ok);
-      // ---- 3. parent.world * local level by level, 16 children per round, one lane PAIR per child ----
+      // ---- 3. parent.world * local level by level, one lane PAIR per child ----
       if (fast && maxL != 0u && dirtyM != 0u)
       {
         const uint32_t own = laneBase + kWwMat;
         sts128(own, W.c0); sts128(own + 512, W.c1); sts128(own + 1024, W.c2); sts128(own + 1536, W.c3);
         __syncwarp();
-        for (uint32_t l = 1; l <= maxL; ++l)
+        // one product: this lane computes columns 2h, 2h+1 (h = lane & 1) of child = parent * child, in place
+        auto level_item = [&](uint32_t child, uint32_t par)
         {
-          const bool mine = nodeDirty && wl == l;
-          const uint32_t m = __ballot_sync(0xffffffffu, mine);
-          if (m == 0u) continue;
-          const uint32_t cnt = __popc(m);
-          if (mine) sts16(warpBase + kWwSched + __popc(m & ((1u << lane) - 1u)) * 2u, lane | (parentLane << 8));
-          __syncwarp();
-          for (uint32_t r = 0; r < cnt; r += 16u)
+          const uint32_t cAddr = warpBase + child * 16u + (lane & 1u) * 1024u;
+          const uint32_t pAddr = warpBase + par * 16u;
+          const float4 P0 = lds128(pAddr + kWwMat), P1 = lds128(pAddr + kWwMat + 512), P2 = lds128(pAddr + kWwMat + 1024);
+          const float4 La = lds128(cAddr + kWwMat), Lb = lds128(cAddr + kWwMat + 512);
+          float4 oa, ob;
+          oa.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, La.x), __fmul_rn(P1.x, La.y)), __fmul_rn(P2.x, La.z));
+          oa.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, La.x), __fmul_rn(P1.y, La.y)), __fmul_rn(P2.y, La.z));
+          oa.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, La.x), __fmul_rn(P1.z, La.y)), __fmul_rn(P2.z, La.z));
+          oa.w = La.w;
+          ob.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, Lb.x), __fmul_rn(P1.x, Lb.y)), __fmul_rn(P2.x, Lb.z));
+          ob.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, Lb.x), __fmul_rn(P1.y, Lb.y)), __fmul_rn(P2.y, Lb.z));
+          ob.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, Lb.x), __fmul_rn(P1.z, Lb.y)), __fmul_rn(P2.z, Lb.z));
+          ob.w = Lb.w;
+          if (lane & 1u)
           {
-            const uint32_t idx = r + (lane >> 1);
-            if (idx < cnt)
+            const float4 P3 = lds128(pAddr + kWwMat + 1536);  // column 3: + parent translation (p[r][3] * 1)
+            ob.x = __fadd_rn(ob.x, P3.x); ob.y = __fadd_rn(ob.y, P3.y); ob.z = __fadd_rn(ob.z, P3.z);
+          }
+          sts128(cAddr + kWwMat, oa);
+          sts128(cAddr + kWwMat + 512, ob);
+        };
+        if (dirtyM == liveMask && (lds32(winAddr) & kWinNoStatic) == 0u)
+        {
+          // every node is recomputed: who multiplies what is a function of the topology alone and was laid down by
+          // k_build_windows in the slotInfo words (6 bits per level)
+#pragma unroll
+          for (uint32_t l = 0; l < 3u; ++l)
+          {
+            if (l < maxL)
             {
-              const uint32_t e = lds16(warpBase + kWwSched + idx * 2u);
-              const uint32_t cAddr = warpBase + (e & 31u) * 16u + (lane & 1u) * 1024u;  // child's columns 2h, 2h+1
-              const uint32_t pAddr = warpBase + (e >> 8) * 16u;
-              const float4 P0 = lds128(pAddr + kWwMat), P1 = lds128(pAddr + kWwMat + 512), P2 = lds128(pAddr + kWwMat + 1024);
-              const float4 La = lds128(cAddr + kWwMat), Lb = lds128(cAddr + kWwMat + 512);
-              float4 oa, ob;
-              oa.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, La.x), __fmul_rn(P1.x, La.y)), __fmul_rn(P2.x, La.z));
-              oa.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, La.x), __fmul_rn(P1.y, La.y)), __fmul_rn(P2.y, La.z));
-              oa.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, La.x), __fmul_rn(P1.z, La.y)), __fmul_rn(P2.z, La.z));
-              oa.w = La.w;
-              ob.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, Lb.x), __fmul_rn(P1.x, Lb.y)), __fmul_rn(P2.x, Lb.z));
-              ob.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, Lb.x), __fmul_rn(P1.y, Lb.y)), __fmul_rn(P2.y, Lb.z));
-              ob.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, Lb.x), __fmul_rn(P1.z, Lb.y)), __fmul_rn(P2.z, Lb.z));
-              ob.w = Lb.w;
-              if (lane & 1u)
+              const uint32_t sch = info >> (kInfoSchedShift + 6u * l);
+              if (sch & 32u)
               {
-                const float4 P3 = lds128(pAddr + kWwMat + 1536);  // column 3: + parent translation (p[r][3] * 1)
-                ob.x = __fadd_rn(ob.x, P3.x); ob.y = __fadd_rn(ob.y, P3.y); ob.z = __fadd_rn(ob.z, P3.z);
+                const uint32_t child = sch & 31u;
+                const uint32_t pinfo = lds32(warpBase + bufOff + 2048 + child * 4u);
+                level_item(child, (pinfo >> kInfoParentShift) & 31u);
               }
-              sts128(cAddr + kWwMat, oa);
-              sts128(cAddr + kWwMat + 512, ob);
+              __syncwarp();
             }
+          }
+        }
+        else
+        {
+          // general case: the nodes of each level that are actually recomputed are compacted into a schedule at run
+          // time, 16 per round
+          for (uint32_t l = 1; l <= maxL; ++l)
+          {
+            const bool mine = nodeDirty && wl == l;
+            const uint32_t m = __ballot_sync(0xffffffffu, mine);
+            if (m == 0u) continue;
+            const uint32_t cnt = __popc(m);
+            if (mine) sts16(warpBase + kWwSched + __popc(m & ((1u << lane) - 1u)) * 2u, lane | (parentLane << 8));
             __syncwarp();
+            for (uint32_t r = 0; r < cnt; r += 16u)
+            {
+              const uint32_t idx = r + (lane >> 1);
+              if (idx < cnt)
+              {
+                const uint32_t e = lds16(warpBase + kWwSched + idx * 2u);
+                level_item(e & 31u, e >> 8);
+              }
+              __syncwarp();
+            }
           }
         }
         W.c0 = lds128(own); W.c1 = lds128(own + 512); W.c2 = lds128(own + 1024); W.c3 = lds128(own + 1536);
