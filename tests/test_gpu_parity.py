@@ -244,3 +244,78 @@ def test_frustum_boundary_shell(hier):
     tot = sum(len(v) for v in port.visible)
     assert 0 < tot < 5 * n, "the shell must straddle the planes"
     g.close()
+
+
+@pytest.mark.parametrize("n,seed", [(60_000, 21)])
+def test_streaming_churn_matches_oracle(n, seed):
+    """BASELINE.json configs[4] in miniature: per frame 10 % of the instances despawn (any node of a group, so
+    children lose their parents and parents their children), 10 % new groups spawn, 30 % get a new local TRS.
+    After every frame: pool order, ordered visible lists and all world matrices against the oracle. Exercises
+    the window builder on topologies that swap-remove has shuffled (long links, windows flagged for the generic
+    path, partially dirty windows -> run-time level schedule)."""
+    rng = np.random.default_rng(seed)
+    sc = scenes.city_hier(n, seed=seed)
+    p = PortScene()
+    g = GpuAdapter(2 * n, max_views=5, max_entity_index=4 * n)
+    vps = scenes.standard_views(5)
+    e = np.arange(n, dtype=np.uint32)
+    par = scenes.parent_handles(sc["parent"], e)
+    for s in (g, p):
+        s.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+        s.update(vps)
+    compare_frame(g, p, e, 5, "churn frame 0")
+    alive = e.copy()
+    next_id = n
+    for frame in range(1, 6):
+        dead = rng.choice(alive, len(alive) // 10, replace=False)
+        alive = np.setdiff1d(alive, dead)
+        m = n // 10
+        fresh = scenes.city_hier(m, seed=seed + 100 * frame)
+        fe = np.arange(next_id, next_id + m, dtype=np.uint32)
+        next_id += m
+        fpar = scenes.parent_handles(fresh["parent"], fe)
+        moved = rng.choice(alive, (3 * len(alive)) // 10, replace=False)
+        trs = random_trs(rng, len(moved), spread=400.0)
+        for s in (g, p):
+            s.despawn(dead)
+            s.spawn(fe, fresh["trs9"], fpar, fresh["aabb6"], fresh["mesh_mat"], fresh["flags"])
+            s.set_local(moved, trs)
+            s.update(vps)
+        alive = np.concatenate([alive, fe])
+        assert np.array_equal(g.dense_entities(), p.entity), f"pool order differs in frame {frame}"
+        compare_frame(g, p, alive, 5, f"churn frame {frame}")
+        assert g.recomputed == p.recomputed, (frame, g.recomputed, p.recomputed)
+    compare_draws(g, p, 0, "churn draws")
+    g.close()
+
+
+@pytest.mark.parametrize("max_back,p_child,seed", [(6, 0.9, 31), (12, 0.8, 32), (200, 0.7, 33), (3, 0.97, 34)])
+def test_random_forest_large(max_back, p_child, seed):
+    """40k-node random forests: dense short links (no uncrossed cut position for long stretches -> forced cuts,
+    parents outside the window), long links, chains deeper than a window, levels wider than 16 children. Two frames:
+    everything dirty, then 20 % dirty (children inherit)."""
+    rng = np.random.default_rng(seed)
+    n = 40_000
+    e = np.arange(n, dtype=np.uint32)
+    parent_idx = random_forest(rng, n, p_child=p_child, max_back=max_back)
+    trs = random_trs(rng, n, spread=300.0)
+    trs[:, 6:9] = rng.uniform(0.7, 1.3, size=(n, 3)).astype(np.float32)  # keep deep chains finite
+    par = scenes.parent_handles(parent_idx, e)
+    aabb = random_aabb(rng, n)
+    p = PortScene()
+    g = GpuAdapter(n, max_views=3)
+    vps = scenes.standard_views(3, center=(0.0, 10.0, 80.0))
+    for s in (g, p):
+        s.spawn(e, trs, par, aabb, None, None)
+        s.update(vps)
+    compare_frame(g, p, e, 3, f"forest max_back={max_back} frame 0")
+    assert g.recomputed == p.recomputed == n
+    idx = rng.choice(n, n // 5, replace=False)
+    t2 = random_trs(rng, len(idx), spread=300.0)
+    t2[:, 6:9] = rng.uniform(0.7, 1.3, size=(len(idx), 3)).astype(np.float32)
+    for s in (g, p):
+        s.set_local(e[idx], t2)
+        s.update(vps)
+    compare_frame(g, p, e, 3, f"forest max_back={max_back} frame 1")
+    assert g.recomputed == p.recomputed
+    g.close()
