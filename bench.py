@@ -91,7 +91,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.001)  # the timed region lasts ~10 ms: sample as fast as NVML answers
 
     def stop(self):
         self._halt.set()

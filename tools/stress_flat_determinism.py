@@ -1,3 +1,4 @@
+"""Stress test used to find the cross-proxy WAR race of the TMA-staged flat kernel: repeats spawn -> update -> read back of a 1M-instance flat city and reports any frame-to-frame difference (python tools/stress_flat_determinism.py 100)."""
 import sys, numpy as np
 sys.path.insert(0,'sc-gameengine_b200'); sys.path.insert(0,'tests')
 import scgpu
