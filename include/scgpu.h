@@ -148,6 +148,30 @@ SCGPU_API void* scgpuGetStream(ScGpuScene* ctx);
 SCGPU_API int scgpuBuildDrawItemsDevice(ScGpuScene* ctx, uint32_t view, uint32_t maxDraws,
                                         const ScGpuDrawItem** outDevice, uint32_t* outEmitted, uint32_t* outDropped);
 
+/* ---- what the renderer does with RenderFrameData::draws, on the device ---------------------
+ * Replaces, for one view, the per-frame CPU work of src/engine/src/sc_vk.cpp:1843-1905: drop draws with an
+ * out-of-range meshId or an unknown material (:1847-1850), sort by (pipelineId of the material, materialId, meshId)
+ * (:1854-1864), and derive the bind-on-change batches of the submission loop (:1866-1905) as RUNS of consecutive
+ * sorted items that share pipeline, material and mesh. std::sort is not stable; this sort is (ties keep
+ * CullingState::visible order), i.e. it yields one of the orders the reference may produce. */
+typedef struct ScGpuDrawRun
+{
+  uint32_t pipelineId; /* sc::PipelineId of the material (src/engine/include/sc_assets.h) */
+  uint32_t materialId;
+  uint32_t meshId;
+  uint32_t first;      /* index of the run's first item in the sorted DrawItem array */
+  uint32_t count;      /* instances in the run */
+} ScGpuDrawRun;
+/* materialPipeline[m] = pipeline id (< 63) of material handle m, or 0xFFFFFFFF when AssetManager::getMaterial(m)
+ * would return null; nMaterials, meshCount <= 2^29. maxDraws as in scgpuReadDrawItems (applied BEFORE the filter,
+ * like RenderPrepStreamingSystem applies its budget before the renderer filters). Results stay valid until the next
+ * scgpuUpdate; the device pointers are context-owned. */
+SCGPU_API int scgpuBuildSortedDraws(ScGpuScene* ctx, uint32_t view, uint32_t maxDraws, const uint32_t* materialPipeline,
+                                    uint32_t nMaterials, uint32_t meshCount, const ScGpuDrawItem** outDevice,
+                                    uint32_t* outKept, const ScGpuDrawRun** outRunsDevice, uint32_t* outRuns);
+SCGPU_API int scgpuReadSortedDraws(ScGpuScene* ctx, ScGpuDrawItem* outItems, uint32_t cap, ScGpuDrawRun* outRuns,
+                                   uint32_t runCap);
+
 /* ---- multi-GPU: one context per process per GPU, instance set sharded by world cell ------------------------
  * The only exchange is the gather of the compacted per-view lists and counts to the submitting rank. */
 #define SCGPU_COMM_ID_BYTES 128

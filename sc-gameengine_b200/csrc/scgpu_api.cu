@@ -5,6 +5,7 @@
 // reference's swap-with-last order exactly, plus device buffer bookkeeping. All arithmetic runs on the GPU.
 #include "../../include/scgpu.h"
 #include "scgpu_kernels.cuh"
+#include "scgpu_draws.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -127,6 +128,13 @@ struct ScGpuScene
   DeviceBuffer staging;   // uploads
   DeviceBuffer scratch;   // read-back gathers / draw items
   DeviceBuffer drawItems;
+  DeviceBuffer sortWork;     // sorted draws: keys / positions / flags / scan / cub temp
+  DeviceBuffer sortedDraws;  // ScGpuDrawItem[kept] in (pipeline, material, mesh) order
+  DeviceBuffer drawRuns;     // ScGpuDrawRun[runs]
+  DeviceBuffer matPipe;      // material -> pipeline table of the last scgpuBuildSortedDraws
+  uint32_t* dSortCounters = nullptr;  // kept, nRuns
+  uint32_t hSortCounters[2] = {0, 0};
+  bool sortedValid = false;
 
   std::vector<uint32_t> hEntity;  // dense handles (ComponentPool::m_denseEntities)
   std::vector<uint32_t> hSparse;  // index -> slot+1 (ComponentPool::m_sparse)
@@ -256,6 +264,7 @@ void freeAll(ScGpuScene* c)
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
   }
   cudaFree(c->staging.ptr); cudaFree(c->scratch.ptr); cudaFree(c->drawItems.ptr);
+  cudaFree(c->sortWork.ptr); cudaFree(c->sortedDraws.ptr); cudaFree(c->drawRuns.ptr); cudaFree(c->matPipe.ptr); cudaFree(c->dSortCounters);
   cudaFree(c->dAllCounts);
   if (c->hTotals) cudaFreeHost(c->hTotals);
   if (c->hAllCounts) cudaFreeHost(c->hAllCounts);
@@ -755,6 +764,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
   c->forceAllDirty = false;
   c->updatedOnce = true;
   c->gatheredValid = false;
+  c->sortedValid = false;
   ++c->frame;
   if (stampOf(c->frame) == 0u) ++c->frame;  // stamp 0 is reserved for "never dirty"
   return 1;
@@ -877,6 +887,101 @@ int scgpuReadDrawItems(ScGpuScene* c, uint32_t view, uint32_t maxDraws, ScGpuDra
     SC_CUDA(c, cudaMemcpyAsync(out, d, (size_t)m * sizeof(ScGpuDrawItem), cudaMemcpyDeviceToHost, c->stream));
     SC_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  return 1;
+}
+
+// ---- sorted draws + instanced runs (sc_vk.cpp:1843-1905 on the device) ----------------------
+int scgpuBuildSortedDraws(ScGpuScene* c, uint32_t view, uint32_t maxDraws, const uint32_t* materialPipeline, uint32_t nMaterials,
+                          uint32_t meshCount, const ScGpuDrawItem** outDevice, uint32_t* outKept,
+                          const ScGpuDrawRun** outRunsDevice, uint32_t* outRuns)
+{
+  static_assert(sizeof(ScGpuDrawRun) == sizeof(DrawRun), "ScGpuDrawRun layout");
+  if (!enter(c)) return 0;
+  if (view >= c->nViews) return (int)fail(c, "scgpuBuildSortedDraws: view %u >= %u", view, c->nViews);
+  if (nMaterials && !materialPipeline) return (int)fail(c, "scgpuBuildSortedDraws: materialPipeline is NULL");
+  if (nMaterials > (1u << kDrawIdBits) || meshCount > (1u << kDrawIdBits))
+    return (int)fail(c, "scgpuBuildSortedDraws: more than 2^%u materials or meshes", kDrawIdBits);
+  if (!waitDone(c)) return 0;
+  c->sortedValid = false;
+  const uint32_t vis = c->hTotals[view];
+  const uint32_t emitted = (maxDraws > 0 && vis > maxDraws) ? maxDraws : vis;  // RenderPrepStreamingSystem's budget first
+  if (!c->dSortCounters && !devAlloc(c, &c->dSortCounters, 2, true)) return 0;
+  SC_CUDA(c, cudaMemsetAsync(c->dSortCounters, 0, 8, c->stream));
+  c->hSortCounters[0] = c->hSortCounters[1] = 0;
+  if (emitted)
+  {
+    // pipeline ids are < 63 by contract; find how many key bits are in use so the radix sort skips the rest
+    uint32_t maxPipe = 0;
+    for (uint32_t m = 0; m < nMaterials; ++m)
+    {
+      const uint32_t pid = materialPipeline[m];
+      if (pid == 0xFFFFFFFFu) continue;
+      if (pid >= 63u) return (int)fail(c, "scgpuBuildSortedDraws: pipeline id %u of material %u is >= 63", pid, m);
+      maxPipe = std::max(maxPipe, pid);
+    }
+    if (!ensure(c, c->matPipe, std::max<size_t>((size_t)nMaterials * 4, 4))) return 0;
+    if (nMaterials) SC_CUDA(c, cudaMemcpyAsync(c->matPipe.ptr, materialPipeline, (size_t)nMaterials * 4, cudaMemcpyHostToDevice, c->stream));
+    size_t tempSort = 0, tempScan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tempSort, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)emitted, 0, 64, c->stream);
+    cub::DeviceScan::InclusiveSum(nullptr, tempScan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)emitted, c->stream);
+    const size_t e8 = ((size_t)emitted * 8 + 255) & ~(size_t)255, e4 = ((size_t)emitted * 4 + 255) & ~(size_t)255;
+    const size_t temp = (std::max(tempSort, tempScan) + 255) & ~(size_t)255;
+    if (!ensure(c, c->sortWork, 2 * e8 + 4 * e4 + temp)) return 0;
+    char* w = (char*)c->sortWork.ptr;
+    uint64_t* keysIn = (uint64_t*)w; uint64_t* keysOut = (uint64_t*)(w + e8);
+    uint32_t* posIn = (uint32_t*)(w + 2 * e8); uint32_t* posOut = (uint32_t*)(w + 2 * e8 + e4);
+    uint32_t* flags = (uint32_t*)(w + 2 * e8 + 2 * e4); uint32_t* runIncl = (uint32_t*)(w + 2 * e8 + 3 * e4);
+    void* dTemp = w + 2 * e8 + 4 * e4;
+    if (!ensure(c, c->sortedDraws, (size_t)emitted * sizeof(ScGpuDrawItem))) return 0;
+    if (!ensure(c, c->drawRuns, (size_t)emitted * sizeof(ScGpuDrawRun))) return 0;
+    k_draw_keys<<<blocksFor(emitted), kBlock, 0, c->stream>>>(c->visSlot[view], c->a.meshMat, (const uint32_t*)c->matPipe.ptr,
+                                                                nMaterials, meshCount, emitted, keysIn, posIn, c->dSortCounters);
+    // key bits in use: mesh [0,29), material [29,58), pipeline [58, 58+bits(maxPipe)); the all-ones invalid key needs
+    // the full width only when it can occur, i.e. always be safe and sort up to bit 64 if any draw was dropped: the
+    // dropped draws are not known on the host yet, so the top bits are always included (2 extra passes at most).
+    int bitsMesh = 1, bitsMat = 1;
+    while (bitsMesh < (int)kDrawIdBits && (meshCount >> bitsMesh)) ++bitsMesh;
+    while (bitsMat < (int)kDrawIdBits && (nMaterials >> bitsMat)) ++bitsMat;
+    (void)maxPipe;
+    size_t tb = temp;
+    // pass 1: mesh bits, pass 2: material bits, pass 3: pipeline + invalid marker bits (stable LSD passes compose)
+    cub::DeviceRadixSort::SortPairs(dTemp, tb, keysIn, keysOut, posIn, posOut, (int)emitted, 0, bitsMesh, c->stream);
+    tb = temp;
+    cub::DeviceRadixSort::SortPairs(dTemp, tb, keysOut, keysIn, posOut, posIn, (int)emitted, (int)kDrawIdBits,
+                                    (int)kDrawIdBits + bitsMat, c->stream);
+    tb = temp;
+    cub::DeviceRadixSort::SortPairs(dTemp, tb, keysIn, keysOut, posIn, posOut, (int)emitted, 2 * (int)kDrawIdBits, 64, c->stream);
+    k_draw_run_flags<<<blocksFor(emitted), kBlock, 0, c->stream>>>(keysOut, c->dSortCounters, emitted, flags);
+    tb = temp;
+    cub::DeviceScan::InclusiveSum(dTemp, tb, flags, runIncl, (int)emitted, c->stream);
+    k_draw_runs<<<blocksFor(emitted), kBlock, 0, c->stream>>>(keysOut, runIncl, c->dSortCounters, (DrawRun*)c->drawRuns.ptr,
+                                                                c->dSortCounters + 1);
+    k_draw_run_counts<<<blocksFor(emitted), kBlock, 0, c->stream>>>((DrawRun*)c->drawRuns.ptr, c->dSortCounters + 1);
+    k_gather_sorted_draws<<<blocksFor((uint64_t)emitted * 5ull), kBlock, 0, c->stream>>>(
+      c->visSlot[view], posOut, c->dSortCounters, c->a.entity, c->a.meshMat, c->a.world[0], c->a.world[1], c->a.world[2],
+      c->a.world[3], (float4*)c->sortedDraws.ptr);
+    c->launches += 5;
+    SC_CUDA(c, cudaGetLastError());
+    SC_CUDA(c, cudaMemcpyAsync(c->hSortCounters, c->dSortCounters, 8, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->sortedValid = true;
+  if (outDevice) *outDevice = (const ScGpuDrawItem*)c->sortedDraws.ptr;
+  if (outKept) *outKept = c->hSortCounters[0];
+  if (outRunsDevice) *outRunsDevice = (const ScGpuDrawRun*)c->drawRuns.ptr;
+  if (outRuns) *outRuns = c->hSortCounters[1];
+  return 1;
+}
+
+int scgpuReadSortedDraws(ScGpuScene* c, ScGpuDrawItem* outItems, uint32_t cap, ScGpuDrawRun* outRuns, uint32_t runCap)
+{
+  if (!enter(c)) return 0;
+  if (!c->sortedValid) return (int)fail(c, "scgpuReadSortedDraws: no scgpuBuildSortedDraws since the last update");
+  const uint32_t n = std::min(cap, c->hSortCounters[0]), r = std::min(runCap, c->hSortCounters[1]);
+  if (n && outItems) SC_CUDA(c, cudaMemcpyAsync(outItems, c->sortedDraws.ptr, (size_t)n * sizeof(ScGpuDrawItem), cudaMemcpyDeviceToHost, c->stream));
+  if (r && outRuns) SC_CUDA(c, cudaMemcpyAsync(outRuns, c->drawRuns.ptr, (size_t)r * sizeof(ScGpuDrawRun), cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
   return 1;
 }
 

@@ -65,6 +65,8 @@ DRAW_ITEM_DTYPE = np.dtype(
     [("entity", "<u4"), ("meshId", "<u4"), ("materialId", "<u4"), ("_pad", "<u4"), ("model", "<f4", (16,))]
 )
 assert DRAW_ITEM_DTYPE.itemsize == 80
+DRAW_RUN_DTYPE = np.dtype([("pipelineId", "<u4"), ("materialId", "<u4"), ("meshId", "<u4"), ("first", "<u4"), ("count", "<u4")])
+assert DRAW_RUN_DTYPE.itemsize == 20
 
 _lib = None
 
@@ -99,6 +101,9 @@ SYMBOLS = {
     "scgpuGetDeviceViews": (C.c_int, [_vp, C.POINTER(DeviceViews)]),
     "scgpuGetStream": (_vp, [_vp]),
     "scgpuBuildDrawItemsDevice": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(_vp), _u32p, _u32p]),
+    "scgpuBuildSortedDraws": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp), _u32p,
+                                        C.POINTER(_vp), _u32p]),
+    "scgpuReadSortedDraws": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint32]),
     "scgpuCommGetUniqueId": (C.c_int, [_vp]),
     "scgpuCommInit": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "scgpuGatherVisible": (C.c_int, [_vp, C.c_uint32]),
@@ -267,6 +272,17 @@ class Scene:
         self._ck(self.lib.scgpuReadDrawItems(self.ctx, view, max_draws, _ptr(out), out.shape[0], C.byref(e), C.byref(d)),
                  "scgpuReadDrawItems")
         return out, e.value, d.value
+
+    def sorted_draws(self, view, material_pipeline, mesh_count, max_draws=0):
+        """(items sorted by (pipeline, material, mesh), runs) for one view"""
+        mp = _arr(material_pipeline, np.uint32)
+        kept, runs = C.c_uint32(0), C.c_uint32(0)
+        self._ck(self.lib.scgpuBuildSortedDraws(self.ctx, view, max_draws, _ptr(mp), mp.shape[0], mesh_count, None,
+                                                C.byref(kept), None, C.byref(runs)), "scgpuBuildSortedDraws")
+        items = np.zeros(kept.value, DRAW_ITEM_DTYPE)
+        r = np.zeros(runs.value, DRAW_RUN_DTYPE)
+        self._ck(self.lib.scgpuReadSortedDraws(self.ctx, _ptr(items), items.shape[0], _ptr(r), r.shape[0]), "scgpuReadSortedDraws")
+        return items, r
 
     def read_world(self, entity):
         e = _arr(entity, np.uint32)

@@ -353,3 +353,31 @@ class RefScene:
         out = np.zeros(24, np.float32)
         self.L.screfGetPlanes(self.w, _p(out))
         return out.reshape(6, 4)
+
+
+# ---- the renderer's per-frame CPU sort of the draws, restated (test infrastructure) ------------
+
+def renderer_sorted_draws(draws, material_pipeline, mesh_count):
+    """What src/engine/src/sc_vk.cpp:1843-1905 does with RenderFrameData::draws, in numpy:
+       :1847-1850  skip draws with meshId >= m_meshes.size() or without a material,
+       :1854-1864  sort by (material->pipelineId, materialId, meshId) — std::sort there (unstable); stable here, which
+                   is one of the orders std::sort may produce,
+       :1866-1905  bind pipeline / material / mesh on change: the maximal runs of equal (pipeline, material, mesh).
+    draws: structured array with meshId / materialId (scgpu.DRAW_ITEM_DTYPE layout or the oracle's dict form).
+    Returns (order: indices into draws, runs: list of (pipeline, material, mesh, first, count))."""
+    mesh = np.asarray(draws["meshId"], np.int64)
+    mat = np.asarray(draws["materialId"], np.int64)
+    mp = np.asarray(material_pipeline, np.int64)
+    known = mat < len(mp)
+    pipe = np.where(known, mp[np.minimum(mat, max(len(mp) - 1, 0))] if len(mp) else 0xFFFFFFFF, 0xFFFFFFFF)
+    keep = (mesh < mesh_count) & known & (pipe != 0xFFFFFFFF)
+    idx = np.nonzero(keep)[0]
+    order = idx[np.lexsort((mesh[idx], mat[idx], pipe[idx]))]  # lexsort: last key is primary; stable
+    runs = []
+    for pos, i in enumerate(order):
+        k = (int(pipe[i]), int(mat[i]), int(mesh[i]))
+        if runs and tuple(runs[-1][:3]) == k:
+            runs[-1][4] += 1
+        else:
+            runs.append([k[0], k[1], k[2], pos, 1])
+    return order, [tuple(r) for r in runs]

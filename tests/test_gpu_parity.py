@@ -319,3 +319,36 @@ def test_random_forest_large(max_back, p_child, seed):
     compare_frame(g, p, e, 3, f"forest max_back={max_back} frame 1")
     assert g.recomputed == p.recomputed
     g.close()
+
+
+@pytest.mark.parametrize("max_draws", [0, 700])
+def test_sorted_draws_and_runs_match_renderer_sort(max_draws):
+    """scgpuBuildSortedDraws against the restated renderer loop (sc_vk.cpp:1843-1905): same kept
+    set, same (pipeline, material, mesh) order, same runs; ties in visible order; models bit-identical."""
+    from oracle_bind import renderer_sorted_draws
+    rng = np.random.default_rng(77)
+    n = 30_000
+    sc = scenes.city_flat(n, seed=9)
+    mm = np.stack([rng.integers(0, 12, n), rng.integers(0, 40, n)], axis=1).astype(np.uint32)  # meshId, materialId
+    e = np.arange(n, dtype=np.uint32)
+    g = GpuAdapter(n, max_views=2)
+    vps = scenes.standard_views(2)
+    g.spawn(e, sc["trs9"], None, sc["aabb6"], mm, sc["flags"])
+    g.update(vps, freeze=True)  # every candidate visible: a long draw list
+    mesh_count = 10                                   # meshIds 10, 11 are out of range -> dropped
+    mat_pipe = rng.integers(0, 2, 37).astype(np.uint32)  # materials 37..39 unknown (beyond the table)
+    mat_pipe[[3, 17]] = 0xFFFFFFFF                    # getMaterial() == nullptr
+    draws, emitted, dropped = g.read_draw_items(0, max_draws)
+    order, runs = renderer_sorted_draws(draws, mat_pipe, mesh_count)
+    items, gruns = g.s.sorted_draws(0, mat_pipe, mesh_count, max_draws)
+    assert len(items) == len(order) and len(order) < emitted
+    want = draws[order]
+    for f in ("entity", "meshId", "materialId"):
+        assert np.array_equal(items[f], want[f]), f
+    assert_same_bits(items["model"], want["model"], "sorted draw models")
+    assert [tuple(int(x) for x in r) for r in gruns] == runs
+    assert sum(r[4] for r in runs) == len(items)
+    # an empty table drops everything
+    items0, runs0 = g.s.sorted_draws(0, np.zeros(0, np.uint32), mesh_count, max_draws)
+    assert len(items0) == 0 and len(runs0) == 0
+    g.close()
