@@ -218,7 +218,9 @@ def workload_config(args, n_per_gpu, sample=False):
         "workload": "synthetic city, depth-4 groups (vehicles+wheels, peds+attachments), main view + 4 shadow "
                     "cascades, all instances dirty every step (BASELINE.json configs[2]; x8 GPUs = configs[3])",
         "instances_per_gpu": int(n_per_gpu), "views": args.views, "dirty_fraction": 1.0,
-        "sharding": "world cell blocks, one process per GPU" if args.gpus > 1 else "single GPU",
+        "sharding": ("world cell blocks, one process per GPU; visible lists gathered to rank 0 through "
+                     + ("NVLink peer memory" if os.environ.get("SCGPU_GATHER", "peer") == "peer" else "NCCL send/recv"))
+        if args.gpus > 1 else "single GPU",
         "l2": "inputs (>= 2 GB per step) exceed the 126 MB L2; no explicit flush" if not sample else "cpu sample",
     }
 
@@ -275,6 +277,8 @@ def main():
         uid = [scgpu.Scene.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         scene.comm_init(world, rank, uid[0])
+        if os.environ.get("SCGPU_GATHER", "peer") == "peer":  # lists travel through NVLink peer memory, not NCCL
+            scene.enable_peer_gather(0)
 
     stream = torch.cuda.ExternalStream(scene.stream, device=torch.device("cuda", local_rank))
 

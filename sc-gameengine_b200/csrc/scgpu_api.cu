@@ -6,6 +6,7 @@
 #include "../../include/scgpu.h"
 #include "scgpu_kernels.cuh"
 #include "scgpu_draws.cuh"
+#include "scgpu_peer.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -44,6 +45,7 @@ struct NcclApi
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
@@ -67,6 +69,7 @@ bool loadNccl(std::string& err)
   SC_SYM(CommInitRank, "ncclCommInitRank")
   SC_SYM(CommDestroy, "ncclCommDestroy")
   SC_SYM(AllGather, "ncclAllGather")
+  SC_SYM(Broadcast, "ncclBroadcast")
   SC_SYM(Send, "ncclSend")
   SC_SYM(Recv, "ncclRecv")
   SC_SYM(GroupStart, "ncclGroupStart")
@@ -149,6 +152,13 @@ struct ScGpuScene
   uint32_t* dAllCounts = nullptr;   // [nRanks][maxViews+1]
   uint32_t* hAllCounts = nullptr;   // pinned
   uint32_t* gathered[kMaxViews] = {};
+  // peer-memory gather (scgpu_peer.cuh)
+  PeerBox peerBox{};            // mailbox in the peer root's memory
+  bool peerEnabled = false;
+  bool peerMapped = false;      // base is a cudaIpc mapping (not the root)
+  uint32_t peerRoot = 0, peerSeq = 0;
+  uint32_t* dPeerState = nullptr;  // [0] ticket counter, [1] error word
+  bool lastGatherPeer = false;
   size_t gatheredCap = 0;
   bool gatheredValid = false;
 };
@@ -266,6 +276,8 @@ void freeAll(ScGpuScene* c)
   cudaFree(c->staging.ptr); cudaFree(c->scratch.ptr); cudaFree(c->drawItems.ptr);
   cudaFree(c->sortWork.ptr); cudaFree(c->sortedDraws.ptr); cudaFree(c->drawRuns.ptr); cudaFree(c->matPipe.ptr); cudaFree(c->dSortCounters);
   cudaFree(c->dAllCounts);
+  if (c->peerBox.base) { if (c->peerMapped) cudaIpcCloseMemHandle(c->peerBox.base); else cudaFree(c->peerBox.base); }
+  cudaFree(c->dPeerState);
   if (c->hTotals) cudaFreeHost(c->hTotals);
   if (c->hAllCounts) cudaFreeHost(c->hAllCounts);
   if (c->evDone) cudaEventDestroy(c->evDone);
@@ -1084,6 +1096,44 @@ int scgpuCommInit(ScGpuScene* c, uint32_t nRanks, uint32_t rank, const void* id1
   return 1;
 }
 
+int scgpuCommEnablePeerGather(ScGpuScene* c, uint32_t root, uint32_t capEntries)
+{
+  if (!enter(c)) return 0;
+  if (!c->comm) return (int)fail(c, "scgpuCommEnablePeerGather: scgpuCommInit was not called");
+  if (root >= c->nRanks) return (int)fail(c, "scgpuCommEnablePeerGather: root %u >= %u ranks", root, c->nRanks);
+  if (c->peerEnabled) return (int)fail(c, "scgpuCommEnablePeerGather: already enabled (root %u)", c->peerRoot);
+  if (capEntries == 0) capEntries = std::min<uint64_t>((uint64_t)c->capacityPad * c->maxViews, 4u << 20);
+  if (!c->dPeerState && !devAlloc(c, &c->dPeerState, 2, true)) return 0;
+  // the root allocates the mailbox and publishes its IPC handle through NCCL (the bootstrap channel we have)
+  cudaIpcMemHandle_t handle{};
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  const size_t bytes = PeerBox::bytes(c->nRanks, capEntries);
+  void* local = nullptr;
+  if (c->rank == root)
+  {
+    SC_CUDA(c, cudaMalloc(&local, bytes));
+    SC_CUDA(c, cudaMemsetAsync(local, 0, bytes, c->stream));
+    SC_CUDA(c, cudaIpcGetMemHandle(&handle, local));
+  }
+  if (!ensure(c, c->scratch, 256)) return 0;
+  if (c->rank == root) SC_CUDA(c, cudaMemcpyAsync(c->scratch.ptr, &handle, 64, cudaMemcpyHostToDevice, c->stream));
+  SC_NCCL(c, g_nccl.Broadcast(c->scratch.ptr, c->scratch.ptr, 16, ncclUint32, (int)root, c->comm, c->stream));
+  SC_CUDA(c, cudaMemcpyAsync(&handle, c->scratch.ptr, 64, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->rank != root)
+  {
+    SC_CUDA(c, cudaIpcOpenMemHandle(&local, handle, cudaIpcMemLazyEnablePeerAccess));
+    c->peerMapped = true;
+  }
+  c->peerBox.base = (uint32_t*)local;
+  c->peerBox.nRanks = c->nRanks;
+  c->peerBox.cap = capEntries;
+  c->peerRoot = root;
+  c->peerSeq = 0;
+  c->peerEnabled = true;
+  return 1;
+}
+
 int scgpuGatherVisible(ScGpuScene* c, uint32_t root)
 {
   if (!enter(c)) return 0;
@@ -1091,6 +1141,32 @@ int scgpuGatherVisible(ScGpuScene* c, uint32_t root)
   if (root >= c->nRanks) return (int)fail(c, "scgpuGatherVisible: root %u >= %u ranks", root, c->nRanks);
   if (!c->updatedOnce) return (int)fail(c, "scgpuGatherVisible: no update issued");
   const size_t row = kMaxViews + 2;
+  if (c->peerEnabled && root == c->peerRoot)
+  {
+    // peer-memory path: pack straight into the root's mailbox over NVLink, flag, root waits on the device
+    PeerPackParams q{};
+    q.box = c->peerBox;
+    q.totals = c->totals;
+    for (uint32_t v = 0; v < kMaxViews; ++v) q.visEntity[v] = c->visEntity[v];
+    q.done = c->dPeerState;
+    q.error = c->dPeerState + 1;
+    q.seq = ++c->peerSeq;
+    q.rank = c->rank;
+    q.nViews = c->nViews;
+    q.isRoot = (c->rank == root) ? 1u : 0u;
+    k_peer_pack<<<32, kBlock, 0, c->stream>>>(q);
+    ++c->launches;
+    if (c->rank == root)
+    {
+      k_peer_wait<<<1, 64, 0, c->stream>>>(c->peerBox, q.seq, c->dAllCounts, c->dPeerState + 1);
+      ++c->launches;
+    }
+    SC_CUDA(c, cudaGetLastError());
+    c->gatheredValid = true;
+    c->lastGatherPeer = true;
+    return 1;
+  }
+  c->lastGatherPeer = false;
   // 1) counts of every rank to every rank (V*4 bytes each; one small allgather)
   SC_NCCL(c, g_nccl.AllGather(c->totals, c->dAllCounts, row, ncclUint32, c->comm, c->stream));
   ++c->launches;
@@ -1149,10 +1225,24 @@ int scgpuGatherVisible(ScGpuScene* c, uint32_t root)
   return 1;
 }
 
+// peer mode: the counts rows and the error word live on the device until somebody asks
+static int peerFetchCounts(ScGpuScene* c)
+{
+  if (c->rank != c->peerRoot) return (int)fail(c, "peer gather: counts and lists exist on the root (rank %u) only", c->peerRoot);
+  uint32_t err = 0;
+  SC_CUDA(c, cudaMemcpyAsync(c->hAllCounts, c->dAllCounts, (size_t)c->nRanks * (kMaxViews + 2) * 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaMemcpyAsync(&err, c->dPeerState + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (err & 2u) return (int)fail(c, "peer gather: a rank did not deliver within the time limit");
+  if (err & 4u) return (int)fail(c, "peer gather: a rank's visible lists exceed the mailbox capacity (scgpuCommEnablePeerGather capEntries)");
+  return 1;
+}
+
 int scgpuGetGatheredCounts(ScGpuScene* c, uint32_t* outCounts, uint32_t capRanks)
 {
   if (!enter(c)) return 0;
   if (!c->gatheredValid || !outCounts) return (int)fail(c, "scgpuGetGatheredCounts: no gather since the last update");
+  if (c->lastGatherPeer && !peerFetchCounts(c)) return 0;
   const size_t row = kMaxViews + 2;
   for (uint32_t r = 0; r < c->nRanks && r < capRanks; ++r)
     for (uint32_t v = 0; v < c->nViews; ++v) outCounts[r * c->nViews + v] = c->hAllCounts[r * row + v];
@@ -1165,6 +1255,25 @@ int scgpuReadGatheredVisible(ScGpuScene* c, uint32_t view, uint32_t* outEntity, 
   if (!c->gatheredValid) return (int)fail(c, "scgpuReadGatheredVisible: no gather since the last update");
   if (view >= c->nViews) return (int)fail(c, "scgpuReadGatheredVisible: bad view");
   const size_t row = kMaxViews + 2;
+  if (c->lastGatherPeer)
+  {
+    if (!peerFetchCounts(c)) return 0;
+    size_t total = 0, done = 0;
+    for (uint32_t r = 0; r < c->nRanks; ++r) total += c->hAllCounts[r * row + view];
+    if (outCount) *outCount = (uint32_t)total;
+    // rank r's slice of this view starts after its earlier views inside its payload
+    for (uint32_t r = 0; r < c->nRanks && outEntity && done < cap; ++r)
+    {
+      size_t off = 0;
+      for (uint32_t v = 0; v < view; ++v) off += c->hAllCounts[r * row + v];
+      const size_t cnt = std::min((size_t)c->hAllCounts[r * row + view], (size_t)cap - done);
+      if (cnt)
+        SC_CUDA(c, cudaMemcpyAsync(outEntity + done, c->peerBox.payload(r, c->peerSeq & 1u) + off, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+      done += cnt;
+    }
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 1;
+  }
   size_t tot = 0;
   for (uint32_t r = 0; r < c->nRanks; ++r) tot += c->hAllCounts[r * row + view];
   if (outCount) *outCount = (uint32_t)tot;

@@ -106,6 +106,7 @@ SYMBOLS = {
     "scgpuReadSortedDraws": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint32]),
     "scgpuCommGetUniqueId": (C.c_int, [_vp]),
     "scgpuCommInit": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "scgpuCommEnablePeerGather": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
     "scgpuGatherVisible": (C.c_int, [_vp, C.c_uint32]),
     "scgpuGetGatheredCounts": (C.c_int, [_vp, _vp, C.c_uint32]),
     "scgpuReadGatheredVisible": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _u32p]),
@@ -354,6 +355,9 @@ class Scene:
         self._ck(self.lib.scgpuCommInit(self.ctx, n_ranks, rank, buf), "scgpuCommInit")
         self.n_ranks = n_ranks
         self.rank = rank
+
+    def enable_peer_gather(self, root=0, cap_entries=0):
+        self._ck(self.lib.scgpuCommEnablePeerGather(self.ctx, root, cap_entries), "scgpuCommEnablePeerGather")
 
     def gather_visible(self, root=0):
         self._ck(self.lib.scgpuGatherVisible(self.ctx, root), "scgpuGatherVisible")

@@ -53,7 +53,28 @@ def main():
             # shard-major stable order: rank r's slice is its own pool-order list
             off = int(counts[:rank, v].sum())
             assert np.array_equal(got[off: off + counts[0, v]], s.read_visible(v))
+        nccl_lists = [s.read_gathered_visible(v) for v in range(views)]
         print("MULTIGPU OK", world, "ranks, visible per view", [int(counts[:, v].sum()) for v in range(views)], flush=True)
+    dist.barrier()
+    # the same gather through NVLink peer memory (no NCCL, no host sync per frame): several frames back to back so
+    # that both mailbox parities and the root-progress handshake are exercised, then the lists must be identical
+    s.enable_peer_gather(0)
+    for frame in range(5):
+        s.mark_all_dirty()
+        s.update()
+        s.gather_visible(0)
+    if rank == 0:
+        pc = s.gathered_counts()
+        assert np.array_equal(pc, counts), (pc, counts)
+        for v in range(views):
+            assert np.array_equal(s.read_gathered_visible(v), nccl_lists[v]), f"peer gather, view {v}"
+        print("MULTIGPU PEER OK", flush=True)
+    else:
+        try:
+            s.gathered_counts()
+            raise AssertionError("peer gather counts must be root-only")
+        except scgpu.ScGpuError:
+            pass
     dist.barrier()
     s.close()
     dist.destroy_process_group()
