@@ -319,8 +319,14 @@ def main():
     vis_counts = [int(counts.visible[v]) for v in range(args.views)]
 
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # per-rank view of the same timed region (diagnostic: which rank sets the max, and is it its kernels or the gather)
+        mine = {"rank": rank, "ms_per_step": dev_ms / args.steps, "kernel_ms": float(np.mean(k_ms)) if len(k_ms) else None,
+                "update_ms": float(np.mean(u_ms)) if len(u_ms) else None, "sm_mhz": clocks.get("sm_mhz")}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     dev_ms_max = float(t.item())
     ms_per_step = dev_ms_max / args.steps
     total_instances = n * world
@@ -387,6 +393,8 @@ def main():
             },
             "visible_per_view": vis_counts, "wall_ms_per_step": t_wall * 1e3 / args.steps,
         }
+        if per_rank:
+            line["per_rank"] = per_rank
         if world == 1 and not args.no_cpu_baseline:
             res = run_cpu_worker(args.ref_sample, args.views, 3, 1)
             if "error" in res:
