@@ -60,6 +60,7 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self.armed = False  # NVML is initialised and the thread started BEFORE the barrier; sampling starts when armed
         self.ok = False
         try:
             import pynvml
@@ -83,6 +84,9 @@ class ClockSampler(threading.Thread):
             nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
         }
         while not self._halt.is_set():
+            if not self.armed:
+                time.sleep(0.0005)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -293,14 +297,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)  # nvmlInit takes tens of ms and differs per process: keep it out of the region
+    sampler.start()
+    scene.enable_timings(True)
     for _ in range(args.warmup):
         step()
     barrier()
 
     # ---- timed region: K steps, device-resident inputs, CUDA events on the context stream -----------------
-    scene.enable_timings(True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    scene.enable_timings(True)  # events exist already: this only resets the ring
+    sampler.armed = True
     launches0 = scene.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
