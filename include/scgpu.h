@@ -172,6 +172,28 @@ SCGPU_API int scgpuBuildSortedDraws(ScGpuScene* ctx, uint32_t view, uint32_t max
 SCGPU_API int scgpuReadSortedDraws(ScGpuScene* ctx, ScGpuDrawItem* outItems, uint32_t cap, ScGpuDrawRun* outRuns,
                                    uint32_t runCap);
 
+/* ---- procedural sectors spawned on the device ------------------------------------------------
+ * Replaces, for procedurally generated sectors, generateSectorSpawnsStatic (src/engine/world/sc_world_partition.cpp:
+ * 105-169) and the per-record World::add<Transform/RenderMesh/Bounds> + setLocal loop of pumpCompletedLoads (:923-954):
+ * the SoA records are generated in HBM from (seed, sector coordinate) with the reference's hash and float expressions;
+ * the host only creates the entity handles (World::create) and passes them in spawn order (ground plane first, then
+ * the props). No TRS, bounds or mesh/material data crosses PCIe. */
+typedef struct ScGpuSectorGen
+{
+  uint32_t struct_size;         /* sizeof(ScGpuSectorGen) */
+  float sectorSizeMeters;       /* WorldPartitionConfig (sc_world_partition.h) */
+  uint32_t seed;
+  uint32_t propsPerSectorMin, propsPerSectorMax;
+  uint32_t includeGroundPlane;
+  uint32_t meshCube, meshTriangle;          /* resolveMeshHandle("meshes/cube" | "meshes/triangle") */
+  uint32_t matUnlit, matChecker, matTest;   /* resolveMaterialHandle("materials/unlit" | "checker" | "test") */
+} ScGpuSectorGen;
+/* number of SpawnRecords the sector yields (= entities the caller must create for it); pure host arithmetic */
+SCGPU_API uint32_t scgpuSectorSpawnCount(const ScGpuSectorGen* gen, int32_t x, int32_t z);
+/* coordXZ: nSectors x (x, z); entity: the handles of all sectors back to back, nEntities = sum of the spawn counts */
+SCGPU_API int scgpuSpawnSectors(ScGpuScene* ctx, const ScGpuSectorGen* gen, uint32_t nSectors, const int32_t* coordXZ,
+                                const uint32_t* entity, uint32_t nEntities);
+
 /* ---- multi-GPU: one context per process per GPU, instance set sharded by world cell ------------------------
  * The only exchange is the gather of the compacted per-view lists and counts to the submitting rank. */
 #define SCGPU_COMM_ID_BYTES 128

@@ -436,28 +436,35 @@ int scgpuSynchronize(ScGpuScene* ctx)
 
 // ---- deltas -------------------------------------------------------------------------------------------
 
+// Host mirror of World::create + add<Transform>: validates the handles against the pool mirror first, so that a failed
+// call leaves the scene untouched, then appends them in pool order.
+static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const char* who)
+{
+  if ((uint64_t)c->count + n > c->capacity) return (int)fail(c, "%s: %u + %u instances exceed max_instances %u", who, c->count, n, c->capacity);
+  if (c->hSparse.size() < c->sparseSize) c->hSparse.resize(c->sparseSize, 0u);
+  for (uint32_t j = 0; j < n; ++j)
+  {
+    const uint32_t idx = entity[j] & 0xFFFFFFu;
+    if (entity[j] == SCGPU_INVALID_ENTITY) { for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u; return (int)fail(c, "%s: entity[%u] is the invalid handle", who, j); }
+    if (idx >= c->sparseSize) { for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u; return (int)fail(c, "%s: entity index %u >= max_entity_index %u", who, idx, c->sparseSize); }
+    if (c->hSparse[idx] != 0u)
+    {
+      for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u;
+      return (int)fail(c, "%s: entity index %u already owns a Transform", who, idx);
+    }
+    c->hSparse[idx] = c->count + j + 1u;
+  }
+  c->hEntity.insert(c->hEntity.end(), entity, entity + n);
+  return 1;
+}
+
 int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* parent, const float* trs9,
                const float* aabb6, const uint32_t* meshMat2, const uint32_t* flags)
 {
   if (!enter(c)) return 0;
   if (n == 0) return 1;
   if (!entity || !trs9) return (int)fail(c, "scgpuSpawn: entity and trs9 are required");
-  if ((uint64_t)c->count + n > c->capacity) return (int)fail(c, "scgpuSpawn: %u + %u instances exceed max_instances %u", c->count, n, c->capacity);
-  // validate against the mirror first so a failed call leaves the scene untouched
-  if (c->hSparse.size() < c->sparseSize) c->hSparse.resize(c->sparseSize, 0u);
-  for (uint32_t j = 0; j < n; ++j)
-  {
-    const uint32_t idx = entity[j] & 0xFFFFFFu;
-    if (entity[j] == SCGPU_INVALID_ENTITY) return (int)fail(c, "scgpuSpawn: entity[%u] is the invalid handle", j);
-    if (idx >= c->sparseSize) return (int)fail(c, "scgpuSpawn: entity index %u >= max_entity_index %u", idx, c->sparseSize);
-    if (c->hSparse[idx] != 0u)
-    {
-      for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u;
-      return (int)fail(c, "scgpuSpawn: entity index %u already owns a Transform", idx);
-    }
-    c->hSparse[idx] = c->count + j + 1u;
-  }
-  c->hEntity.insert(c->hEntity.end(), entity, entity + n);
+  if (!registerSpawn(c, n, entity, "scgpuSpawn")) return 0;
 
   const uint32_t chunkMax = 1u << 20;
   for (uint32_t off = 0; off < n; off += chunkMax)
@@ -492,6 +499,56 @@ int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t
     if (any) { c->anyParentEver = true; c->topologyDirty = true; }
   }
   // a new Transform can turn a dangling parent handle valid (and shifts nothing else): re-resolve if any hierarchy exists
+  if (c->anyParentEver) c->topologyDirty = true;
+  c->count += n;
+  return 1;
+}
+
+// ---- procedural sectors spawned on the device -------------------------------------------------
+static SectorGen toSectorGen(const ScGpuSectorGen* g)
+{
+  SectorGen o{};
+  o.sectorSizeMeters = g->sectorSizeMeters; o.seed = g->seed; o.propsMin = g->propsPerSectorMin; o.propsMax = g->propsPerSectorMax;
+  o.includeGround = g->includeGroundPlane ? 1u : 0u;
+  o.meshCube = g->meshCube; o.meshTriangle = g->meshTriangle;
+  o.matUnlit = g->matUnlit; o.matChecker = g->matChecker; o.matTest = g->matTest;
+  return o;
+}
+
+uint32_t scgpuSectorSpawnCount(const ScGpuSectorGen* gen, int32_t x, int32_t z)
+{
+  if (!gen || gen->propsPerSectorMax < gen->propsPerSectorMin) return 0;
+  const SectorGen g = toSectorGen(gen);
+  return sg_prop_count(g, x, z) + g.includeGround;
+}
+
+int scgpuSpawnSectors(ScGpuScene* c, const ScGpuSectorGen* gen, uint32_t nSectors, const int32_t* coordXZ, const uint32_t* entity,
+                      uint32_t nEntities)
+{
+  if (!enter(c)) return 0;
+  if (nSectors == 0) return 1;
+  if (!gen || !coordXZ || !entity) return (int)fail(c, "scgpuSpawnSectors: NULL argument");
+  if (gen->propsPerSectorMax < gen->propsPerSectorMin) return (int)fail(c, "scgpuSpawnSectors: propsPerSectorMax < propsPerSectorMin");
+  const SectorGen g = toSectorGen(gen);
+  std::vector<uint32_t> first(nSectors + 1, 0u);
+  for (uint32_t k = 0; k < nSectors; ++k)
+    first[k + 1] = first[k] + sg_prop_count(g, coordXZ[2 * k], coordXZ[2 * k + 1]) + g.includeGround;
+  const uint32_t n = first[nSectors];
+  if (n != nEntities)
+    return (int)fail(c, "scgpuSpawnSectors: the sectors yield %u spawn records but %u entity handles were passed", n, nEntities);
+  if (!registerSpawn(c, n, entity, "scgpuSpawnSectors")) return 0;
+  const size_t oCoord = 0, oFirst = (size_t)nSectors * 8, oEntity = oFirst + ((size_t)nSectors + 1) * 4;
+  const size_t bytes = oEntity + (size_t)n * 4;
+  if (!ensure(c, c->staging, bytes)) return 0;
+  char* s = (char*)c->staging.ptr;
+  if (!uploadTo(c, s + oCoord, coordXZ, (size_t)nSectors * 8)) return 0;
+  if (!uploadTo(c, s + oFirst, first.data(), ((size_t)nSectors + 1) * 4)) return 0;
+  if (!uploadTo(c, s + oEntity, entity, (size_t)n * 4)) return 0;
+  k_spawn_sectors<<<nSectors, 64, 0, c->stream>>>(c->a, g, c->count, (const int32_t*)(s + oCoord), (const uint32_t*)(s + oFirst),
+                                                  (const uint32_t*)(s + oEntity), stampOf(c->frame));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));  // `first` is a local: the pageable upload must have left it
   if (c->anyParentEver) c->topologyDirty = true;
   c->count += n;
   return 1;

@@ -1397,6 +1397,99 @@ __global__ void __launch_bounds__(kBlock) k_spawn(SceneArrays a, uint32_t slot0,
   if (idx < a.sparseSize) a.sparse[idx] = s + 1u;
 }
 
+// ---- procedural sectors spawned on the device ----------------------------------------------------
+// generateSectorSpawnsStatic (src/engine/world/sc_world_partition.cpp:105-169) + the per-record World::add loop of
+// pumpCompletedLoads (:923-954), writing the SoA records directly: the host only creates the entity handles. Same
+// integer hash (mix32 / hashCoordSeed / rand01, :34-57) and the same float expressions, unfused.
+struct SectorGen  // == ScGpuSectorGen without struct_size
+{
+  float sectorSizeMeters;
+  uint32_t seed, propsMin, propsMax, includeGround;
+  uint32_t meshCube, meshTriangle, matUnlit, matChecker, matTest;
+};
+
+__host__ __device__ __forceinline__ uint32_t sg_mix32(uint32_t x)
+{
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t sg_hash_coord(uint32_t seed, int32_t cx, int32_t cz)
+{
+  uint32_t h = seed;
+  h ^= sg_mix32((uint32_t)cx * 73856093u);
+  h ^= sg_mix32((uint32_t)cz * 19349663u);
+  return sg_mix32(h + 0x9e3779b9u);
+}
+__host__ __device__ __forceinline__ uint32_t sg_prop_count(const SectorGen& g, int32_t cx, int32_t cz)
+{
+  const uint32_t rng = sg_hash_coord(g.seed, cx, cz);
+  const uint32_t range = g.propsMax - g.propsMin + 1u;
+  return g.propsMin + (range > 0 ? (sg_mix32(rng) % range) : 0u);
+}
+__device__ __forceinline__ float sg_rand01(uint32_t& state)
+{
+  state = sg_mix32(state + 0x6d2b79f5u);
+  return __fdiv_rn((float)(state & 0x00FFFFFFu), 16777215.0f);
+}
+__device__ __forceinline__ float sg_lerp(float a, float b, float t) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t)); }
+
+// one CTA per sector, one thread per SpawnRecord (ground plane first, then the props in generation order)
+__global__ void __launch_bounds__(64) k_spawn_sectors(SceneArrays a, SectorGen g, uint32_t slot0, const int32_t* __restrict__ coordXZ,
+                                                      const uint32_t* __restrict__ first, const uint32_t* __restrict__ entity,
+                                                      uint32_t stamp)
+{
+  const uint32_t sec = blockIdx.x;
+  const int32_t cx = coordXZ[2 * sec], cz = coordXZ[2 * sec + 1];
+  const uint32_t base = first[sec], n = first[sec + 1] - base;
+  const float size = g.sectorSizeMeters;
+  const float minX = __fmul_rn((float)cx, size), minZ = __fmul_rn((float)cz, size);
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+  {
+    float px, py, pz, ry = 0.0f, sx, sy, sz;
+    uint32_t mesh, mat;
+    if (g.includeGround && i == 0)
+    {
+      px = __fadd_rn(minX, __fmul_rn(size, 0.5f)); py = -0.55f; pz = __fadd_rn(minZ, __fmul_rn(size, 0.5f));
+      sx = size; sy = 0.10f; sz = size;
+      mesh = g.meshCube; mat = g.matUnlit;
+    }
+    else
+    {
+      const uint32_t prop = i - (g.includeGround ? 1u : 0u);
+      uint32_t rng = sg_hash_coord(g.seed, cx, cz);
+      for (uint32_t k = 0; k < prop * 8u; ++k) rng = sg_mix32(rng + 0x6d2b79f5u);  // 8 draws per earlier prop
+      const float pad = 1.0f;
+      px = sg_lerp(__fadd_rn(minX, pad), __fsub_rn(__fadd_rn(minX, size), pad), sg_rand01(rng));
+      pz = sg_lerp(__fadd_rn(minZ, pad), __fsub_rn(__fadd_rn(minZ, size), pad), sg_rand01(rng));
+      sx = sg_lerp(0.4f, 1.9f, sg_rand01(rng));
+      sy = sg_lerp(0.5f, 3.2f, sg_rand01(rng));
+      sz = sg_lerp(0.4f, 1.9f, sg_rand01(rng));
+      py = __fmul_rn(sy, 0.5f);
+      ry = __fmul_rn(sg_rand01(rng), 3.1415926535f * 2.0f);
+      const float m = sg_rand01(rng);
+      mat = (m < 0.40f) ? g.matChecker : ((m < 0.80f) ? g.matTest : g.matUnlit);
+      mesh = (sg_rand01(rng) < 0.90f) ? g.meshCube : g.meshTriangle;
+    }
+    const uint32_t s = slot0 + base + i;
+    const uint32_t f = (kFlagBounds | kFlagMesh) | (stamp << kStampShift);
+    a.rec[0][s] = make_float4(px, py, pz, 0.0f);
+    a.rec[1][s] = make_float4(ry, 0.0f, sx, sy);
+    a.rec[2][s] = make_float4(sz, -0.5f, -0.5f, -0.5f);
+    a.rec[3][s] = make_float4(0.5f, 0.5f, 0.5f, __uint_as_float(f));
+    a.world[0][s] = make_float4(1.f, 0.f, 0.f, 0.f);
+    a.world[1][s] = make_float4(0.f, 1.f, 0.f, 0.f);
+    a.world[2][s] = make_float4(0.f, 0.f, 1.f, 0.f);
+    a.world[3][s] = make_float4(0.f, 0.f, 0.f, 1.f);
+    const uint32_t e = entity[base + i];
+    a.entity[s] = e;
+    a.parent[s] = kNone;
+    a.parentSlot[s] = kNone;
+    a.meshMat[s] = make_uint2(mesh, mat);
+    const uint32_t idx = e & 0xFFFFFFu;
+    if (idx < a.sparseSize) a.sparse[idx] = s + 1u;
+  }
+}
+
 __device__ __forceinline__ uint32_t find_slot(const SceneArrays& a, uint32_t handle)
 {
   if (handle == kNone) return kNone;

@@ -65,6 +65,16 @@ DRAW_ITEM_DTYPE = np.dtype(
     [("entity", "<u4"), ("meshId", "<u4"), ("materialId", "<u4"), ("_pad", "<u4"), ("model", "<f4", (16,))]
 )
 assert DRAW_ITEM_DTYPE.itemsize == 80
+class SectorGen(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("sectorSizeMeters", C.c_float), ("seed", C.c_uint32),
+                ("propsPerSectorMin", C.c_uint32), ("propsPerSectorMax", C.c_uint32), ("includeGroundPlane", C.c_uint32),
+                ("meshCube", C.c_uint32), ("meshTriangle", C.c_uint32),
+                ("matUnlit", C.c_uint32), ("matChecker", C.c_uint32), ("matTest", C.c_uint32)]
+
+    def __init__(self, **kw):
+        super().__init__(struct_size=C.sizeof(SectorGen), **kw)
+
+
 DRAW_RUN_DTYPE = np.dtype([("pipelineId", "<u4"), ("materialId", "<u4"), ("meshId", "<u4"), ("first", "<u4"), ("count", "<u4")])
 assert DRAW_RUN_DTYPE.itemsize == 20
 
@@ -81,6 +91,8 @@ SYMBOLS = {
     "scgpuLastError": (C.c_char_p, [_vp]),
     "scgpuSpawn": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scgpuDespawn": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "scgpuSectorSpawnCount": (C.c_uint32, [C.POINTER(SectorGen), C.c_int32, C.c_int32]),
+    "scgpuSpawnSectors": (C.c_int, [_vp, C.POINTER(SectorGen), C.c_uint32, _vp, _vp, C.c_uint32]),
     "scgpuSetLocal": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "scgpuSetParent": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "scgpuMarkDirty": (C.c_int, [_vp, C.c_uint32, _vp]),
@@ -196,6 +208,12 @@ class Scene:
         n = e.shape[0]
         assert t.shape[0] == n
         self._ck(self.lib.scgpuSpawn(self.ctx, n, _ptr(e), _ptr(p), _ptr(t), _ptr(b), _ptr(m), _ptr(f)), "scgpuSpawn")
+
+    def spawn_sectors(self, gen: "SectorGen", coord_xz, entity):
+        """procedural sectors generated on the device; entity = handles of all sectors back to back"""
+        cxz = _arr(coord_xz, np.int32).reshape(-1, 2)
+        e = _arr(entity, np.uint32)
+        self._ck(self.lib.scgpuSpawnSectors(self.ctx, C.byref(gen), cxz.shape[0], _ptr(cxz), _ptr(e), e.shape[0]), "scgpuSpawnSectors")
 
     def despawn(self, entity):
         e = _arr(entity, np.uint32)

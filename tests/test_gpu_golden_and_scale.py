@@ -8,7 +8,8 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from scenarios import GpuAdapter, assert_same_bits, load_golden, replay_default_scene, replay_forest_scene
+from scenarios import (GpuAdapter, assert_same_bits, check_snapshot, load_golden, replay_default_scene,
+                       replay_forest_scene)
 from scgpu import scenes
 
 pytestmark = pytest.mark.gpu
@@ -125,3 +126,81 @@ def test_dropin_adapter_systems_against_reference_systems():
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "DROPIN OK" in r.stdout
+
+
+def _default_scene_sectors(g):
+    """(coords in activation order, rows of each sector) of the reference's default scene: every streamed sector
+    starts with its ground plane (scale 64 x 0.1 x 64 at the sector centre)."""
+    t = g["trs_after"]
+    ground = np.nonzero((t[:, 6] == 64.0) & (t[:, 7] == np.float32(0.10)) & (t[:, 8] == 64.0))[0]
+    coords = np.stack([np.floor(t[ground, 0] / 64.0), np.floor(t[ground, 2] / 64.0)], axis=1).astype(np.int32)
+    ends = np.append(ground[1:], len(t))
+    return coords, ground, ends
+
+
+def _default_sector_gen(g):
+    import scgpu
+    mm = g["mesh_mat"]
+    coords, ground, ends = _default_scene_sectors(g)
+    cube = int(mm[ground[0], 0])
+    others = np.setdiff1d(np.unique(mm[ground[0]:, 0]), [cube])
+    tri = int(others[0]) if len(others) else cube
+    # WorldPartitionConfig of the sandbox (src/sandbox/src/main.cpp:74-99): 64 m, seed 424242, 18..34 props, ground plane
+    return scgpu.SectorGen(sectorSizeMeters=64.0, seed=424242, propsPerSectorMin=18, propsPerSectorMax=34,
+                           includeGroundPlane=1, meshCube=cube, meshTriangle=tri, matUnlit=0, matChecker=0, matTest=0)
+
+
+def test_sector_spawn_on_device_reproduces_the_reference_scene():
+    """the 25 sectors of the sandbox's default scene generated ON THE DEVICE from (seed, coordinate)
+    — scgpuSpawnSectors — give the frame the reference produced from its own generateSectorSpawnsStatic + World::add
+    loop: world matrices of all 721 entities, the ordered visible list and the draw items (golden fixture)."""
+    import scgpu
+    g = load_golden("default_scene.npz")
+    coords, ground, ends = _default_scene_sectors(g)
+    first = int(ground[0])
+    e = g["entity"]
+    gen = _default_sector_gen(g)
+    a = GpuAdapter(1024, max_views=1)
+    # camera, Root, TriangleEntity, CubeEntity (sc_ecs.cpp:320-365) come from the host as before
+    a.spawn(e[:first], g["trs_after"][:first], g["parent_after"][:first], g["aabb"][:first], g["mesh_mat"][:first], g["flags"][:first])
+    counts = [a.s.lib.scgpuSectorSpawnCount(gen, int(x), int(z)) for x, z in coords]
+    assert counts == [int(b - s0) for s0, b in zip(ground, ends)]
+    a.s.spawn_sectors(gen, coords, e[first:])
+    a.update(g["view_proj"])
+    check_snapshot(a, g, "", 1, "device-generated default scene")
+    assert np.array_equal(a.dense_entities(), e)
+    a.close()
+
+
+def test_sector_spawn_on_device_equals_host_generated_city():
+    """N2 with distinct mesh / material handles and no ground planes: the device generator against the numpy
+    restatement of generateSectorSpawnsStatic that feeds every other test (scgpu.scenes.city_props)."""
+    import scgpu
+    n = 20_000
+    p = scenes.city_props(n, seed=777)
+    sec = p["sector"]
+    change = np.nonzero(np.any(np.diff(sec, axis=0) != 0, axis=1))[0] + 1
+    coords = sec[np.concatenate([[0], change])]
+    gen = scgpu.SectorGen(sectorSizeMeters=64.0, seed=777, propsPerSectorMin=18, propsPerSectorMax=34, includeGroundPlane=0,
+                          meshCube=1, meshTriangle=2, matChecker=1, matTest=2, matUnlit=3)
+    dev = GpuAdapter(n + 64, max_views=1)
+    counts = [dev.s.lib.scgpuSectorSpawnCount(gen, int(x), int(z)) for x, z in coords]
+    total = int(np.sum(counts))
+    assert total >= n
+    e = np.arange(total, dtype=np.uint32)
+    dev.s.spawn_sectors(gen, coords, e)
+    host = GpuAdapter(n + 64, max_views=1)
+    host.spawn(e[:n], p["trs9"], None, None, p["mesh_mat"], None)
+    vps = scenes.standard_views(1)
+    for s in (dev, host):
+        s.update(vps, freeze=True)
+    assert_same_bits(dev.read_world(e[:n]), host.read_world(e[:n]), "device-generated sectors")
+    dd, _, _ = dev.read_draw_items(0, 0)
+    hd, _, _ = host.read_draw_items(0, 0)
+    assert np.array_equal(dd["meshId"][:n], hd["meshId"]) and np.array_equal(dd["materialId"][:n], hd["materialId"])
+    # a wrong handle count is refused and leaves the scene untouched
+    with pytest.raises(scgpu.ScGpuError):
+        dev.s.spawn_sectors(gen, coords[:2], np.arange(total, total + 3, dtype=np.uint32))
+    assert dev.s.counts().transforms == total
+    dev.close()
+    host.close()
