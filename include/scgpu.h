@@ -194,6 +194,32 @@ SCGPU_API uint32_t scgpuSectorSpawnCount(const ScGpuSectorGen* gen, int32_t x, i
 SCGPU_API int scgpuSpawnSectors(ScGpuScene* ctx, const ScGpuSectorGen* gen, uint32_t nSectors, const int32_t* coordXZ,
                                 const uint32_t* entity, uint32_t nEntities);
 
+/* ---- authored sectors, .scsector INST chunk -> SoA ----------------------------------------------
+ * Replaces, for sectors stored on disk, sc_world::ReadSectorFile's INST branch (tools/shared/world_format.cpp:207-281),
+ * WorldPartition::readSectorFile (src/engine/world/sc_world_partition.cpp:695-732) and the World::add loop of
+ * pumpCompletedLoads (:923-954): the caller hands over the file image as it lies on disk; the chunk table is walked on
+ * the host exactly like the reference's reader does (format versions 1..4: optional model id, name, overrides, padding),
+ * the raw INST payload is uploaded and unpacked into the record planes by one kernel. Asset ids resolve like
+ * resolveMeshHandle / resolveMaterialHandle (:746-800): id 0 -> handle 0, listed id -> its handle, else the default. */
+typedef struct ScGpuAssetBinding
+{
+  uint64_t assetId; /* sc_world::AssetId (FNV-1a of the normalised path, world_format.cpp:63-74) */
+  uint32_t handle;  /* MeshHandle / MaterialHandle the engine resolved it to */
+  uint32_t _pad;
+} ScGpuAssetBinding;
+typedef struct ScGpuAssetTable
+{
+  const ScGpuAssetBinding* meshes;
+  uint32_t nMeshes, defaultMesh;        /* default: the handle of "meshes/cube" */
+  const ScGpuAssetBinding* materials;
+  uint32_t nMaterials, defaultMaterial; /* default: the handle of "materials/unlit" */
+} ScGpuAssetTable;
+/* host only: sector coordinate, format version and instance count of a file image (0 on a malformed image) */
+SCGPU_API int scgpuSectorFileInfo(const void* bytes, size_t nBytes, int32_t* outXZ, uint32_t* outVersion, uint32_t* outInstances);
+/* entity: one handle per instance in file order (the caller created them with World::create) */
+SCGPU_API int scgpuSpawnSectorFile(ScGpuScene* ctx, const void* bytes, size_t nBytes, const uint32_t* entity, uint32_t nEntities,
+                                   const ScGpuAssetTable* assets);
+
 /* ---- multi-GPU: one context per process per GPU, instance set sharded by world cell ------------------------
  * The only exchange is the gather of the compacted per-view lists and counts to the submitting rank. */
 #define SCGPU_COMM_ID_BYTES 128

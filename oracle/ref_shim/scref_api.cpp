@@ -8,8 +8,10 @@
 #include "sc_scheduler.h"
 #include "sc_time.h"
 #include "sc_world_partition.h"
+#include "world_format.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
@@ -461,5 +463,56 @@ void screfSinCosSweep(uint32_t first, uint64_t count, uint32_t stride, uint64_t*
   }
   *outSinHash = hs; *outCosHash = hc;
 }
+
+// ---- .scsector files through the reference's own writer / reader (tools/shared/world_format.cpp:76-334) ----------
+int screfWriteSectorFile(const char* path, uint32_t version, int32_t x, int32_t z, uint32_t n, const uint64_t* id,
+                         const uint64_t* modelId, const uint64_t* meshId, const uint64_t* materialId, const float* trs9,
+                         const uint32_t* tags, uint32_t nExtraChunkBytes)
+{
+  sc_world::SectorFile f{};
+  f.version = version;
+  f.sector = { x, z };
+  f.instances.resize(n);
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    sc_world::Instance& in = f.instances[i];
+    in.id = id[i]; in.model_id = modelId[i]; in.mesh_id = meshId[i]; in.material_id = materialId[i];
+    std::memcpy(in.transform.position, trs9 + 9 * i, 12);
+    std::memcpy(in.transform.rotation, trs9 + 9 * i + 3, 12);
+    std::memcpy(in.transform.scale, trs9 + 9 * i + 6, 12);
+    std::snprintf(in.name, sc_world::kInstanceNameMax, "Inst_%u", i);
+    in.tags = tags[i];
+    in.albedo_texture_id = 77 + i; in.material_flags = i & 1u;
+  }
+  // other chunk kinds before/after do not matter to the INST reader; add a lane and a spawner so that the walk is tested
+  if (nExtraChunkBytes)
+  {
+    sc_world::Lane lane{}; lane.id = 5; lane.flags = 1; lane.points = { {0, 0, 0}, {1, 0, 2}, {3, 0, 4} };
+    f.lanes.push_back(lane);
+    sc_world::Spawner sp{}; sp.id = 9; sp.type = 2; sp.rate = 0.5f;
+    f.spawners.push_back(sp);
+  }
+  return sc_world::WriteSectorFile(path, f) ? 1 : 0;
+}
+
+// returns the instance count (or -1); fills up to cap entries
+int screfReadSectorInstances(const char* path, uint32_t cap, int32_t* outXZ, uint64_t* outId, uint64_t* outMeshId,
+                             uint64_t* outMaterialId, float* outTrs9)
+{
+  sc_world::SectorFile f{};
+  if (!sc_world::ReadSectorFile(path, &f)) return -1;
+  outXZ[0] = f.sector.x; outXZ[1] = f.sector.z;
+  for (uint32_t i = 0; i < f.instances.size() && i < cap; ++i)
+  {
+    const sc_world::Instance& in = f.instances[i];
+    outId[i] = in.id; outMeshId[i] = in.mesh_id; outMaterialId[i] = in.material_id;
+    std::memcpy(outTrs9 + 9 * i, in.transform.position, 12);
+    std::memcpy(outTrs9 + 9 * i + 3, in.transform.rotation, 12);
+    std::memcpy(outTrs9 + 9 * i + 6, in.transform.scale, 12);
+  }
+  return (int)f.instances.size();
+}
+
+uint64_t screfHashAssetPath(const char* path) { return sc_world::HashAssetPath(path); }
 
 }  // extern "C"

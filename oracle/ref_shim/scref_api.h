@@ -94,6 +94,14 @@ float screfCosf(float x);
 /* XOR-fold hash of sinf/cosf bits over float bit patterns [first, first+count) with stride */
 void screfSinCosSweep(uint32_t first, uint64_t count, uint32_t stride, uint64_t* outSinHash, uint64_t* outCosHash);
 
+/* .scsector files through the reference's own writer / reader (tools/shared/world_format.cpp:76-334) */
+int screfWriteSectorFile(const char* path, uint32_t version, int32_t x, int32_t z, uint32_t n, const uint64_t* id,
+                         const uint64_t* modelId, const uint64_t* meshId, const uint64_t* materialId, const float* trs9,
+                         const uint32_t* tags, uint32_t nExtraChunkBytes);
+int screfReadSectorInstances(const char* path, uint32_t cap, int32_t* outXZ, uint64_t* outId, uint64_t* outMeshId,
+                             uint64_t* outMaterialId, float* outTrs9);
+uint64_t screfHashAssetPath(const char* path);
+
 #ifdef __cplusplus
 }
 #endif

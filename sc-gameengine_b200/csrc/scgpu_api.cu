@@ -554,6 +554,106 @@ int scgpuSpawnSectors(ScGpuScene* c, const ScGpuSectorGen* gen, uint32_t nSector
   return 1;
 }
 
+// ---- .scsector files ----------------------------------------------------------------------------
+namespace
+{
+struct SectorFileInfo
+{
+  uint32_t version = 0;
+  int32_t x = 0, z = 0;
+  uint32_t count = 0;          // instances of the (last) INST chunk
+  size_t payload = 0;          // byte offset of its first record
+  uint32_t recordSize = 0;     // bytes per record as the reader derives it
+  uint32_t meshOffset = 0;     // byte offset of mesh_id inside a record
+};
+
+// The chunk walk of sc_world::ReadSectorFile (tools/shared/world_format.cpp:178-334) over a memory image of the file.
+// Returns an error text or nullptr.
+const char* parseSectorFile(const void* bytes, size_t n, SectorFileInfo& o)
+{
+  const unsigned char* b = (const unsigned char*)bytes;
+  auto u32 = [&](size_t at) { uint32_t v; memcpy(&v, b + at, 4); return v; };
+  if (!bytes || n < 16) return "file shorter than its header";
+  if (u32(0) != 0x54434553u) return "not a sector file (magic != 'SECT')";
+  o.version = u32(4);
+  o.x = (int32_t)u32(8);
+  o.z = (int32_t)u32(12);
+  const uint32_t kInst = (uint32_t)'I' | ((uint32_t)'N' << 8) | ((uint32_t)'S' << 16) | ((uint32_t)'T' << 24);
+  size_t pos = 16;
+  while (pos + 8 <= n)
+  {
+    const uint32_t id = u32(pos), size = u32(pos + 4);
+    pos += 8;
+    if (size == 0) continue;
+    if (id != kInst)
+    {
+      pos += size;  // LANE / SPWN / COLL are consumed by content (== size for a well-formed file), the rest is skipped
+      continue;
+    }
+    if (pos + 4 > n) return "INST chunk cut short";
+    const uint32_t count = u32(pos);
+    const uint32_t baseV3 = 8 + 8 + 8 + 36 + 4, baseV4 = baseV3 + 8;
+    uint32_t recordSize = baseV3;
+    if (count > 0 && size >= 4) recordSize = (size - 4) / count;
+    const bool hasModel = o.version >= 4;
+    if (count > 0 && recordSize < (hasModel ? baseV4 : baseV3)) return "INST record smaller than its fixed fields";
+    if ((uint64_t)pos + 4 + (uint64_t)count * recordSize > n) return "INST chunk cut short";
+    o.count = count;
+    o.payload = pos + 4;
+    o.recordSize = recordSize;
+    o.meshOffset = hasModel ? 16u : 8u;
+    pos += 4 + (size_t)count * recordSize;
+  }
+  return nullptr;
+}
+}  // namespace
+
+int scgpuSectorFileInfo(const void* bytes, size_t nBytes, int32_t* outXZ, uint32_t* outVersion, uint32_t* outInstances)
+{
+  SectorFileInfo f;
+  if (parseSectorFile(bytes, nBytes, f)) return 0;
+  if (outXZ) { outXZ[0] = f.x; outXZ[1] = f.z; }
+  if (outVersion) *outVersion = f.version;
+  if (outInstances) *outInstances = f.count;
+  return 1;
+}
+
+int scgpuSpawnSectorFile(ScGpuScene* c, const void* bytes, size_t nBytes, const uint32_t* entity, uint32_t nEntities,
+                         const ScGpuAssetTable* assets)
+{
+  static_assert(sizeof(ScGpuAssetBinding) == sizeof(AssetBinding), "ScGpuAssetBinding layout");
+  if (!enter(c)) return 0;
+  SectorFileInfo f;
+  if (const char* err = parseSectorFile(bytes, nBytes, f)) return (int)fail(c, "scgpuSpawnSectorFile: %s", err);
+  if (f.count != nEntities)
+    return (int)fail(c, "scgpuSpawnSectorFile: the file holds %u instances but %u entity handles were passed", f.count, nEntities);
+  if (f.count == 0) return 1;
+  if (!entity || !assets) return (int)fail(c, "scgpuSpawnSectorFile: NULL argument");
+  if ((f.payload | f.recordSize | f.meshOffset) & 3u) return (int)fail(c, "scgpuSpawnSectorFile: INST records are not 4-byte aligned");
+  if ((assets->nMeshes && !assets->meshes) || (assets->nMaterials && !assets->materials))
+    return (int)fail(c, "scgpuSpawnSectorFile: asset table pointer is NULL");
+  if (!registerSpawn(c, f.count, entity, "scgpuSpawnSectorFile")) return 0;
+  const size_t payloadBytes = (size_t)f.count * f.recordSize;
+  const size_t oPay = 0, oEnt = (payloadBytes + 255) & ~(size_t)255, oMesh = oEnt + (((size_t)f.count * 4 + 255) & ~(size_t)255);
+  const size_t oMat = oMesh + (((size_t)assets->nMeshes * 16 + 255) & ~(size_t)255);
+  const size_t total = oMat + (size_t)assets->nMaterials * 16 + 16;
+  if (!ensure(c, c->staging, total)) return 0;
+  char* s = (char*)c->staging.ptr;
+  if (!uploadTo(c, s + oPay, (const char*)bytes + f.payload, payloadBytes)) return 0;
+  if (!uploadTo(c, s + oEnt, entity, (size_t)f.count * 4)) return 0;
+  if (assets->nMeshes && !uploadTo(c, s + oMesh, assets->meshes, (size_t)assets->nMeshes * 16)) return 0;
+  if (assets->nMaterials && !uploadTo(c, s + oMat, assets->materials, (size_t)assets->nMaterials * 16)) return 0;
+  k_spawn_sector_file<<<blocksFor(f.count), kBlock, 0, c->stream>>>(
+    c->a, c->count, f.count, (const uint32_t*)(s + oPay), f.recordSize / 4u, f.meshOffset / 4u, (const uint32_t*)(s + oEnt),
+    (const AssetBinding*)(s + oMesh), assets->nMeshes, assets->defaultMesh, (const AssetBinding*)(s + oMat), assets->nMaterials,
+    assets->defaultMaterial, stampOf(c->frame));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  if (c->anyParentEver) c->topologyDirty = true;
+  c->count += f.count;
+  return 1;
+}
+
 int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
 {
   if (!enter(c)) return 0;

@@ -1490,6 +1490,60 @@ __global__ void __launch_bounds__(64) k_spawn_sectors(SceneArrays a, SectorGen g
   }
 }
 
+// ---- .scsector INST chunk -> SoA ------------------------------------------------------------------
+// The raw INST payload (tools/shared/world_format.cpp:92-125 writes it, :207-281 reads it) is uploaded as it lies in
+// the file; one thread per record unpacks mesh id, material id and the 9-float transform straight into the record
+// planes — what WorldPartition::readSectorFile (sc_world_partition.cpp:695-732) + the World::add loop (:923-954) do on
+// the CPU. Asset ids resolve through a small table (resolveMeshHandle / resolveMaterialHandle, :746-800: id 0 -> handle
+// 0, unknown id -> the default asset).
+struct AssetBinding  // == ScGpuAssetBinding
+{
+  uint32_t idLo, idHi, handle, pad;
+};
+
+__device__ __forceinline__ uint32_t resolve_asset(const AssetBinding* __restrict__ tab, uint32_t n, uint32_t dflt, uint32_t lo, uint32_t hi)
+{
+  if ((lo | hi) == 0u) return 0u;
+  for (uint32_t k = 0; k < n; ++k)
+    if (tab[k].idLo == lo && tab[k].idHi == hi) return tab[k].handle;
+  return dflt;
+}
+
+__global__ void __launch_bounds__(kBlock) k_spawn_sector_file(SceneArrays a, uint32_t slot0, uint32_t n, const uint32_t* __restrict__ payload,
+                                                              uint32_t recordWords, uint32_t meshWord, const uint32_t* __restrict__ entity,
+                                                              const AssetBinding* __restrict__ meshes, uint32_t nMeshes, uint32_t defaultMesh,
+                                                              const AssetBinding* __restrict__ materials, uint32_t nMaterials,
+                                                              uint32_t defaultMaterial, uint32_t stamp)
+{
+  const uint32_t j = blockIdx.x * kBlock + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t* r = payload + (size_t)j * recordWords + meshWord;  // mesh id (u64), material id (u64), Transform (9 floats)
+  const uint32_t mesh = resolve_asset(meshes, nMeshes, defaultMesh, r[0], r[1]);
+  const uint32_t mat = resolve_asset(materials, nMaterials, defaultMaterial, r[2], r[3]);
+  float t[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) t[k] = __uint_as_float(r[4 + k]);
+  float sx = t[6], sy = t[7], sz = t[8];
+  if (sx == 0.0f && sy == 0.0f && sz == 0.0f) { sx = sy = sz = 1.0f; }  // TransformSystem's zero-scale patch, as k_spawn
+  const uint32_t s = slot0 + j;
+  const uint32_t f = (kFlagBounds | kFlagMesh) | (stamp << kStampShift);
+  a.rec[0][s] = make_float4(t[0], t[1], t[2], t[3]);
+  a.rec[1][s] = make_float4(t[4], t[5], sx, sy);
+  a.rec[2][s] = make_float4(sz, -0.5f, -0.5f, -0.5f);  // kUnitCubeBounds (sc_world_partition.cpp:27, 725)
+  a.rec[3][s] = make_float4(0.5f, 0.5f, 0.5f, __uint_as_float(f));
+  a.world[0][s] = make_float4(1.f, 0.f, 0.f, 0.f);
+  a.world[1][s] = make_float4(0.f, 1.f, 0.f, 0.f);
+  a.world[2][s] = make_float4(0.f, 0.f, 1.f, 0.f);
+  a.world[3][s] = make_float4(0.f, 0.f, 0.f, 1.f);
+  const uint32_t e = entity[j];
+  a.entity[s] = e;
+  a.parent[s] = kNone;
+  a.parentSlot[s] = kNone;
+  a.meshMat[s] = make_uint2(mesh, mat);
+  const uint32_t idx = e & 0xFFFFFFu;
+  if (idx < a.sparseSize) a.sparse[idx] = s + 1u;
+}
+
 __device__ __forceinline__ uint32_t find_slot(const SceneArrays& a, uint32_t handle)
 {
   if (handle == kNone) return kNone;

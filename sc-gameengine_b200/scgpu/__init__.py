@@ -65,6 +65,24 @@ DRAW_ITEM_DTYPE = np.dtype(
     [("entity", "<u4"), ("meshId", "<u4"), ("materialId", "<u4"), ("_pad", "<u4"), ("model", "<f4", (16,))]
 )
 assert DRAW_ITEM_DTYPE.itemsize == 80
+class AssetBinding(C.Structure):
+    _fields_ = [("assetId", C.c_uint64), ("handle", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class AssetTable(C.Structure):
+    _fields_ = [("meshes", C.POINTER(AssetBinding)), ("nMeshes", C.c_uint32), ("defaultMesh", C.c_uint32),
+                ("materials", C.POINTER(AssetBinding)), ("nMaterials", C.c_uint32), ("defaultMaterial", C.c_uint32)]
+
+
+def make_asset_table(meshes: dict, default_mesh: int, materials: dict, default_material: int) -> "AssetTable":
+    """{assetId: handle} dicts -> ScGpuAssetTable (keeps the arrays alive on the returned object)"""
+    m = (AssetBinding * max(len(meshes), 1))(*[AssetBinding(int(k), int(h), 0) for k, h in meshes.items()])
+    t = (AssetBinding * max(len(materials), 1))(*[AssetBinding(int(k), int(h), 0) for k, h in materials.items()])
+    tab = AssetTable(m, len(meshes), default_mesh, t, len(materials), default_material)
+    tab._keep = (m, t)
+    return tab
+
+
 class SectorGen(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("sectorSizeMeters", C.c_float), ("seed", C.c_uint32),
                 ("propsPerSectorMin", C.c_uint32), ("propsPerSectorMax", C.c_uint32), ("includeGroundPlane", C.c_uint32),
@@ -91,6 +109,8 @@ SYMBOLS = {
     "scgpuLastError": (C.c_char_p, [_vp]),
     "scgpuSpawn": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scgpuDespawn": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "scgpuSectorFileInfo": (C.c_int, [_vp, C.c_size_t, _vp, _u32p, _u32p]),
+    "scgpuSpawnSectorFile": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_uint32, C.POINTER(AssetTable)]),
     "scgpuSectorSpawnCount": (C.c_uint32, [C.POINTER(SectorGen), C.c_int32, C.c_int32]),
     "scgpuSpawnSectors": (C.c_int, [_vp, C.POINTER(SectorGen), C.c_uint32, _vp, _vp, C.c_uint32]),
     "scgpuSetLocal": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
@@ -214,6 +234,13 @@ class Scene:
         cxz = _arr(coord_xz, np.int32).reshape(-1, 2)
         e = _arr(entity, np.uint32)
         self._ck(self.lib.scgpuSpawnSectors(self.ctx, C.byref(gen), cxz.shape[0], _ptr(cxz), _ptr(e), e.shape[0]), "scgpuSpawnSectors")
+
+    def spawn_sector_file(self, file_bytes, entity, assets: "AssetTable"):
+        """a .scsector file image; its INST chunk is unpacked into the SoA on the device"""
+        raw = np.ascontiguousarray(np.frombuffer(bytes(file_bytes), np.uint8))
+        e = _arr(entity, np.uint32)
+        self._ck(self.lib.scgpuSpawnSectorFile(self.ctx, _ptr(raw), raw.shape[0], _ptr(e), e.shape[0], C.byref(assets)),
+                 "scgpuSpawnSectorFile")
 
     def despawn(self, entity):
         e = _arr(entity, np.uint32)

@@ -61,3 +61,25 @@ def test_product_never_links_the_oracle():
     assert "scoracle" not in out and "scref" not in out
     for py in (ROOT / "sc-gameengine_b200" / "scgpu").glob("*.py"):
         assert "oracle" not in py.read_text().replace("the oracle", "").replace("oracle restates", ""), py
+
+
+def test_sector_file_info_matches_the_reference_reader():
+    """SURVEY 8(f) N3, host half: the chunk walk over .scsector images written by the reference's WriteSectorFile
+    (tests/golden/sector_files.npz, made by make_sector_golden.py) yields the coordinate, version and instance count
+    the reference's ReadSectorFile read; malformed images are refused. No GPU involved."""
+    import ctypes as C
+    import numpy as np
+    import scgpu
+    lib = scgpu.load_library()
+    g = np.load(Path(__file__).resolve().parent / "golden" / "sector_files.npz")
+    for k in range(int(g["n_files"])):
+        raw = np.ascontiguousarray(g[f"f{k}_bytes"])
+        xz = np.zeros(2, np.int32)
+        ver, cnt = C.c_uint32(0), C.c_uint32(0)
+        assert lib.scgpuSectorFileInfo(raw.ctypes.data_as(C.c_void_p), raw.size, xz.ctypes.data_as(C.c_void_p), C.byref(ver), C.byref(cnt)) == 1
+        assert (list(xz), ver.value, cnt.value) == (list(g[f"f{k}_xz"]), int(g[f"f{k}_version"]), len(g[f"f{k}_id"]))
+    raw = np.ascontiguousarray(g["f0_bytes"]).copy()
+    bad = raw.copy(); bad[0] ^= 0xFF
+    assert lib.scgpuSectorFileInfo(bad.ctypes.data_as(C.c_void_p), bad.size, None, None, None) == 0      # magic
+    assert lib.scgpuSectorFileInfo(raw.ctypes.data_as(C.c_void_p), 200, None, None, None) == 0           # cut short
+    assert lib.scgpuSectorFileInfo(raw.ctypes.data_as(C.c_void_p), 8, None, None, None) == 0

@@ -204,3 +204,39 @@ def test_sector_spawn_on_device_equals_host_generated_city():
     assert dev.s.counts().transforms == total
     dev.close()
     host.close()
+
+
+def test_sector_files_unpacked_on_device_match_the_reference_reader():
+    """.scsector images written by the reference (format versions 1, 3, 4; with lane / spawner chunks
+    around the INST chunk) spawned through scgpuSpawnSectorFile give the frame that the instances READ BY THE
+    REFERENCE'S OWN READER give when spawned the ordinary way: world matrices, lists, mesh / material handles."""
+    import scgpu
+    from oracle_bind import PortScene
+    g = load_golden("sector_files.npz")
+    ids = {str(n): int(i) for n, i in zip(g["asset_names"], g["asset_ids"])}
+    mesh_handles = {ids["meshes/cube"]: 3, ids["meshes/triangle"]: 4}
+    mat_handles = {ids["materials/unlit"]: 5, ids["materials/checker"]: 6, ids["materials/test"]: 7}
+    tab = scgpu.make_asset_table(mesh_handles, 3, mat_handles, 5)
+    dev, p = GpuAdapter(1024, max_views=1), PortScene()
+    base = 0
+    for k in range(int(g["n_files"])):
+        n = len(g[f"f{k}_id"])
+        e = np.arange(base, base + n, dtype=np.uint32)
+        base += n
+        dev.s.spawn_sector_file(g[f"f{k}_bytes"].tobytes(), e, tab)
+        mm = np.stack([[0 if i == 0 else mesh_handles.get(int(i), 3) for i in g[f"f{k}_mesh"]],
+                       [0 if i == 0 else mat_handles.get(int(i), 5) for i in g[f"f{k}_mat"]]], axis=1).astype(np.uint32).reshape(n, 2)
+        if n:
+            p.spawn(e, g[f"f{k}_trs"], None, None, mm, None)
+    vps = scenes.standard_views(1, center=(0.0, 20.0, 0.0))
+    for s in (dev, p):
+        s.update(vps)
+    allE = np.arange(base, dtype=np.uint32)
+    from scenarios import compare_frame, compare_draws
+    compare_frame(dev, p, allE, 1, "sector files")
+    for s in (dev, p):
+        s.update(vps, freeze=True)
+    compare_draws(dev, p, 0, "sector files, every draw")
+    with pytest.raises(scgpu.ScGpuError):   # handle count must match the file
+        dev.s.spawn_sector_file(g["f1_bytes"].tobytes(), np.arange(base, base + 3, dtype=np.uint32), tab)
+    dev.close()
