@@ -1,1 +1,1 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; tail -15 gpurun_out/tests_full.log
+timeout 600 python tools/bench_next_rows.py > gpurun_out/next_rows.json 2> gpurun_out/next_rows.err; cat gpurun_out/next_rows.json; tail -5 gpurun_out/next_rows.err
