@@ -251,7 +251,8 @@ __device__ __forceinline__ void cp_async_wait()
 // signed plane distance in the reference's order: ((n0*c0 + n1*c1) + n2*c2) + d
 __device__ __forceinline__ float plane_dist(const float4 pl, float cx, float cy, float cz)
 {
-  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pl.x, cx), __fmul_rn(pl.y, cy)), __fmul_rn(pl.z, cz)), pl.w);
+  const float2 xy = fmul2_rn(pl.x, pl.y, cx, cy);
+  return __fadd_rn(__fadd_rn(__fadd_rn(xy.x, xy.y), __fmul_rn(pl.z, cz)), pl.w);
 }
 
 // ---- warp-cooperative pieces shared by the two frame kernels --------------------------------------------------------
@@ -1010,14 +1011,20 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
           const float4 P0 = lds128(pAddr + kWwMat), P1 = lds128(pAddr + kWwMat + 512), P2 = lds128(pAddr + kWwMat + 1024);
           const float4 La = lds128(cAddr + kWwMat), Lb = lds128(cAddr + kWwMat + 512);
           float4 oa, ob;
-          oa.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, La.x), __fmul_rn(P1.x, La.y)), __fmul_rn(P2.x, La.z));
-          oa.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, La.x), __fmul_rn(P1.y, La.y)), __fmul_rn(P2.y, La.z));
-          oa.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, La.x), __fmul_rn(P1.z, La.y)), __fmul_rn(P2.z, La.z));
-          oa.w = La.w;
-          ob.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.x, Lb.x), __fmul_rn(P1.x, Lb.y)), __fmul_rn(P2.x, Lb.z));
-          ob.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.y, Lb.x), __fmul_rn(P1.y, Lb.y)), __fmul_rn(P2.y, Lb.z));
-          ob.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, Lb.x), __fmul_rn(P1.z, Lb.y)), __fmul_rn(P2.z, Lb.z));
-          ob.w = Lb.w;
+          {
+            const float2 m0 = fmul2_rn(P0.x, P0.y, La.x), m1 = fmul2_rn(P1.x, P1.y, La.y), m2 = fmul2_rn(P2.x, P2.y, La.z);
+            oa.x = __fadd_rn(__fadd_rn(m0.x, m1.x), m2.x);
+            oa.y = __fadd_rn(__fadd_rn(m0.y, m1.y), m2.y);
+            oa.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, La.x), __fmul_rn(P1.z, La.y)), __fmul_rn(P2.z, La.z));
+            oa.w = La.w;
+          }
+          {
+            const float2 m0 = fmul2_rn(P0.x, P0.y, Lb.x), m1 = fmul2_rn(P1.x, P1.y, Lb.y), m2 = fmul2_rn(P2.x, P2.y, Lb.z);
+            ob.x = __fadd_rn(__fadd_rn(m0.x, m1.x), m2.x);
+            ob.y = __fadd_rn(__fadd_rn(m0.y, m1.y), m2.y);
+            ob.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, Lb.x), __fmul_rn(P1.z, Lb.y)), __fmul_rn(P2.z, Lb.z));
+            ob.w = Lb.w;
+          }
           if (lane & 1u)
           {
             const float4 P3 = lds128(pAddr + kWwMat + 1536);  // column 3: + parent translation (p[r][3] * 1)

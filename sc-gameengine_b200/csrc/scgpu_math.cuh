@@ -145,6 +145,41 @@ __device__ __forceinline__ void sincosf_glibc(float y, float& sn, float& cs)
   sincosf_glibc_nt(y, sn, cs);
 }
 
+// Two IEEE single-precision products in ONE instruction (Blackwell FMUL2, PTX mul.rn.f32x2): each lane is rounded to
+// nearest like a scalar mul.rn.f32, so results are bit-identical; the kernels are issue-bound, so halving the
+// multiply count matters. Only multiplies are paired: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with
+// -fmad=false and explicit .rn, which would break parity, whereas the scalar add.rn.f32 that consumes these products
+// is never contracted.
+__device__ __forceinline__ float2 fmul2_rn(float ax, float ay, float b)
+{
+#if defined(__CUDA_ARCH__)
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(b));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+#else
+  return make_float2(__fmul_rn(ax, b), __fmul_rn(ay, b));
+#endif
+}
+// (ax*bx, ay*by)
+__device__ __forceinline__ float2 fmul2_rn(float ax, float ay, float bx, float by)
+{
+#if defined(__CUDA_ARCH__)
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(bx), "f"(by));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+#else
+  return make_float2(__fmul_rn(ax, bx), __fmul_rn(ay, by));
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // dense 4x4 products, reference operation order
 // ---------------------------------------------------------------------------------------------------
@@ -371,16 +406,20 @@ __device__ __forceinline__ void world_bounds_sphere(const Mat4& m, float bminx, 
   const float ey = __fmul_rn(__fsub_rn(bmaxy, bminy), 0.5f);
   const float ez = __fmul_rn(__fsub_rn(bmaxz, bminz), 0.5f);
 
-  ox = __fadd_rn(sum3_ref(__fmul_rn(m.c0.x, cx), __fmul_rn(m.c1.x, cy), __fmul_rn(m.c2.x, cz)), m.c3.x);
-  oy = __fadd_rn(sum3_ref(__fmul_rn(m.c0.y, cx), __fmul_rn(m.c1.y, cy), __fmul_rn(m.c2.y, cz)), m.c3.y);
+  // products in pairs (x, y) per column; the sums keep the reference's order and stay scalar
+  const float2 a0 = fmul2_rn(m.c0.x, m.c0.y, cx), a1 = fmul2_rn(m.c1.x, m.c1.y, cy), a2 = fmul2_rn(m.c2.x, m.c2.y, cz);
+  ox = __fadd_rn(sum3_ref(a0.x, a1.x, a2.x), m.c3.x);
+  oy = __fadd_rn(sum3_ref(a0.y, a1.y, a2.y), m.c3.y);
   oz = __fadd_rn(sum3_ref(__fmul_rn(m.c0.z, cx), __fmul_rn(m.c1.z, cy), __fmul_rn(m.c2.z, cz)), m.c3.z);
 
   // std::max(sx, std::max(sy, sz)) of the three column norms. sqrt is monotonic and correctly rounded, so the
   // maximum of the square roots is the square root of the maximum of the squares (same comparison structure:
   // NaN operands and ties select the same side in both domains): one sqrt instead of three.
-  const float qx = sum3_ref(__fmul_rn(m.c0.x, m.c0.x), __fmul_rn(m.c0.y, m.c0.y), __fmul_rn(m.c0.z, m.c0.z));
-  const float qy = sum3_ref(__fmul_rn(m.c1.x, m.c1.x), __fmul_rn(m.c1.y, m.c1.y), __fmul_rn(m.c1.z, m.c1.z));
-  const float qz = sum3_ref(__fmul_rn(m.c2.x, m.c2.x), __fmul_rn(m.c2.y, m.c2.y), __fmul_rn(m.c2.z, m.c2.z));
+  const float2 s0 = fmul2_rn(m.c0.x, m.c0.y, m.c0.x, m.c0.y), s1 = fmul2_rn(m.c1.x, m.c1.y, m.c1.x, m.c1.y);
+  const float2 s2 = fmul2_rn(m.c2.x, m.c2.y, m.c2.x, m.c2.y);
+  const float qx = sum3_ref(s0.x, s0.y, __fmul_rn(m.c0.z, m.c0.z));
+  const float qy = sum3_ref(s1.x, s1.y, __fmul_rn(m.c1.z, m.c1.z));
+  const float qz = sum3_ref(s2.x, s2.y, __fmul_rn(m.c2.z, m.c2.z));
   const float maxScale = __fsqrt_rn(std_max(qx, std_max(qy, qz)));
   const float localRadius = __fsqrt_rn(sum3_ref(__fmul_rn(ex, ex), __fmul_rn(ey, ey), __fmul_rn(ez, ez)));
   radius = __fmul_rn(localRadius, maxScale);

@@ -11,6 +11,8 @@
 #define __noinline__
 #define __constant__ static const
 #define __restrict__
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
