@@ -280,22 +280,24 @@ __device__ __forceinline__ bool trs_inputs_tame(float px, float py, float pz, fl
 __device__ __forceinline__ Mat4 mat4_trs_from_sincos(float px, float py, float pz, float sx, float cx, float sy, float cy,
                                                      float sz, float cz, float sx_, float sy_, float sz_)
 {
-  // A = Rz*Ry
-  const float a00 = __fmul_rn(cz, cy), a10 = __fmul_rn(sz, cy), a20 = -sy;
-  const float a01 = -sz, a11 = cz;  // a21 = 0
-  const float a02 = __fmul_rn(cz, sy), a12 = __fmul_rn(sz, sy), a22 = cy;
+  // A = Rz*Ry  (products in pairs, FMUL2; every sum stays a scalar add in the reference's order)
+  const float2 a0 = fmul2_rn(cz, sz, cy);          // a00, a10
+  const float a20 = -sy;
+  const float a01 = -sz, a11 = cz;                 // a21 = 0
+  const float2 a2 = fmul2_rn(cz, sz, sy);          // a02, a12
+  const float a22 = cy;
   // R = A*Rx : col0 = A.col0 ; col1 = A.col1*cx + A.col2*sx ; col2 = A.col1*(-sx) + A.col2*cx
   const float nsx = -sx;
-  const float r01 = __fadd_rn(__fmul_rn(a01, cx), __fmul_rn(a02, sx));
-  const float r11 = __fadd_rn(__fmul_rn(a11, cx), __fmul_rn(a12, sx));
-  const float r21 = __fmul_rn(a22, sx);
-  const float r02 = __fadd_rn(__fmul_rn(a01, nsx), __fmul_rn(a02, cx));
-  const float r12 = __fadd_rn(__fmul_rn(a11, nsx), __fmul_rn(a12, cx));
-  const float r22 = __fmul_rn(a22, cx);
+  const float2 p1 = fmul2_rn(a01, a11, cx), q1 = fmul2_rn(a2.x, a2.y, sx);
+  const float r01 = __fadd_rn(p1.x, q1.x), r11 = __fadd_rn(p1.y, q1.y);
+  const float2 p2 = fmul2_rn(a01, a11, nsx), q2 = fmul2_rn(a2.x, a2.y, cx);
+  const float r02 = __fadd_rn(p2.x, q2.x), r12 = __fadd_rn(p2.y, q2.y);
+  const float2 r2 = fmul2_rn(sx, cx, a22);         // r21, r22
   Mat4 m;
-  m.c0 = make_float4(__fmul_rn(a00, sx_), __fmul_rn(a10, sx_), __fmul_rn(a20, sx_), 0.f);
-  m.c1 = make_float4(__fmul_rn(r01, sy_), __fmul_rn(r11, sy_), __fmul_rn(r21, sy_), 0.f);
-  m.c2 = make_float4(__fmul_rn(r02, sz_), __fmul_rn(r12, sz_), __fmul_rn(r22, sz_), 0.f);
+  const float2 c0 = fmul2_rn(a0.x, a0.y, sx_), c1 = fmul2_rn(r01, r11, sy_), c2 = fmul2_rn(r02, r12, sz_);
+  m.c0 = make_float4(c0.x, c0.y, __fmul_rn(a20, sx_), 0.f);
+  m.c1 = make_float4(c1.x, c1.y, __fmul_rn(r2.x, sy_), 0.f);
+  m.c2 = make_float4(c2.x, c2.y, __fmul_rn(r2.y, sz_), 0.f);
   m.c3 = make_float4(px, py, pz, 1.f);
   return m;
 }
