@@ -220,6 +220,22 @@ SCGPU_API int scgpuSectorFileInfo(const void* bytes, size_t nBytes, int32_t* out
 SCGPU_API int scgpuSpawnSectorFile(ScGpuScene* ctx, const void* bytes, size_t nBytes, const uint32_t* entity, uint32_t nEntities,
                                    const ScGpuAssetTable* assets);
 
+/* ---- SURVEY.md 8(f) N4 (the second mat4_trs caller): the world editor's draw list ------------------------------
+ * Replaces BuildDrawItems (tools/world_editor/editor_core/editor_core.cpp:242-264): one ScRenderDrawItem
+ * (src/engine/include/sc_engine_render.h:24,51-57: 64-bit mesh and material handles, model[16], flags; 88 bytes) per
+ * entity whose mesh and
+ * material handles are non-zero, model = mat4_trs(position, rotation, scale), document order kept. Stateless with
+ * respect to the scene: the context only lends its device and stream. *outCount = kept entities (may exceed cap). */
+typedef struct ScGpuEditorDrawItem
+{
+  uint64_t mesh;     /* ScRenderHandle */
+  uint64_t material; /* ScRenderHandle */
+  float model[16];
+  uint32_t flags;
+} ScGpuEditorDrawItem;
+SCGPU_API int scgpuBuildEditorDraws(ScGpuScene* ctx, uint32_t n, const float* trs9, const uint64_t* meshHandle,
+                                    const uint64_t* materialHandle, ScGpuEditorDrawItem* out, uint32_t cap, uint32_t* outCount);
+
 /* ---- multi-GPU: one context per process per GPU, instance set sharded by world cell ------------------------
  * The only exchange is the gather of the compacted per-view lists and counts to the submitting rank. */
 #define SCGPU_COMM_ID_BYTES 128

@@ -654,6 +654,43 @@ int scgpuSpawnSectorFile(ScGpuScene* c, const void* bytes, size_t nBytes, const 
   return 1;
 }
 
+// ---- the editor's BuildDrawItems (editor_core.cpp:242-264) -------------------------------------
+int scgpuBuildEditorDraws(ScGpuScene* c, uint32_t n, const float* trs9, const uint64_t* meshHandle, const uint64_t* materialHandle,
+                          ScGpuEditorDrawItem* out, uint32_t cap, uint32_t* outCount)
+{
+  static_assert(sizeof(ScGpuEditorDrawItem) == 88, "ScRenderDrawItem is 88 bytes");
+  if (!enter(c)) return 0;
+  if (outCount) *outCount = 0;
+  if (n == 0) return 1;
+  if (!trs9 || !meshHandle || !materialHandle) return (int)fail(c, "scgpuBuildEditorDraws: NULL argument");
+  const uint32_t blocks = blocksFor(n);
+  const size_t oTrs = 0, oMesh = ((size_t)n * 36 + 255) & ~(size_t)255, oMat = oMesh + (((size_t)n * 8 + 255) & ~(size_t)255);
+  const size_t oCnt = oMat + (((size_t)n * 8 + 255) & ~(size_t)255), oOff = oCnt + (((size_t)blocks * 4 + 255) & ~(size_t)255);
+  const size_t oTot = oOff + (((size_t)blocks * 4 + 255) & ~(size_t)255), oOut = oTot + 256;
+  if (!ensure(c, c->scratch, oOut + (size_t)n * 88)) return 0;
+  char* s = (char*)c->scratch.ptr;
+  if (!uploadTo(c, s + oTrs, trs9, (size_t)n * 36)) return 0;
+  if (!uploadTo(c, s + oMesh, meshHandle, (size_t)n * 8)) return 0;
+  if (!uploadTo(c, s + oMat, materialHandle, (size_t)n * 8)) return 0;
+  k_editor_count<<<blocks, kBlock, 0, c->stream>>>((const uint64_t*)(s + oMesh), (const uint64_t*)(s + oMat), n, (uint32_t*)(s + oCnt));
+  k_scan_tiles<<<1, 1024, 0, c->stream>>>((const uint32_t*)(s + oCnt), (uint32_t*)(s + oOff), (uint32_t*)(s + oTot), blocks);
+  k_editor_write<<<blocks, kBlock, 0, c->stream>>>((const float*)(s + oTrs), (const uint64_t*)(s + oMesh), (const uint64_t*)(s + oMat), n,
+                                                   (const uint32_t*)(s + oOff), (uint32_t*)(s + oOut));
+  c->launches += 3;
+  SC_CUDA(c, cudaGetLastError());
+  uint32_t total = 0;
+  SC_CUDA(c, cudaMemcpyAsync(&total, s + oTot, 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (outCount) *outCount = total;
+  const uint32_t m = std::min(total, cap);
+  if (m && out)
+  {
+    SC_CUDA(c, cudaMemcpyAsync(out, s + oOut, (size_t)m * 88, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return 1;
+}
+
 int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
 {
   if (!enter(c)) return 0;

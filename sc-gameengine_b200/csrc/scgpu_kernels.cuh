@@ -1127,6 +1127,61 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   }
 }
 
+// ---- SURVEY.md 8(f) N4 (second mat4_trs caller): the world editor's BuildDrawItems --------------------------------
+// tools/world_editor/editor_core/editor_core.cpp:242-264: for every entity with a mesh and a material handle,
+// ScRenderDrawItem{mesh, material (64-bit handles), model = mat4_trs(position, rotation, scale), flags = 0}, in
+// document order.
+// Pass 1 counts the kept entities per 256-entity block, k_scan_tiles turns the counts into offsets, pass 2 builds the
+// matrices (same warp-cooperative sincos + structured TRS as the frame kernels, dense fallback for hostile values)
+// and writes the 88-byte items at their stable positions.
+__global__ void __launch_bounds__(kBlock) k_editor_count(const uint64_t* __restrict__ mesh, const uint64_t* __restrict__ material,
+                                                         uint32_t n, uint32_t* __restrict__ blockCounts)
+{
+  const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+  const bool keep = i < n && mesh[i] != 0ull && material[i] != 0ull;
+  const uint32_t c = __syncthreads_count(keep);
+  if (threadIdx.x == 0) blockCounts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(kBlock) k_editor_write(const float* __restrict__ trs9, const uint64_t* __restrict__ mesh,
+                                                         const uint64_t* __restrict__ material, uint32_t n,
+                                                         const uint32_t* __restrict__ blockOffsets, uint32_t* __restrict__ out22)
+{
+  __shared__ uint32_t sWarp[kBlock / 32];
+  const uint32_t i = blockIdx.x * kBlock + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool keep = i < n && mesh[i] != 0ull && material[i] != 0ull;
+  float t[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) t[k] = keep ? trs9[(size_t)i * 9 + k] : 0.0f;
+  const bool tame = trs_inputs_tame(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
+  float sx, cx, sy, cy, sz, cz;
+  sincos3_warp(keep && tame, t[3], t[4], t[5], sx, cx, sy, cy, sz, cz);
+  Mat4 W = mat4_identity();
+  if (keep)
+  {
+    if (tame) W = mat4_trs_from_sincos(t[0], t[1], t[2], sx, cx, sy, cy, sz, cz, t[6], t[7], t[8]);
+    else W = mat4_trs_dense_call(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
+  }
+  // stable position: block offset + rank inside the block
+  const uint32_t m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) sWarp[warp] = __popc(m);
+  __syncthreads();
+  uint32_t pos = blockOffsets[blockIdx.x] + __popc(m & ((1u << lane) - 1u));
+  for (uint32_t w = 0; w < warp; ++w) pos += sWarp[w];
+  if (!keep) return;
+  uint32_t* o = out22 + (size_t)pos * 22u;  // ScRenderDrawItem: u64 mesh, u64 material, model[16], flags, pad (88 bytes)
+  const uint64_t mh = mesh[i], th = material[i];
+  o[0] = (uint32_t)mh; o[1] = (uint32_t)(mh >> 32); o[2] = (uint32_t)th; o[3] = (uint32_t)(th >> 32);
+  const float4 c[4] = { W.c0, W.c1, W.c2, W.c3 };
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+  {
+    o[4 + 4 * k] = __float_as_uint(c[k].x); o[5 + 4 * k] = __float_as_uint(c[k].y);
+    o[6 + 4 * k] = __float_as_uint(c[k].z); o[7 + 4 * k] = __float_as_uint(c[k].w);
+  }
+  o[20] = 0u; o[21] = 0u;
+}
+
 // ---- K3a: exclusive scan of the per-tile counts, one CTA per row (view) -----------------------------------
 __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict__ tileCounts,
                                                      uint32_t* __restrict__ tileOffsets, uint32_t* __restrict__ totals,

@@ -93,6 +93,8 @@ class SectorGen(C.Structure):
         super().__init__(struct_size=C.sizeof(SectorGen), **kw)
 
 
+EDITOR_DRAW_DTYPE = np.dtype([("mesh", "<u8"), ("material", "<u8"), ("model", "<f4", (16,)), ("flags", "<u4"), ("_pad", "<u4")])
+assert EDITOR_DRAW_DTYPE.itemsize == 88
 DRAW_RUN_DTYPE = np.dtype([("pipelineId", "<u4"), ("materialId", "<u4"), ("meshId", "<u4"), ("first", "<u4"), ("count", "<u4")])
 assert DRAW_RUN_DTYPE.itemsize == 20
 
@@ -109,6 +111,7 @@ SYMBOLS = {
     "scgpuLastError": (C.c_char_p, [_vp]),
     "scgpuSpawn": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "scgpuDespawn": (C.c_int, [_vp, C.c_uint32, _vp]),
+    "scgpuBuildEditorDraws": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint32, _u32p]),
     "scgpuSectorFileInfo": (C.c_int, [_vp, C.c_size_t, _vp, _u32p, _u32p]),
     "scgpuSpawnSectorFile": (C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_uint32, C.POINTER(AssetTable)]),
     "scgpuSectorSpawnCount": (C.c_uint32, [C.POINTER(SectorGen), C.c_int32, C.c_int32]),
@@ -241,6 +244,16 @@ class Scene:
         e = _arr(entity, np.uint32)
         self._ck(self.lib.scgpuSpawnSectorFile(self.ctx, _ptr(raw), raw.shape[0], _ptr(e), e.shape[0], C.byref(assets)),
                  "scgpuSpawnSectorFile")
+
+    def editor_draws(self, trs9, mesh, material):
+        """the world editor's BuildDrawItems on the device"""
+        t = _arr(trs9, np.float32).reshape(-1, 9)
+        m, a = _arr(mesh, np.uint64), _arr(material, np.uint64)
+        out = np.zeros(t.shape[0], EDITOR_DRAW_DTYPE)
+        n = C.c_uint32(0)
+        self._ck(self.lib.scgpuBuildEditorDraws(self.ctx, t.shape[0], _ptr(t), _ptr(m), _ptr(a), _ptr(out), out.shape[0], C.byref(n)),
+                 "scgpuBuildEditorDraws")
+        return out[: n.value]
 
     def despawn(self, entity):
         e = _arr(entity, np.uint32)

@@ -240,3 +240,38 @@ def test_sector_files_unpacked_on_device_match_the_reference_reader():
     with pytest.raises(scgpu.ScGpuError):   # handle count must match the file
         dev.s.spawn_sector_file(g["f1_bytes"].tobytes(), np.arange(base, base + 3, dtype=np.uint32), tab)
     dev.close()
+
+
+def test_editor_draw_items_match_reference_trs_goldens():
+    """SURVEY 8(f) N4 (the second mat4_trs caller): scgpuBuildEditorDraws against BuildDrawItems
+    (editor_core.cpp:242-264) restated over the REFERENCE's own mat4_trs outputs (tests/golden/kats.npz): entities
+    without a mesh or a material handle are skipped, document order is kept, model matrices are bit-identical,
+    flags are 0; plus hostile values (NaN / Inf / huge scale) against the plain-C oracle."""
+    import ctypes as C
+    import oracle_bind
+    import scgpu
+    k = load_golden("kats.npz")
+    trs, want = k["rand_trs_in"], k["rand_trs_out"]
+    n = len(trs)
+    rng = np.random.default_rng(3)
+    mesh = rng.integers(0, 4, n).astype(np.uint64) * np.uint64(0x100000001)      # 0 = no mesh; 64-bit handles
+    mat = rng.integers(0, 3, n).astype(np.uint64) * np.uint64(0x200000003)
+    s = scgpu.Scene(16, max_views=1)
+    got = s.editor_draws(trs, mesh, mat)
+    keep = (mesh != 0) & (mat != 0)
+    assert 0 < keep.sum() < n and len(got) == keep.sum()
+    assert np.array_equal(got["mesh"], mesh[keep]) and np.array_equal(got["material"], mat[keep])
+    assert np.all(got["flags"] == 0)
+    assert_same_bits(got["model"], want[keep], "editor draw models")
+    # hostile inputs take the dense path: compare with the oracle's mat4_trs
+    port = oracle_bind.port_lib()
+    bad = np.tile(np.array([1, 2, 3, .1, .2, .3, 1, 1, 1], np.float32), (6, 1))
+    bad[0, 0] = np.nan; bad[1, 4] = np.inf; bad[2, 6] = 3e38; bad[3, 6:9] = 0; bad[4, 3] = 1e30; bad[5, 7] = -0.0
+    exp = np.zeros((6, 16), np.float32)
+    f = lambda a: a.ctypes.data_as(C.c_void_p)
+    for i in range(6):
+        port.sco_mat4_trs(f(bad[i, 0:3].copy()), f(bad[i, 3:6].copy()), f(bad[i, 6:9].copy()), f(exp[i]))
+    got2 = s.editor_draws(bad, np.ones(6, np.uint64), np.ones(6, np.uint64))
+    assert_same_bits(got2["model"], exp, "editor draw models, hostile values")
+    assert len(s.editor_draws(np.zeros((0, 9), np.float32), np.zeros(0, np.uint64), np.zeros(0, np.uint64))) == 0
+    s.close()
