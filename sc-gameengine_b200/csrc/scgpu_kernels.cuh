@@ -328,6 +328,28 @@ __device__ __forceinline__ uint32_t cull_views_warp(const ViewPlanes& vp, bool t
   return alive;
 }
 
+// Bounding sphere + plane tests of one warp. Far from every frustum - the normal case - the decision needs no square
+// root: with the cheap UPPER bound of the radius, "the favourite plane culls every lane in every view" is already
+// certain (d < -bound implies the reference's d < -radius). Only warps near a frustum compute the exact radius and run
+// the exact tests; the result is the reference's in both cases.
+template <int kViews>
+__device__ __forceinline__ uint32_t sphere_cull_warp(const ViewPlanes& vp, bool test, const Mat4& W, float4 r2, float4 r3,
+                                                     uint32_t& order)
+{
+  float ox, oy, oz, ex, ey, ez;
+  world_bounds_centre(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, ex, ey, ez);
+  const float negBound = -world_bounds_radius_bound(W, ex, ey, ez);
+  bool certain = true;
+#pragma unroll
+  for (int v = 0; v < kViews; ++v)
+  {
+    const uint32_t k0 = (order >> (3 * v)) & 7u;
+    certain = certain && (plane_dist(vp.planes[v][k0], ox, oy, oz) < negBound);
+  }
+  if (__all_sync(0xffffffffu, certain || !test)) return 0u;
+  return cull_views_warp<kViews>(vp, test, ox, oy, oz, -world_bounds_radius(W, ex, ey, ez), order);
+}
+
 // ---- K1+K2, flat scenes: fused transform + cull, all views in one pass ------------------------------------------------
 // No instance has a parent: pure streaming. One thread per slot, kSubTiles sub-tiles of kBlock consecutive slots per
 // CTA; the four record planes of a sub-tile are staged in shared memory by TMA bulk copies two sub-tiles ahead, so the
@@ -436,9 +458,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
     uint32_t mask = 0;
     if (__any_sync(0xffffffffu, test))
     {
-      float ox, oy, oz, radius;
-      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, radius);
-      mask = cull_views_warp<kViews>(vp, test, ox, oy, oz, -radius, order);
+      mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
     }
     if (cand && !test) mask = allMask;  // frozen culling or no Bounds component: always visible
     if (live) p.vismask[s] = (uint8_t)mask;
@@ -882,9 +902,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     {
       float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) r2 = lds128(recAddr + 1024);
-      float ox, oy, oz, radius;
-      world_bounds_sphere(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, radius);
-      mask = cull_views_warp<kViews>(vp, test, ox, oy, oz, -radius, order);
+      mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
     }
     if (cand && !test) mask = allMask;
     if (live) p.vismask[a + lane] = (uint8_t)mask;

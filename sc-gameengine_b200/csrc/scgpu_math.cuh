@@ -396,24 +396,27 @@ __device__ __forceinline__ float sum3_ref(float a, float b, float c)
 
 __device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }  // std::max
 
-// computeWorldBoundsSphere: center = M * aabb-centre (affine, left-to-right sum), radius = |extent| * max column norm
-__device__ __forceinline__ void world_bounds_sphere(const Mat4& m, float bminx, float bminy, float bminz, float bmaxx,
-                                                    float bmaxy, float bmaxz, float& ox, float& oy, float& oz,
-                                                    float& radius)
+// computeWorldBoundsSphere (sc_world_partition.cpp:1119-1144) in two halves: centre = M * aabb-centre (affine,
+// left-to-right sum) + the AABB half extents, and radius = |extent| * max column norm.
+__device__ __forceinline__ void world_bounds_centre(const Mat4& m, float bminx, float bminy, float bminz, float bmaxx,
+                                                    float bmaxy, float bmaxz, float& ox, float& oy, float& oz, float& ex,
+                                                    float& ey, float& ez)
 {
   const float cx = __fmul_rn(__fadd_rn(bminx, bmaxx), 0.5f);
   const float cy = __fmul_rn(__fadd_rn(bminy, bmaxy), 0.5f);
   const float cz = __fmul_rn(__fadd_rn(bminz, bmaxz), 0.5f);
-  const float ex = __fmul_rn(__fsub_rn(bmaxx, bminx), 0.5f);
-  const float ey = __fmul_rn(__fsub_rn(bmaxy, bminy), 0.5f);
-  const float ez = __fmul_rn(__fsub_rn(bmaxz, bminz), 0.5f);
-
+  ex = __fmul_rn(__fsub_rn(bmaxx, bminx), 0.5f);
+  ey = __fmul_rn(__fsub_rn(bmaxy, bminy), 0.5f);
+  ez = __fmul_rn(__fsub_rn(bmaxz, bminz), 0.5f);
   // products in pairs (x, y) per column; the sums keep the reference's order and stay scalar
   const float2 a0 = fmul2_rn(m.c0.x, m.c0.y, cx), a1 = fmul2_rn(m.c1.x, m.c1.y, cy), a2 = fmul2_rn(m.c2.x, m.c2.y, cz);
   ox = __fadd_rn(sum3_ref(a0.x, a1.x, a2.x), m.c3.x);
   oy = __fadd_rn(sum3_ref(a0.y, a1.y, a2.y), m.c3.y);
   oz = __fadd_rn(sum3_ref(__fmul_rn(m.c0.z, cx), __fmul_rn(m.c1.z, cy), __fmul_rn(m.c2.z, cz)), m.c3.z);
+}
 
+__device__ __forceinline__ float world_bounds_radius(const Mat4& m, float ex, float ey, float ez)
+{
   // std::max(sx, std::max(sy, sz)) of the three column norms. sqrt is monotonic and correctly rounded, so the
   // maximum of the square roots is the square root of the maximum of the squares (same comparison structure:
   // NaN operands and ties select the same side in both domains): one sqrt instead of three.
@@ -424,7 +427,31 @@ __device__ __forceinline__ void world_bounds_sphere(const Mat4& m, float bminx, 
   const float qz = sum3_ref(s2.x, s2.y, __fmul_rn(m.c2.z, m.c2.z));
   const float maxScale = __fsqrt_rn(std_max(qx, std_max(qy, qz)));
   const float localRadius = __fsqrt_rn(sum3_ref(__fmul_rn(ex, ex), __fmul_rn(ey, ey), __fmul_rn(ez, ez)));
-  radius = __fmul_rn(localRadius, maxScale);
+  return __fmul_rn(localRadius, maxScale);
+}
+
+// A cheap UPPER bound of world_bounds_radius(): sqrt(a^2+b^2+c^2) <= |a|+|b|+|c| for the extent, and every column
+// norm <= the sum of the magnitudes of all nine entries. The factor and the absolute term swallow every rounding error
+// on either side (about twenty roundings of 2^-24 each, denormal results included), so for finite inputs
+// bound >= radius holds for the VALUES THE REFERENCE COMPUTES. NaN, Inf and magnitudes above 1e18 give +Inf, which
+// makes every "d < -bound" test false. Used only to prove "culled" early: d < -bound implies d < -radius.
+__device__ __forceinline__ float world_bounds_radius_bound(const Mat4& m, float ex, float ey, float ez)
+{
+  const float e = fabsf(ex) + fabsf(ey) + fabsf(ez);
+  const float a = ((fabsf(m.c0.x) + fabsf(m.c0.y)) + (fabsf(m.c0.z) + fabsf(m.c1.x))) +
+                  ((fabsf(m.c1.y) + fabsf(m.c1.z)) + (fabsf(m.c2.x) + fabsf(m.c2.y))) + fabsf(m.c2.z);
+  // Beyond 1e18 the reference's squares can overflow (radius = Inf or NaN: "never culled") while these sums stay
+  // finite: give up there. NaN fails both comparisons and ends up at +Inf as well.
+  return (e < 1e18f && a < 1e18f) ? e * a * 1.0001f + 1e-30f : __int_as_float(0x7f800000);
+}
+
+__device__ __forceinline__ void world_bounds_sphere(const Mat4& m, float bminx, float bminy, float bminz, float bmaxx,
+                                                    float bmaxy, float bmaxz, float& ox, float& oy, float& oz,
+                                                    float& radius)
+{
+  float ex, ey, ez;
+  world_bounds_centre(m, bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, ox, oy, oz, ex, ey, ez);
+  radius = world_bounds_radius(m, ex, ey, ez);
 }
 
 // sphereInFrustum for one view: culled iff any plane has ((n0*c0 + n1*c1) + n2*c2) + d < -radius (NaN => kept)

@@ -352,3 +352,32 @@ def test_sorted_draws_and_runs_match_renderer_sort(max_draws):
     items0, runs0 = g.s.sorted_draws(0, np.zeros(0, np.uint32), mesh_count, max_draws)
     assert len(items0) == 0 and len(runs0) == 0
     g.close()
+
+
+@pytest.mark.parametrize("hier", [False, True])
+def test_radius_overflow_is_never_culled_early(hier):
+    """The early 'certainly culled' exit of sphere_cull_warp works with an upper bound of the radius. Where the
+    reference's own radius overflows (column norms beyond sqrt(FLT_MAX) -> radius Inf -> 'd < -radius' is false ->
+    VISIBLE) the bound must give up too, however far outside the frustum the instance lies."""
+    n = 64
+    trs = np.zeros((n, 9), np.float32)
+    trs[:, 6:9] = 1.0
+    trs[:, 0] = np.linspace(1e3, 1e6, n)          # ordinary far-away instances: culled
+    big = [3, 17, 40]
+    trs[big, 0] = [1e25, -3e30, 5e21]
+    trs[big, 6] = [1e20, 4e19, 2.5e19]              # column norm^2 overflows
+    trs[41, 0] = 1e25; trs[41, 6] = 1e17            # large but finite radius: culled like the oracle says
+    e = np.arange(n, dtype=np.uint32)
+    par = None
+    if hier:
+        idx = np.full(n, -1, np.int64)
+        idx[1:8] = 0                                 # a group at the front, the rest roots
+        par = scenes.parent_handles(idx, e)
+    p, g = PortScene(), GpuAdapter(n, max_views=2)
+    vps = scenes.standard_views(2)
+    for s in (g, p):
+        s.spawn(e, trs, par, None, None, None)
+        s.update(vps)
+    compare_frame(g, p, e, 2, "radius overflow")
+    assert all(b in g.visible[0] for b in big)
+    g.close()
