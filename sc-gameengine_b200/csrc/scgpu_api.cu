@@ -297,8 +297,8 @@ template <int V>
 cudaError_t optInSmem()
 {
   cudaError_t e = cudaFuncSetAttribute(k_update_flat<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemFlat);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_update_win<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmemWin);
+  static_assert(kUpdateSmemWin <= 48 * 1024, "k_update_win keeps its shared memory static");
+  return e;
 }
 
 int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
@@ -918,7 +918,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
 #define SC_LAUNCH_UPDATE(V)                                                                                              \
   case V:                                                                                                                \
     if (c->anyParentEver)                                                                                                \
-      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kWinBlock, kUpdateSmemWin, c->stream>>>(p, c->planes, c->slotInfo, \
+      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kWinBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, \
                                                                                                      c->winList, c->tileWinBase); \
     else                                                                                                                 \
       k_update_flat<V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                                   \

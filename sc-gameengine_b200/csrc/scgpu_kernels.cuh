@@ -845,6 +845,14 @@ __device__ __forceinline__ uint32_t warp_slow_slot(uint32_t sBase)
   return old;
 }
 
+}  // namespace scgpu
+// The window kernel's shared memory as a file-scope array with an unmangled name: its shared-window address is then a
+// link-time IMMEDIATE ("mov.u32 r, scgpu_win_smem") that costs no register, where the address of a dynamic array is
+// a computed value that ptxas kept spilling to local memory across the window loop.
+extern "C" __shared__ __align__(128) unsigned char scgpu_win_smem[scgpu::kUpdateSmemWin];
+namespace scgpu
+{
+
 template <int kViews>
 __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(const __grid_constant__ UpdateParams p,
                                                           const __grid_constant__ ViewPlanes vp,
@@ -852,8 +860,9 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
                                                           const uint32_t* __restrict__ winList,
                                                           const uint32_t* __restrict__ tileWinBase)
 {
-  extern __shared__ __align__(128) unsigned char sDynW[];
-  const uint32_t sBase = smem_u32(sDynW);
+  unsigned char* const sDynW = scgpu_win_smem;
+  uint32_t sBase;
+  asm("mov.u32 %0, scgpu_win_smem;" : "=r"(sBase));
   const uint32_t tid = threadIdx.x;
   // lane / warp ids through volatile asm: the compiler then keeps them in registers instead of re-reading the
   // special register (S2R, ~20 cycles each) wherever register pressure makes rematerialisation look cheap
