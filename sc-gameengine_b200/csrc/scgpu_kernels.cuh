@@ -1122,7 +1122,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   {
     const uint32_t nSlow = lds32(sBase + kWsNext + 4);
 #pragma unroll 1
-    for (uint32_t k = warp; k < nSlow; k += kWinWarps)
+    for (uint32_t k = threadIdx.x >> 5; k < nSlow; k += kWinWarps)
     {
       const uint32_t w = lds16(sBase + kWsSlow + k * 2u);
       const uint32_t a = lds32(sBase + kWsWin + w * 4) & kWinSlotMask;
