@@ -1018,10 +1018,13 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);  // roots: world == local
         ok = tame;
       }
-      else if (live)
+      if (dirtyM != liveMask)  // warp-uniform: a fully dirty window loads no stored matrix at all
       {
-        W = load_world(p, (lds32(winAddr) & kWinSlotMask) + lane);
-        ok = mat4_is_affine(W);
+        if (live && !nodeDirty)
+        {
+          W = load_world(p, (lds32(winAddr) & kWinSlotMask) + lane);
+          ok = mat4_is_affine(W);
+        }
       }
       fast = __all_sync(0xffffffffu, ok);
       // ---- 3. parent.world * local level by level, one lane PAIR per child ----
