@@ -1,0 +1,2 @@
+CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline"
+ncu --set full --clock-control none --import-source on -k regex:k_update_win -s 3 -c 1 -o gpurun_out/r01_k_update_win_v10 $CMD > gpurun_out/ncu_a.log 2>&1

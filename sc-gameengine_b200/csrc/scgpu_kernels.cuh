@@ -791,6 +791,15 @@ __device__ __forceinline__ uint32_t warp_atoms_add(uint32_t a, uint32_t v)
                : "memory");
   return __shfl_sync(0xffffffffu, old, leader);
 }
+// the two halves of warp_atoms_add, for callers that have work to do while the atomic is in flight
+__device__ __forceinline__ void warp_atoms_add_issue(uint32_t a, uint32_t v, uint32_t& old, uint32_t& leader)
+{
+  old = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.shared.add.u32 %0, [%2], %3;\n\t}"
+               : "+r"(old), "=r"(leader)
+               : "r"(a), "r"(v)
+               : "memory");
+}
 __device__ __forceinline__ void warp_reds_add(uint32_t a, uint32_t v)
 {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\t@p red.shared.add.u32 [%0], %1;\n\t}" ::"r"(a), "r"(v) : "memory");
@@ -967,10 +976,11 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
 #pragma unroll 1
   while (w < nWin)
   {
-    const uint32_t wNext = warp_atoms_add(sBase + kWsNext, 1u);
-    if (wNext < nWin) fetch(wNext, bufOff ^ kWsBuf);  // in flight while this window is computed
-    cp_async_commit();
-    cp_async_wait<1>();
+    // claim the next window now, look at the answer after the transform phase: the shared atomic and the shuffle that
+    // broadcasts its result are off the critical path
+    uint32_t claimOld, claimLeader;
+    warp_atoms_add_issue(sBase + kWsNext, 1u, claimOld, claimLeader);
+    cp_async_wait<0>();
     const uint32_t recAddr = laneBase + bufOff;
     const uint32_t winAddr = sBase + kWsWin + w * 4;
     bool live, nodeDirty = false, fast;
@@ -985,7 +995,14 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     }
     const uint32_t wl = info & kInfoDepthMask;
     const uint32_t maxL = __reduce_max_sync(0xffffffffu, wl);
-    if (fast)
+    uint32_t wNext;
+    if (!fast)  // window flagged for the generic path: nothing to overlap with
+    {
+      wNext = __shfl_sync(0xffffffffu, claimOld, claimLeader);
+      if (wNext < nWin) fetch(wNext, bufOff ^ kWsBuf);
+      cp_async_commit();
+    }
+    else
     {
       float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
       float sclZ = 0.f;
@@ -1027,6 +1044,10 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         }
       }
       fast = __all_sync(0xffffffffu, ok);
+      // the claimed window's records + slotInfo words are fetched while this window is composed and culled
+      wNext = __shfl_sync(0xffffffffu, claimOld, claimLeader);
+      if (wNext < nWin) fetch(wNext, bufOff ^ kWsBuf);
+      cp_async_commit();
       // ---- 3. parent.world * local level by level, one lane PAIR per child ----
       if (fast && maxL != 0u && dirtyM != 0u)
       {
