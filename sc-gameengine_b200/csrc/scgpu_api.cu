@@ -109,6 +109,8 @@ struct ScGpuScene
   uint32_t* tileWinCount = nullptr;  // [tiles]
   uint32_t* tileWinBase = nullptr;   // [tiles+1] exclusive scan of tileWinCount, total at the end
   uint32_t* winList = nullptr;       // [total+1] absolute start slot of every window (bit 31: generic path)
+  uint32_t* slowList = nullptr;      // windows k_update_win hands to k_update_win_slow (start | len << 24)
+  uint32_t numSMs = 148;
   uint8_t* vismask = nullptr;
   uint32_t* tileCounts = nullptr;
   uint32_t* tileOffsets = nullptr;
@@ -268,7 +270,7 @@ void freeAll(ScGpuScene* c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
-  cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
+  cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->slowList); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
@@ -312,6 +314,7 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   SC_CUDA(c, cudaSetDevice(c->device));
   cudaDeviceProp prop{};
   SC_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+  c->numSMs = (uint32_t)prop.multiProcessorCount;
   if (prop.major < 10)
     return (int)fail(c, "device %d is sm_%d%d; libscgpu is built for sm_100a (B200) only", c->device, prop.major, prop.minor);
   SC_CUDA(c, optInSmem<1>()); SC_CUDA(c, optInSmem<2>()); SC_CUDA(c, optInSmem<3>()); SC_CUDA(c, optInSmem<4>());
@@ -345,9 +348,10 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   if (!devAlloc(c, &c->tileWinCount, (size_t)c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->tileWinBase, (size_t)c->maxTiles + 1, true)) return 0;
   if (!devAlloc(c, &c->winList, (size_t)c->maxTiles * kMaxWin + 1, true)) return 0;
+  if (!devAlloc(c, &c->slowList, (size_t)c->maxTiles * kMaxWin + 1, true)) return 0;
   if (!devAlloc(c, &c->tileCounts, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->tileOffsets, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
-  if (!devAlloc(c, &c->totals, (size_t)kMaxViews + 2, true)) return 0;
+  if (!devAlloc(c, &c->totals, (size_t)kTotalsWords, true)) return 0;
   for (uint32_t v = 0; v < c->maxViews; ++v)
   {
     if (!devAlloc(c, &c->visEntity[v], n, false)) return 0;
@@ -896,7 +900,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
   }
   c->topologyDirty = false;
 
-  SC_CUDA(c, cudaMemsetAsync(c->totals, 0, sizeof(uint32_t) * (kMaxViews + 2), c->stream));
+  SC_CUDA(c, cudaMemsetAsync(c->totals, 0, sizeof(uint32_t) * kTotalsWords, c->stream));
   if (numTiles)
   {
     UpdateParams p{};
@@ -918,8 +922,13 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
 #define SC_LAUNCH_UPDATE(V)                                                                                              \
   case V:                                                                                                                \
     if (c->anyParentEver)                                                                                                \
-      k_update_win<V><<<(numTiles + kWinTilesPerCta - 1) / kWinTilesPerCta, kWinBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, \
-                                                                                                     c->winList, c->tileWinBase); \
+    {                                                                                                                    \
+      k_update_win<V><<<c->numSMs * SCGPU_WIN_MINBLOCKS, kWinBlock, 0, c->stream>>>(                                     \
+        p, c->planes, c->slotInfo, c->winList, c->tileWinBase + numTiles, c->totals + kQueueNext, c->slowList);          \
+      k_update_win_slow<V><<<c->numSMs, kWinBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->totals + kQueueSlow,    \
+                                                                   c->slowList);                                         \
+      ++c->launches;                                                                                                     \
+    }                                                                                                                    \
     else                                                                                                                 \
       k_update_flat<V><<<numTiles, kBlock, kUpdateSmemFlat, c->stream>>>(p, c->planes);                                   \
     break;

@@ -769,6 +769,10 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v)
+{
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds16(uint32_t a)
 {
   uint16_t v;
@@ -830,28 +834,94 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem, const void* gmem)
 #ifndef SCGPU_WIN_BLOCK
 #define SCGPU_WIN_BLOCK 128
 #define SCGPU_WIN_MINBLOCKS 8
-#define SCGPU_WIN_TILES 2
 #endif
 constexpr uint32_t kWinBlock = SCGPU_WIN_BLOCK;          // threads per CTA of k_update_win
-constexpr uint32_t kWinTilesPerCta = SCGPU_WIN_TILES;    // tiles per CTA: ~18 windows per warp
 constexpr uint32_t kWinWarps = kWinBlock / 32;
-// dynamic shared memory of k_update_win (byte offsets). Everything a warp touches in the loop sits in ONE per-warp
-// block, so that every address is "lane base + constant" and folds into the instruction's immediate offset.
+constexpr uint32_t kWinChunk = 8;                        // consecutive windows per claim from the global queue
+// shared memory of k_update_win (byte offsets). Everything a warp touches in the loop sits in ONE per-warp block, so
+// that every address is "lane base + constant" and folds into the instruction's immediate offset.
 constexpr uint32_t kWsBuf = 4 * 512 + 128;              // one prefetch buffer: 4 record planes + 32 slotInfo words
 constexpr uint32_t kWwMat = 2 * kWsBuf;                 // [4][32] float4: matrix columns of the level loop
 constexpr uint32_t kWwSched = kWwMat + 4 * 512;         // [32] u16: children of the current level
-constexpr uint32_t kWwSize = kWwSched + 64;             // per-warp block
-constexpr uint32_t kWsWin = kWinWarps * kWwSize;        // [4*kMaxWin+1] u32: this CTA's slice of the window list
-constexpr uint32_t kWsCnt = kWsWin + ((kWinTilesPerCta * kMaxWin + 1) * 4 + 15) / 16 * 16;  // [tiles+1][kMaxViews+2] u32
-constexpr uint32_t kWsNext = kWsCnt + ((kWinTilesPerCta + 1) * (kMaxViews + 2) * 4 + 15) / 16 * 16;
-constexpr uint32_t kWsSlow = kWsNext + 16;            // [tiles*kMaxWin] u16: windows deferred to the generic path (count at kWsNext+4)
-constexpr uint32_t kUpdateSmemWin = kWsSlow + (kWinTilesPerCta * kMaxWin * 2 + 15) / 16 * 16;
+constexpr uint32_t kWwList = kWwSched + 64;             // 2 x [kWinChunk+1] u32 (64 B each): window starts of the current
+                                                        // and of the next claimed chunk
+constexpr uint32_t kWwSize = kWwList + 128;             // per-warp block
+constexpr uint32_t kWsRecomputed = kWinWarps * kWwSize; // u32: world matrices rewritten by this CTA
+constexpr uint32_t kUpdateSmemWin = kWsRecomputed + 16;
+// device-side work queue of k_update_win: totals[kQueueNext] = next unclaimed window, totals[kQueueSlow] = number of
+// windows handed to k_update_win_slow (both zeroed with the totals before every launch)
+constexpr uint32_t kQueueNext = kMaxViews + 2, kQueueSlow = kMaxViews + 3, kTotalsWords = kMaxViews + 4;
 
-__device__ __forceinline__ uint32_t warp_slow_slot(uint32_t sBase)
+__device__ __forceinline__ void red_global_add(uint32_t* p, uint32_t v)
 {
-  uint32_t old;
-  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(sBase + kWsNext + 4) : "memory");
-  return old;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q red.global.add.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v) : "memory");
+}
+// claim of kWinChunk windows: issue now (one elected lane), read the answer later
+__device__ __forceinline__ void queue_claim_issue(uint32_t* queue, uint32_t& old)
+{
+  old = 0;
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q atom.global.add.u32 %0, [%1], %2;\n\t}"
+               : "+r"(old) : "l"(queue), "n"(kWinChunk) : "memory");
+}
+__device__ __forceinline__ uint32_t queue_claim_result(uint32_t old)
+{
+  uint32_t leader;  // elect.sync is deterministic for a given member mask: the same lane that issued the atomic
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync %0|q, 0xffffffff;\n\t}" : "=r"(leader));
+  return __shfl_sync(0xffffffffu, old, leader);
+}
+
+// store + bounding sphere + plane tests + per-tile counts of one resolved window (records in shared memory at recAddr)
+template <int kViews>
+__device__ __forceinline__ void finish_window(const UpdateParams& p, const ViewPlanes& vp, uint32_t a, uint32_t lane, uint32_t recAddr,
+                                              bool live, bool nodeDirty, const Mat4& W, uint32_t& order, uint32_t recomputedAddr)
+{
+  constexpr uint32_t allMask = (1u << kViews) - 1u;
+  const bool freeze = (p.flags & kUpdFreeze) != 0;
+  if (nodeDirty) store_world(p, a + lane, W);
+  {
+    const uint32_t nd = __ballot_sync(0xffffffffu, nodeDirty);
+    if (nd) warp_reds_add(recomputedAddr, __popc(nd));
+  }
+  float4 r3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) r3 = lds128(recAddr + 1536);
+  const uint32_t fl = __float_as_uint(r3.w);
+  const bool cand = live && (fl & kFlagMesh);
+  const bool test = cand && !freeze && (fl & kFlagBounds);
+  uint32_t mask = 0;
+  if (__any_sync(0xffffffffu, test))
+  {
+    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) r2 = lds128(recAddr + 1024);
+    mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
+  }
+  if (cand && !test) mask = allMask;
+  if (live) p.vismask[a + lane] = (uint8_t)mask;
+  // per-tile counts (zeroed by the host before the launch): ballots, one global reduction per counter by an elected
+  // lane; a window may straddle a tile boundary
+  const uint32_t candM = __ballot_sync(0xffffffffu, cand);
+  if (candM)
+  {
+    const uint32_t tile = a / kTile;
+    const uint32_t room = (tile + 1u) * kTile - a;  // slots left in the window's first tile
+    const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
+    const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
+    uint32_t* cnt = p.tileCounts + tile;
+    red_global_add(cnt + (size_t)kViews * p.numTiles, __popc(candM & lowMask));
+    if (candM & ~lowMask) red_global_add(cnt + (size_t)kViews * p.numTiles + 1, __popc(candM & ~lowMask));
+    if (anyVis)
+    {
+#pragma unroll
+      for (int v = 0; v < kViews; ++v)
+      {
+        const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
+        if (m)
+        {
+          red_global_add(cnt + (size_t)v * p.numTiles, __popc(m & lowMask));
+          if (m & ~lowMask) red_global_add(cnt + (size_t)v * p.numTiles + 1, __popc(m & ~lowMask));
+        }
+      }
+    }
+  }
 }
 
 }  // namespace scgpu
@@ -862,103 +932,47 @@ extern "C" __shared__ __align__(128) unsigned char scgpu_win_smem[scgpu::kUpdate
 namespace scgpu
 {
 
+// PERSISTENT: the grid is 8 CTAs per SM; warps pull chunks of kWinChunk consecutive windows from a device-wide queue
+// (one global atomic per chunk, issued a whole chunk ahead of its use), so there is no CTA-level barrier, no per-CTA
+// prologue per tile, and the tail of the launch is one chunk per warp. Windows that need the generic path are appended
+// to a global list and handled by k_update_win_slow afterwards.
 template <int kViews>
 __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(const __grid_constant__ UpdateParams p,
                                                           const __grid_constant__ ViewPlanes vp,
                                                           const uint32_t* __restrict__ slotInfo,
                                                           const uint32_t* __restrict__ winList,
-                                                          const uint32_t* __restrict__ tileWinBase)
+                                                          const uint32_t* __restrict__ totalWindows,
+                                                          uint32_t* __restrict__ queue,  // &totals[kQueueNext], [1] = slow count
+                                                          uint32_t* __restrict__ slowList)
 {
-  unsigned char* const sDynW = scgpu_win_smem;
   uint32_t sBase;
   asm("mov.u32 %0, scgpu_win_smem;" : "=r"(sBase));
+  asm volatile("" ::"l"(scgpu_win_smem));  // keeps the array emitted: every other access goes through sBase
   const uint32_t tid = threadIdx.x;
   // lane / warp ids through volatile asm: the compiler then keeps them in registers instead of re-reading the
   // special register (S2R, ~20 cycles each) wherever register pressure makes rematerialisation look cheap
   uint32_t lane, warp;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
   asm volatile("shr.u32 %0, %1, 5;" : "=r"(warp) : "r"(tid));
-  const uint32_t firstTile = blockIdx.x * kWinTilesPerCta;
-  const uint32_t nTiles = min(kWinTilesPerCta, p.numTiles - firstTile);
-  const uint32_t wBeg = tileWinBase[firstTile];
-  const uint32_t nWin = tileWinBase[firstTile + nTiles] - wBeg;
-  {
-    uint32_t* sWin = reinterpret_cast<uint32_t*>(sDynW + kWsWin);
-    uint32_t* sCnt = reinterpret_cast<uint32_t*>(sDynW + kWsCnt);
-    for (uint32_t k = tid; k <= nWin; k += kWinBlock) sWin[k] = winList[wBeg + k];
-    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kMaxViews + 2); k += kWinBlock) sCnt[k] = 0;
-    if (tid < 2) reinterpret_cast<uint32_t*>(sDynW + kWsNext)[tid] = 0;  // next unclaimed window, deferred count
-  }
+  if (tid == 0) *reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed) = 0u;  // (also keeps the symbol referenced)
   __syncthreads();
+  const uint32_t total = *totalWindows;
 
-  constexpr uint32_t allMask = (1u << kViews) - 1u;
-  constexpr uint32_t kCntRow = (kMaxViews + 2) * 4;  // bytes per tile row of the count table
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
-  const bool freeze = (p.flags & kUpdFreeze) != 0;
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
   const uint32_t warpBase = sBase + warp * kWwSize;
   const uint32_t laneBase = warpBase + lane * 16;  // this lane's float4 of plane 0, buffer 0
 
-  // store + bounding sphere + plane tests + per-tile counts of one resolved window
-  auto finish = [&](uint32_t w, uint32_t recAddr, bool live, bool nodeDirty, const Mat4& W)
+  // window starts of chunk [cs, cs + kWinChunk] -> list slot `slot` (0/1) of this warp, asynchronously
+  auto stage_list = [&](uint32_t cs, uint32_t slot)
   {
-    const uint32_t a = lds32(sBase + kWsWin + w * 4) & kWinSlotMask;
-    if (nodeDirty) store_world(p, a + lane, W);
-    {
-      const uint32_t nd = __ballot_sync(0xffffffffu, nodeDirty);
-      if (nd) warp_reds_add(sBase + kWsCnt + (kMaxViews + 1) * 4, __popc(nd));
-    }
-    // ---- bounding sphere + plane tests in registers ----
-    float4 r3 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) r3 = lds128(recAddr + 1536);
-    const uint32_t fl = __float_as_uint(r3.w);
-    const bool cand = live && (fl & kFlagMesh);
-    const bool test = cand && !freeze && (fl & kFlagBounds);
-    uint32_t mask = 0;
-    if (__any_sync(0xffffffffu, test))
-    {
-      float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) r2 = lds128(recAddr + 1024);
-      mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
-    }
-    if (cand && !test) mask = allMask;
-    if (live) p.vismask[a + lane] = (uint8_t)mask;
-    // ---- per-tile counts: ballots, one shared-memory reduction per counter; a window may straddle a tile boundary ----
-    const uint32_t candM = __ballot_sync(0xffffffffu, cand);
-    if (candM)
-    {
-      const uint32_t tl = (a / kTile) - firstTile;
-      const uint32_t room = (a / kTile + 1u) * kTile - a;  // slots left in the window's first tile
-      const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
-      const uint32_t cntAddr = sBase + kWsCnt + tl * kCntRow;
-      const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
-      warp_reds_add(cntAddr + kViews * 4, __popc(candM & lowMask));
-      if (candM & ~lowMask) warp_reds_add(cntAddr + kCntRow + kViews * 4, __popc(candM & ~lowMask));
-      if (anyVis)
-      {
-#pragma unroll
-        for (int v = 0; v < kViews; ++v)
-        {
-          const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
-          if (m)
-          {
-            warp_reds_add(cntAddr + v * 4, __popc(m & lowMask));
-            if (m & ~lowMask) warp_reds_add(cntAddr + kCntRow + v * 4, __popc(m & ~lowMask));
-          }
-        }
-      }
-    }
+    if (lane <= kWinChunk) cp_async4s(warpBase + kWwList + slot * 64u + lane * 4u, winList + min(cs + lane, total));
   };
-
-  // A warp that finishes a window claims the next unclaimed one of its CTA (one shared atomic by an elected lane);
-  // the record planes and the slotInfo words of the claimed window are fetched with cp.async while the current
-  // window is being computed, so nothing of the next window occupies a register meanwhile. For the same reason
-  // the window geometry and the flag word are RE-READ from shared memory in each phase instead of being carried
-  // across the level loop in registers (the kernel lives at 64 registers / 4 CTAs per SM).
-  auto fetch = [&](uint32_t w, uint32_t off)
+  // records + slotInfo words of the window whose list entry sits at listAddr -> prefetch buffer at byte offset off
+  auto fetch = [&](uint32_t listAddr, uint32_t off)
   {
-    const uint32_t e0 = lds32(sBase + kWsWin + w * 4) & kWinSlotMask, e1 = lds32(sBase + kWsWin + w * 4 + 4) & kWinSlotMask;
+    const uint32_t e0 = lds32(listAddr) & kWinSlotMask, e1 = lds32(listAddr + 4) & kWinSlotMask;
     if (lane < e1 - e0)
     {
       const uint32_t q = e0 + lane;
@@ -970,39 +984,46 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
       cp_async4s(d + 2048 - lane * 12, slotInfo + q);
     }
   };
-  uint32_t w = warp_atoms_add(sBase + kWsNext, 1u), bufOff = 0;
-  if (w < nWin) fetch(w, 0);
-  cp_async_commit();
-#pragma unroll 1
-  while (w < nWin)
+
+  // ---- prologue: first chunk (its list is waited for), second chunk claimed and staged, third claim in flight ----
+  uint32_t claimOld;
+  queue_claim_issue(queue, claimOld);
+  uint32_t cs = queue_claim_result(claimOld);
+  uint32_t cnt = cs < total ? min(kWinChunk, total - cs) : 0u;  // windows in the current chunk
+  uint32_t pos = 0;                                             // index of the current window in it
+  uint32_t cntNext = 0;                                         // windows in the staged next chunk
+  uint32_t listAddr = warpBase + kWwList;                       // shared address of the current window's list entry
+  uint32_t bufOff = 0;
+  if (cnt)
   {
-    // claim the next window now, look at the answer after the transform phase: the shared atomic and the shuffle that
-    // broadcasts its result are off the critical path
-    uint32_t claimOld, claimLeader;
-    warp_atoms_add_issue(sBase + kWsNext, 1u, claimOld, claimLeader);
+    stage_list(cs, 0);
+    cp_async_commit();
     cp_async_wait<0>();
+    __syncwarp();
+    fetch(listAddr, 0);
+  }
+  cp_async_commit();
+  queue_claim_issue(queue, claimOld);
+#pragma unroll 1
+  while (cnt)
+  {
+    cp_async_wait<0>();
+    __syncwarp();  // the staged list words were copied by other lanes
     const uint32_t recAddr = laneBase + bufOff;
-    const uint32_t winAddr = sBase + kWsWin + w * 4;
     bool live, nodeDirty = false, fast;
     uint32_t info;
     Mat4 W = mat4_identity();
     {
-      const uint32_t e0 = lds32(winAddr);
-      const uint32_t len = (lds32(winAddr + 4) & kWinSlotMask) - (e0 & kWinSlotMask);
+      const uint32_t e0 = lds32(listAddr);
+      const uint32_t len = (lds32(listAddr + 4) & kWinSlotMask) - (e0 & kWinSlotMask);
       live = lane < len;
       fast = (e0 & kWinSlow) == 0u;
       info = live ? lds32(recAddr + 2048 - lane * 12) : 0u;
     }
     const uint32_t wl = info & kInfoDepthMask;
     const uint32_t maxL = __reduce_max_sync(0xffffffffu, wl);
-    uint32_t wNext;
-    if (!fast)  // window flagged for the generic path: nothing to overlap with
-    {
-      wNext = __shfl_sync(0xffffffffu, claimOld, claimLeader);
-      if (wNext < nWin) fetch(wNext, bufOff ^ kWsBuf);
-      cp_async_commit();
-    }
-    else
+    uint32_t dirtyM = 0, liveMask = 0, parentLane = 0;
+    if (fast)
     {
       float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
       float sclZ = 0.f;
@@ -1013,10 +1034,10 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         fl = lds32(recAddr + 1536 + 12);
       }
       nodeDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
-      const uint32_t parentLane = (info >> kInfoParentShift) & 31u;
+      parentLane = (info >> kInfoParentShift) & 31u;
       // ---- 1. children inherit dirtiness level by level ----
-      const uint32_t liveMask = __ballot_sync(0xffffffffu, live);
-      uint32_t dirtyM = __ballot_sync(0xffffffffu, nodeDirty);
+      liveMask = __ballot_sync(0xffffffffu, live);
+      dirtyM = __ballot_sync(0xffffffffu, nodeDirty);
       if (dirtyM != liveMask && dirtyM != 0u)
       {
         for (uint32_t l = 1; l <= maxL; ++l)
@@ -1039,17 +1060,38 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
       {
         if (live && !nodeDirty)
         {
-          W = load_world(p, (lds32(winAddr) & kWinSlotMask) + lane);
+          W = load_world(p, (lds32(listAddr) & kWinSlotMask) + lane);
           ok = mat4_is_affine(W);
         }
       }
       fast = __all_sync(0xffffffffu, ok);
-      // the claimed window's records + slotInfo words are fetched while this window is composed and culled
-      wNext = __shfl_sync(0xffffffffu, claimOld, claimLeader);
-      if (wNext < nWin) fetch(wNext, bufOff ^ kWsBuf);
-      cp_async_commit();
+    }
+    // ---- what comes next for this warp: the next window of the chunk, or the first one of the staged next chunk ----
+    const uint32_t a = lds32(listAddr) & kWinSlotMask;  // this window's start: the list slot may be recycled below
+    uint32_t nextList = listAddr + 4u;
+    if (pos == 1u)
+    {
+      // the other list slot is dead since the previous chunk's last window finished: take the claim that has been
+      // in flight for a whole chunk, stage that chunk's window starts there, and put the next claim in flight
+      const uint32_t csNext = queue_claim_result(claimOld);
+      cntNext = csNext < total ? min(kWinChunk, total - csNext) : 0u;
+      if (cntNext) stage_list(csNext, ((listAddr - warpBase - kWwList) < 64u) ? 1u : 0u);
+      queue_claim_issue(queue, claimOld);
+    }
+    ++pos;
+    if (pos == cnt)
+    {
+      nextList = warpBase + kWwList + (((listAddr - warpBase - kWwList) < 64u) ? 64u : 0u);
+      cnt = cntNext;
+      cntNext = 0u;
+      pos = 0u;
+    }
+    if (cnt) fetch(nextList, bufOff ^ kWsBuf);  // in flight while this window is composed and culled
+    cp_async_commit();
+    if (fast)
+    {
       // ---- 3. parent.world * local level by level, one lane PAIR per child ----
-      if (fast && maxL != 0u && dirtyM != 0u)
+      if (maxL != 0u && dirtyM != 0u)
       {
         const uint32_t own = laneBase + kWwMat;
         sts128(own, W.c0); sts128(own + 512, W.c1); sts128(own + 1024, W.c2); sts128(own + 1536, W.c3);
@@ -1084,7 +1126,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
           sts128(cAddr + kWwMat, oa);
           sts128(cAddr + kWwMat + 512, ob);
         };
-        if (dirtyM == liveMask && (lds32(winAddr) & kWinNoStatic) == 0u)
+        if (dirtyM == liveMask && (lds32(listAddr) & kWinNoStatic) == 0u)
         {
           // every node is recomputed: who multiplies what is a function of the topology alone and was laid down by
           // k_build_windows in the slotInfo words (6 bits per level)
@@ -1135,46 +1177,65 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
       }
     }
-    if (fast) finish(w, recAddr, live, nodeDirty, W);
-    else if (lane == 0) sts16(sBase + kWsSlow + warp_slow_slot(sBase) * 2u, w);  // redone by the generic path below
-    w = wNext;
+    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, sBase + kWsRecomputed);
+    else
+    {
+      // redone by k_update_win_slow (generic path), which also culls and counts it
+      uint32_t slot = 0;
+      if (lane == 0) slot = atomicAdd(queue + 1, 1u);
+      if (lane == 0) slowList[slot] = a | (((lds32(listAddr + 4) & kWinSlotMask) - a) << 24);
+    }
+    listAddr = nextList;
     bufOff ^= kWsBuf;
   }
   __syncthreads();
-  // ---- deferred windows: the generic path, kept OUT of the loop above so that the out-of-line call does not force
-  // the loop-carried values of the hot path into local memory ----
+  if (tid == 0)
   {
-    const uint32_t nSlow = lds32(sBase + kWsNext + 4);
+    const uint32_t r = lds32(sBase + kWsRecomputed);
+    if (r) atomicAdd(p.recomputed, r);
+  }
+}
+
+// The generic path for the windows k_update_win put aside (parents outside the window, cycles, non-affine or
+// non-finite matrices, hostile TRS values): exact for any input, not tuned. One warp per window, strided over the list.
+template <int kViews>
+__global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_constant__ UpdateParams p,
+                                                               const __grid_constant__ ViewPlanes vp,
+                                                               const uint32_t* __restrict__ slotInfo,
+                                                               const uint32_t* __restrict__ slowCount,
+                                                               const uint32_t* __restrict__ slowList)
+{
+  uint32_t sBase;
+  asm("mov.u32 %0, scgpu_win_smem;" : "=r"(sBase));
+  asm volatile("" ::"l"(scgpu_win_smem));  // keeps the array emitted: every other access goes through sBase
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) *reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed) = 0u;  // (also keeps the symbol referenced)
+  __syncthreads();
+  const uint32_t nSlow = *slowCount;
+  const uint32_t laneBase = sBase + warp * kWwSize + lane * 16;
+  uint32_t order = 0;
 #pragma unroll 1
-    for (uint32_t k = threadIdx.x >> 5; k < nSlow; k += kWinWarps)
+  for (uint32_t k = blockIdx.x * kWinWarps + warp; k < nSlow; k += gridDim.x * kWinWarps)
+  {
+    const uint32_t e = slowList[k];
+    const uint32_t a = e & 0xFFFFFFu, len = e >> 24;
+    const bool live = lane < len;
+    __syncwarp();
+    if (live)
     {
-      const uint32_t w = lds16(sBase + kWsSlow + k * 2u);
-      const uint32_t a = lds32(sBase + kWsWin + w * 4) & kWinSlotMask;
-      const uint32_t len = (lds32(sBase + kWsWin + w * 4 + 4) & kWinSlotMask) - a;
-      const bool live = lane < len;
-      // the prefetch buffers are free now: stage this window's records once more for finish()
-      if (live)
-      {
-        sts128(laneBase, p.rec0[a + lane]); sts128(laneBase + 512, p.rec1[a + lane]);
-        sts128(laneBase + 1024, p.rec2[a + lane]); sts128(laneBase + 1536, p.rec3[a + lane]);
-      }
-      const uint32_t info = live ? slotInfo[a + lane] : 0u;
-      float4 wb[4];
-      const bool nodeDirty = window_slow(p, a, len, info, wb) != 0u;
-      finish(w, laneBase, live, nodeDirty, xs_load(wb));
+      sts128(laneBase, p.rec0[a + lane]); sts128(laneBase + 512, p.rec1[a + lane]);
+      sts128(laneBase + 1024, p.rec2[a + lane]); sts128(laneBase + 1536, p.rec3[a + lane]);
     }
+    const uint32_t info = live ? slotInfo[a + lane] : 0u;
+    float4 wb[4];
+    const bool nodeDirty = window_slow(p, a, len, info, wb) != 0u;
+    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, sBase + kWsRecomputed);
   }
   __syncthreads();
-  // flush: the first tile of this CTA may also receive counts from the previous CTA's last window => atomics
+  if (tid == 0)
   {
-    const uint32_t* sCnt = reinterpret_cast<const uint32_t*>(sDynW + kWsCnt);
-    for (uint32_t k = tid; k < (kWinTilesPerCta + 1) * (kViews + 1); k += kWinBlock)
-    {
-      const uint32_t tl = k / (kViews + 1), v = k % (kViews + 1);
-      const uint32_t c = sCnt[tl * (kMaxViews + 2) + v];
-      if (c && firstTile + tl < p.numTiles) atomicAdd(&p.tileCounts[v * p.numTiles + firstTile + tl], c);
-    }
-    if (tid == 0 && sCnt[kMaxViews + 1]) atomicAdd(p.recomputed, sCnt[kMaxViews + 1]);
+    const uint32_t r = lds32(sBase + kWsRecomputed);
+    if (r) atomicAdd(p.recomputed, r);
   }
 }
 
