@@ -6,5 +6,5 @@ PY
 }
 B="timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline"
 $B > gpurun_out/h.json 2>> gpurun_out/b.err; show gpurun_out/h.json
-SCGPU_LIB=scratch/libscgpu_t1.so $B > gpurun_out/h1.json 2>> gpurun_out/b.err; show gpurun_out/h1.json
-SCGPU_LIB=scratch/libscgpu_t4.so $B > gpurun_out/h4.json 2>> gpurun_out/b.err; show gpurun_out/h4.json
+SCGPU_LIB=scratch/libscgpu_c4.so $B > gpurun_out/h1.json 2>> gpurun_out/b.err; show gpurun_out/h1.json
+SCGPU_LIB=scratch/libscgpu_c14.so $B > gpurun_out/h4.json 2>> gpurun_out/b.err; show gpurun_out/h4.json

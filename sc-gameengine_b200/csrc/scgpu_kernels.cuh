@@ -837,7 +837,10 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem, const void* gmem)
 #endif
 constexpr uint32_t kWinBlock = SCGPU_WIN_BLOCK;          // threads per CTA of k_update_win
 constexpr uint32_t kWinWarps = kWinBlock / 32;
-constexpr uint32_t kWinChunk = 8;                        // consecutive windows per claim from the global queue
+#ifndef SCGPU_WIN_CHUNK
+#define SCGPU_WIN_CHUNK 8
+#endif
+constexpr uint32_t kWinChunk = SCGPU_WIN_CHUNK;                        // consecutive windows per claim from the global queue
 // shared memory of k_update_win (byte offsets). Everything a warp touches in the loop sits in ONE per-warp block, so
 // that every address is "lane base + constant" and folds into the instruction's immediate offset.
 constexpr uint32_t kWsBuf = 4 * 512 + 128;              // one prefetch buffer: 4 record planes + 32 slotInfo words
