@@ -1,10 +1,2 @@
-show() { python - "$1" <<'PY'
-import json,sys
-d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print(sys.argv[1], "ms/step %.3f"%d["ms_per_step"], "kernel ms %.3f"%d["roofline"]["kernel_ms_avg"], "frac %.3f"%d["roofline"]["frac"])
-PY
-}
-B="timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline"
-$B > gpurun_out/h.json 2>> gpurun_out/b.err; show gpurun_out/h.json
-SCGPU_LIB=scratch/libscgpu_c4.so $B > gpurun_out/h1.json 2>> gpurun_out/b.err; show gpurun_out/h1.json
-SCGPU_LIB=scratch/libscgpu_c14.so $B > gpurun_out/h4.json 2>> gpurun_out/b.err; show gpurun_out/h4.json
+CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline"
+ncu --set full --clock-control none --import-source on -k 'regex:^k_update_win$' -s 3 -c 1 -f -o gpurun_out/r01_k_update_win $CMD > gpurun_out/ncu_a.log 2>&1; tail -2 gpurun_out/ncu_a.log

@@ -1015,7 +1015,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     const uint32_t recAddr = laneBase + bufOff;
     bool live, nodeDirty = false, fast;
     uint32_t info;
-    Mat4 W = mat4_identity();
+    Mat4 W;  // assigned on every path that reads it
     {
       const uint32_t e0 = lds32(listAddr);
       const uint32_t len = (lds32(listAddr + 4) & kWinSlotMask) - (e0 & kWinSlotMask);
@@ -1053,12 +1053,10 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
       const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, sclZ);
       float sx, cx, sy, cy, sz, cz;
       sincos3_warp(nodeDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
-      bool ok = true;
-      if (nodeDirty)
-      {
-        W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);  // roots: world == local
-        ok = tame;
-      }
+      // every lane builds a matrix (lanes beyond the window from all-zero records, clean lanes one that is replaced
+      // right below): no per-lane branch around sixteen live registers. Roots: world == local.
+      W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);
+      bool ok = tame || !nodeDirty;
       if (dirtyM != liveMask)  // warp-uniform: a fully dirty window loads no stored matrix at all
       {
         if (live && !nodeDirty)
