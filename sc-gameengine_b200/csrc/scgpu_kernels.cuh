@@ -876,15 +876,12 @@ __device__ __forceinline__ uint32_t queue_claim_result(uint32_t old)
 // store + bounding sphere + plane tests + per-tile counts of one resolved window (records in shared memory at recAddr)
 template <int kViews>
 __device__ __forceinline__ void finish_window(const UpdateParams& p, const ViewPlanes& vp, uint32_t a, uint32_t lane, uint32_t recAddr,
-                                              bool live, bool nodeDirty, const Mat4& W, uint32_t& order, uint32_t recomputedAddr)
+                                              bool live, bool nodeDirty, const Mat4& W, uint32_t& order, uint32_t& nRecomputed)
 {
   constexpr uint32_t allMask = (1u << kViews) - 1u;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
   if (nodeDirty) store_world(p, a + lane, W);
-  {
-    const uint32_t nd = __ballot_sync(0xffffffffu, nodeDirty);
-    if (nd) warp_reds_add(recomputedAddr, __popc(nd));
-  }
+  nRecomputed += __popc(__ballot_sync(0xffffffffu, nodeDirty));  // warp-uniform running count, flushed once per warp
   float4 r3 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live) r3 = lds128(recAddr + 1536);
   const uint32_t fl = __float_as_uint(r3.w);
@@ -964,6 +961,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
+  uint32_t nRecomputed = 0;
   const uint32_t warpBase = sBase + warp * kWwSize;
   const uint32_t laneBase = warpBase + lane * 16;  // this lane's float4 of plane 0, buffer 0
 
@@ -1178,7 +1176,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
       }
     }
-    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, sBase + kWsRecomputed);
+    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed);
     else
     {
       // redone by k_update_win_slow (generic path), which also culls and counts it
@@ -1189,6 +1187,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     listAddr = nextList;
     bufOff ^= kWsBuf;
   }
+  if (nRecomputed) warp_reds_add(sBase + kWsRecomputed, nRecomputed);
   __syncthreads();
   if (tid == 0)
   {
@@ -1214,7 +1213,7 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
   __syncthreads();
   const uint32_t nSlow = *slowCount;
   const uint32_t laneBase = sBase + warp * kWwSize + lane * 16;
-  uint32_t order = 0;
+  uint32_t order = 0, nRecomputed = 0;
 #pragma unroll 1
   for (uint32_t k = blockIdx.x * kWinWarps + warp; k < nSlow; k += gridDim.x * kWinWarps)
   {
@@ -1230,8 +1229,9 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
     const uint32_t info = live ? slotInfo[a + lane] : 0u;
     float4 wb[4];
     const bool nodeDirty = window_slow(p, a, len, info, wb) != 0u;
-    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, sBase + kWsRecomputed);
+    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, nRecomputed);
   }
+  if (nRecomputed) warp_reds_add(sBase + kWsRecomputed, nRecomputed);
   __syncthreads();
   if (tid == 0)
   {
