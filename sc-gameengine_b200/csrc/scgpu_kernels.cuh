@@ -876,7 +876,8 @@ __device__ __forceinline__ uint32_t queue_claim_result(uint32_t old)
 // store + bounding sphere + plane tests + per-tile counts of one resolved window (records in shared memory at recAddr)
 template <int kViews>
 __device__ __forceinline__ void finish_window(const UpdateParams& p, const ViewPlanes& vp, uint32_t a, uint32_t lane, uint32_t recAddr,
-                                              bool live, bool nodeDirty, const Mat4& W, uint32_t& order, uint32_t& nRecomputed)
+                                              bool live, bool nodeDirty, const Mat4& W, uint32_t& order, uint32_t& nRecomputed,
+                                              uint32_t& accTile, uint32_t& accCand)
 {
   constexpr uint32_t allMask = (1u << kViews) - 1u;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
@@ -896,32 +897,54 @@ __device__ __forceinline__ void finish_window(const UpdateParams& p, const ViewP
   }
   if (cand && !test) mask = allMask;
   if (live) p.vismask[a + lane] = (uint8_t)mask;
-  // per-tile counts (zeroed by the host before the launch): ballots, one global reduction per counter by an elected
-  // lane; a window may straddle a tile boundary
+  // per-tile counts (zeroed by the host before the launch). Candidates: consecutive windows of a warp mostly lie in
+  // the same tile, so their count is accumulated warp-uniformly (accTile / accCand) and written with one global
+  // reduction when the tile changes; a window that straddles a tile boundary is written at once, per part. Visible
+  // counts (rare in an open world) go out per window.
   const uint32_t candM = __ballot_sync(0xffffffffu, cand);
   if (candM)
   {
     const uint32_t tile = a / kTile;
     const uint32_t room = (tile + 1u) * kTile - a;  // slots left in the window's first tile
-    const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
-    const uint32_t anyVis = __ballot_sync(0xffffffffu, mask != 0u);
-    uint32_t* cnt = p.tileCounts + tile;
-    red_global_add(cnt + (size_t)kViews * p.numTiles, __popc(candM & lowMask));
-    if (candM & ~lowMask) red_global_add(cnt + (size_t)kViews * p.numTiles + 1, __popc(candM & ~lowMask));
-    if (anyVis)
+    uint32_t lowMask = 0xffffffffu;
+    if (room >= 32u)
     {
+      if (tile != accTile)
+      {
+        if (accCand) red_global_add(p.tileCounts + (size_t)kViews * p.numTiles + accTile, accCand);
+        accTile = tile;
+        accCand = 0u;
+      }
+      accCand += __popc(candM);
+    }
+    else
+    {
+      lowMask = (1u << room) - 1u;
+      uint32_t* cc = p.tileCounts + (size_t)kViews * p.numTiles + tile;
+      if (candM & lowMask) red_global_add(cc, __popc(candM & lowMask));
+      if (candM & ~lowMask) red_global_add(cc + 1, __popc(candM & ~lowMask));
+    }
+    if (__any_sync(0xffffffffu, mask != 0u))
+    {
+      uint32_t* cnt = p.tileCounts + tile;
 #pragma unroll
       for (int v = 0; v < kViews; ++v)
       {
         const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
         if (m)
         {
-          red_global_add(cnt + (size_t)v * p.numTiles, __popc(m & lowMask));
+          if (m & lowMask) red_global_add(cnt + (size_t)v * p.numTiles, __popc(m & lowMask));
           if (m & ~lowMask) red_global_add(cnt + (size_t)v * p.numTiles + 1, __popc(m & ~lowMask));
         }
       }
     }
   }
+}
+
+// the candidates accumulated by finish_window and not yet written
+__device__ __forceinline__ void flush_window_counts(const UpdateParams& p, uint32_t kViews, uint32_t accTile, uint32_t accCand)
+{
+  if (accCand) red_global_add(p.tileCounts + (size_t)kViews * p.numTiles + accTile, accCand);
 }
 
 }  // namespace scgpu
@@ -961,7 +984,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
-  uint32_t nRecomputed = 0;
+  uint32_t nRecomputed = 0, accTile = 0, accCand = 0;
   const uint32_t warpBase = sBase + warp * kWwSize;
   const uint32_t laneBase = warpBase + lane * 16;  // this lane's float4 of plane 0, buffer 0
 
@@ -1176,7 +1199,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
       }
     }
-    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed);
+    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed, accTile, accCand);
     else
     {
       // redone by k_update_win_slow (generic path), which also culls and counts it
@@ -1187,6 +1210,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     listAddr = nextList;
     bufOff ^= kWsBuf;
   }
+  flush_window_counts(p, kViews, accTile, accCand);
   if (nRecomputed) warp_reds_add(sBase + kWsRecomputed, nRecomputed);
   __syncthreads();
   if (tid == 0)
@@ -1213,7 +1237,7 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
   __syncthreads();
   const uint32_t nSlow = *slowCount;
   const uint32_t laneBase = sBase + warp * kWwSize + lane * 16;
-  uint32_t order = 0, nRecomputed = 0;
+  uint32_t order = 0, nRecomputed = 0, accTile = 0, accCand = 0;
 #pragma unroll 1
   for (uint32_t k = blockIdx.x * kWinWarps + warp; k < nSlow; k += gridDim.x * kWinWarps)
   {
@@ -1229,8 +1253,9 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
     const uint32_t info = live ? slotInfo[a + lane] : 0u;
     float4 wb[4];
     const bool nodeDirty = window_slow(p, a, len, info, wb) != 0u;
-    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, nRecomputed);
+    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, nRecomputed, accTile, accCand);
   }
+  flush_window_counts(p, kViews, accTile, accCand);
   if (nRecomputed) warp_reds_add(sBase + kWsRecomputed, nRecomputed);
   __syncthreads();
   if (tid == 0)
