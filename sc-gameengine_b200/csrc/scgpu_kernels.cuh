@@ -8,13 +8,15 @@
 //   rec3[slot] = { aabbMax.x, aabbMax.y, aabbMax.z, flags }     exactly SURVEY.md §8(d)'s read set.
 //   world0..3[slot] = world matrix columns (float4 planes, coalesced 128-bit stores)
 //   parentSlot[slot] = resolved parent slot or kNone (maintained by k_resolve_parents on topology changes)
-//   slotInfo[slot]   = depth of the slot inside its hierarchy window (+ flags), winStart[tile][..] = window starts:
-//                      hierarchical scenes are cut into windows of <= 32 consecutive slots that no parent link
-//                      crosses; one warp resolves one window with shuffles (k_build_windows / k_update_win).
+//   slotInfo[slot]   = depth + parent lane of the slot inside its hierarchy window, flags, 3-level work schedule;
+//   winList[w]       = start slot of window w (+ flags): hierarchical scenes are cut into windows of <= 32 consecutive
+//                      slots that no parent link crosses; one warp resolves one window (k_build_windows ->
+//                      k_scan_tiles -> k_flatten_windows on topology changes; k_update_win every frame).
 //   flags: bit0 HAS_BOUNDS, bit1 HAS_MESH, bits 8..31 = dirty stamp (id of the update that must recompute
 //          the instance). A stamp instead of a dirty bit means the frame kernel never writes the records.
 //
-// Frame = k_update_flat | k_update_win (transform + sphere + V-view plane tests + per-tile counts, one pass)
+// Frame = k_update_flat | k_update_win + k_update_win_slow (transform + sphere + V-view plane tests + per-tile
+//         counts, one pass over the instances)
 //         -> k_scan_tiles (exclusive scan of the per-tile counts, V+1 rows)
 //         -> k_scatter_visible (stable per-view compaction of entity handles / slots)
 #pragma once
@@ -530,6 +532,7 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
   __shared__ uint32_t sWinFlag[kMaxWin];         // bit 0: generic path, bit 1: no static schedule
   __shared__ uint32_t sLvl[kMaxWin][3];          // lanes of the window at depth 1, 2, 3
   __shared__ uint32_t sInfo[kTile + kHalo];
+  __shared__ uint16_t sPar[kSpan];               // parent of every slot of the span, relative to `origin` (see kPar*)
   __shared__ uint32_t sWarpSum[kBlock / 32];
   __shared__ uint32_t sNumWin, sBeg, sEnd;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -541,11 +544,16 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
   for (uint32_t k = tid; k < kMaxWin; k += kBlock) { sWinFlag[k] = 0; sLvl[k][0] = sLvl[k][1] = sLvl[k][2] = 0; }
   __syncthreads();
   // a link between slots lo < hi shorter than a window crosses every cut position c with lo < c <= hi
+  // (parentSlot is read from global memory ONCE, here; the depth walk below follows the links in shared memory)
+  constexpr uint16_t kParNone = 0xFFFFu, kParFar = 0xFFFEu;  // no parent / parent too far away to share a window
   for (uint32_t k = origin + tid; k < spanEnd; k += kBlock)
   {
     const uint32_t ps = parentSlot[k];
-    if (ps == kNone || ps == k || ps >= count) continue;
+    if (ps == kNone) { sPar[k - origin] = kParNone; continue; }
     const uint32_t lo = min(k, ps), hi = max(k, ps);
+    const bool near = ps != k && ps < count && hi - lo < 32u && ps >= origin && ps < spanEnd;
+    sPar[k - origin] = near ? (uint16_t)(ps - origin) : kParFar;
+    if (ps == k || ps >= count) continue;
     if (hi - lo >= 32u) continue;  // can never sit inside one window: the child is flagged external below
     // positions lo+1 .. hi, clipped to the span (difference array, summed below)
     const uint32_t from = max(lo + 1u, origin), to = min(hi + 1u, origin + kSpan + 4u);
@@ -623,9 +631,10 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
     uint32_t cur = k, depth = 0, info = 0;
     for (;;)
     {
-      const uint32_t ps = parentSlot[tileBase + cur];
-      if (ps == kNone) break;
-      const bool inside = ps >= tileBase + wa && ps < tileBase + wb;
+      const uint32_t code = sPar[tileBase + cur - origin];
+      if (code == kParNone) break;
+      const uint32_t ps = origin + code;  // meaningless for kParFar, which fails the test below
+      const bool inside = code != kParFar && ps >= tileBase + wa && ps < tileBase + wb;
       if (!inside)
       {
         if (depth == 0) info = kInfoExternal;  // deeper nodes hang off an ancestor that carries the flag itself
