@@ -531,6 +531,7 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
   __shared__ uint16_t sWinOf[kTile + kHalo];     // window index of every owned slot (relative to tileBase)
   __shared__ uint32_t sWinFlag[kMaxWin];         // bit 0: generic path, bit 1: no static schedule
   __shared__ uint32_t sLvl[kMaxWin][3];          // lanes of the window at depth 1, 2, 3
+  __shared__ uint8_t sChild[kMaxWin][3][16];     // the j-th lane of that depth (static schedule)
   __shared__ uint32_t sInfo[kTile + kHalo];
   __shared__ uint16_t sPar[kSpan];               // parent of every slot of the span, relative to `origin` (see kPar*)
   __shared__ uint32_t sWarpSum[kBlock / 32];
@@ -651,7 +652,19 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
   }
   __syncthreads();
   // static schedule of the level loop (used by k_update_win when every node of the window is recomputed): in
-  // level l, lanes 2j and 2j+1 of the window take the j-th node of that level
+  // level l, lanes 2j and 2j+1 of the window take the j-th node of that level. First every node writes its lane at
+  // its rank among the nodes of its level, then every lane looks up the node it helps with.
+  for (uint32_t k = (beg - tileBase) + tid; k < end - tileBase; k += kBlock)
+  {
+    const uint32_t d = sInfo[k] & kInfoDepthMask;
+    if (d >= 1u && d <= 3u && !(sInfo[k] & kInfoUnreachable))
+    {
+      const uint32_t w = sWinOf[k], h = k - sStart[w];
+      const uint32_t j = __popc(sLvl[w][d - 1u] & ((1u << h) - 1u));
+      if (j < 16u) sChild[w][d - 1u][j] = (uint8_t)h;
+    }
+  }
+  __syncthreads();
   for (uint32_t k = (beg - tileBase) + tid; k < end - tileBase; k += kBlock)
   {
     const uint32_t w = sWinOf[k], wa = sStart[w], len = sStart[w + 1] - wa, h = k - wa;
@@ -659,13 +672,11 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
 #pragma unroll
     for (uint32_t l = 0; l < 3u; ++l)
     {
-      uint32_t m = sLvl[w][l];
-      const uint32_t cnt = __popc(m);
+      const uint32_t cnt = __popc(sLvl[w][l]);
       if (2u * cnt > len) { if (h == 0u) atomicOr(&sWinFlag[w], 2u); continue; }
       const uint32_t j = h >> 1;
       if (j >= cnt) continue;
-      for (uint32_t q = 0; q < j; ++q) m &= m - 1u;
-      info |= (32u | (uint32_t)(__ffs(m) - 1)) << (kInfoSchedShift + 6u * l);
+      info |= (32u | (uint32_t)sChild[w][l][j]) << (kInfoSchedShift + 6u * l);
     }
     slotInfo[tileBase + k] = info;
   }
