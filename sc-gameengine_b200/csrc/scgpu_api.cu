@@ -951,7 +951,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     sp.vismask = c->vismask; sp.entity = c->a.entity; sp.tileCounts = c->tileCounts; sp.tileOffsets = c->tileOffsets;
     for (uint32_t v = 0; v < kMaxViews; ++v) { sp.outEntity[v] = c->visEntity[v]; sp.outSlot[v] = c->visSlot[v]; }
     sp.count = c->count; sp.numTiles = numTiles; sp.nViews = c->nViews;
-    k_scatter_visible<<<numTiles, kBlock, 0, c->stream>>>(sp);
+    k_scatter_visible<<<std::min(numTiles, c->numSMs * 8u), kBlock, 0, c->stream>>>(sp);
     ++c->launches;
     SC_CUDA(c, cudaGetLastError());
 

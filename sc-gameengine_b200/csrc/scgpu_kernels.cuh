@@ -1345,6 +1345,8 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict_
                                                      uint32_t* __restrict__ tileOffsets, uint32_t* __restrict__ totals,
                                                      uint32_t numTiles)
 {
+  // 16 consecutive counts per thread: 16 Ki tiles (a full context) are scanned in ONE pass with two barriers
+  constexpr uint32_t kPer = 16;
   __shared__ uint32_t sWarp[32];
   __shared__ uint32_t sCarry;
   const uint32_t row = blockIdx.x;
@@ -1353,11 +1355,17 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict_
   uint32_t* out = tileOffsets + (size_t)row * numTiles;
   if (tid == 0) sCarry = 0;
   __syncthreads();
-  for (uint32_t start = 0; start < numTiles; start += 1024)
+  for (uint32_t start = 0; start < numTiles; start += 1024 * kPer)
   {
-    const uint32_t idx = start + tid;
-    const uint32_t v = idx < numTiles ? in[idx] : 0u;
-    uint32_t x = v;
+    const uint32_t base = start + tid * kPer;
+    uint32_t v[kPer], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < kPer; ++j)
+    {
+      v[j] = (base + j < numTiles) ? in[base + j] : 0u;
+      sum += v[j];
+    }
+    uint32_t x = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
@@ -1379,10 +1387,15 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict_
     }
     __syncthreads();
     const uint32_t carry = sCarry;
-    const uint32_t warpExcl = warp ? sWarp[warp - 1] : 0u;
-    if (idx < numTiles) out[idx] = carry + warpExcl + x - v;
+    uint32_t run = carry + (warp ? sWarp[warp - 1] : 0u) + x - sum;  // exclusive prefix of this thread's first count
+#pragma unroll
+    for (uint32_t j = 0; j < kPer; ++j)
+    {
+      if (base + j < numTiles) out[base + j] = run;
+      run += v[j];
+    }
     __syncthreads();
-    if (tid == 1023) sCarry = carry + warpExcl + x;
+    if (tid == 1023) sCarry = run;
     __syncthreads();
   }
   if (tid == 0) totals[row] = sCarry;
@@ -1437,13 +1450,19 @@ __global__ void __launch_bounds__(kBlock) k_scatter_visible(const __grid_constan
 {
   __shared__ uint32_t sCnt[kMaxViews];
   __shared__ uint64_t sWarp[kBlock / 32];
-  const uint32_t tile = blockIdx.x, tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x;
+  // grid-stride over the tiles: most tiles of an open world are fully culled, and 16 Ki CTAs that only read their
+  // counts and exit cost more in launch overhead than the compaction itself
+#pragma unroll 1
+  for (uint32_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x)
+  {
+  __syncthreads();  // sCnt of the previous tile is no longer read
   if (tid < kMaxViews) sCnt[tid] = tid < p.nViews ? p.tileCounts[tid * p.numTiles + tile] : 0u;
   __syncthreads();
   uint32_t anyVis = 0;
 #pragma unroll
   for (uint32_t v = 0; v < kMaxViews; ++v) anyVis |= sCnt[v];
-  if (!anyVis) return;  // block-uniform: most tiles of an open world are fully culled
+  if (!anyVis) continue;  // block-uniform
 
   const uint32_t slot0 = tile * kTile + tid * 4u;
   uint32_t m4 = 0;
@@ -1485,6 +1504,7 @@ __global__ void __launch_bounds__(kBlock) k_scatter_visible(const __grid_constan
         }
       }
     }
+  }
   }
 }
 
