@@ -925,7 +925,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     {                                                                                                                    \
       k_update_win<V><<<c->numSMs * SCGPU_WIN_MINBLOCKS, kWinBlock, 0, c->stream>>>(                                     \
         p, c->planes, c->slotInfo, c->winList, c->tileWinBase + numTiles, c->totals + kQueueNext, c->slowList);          \
-      k_update_win_slow<V><<<c->numSMs, kWinBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->totals + kQueueSlow,    \
+      k_update_win_slow<V><<<c->numSMs * 4u, kWinBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->totals + kQueueSlow, \
                                                                    c->slowList);                                         \
       ++c->launches;                                                                                                     \
     }                                                                                                                    \

