@@ -236,6 +236,56 @@ typedef struct ScGpuEditorDrawItem
 SCGPU_API int scgpuBuildEditorDraws(ScGpuScene* ctx, uint32_t n, const float* trs9, const uint64_t* meshHandle,
                                     const uint64_t* materialHandle, ScGpuEditorDrawItem* out, uint32_t cap, uint32_t* outCount);
 
+/* ---- traffic on rails, a device-resident dirty producer -------------------------------------
+ * Replaces, for the agents whose TrafficVehicle::mode is OnRails, the per-agent body of sc::TrafficAISystem
+ * (src/engine/traffic/sc_traffic_ai.cpp:165-487, on-rails branch :434-458): speed smoothing (smoothExp :58-62),
+ * TrafficLaneGraph::advanceAlongLane / chooseNextSegment / queryNearestLane / laneSpeedLimit
+ * (src/engine/traffic/sc_traffic_lanes.cpp:150-169, 239-345, 392-400) and yawFromDir (:72-75). localPos / localRot
+ * of the agents' Transforms are written in HBM and stamped dirty for the next scgpuUpdate: nothing crosses PCIe
+ * per frame. Bit-exact with the reference (glibc 2.39 expf / atan2f restated on the device).
+ * The physics and kinematic tiers (at most 24 + 64 vehicles, sc_traffic_common.h:70-73) need the Bullet world and
+ * stay on the host; tier changes (sc_traffic_lod.cpp) are the host calling scgpuTrafficSetAgents again. */
+typedef struct ScGpuLaneGraph
+{
+  uint32_t struct_size;           /* sizeof(ScGpuLaneGraph) */
+  uint32_t nNodes, nSegments, nConnections;
+  const float* nodePos;           /* [nNodes*3]   LaneNode::pos        (sc_traffic_lanes.h:14-20) */
+  const float* nodeSpeedLimit;    /* [nNodes]     LaneNode::speedLimit */
+  const uint32_t* nodeConnOffset; /* [nNodes+1]   CSR offsets of LaneNode::connections */
+  const uint32_t* nodeConn;       /* [nConnections] segment ids (ids >= nSegments are skipped like :156-157) */
+  const uint32_t* segNodes;       /* [nSegments*2] LaneSegment::startNode, endNode (sc_traffic_lanes.h:22-31) */
+  const float* segDir;            /* [nSegments*3] LaneSegment::dir */
+  const float* segLength;         /* [nSegments]   LaneSegment::length */
+  const uint8_t* segActive;       /* [nSegments]   LaneSegment::active; NULL = all active */
+  float defaultSpeedLimit;        /* TrafficLaneGraph::speedLimit() */
+} ScGpuLaneGraph;
+/* uploads (replaces) the lane graph; node indices of segments must be < nNodes */
+SCGPU_API int scgpuTrafficSetLanes(ScGpuScene* ctx, const ScGpuLaneGraph* graph);
+/* TrafficLaneGraph::removeSector / re-activation (sc_traffic_lanes.cpp:171-183, 224-236) for n segments */
+SCGPU_API int scgpuTrafficSetLaneActive(ScGpuScene* ctx, uint32_t n, const uint32_t* segment, const uint8_t* active);
+/* replaces the on-rails agent set: TrafficAgent::{laneId, laneS, targetSpeed, lookAheadDist} per entity
+ * (sc_traffic_common.h:27-37). Entities without a Transform in the context are skipped by the step. */
+SCGPU_API int scgpuTrafficSetAgents(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const uint32_t* laneId,
+                                    const float* laneS, const float* targetSpeed, const float* lookAheadDist);
+typedef struct ScGpuTrafficStep
+{
+  uint32_t struct_size;       /* sizeof(ScGpuTrafficStep) */
+  float dt;
+  uint32_t hasDebug;          /* TrafficAIState::debug != nullptr: the two fields below apply (:237-238, :296-297) */
+  float lookAheadDist;        /* TrafficDebugState::lookAheadDist */
+  float speedMultiplier;      /* TrafficDebugState::speedMultiplier */
+  const float* obstacleBrake; /* [nAgents] host raycast result (:300-347) or NULL = 0 (TrafficAIState::physics null) */
+  const uint8_t* skip;        /* [nAgents] non-zero = agent's sector is not Active (:218-226) or NULL */
+} ScGpuTrafficStep;
+/* one TrafficAISystem pass over the on-rails agents, asynchronous on the context stream; *outMoved (optional,
+ * forces a synchronisation) = number of Transforms written */
+SCGPU_API int scgpuTrafficAdvance(ScGpuScene* ctx, const ScGpuTrafficStep* step, uint32_t* outMoved);
+/* agent state in scgpuTrafficSetAgents order */
+SCGPU_API int scgpuTrafficReadAgents(ScGpuScene* ctx, uint32_t cap, uint32_t* outLaneId, float* outLaneS,
+                                     float* outTargetSpeed, float* outLookAheadDist, uint32_t* outCount);
+/* Transform::localPos / localRot / localScale of n entities (9 floats each) */
+SCGPU_API int scgpuReadLocal(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, float* outTrs9);
+
 /* ---- multi-GPU: one context per process per GPU, instance set sharded by world cell ------------------------
  * The only exchange is the gather of the compacted per-view lists and counts to the submitting rank. */
 #define SCGPU_COMM_ID_BYTES 128

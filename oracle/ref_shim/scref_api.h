@@ -102,6 +102,31 @@ int screfReadSectorInstances(const char* path, uint32_t cap, int32_t* outXZ, uin
                              uint64_t* outMaterialId, float* outTrs9);
 uint64_t screfHashAssetPath(const char* path);
 
+/* Traffic: the reference's TrafficLaneGraph and TrafficAISystem, scref_traffic.cpp */
+typedef struct ScRefLanes ScRefLanes;
+ScRefLanes* screfLanesCreate(float laneWidth, float speedLimit);
+void screfLanesDestroy(ScRefLanes* l);
+uint32_t screfLanesAddNode(ScRefLanes* l, const float* pos3, const float* dir3, float speedLimit);
+uint32_t screfLanesAddSegment(ScRefLanes* l, uint32_t a, uint32_t b, const float* dir3, int32_t ownerX, int32_t ownerZ);
+/* buildProceduralForSector / removeSector (sc_traffic_lanes.cpp:171-237) with the sector's ground square as bounds */
+void screfLanesBuildSector(ScRefLanes* l, int32_t x, int32_t z, float sectorSize);
+void screfLanesRemoveSector(ScRefLanes* l, int32_t x, int32_t z);
+void screfLanesSetActive(ScRefLanes* l, uint32_t segment, int active);
+void screfLanesCounts(ScRefLanes* l, uint32_t* nNodes, uint32_t* nSegs, uint32_t* nConn);
+void screfLanesExport(ScRefLanes* l, float* nodePos3, float* nodeSpeed, uint32_t* connOffset, uint32_t* conn,
+                      uint32_t* segNodes2, float* segDir3, float* segLen, uint8_t* segActive, float* defaultSpeed);
+int screfLaneAdvance(ScRefLanes* l, uint32_t* laneId, float* s, float distance, float* outPos3, float* outDir3);
+uint32_t screfLaneQueryNearest(ScRefLanes* l, const float* pos3, float* outS);
+void screfTrafficAddAgents(ScRefWorld* w, uint32_t n, const uint32_t* entity, const uint32_t* laneId, const float* laneS,
+                           const float* targetSpeed, const float* lookAhead);
+void screfTrafficSetPlayer(ScRefWorld* w, uint32_t entity);
+void screfRunTrafficAI(ScRefWorld* w, ScRefLanes* l, float dt, int useDebug, float lookAheadDist, float speedMultiplier);
+void screfTrafficReadAgents(ScRefWorld* w, uint32_t n, const uint32_t* entity, uint32_t* laneId, float* laneS,
+                            float* targetSpeed, float* lookAhead);
+float screfExpf(float x);
+float screfAtanf(float x);
+float screfAtan2f(float y, float x);
+
 #ifdef __cplusplus
 }
 #endif

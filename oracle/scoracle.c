@@ -589,3 +589,366 @@ int64_t sco_frame(uint32_t n, const uint32_t* entity, uint32_t* parent, float* t
                        NULL, NULL);
   return r;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Traffic on rails.
+ *
+ * libm: glibc 2.39 expf / atanf / atan2f, generic variants. Third-party dependency of the reference
+ * (std::exp in smoothExp, src/engine/traffic/sc_traffic_ai.cpp:58-62; std::atan2 in yawFromDir, :72-75), not
+ * vendored in /root/reference. Published algorithms: expf = ARM optimized-routines single-precision exp as
+ * imported in glibc 2.27 (sysdeps/ieee754/flt-32/e_expf.c, e_exp2f_data.c: N = 32 table of 2^(i/N), degree-3
+ * polynomial in double, one rounding); atanf / atan2f = the fdlibm float routines (s_atanf.c, e_atan2f.c).
+ * Checked here against the host's glibc 2.39 with GLIBC_TUNABLES=glibc.cpu.hwcaps=-FMA,-AVX2: expf and atanf
+ * over all 2^32 inputs and atan2f over 4e8 pairs, 0 mismatches (the FMA ifunc variant of expf differs on 2 of
+ * 2^32 inputs: 0x4202422f and 0xc27c65d9; atanf / atan2f have no FMA variant that differs).
+ * ---------------------------------------------------------------------------------------------- */
+
+static inline uint32_t tr_fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float tr_bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* e_exp2f_data.c: tab[i] = asuint64(2^(i/32)) - (i << 47) */
+static const uint64_t k_exp2f_tab[32] = {
+  0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+  0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+  0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+  0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+  0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+  0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+  0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+  0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull
+};
+
+float sco_expf(float x)
+{
+  const double N = 32.0;
+  const double inv_ln2_n = 0x1.71547652b82fep+0 * N;
+  const double shift = 0x1.8p+52;
+  const double c0 = 0x1.c6af84b912394p-5 / N / N / N, c1 = 0x1.ebfce50fac4f3p-3 / N / N, c2 = 0x1.62e42ff0c52d6p-1 / N;
+  const uint32_t abstop = (tr_fbits(x) >> 20) & 0x7ff;
+  if (abstop >= (tr_fbits(88.0f) >> 20))
+  {
+    if (tr_fbits(x) == tr_fbits(-INFINITY)) return 0.0f;
+    if (abstop >= (tr_fbits(INFINITY) >> 20)) return x + x;
+    if (x > 0x1.62e42ep6f) return INFINITY; /* __math_oflowf */
+    if (x < -0x1.9fe368p6f) return 0.0f;    /* __math_uflowf */
+  }
+  const double xd = (double)x;
+  double z = inv_ln2_n * xd;
+  double kd = z + shift;
+  uint64_t ki;
+  memcpy(&ki, &kd, 8);
+  kd -= shift;
+  const double r = z - kd;
+  uint64_t t = k_exp2f_tab[ki % 32];
+  t += ki << (52 - 5);
+  double s;
+  memcpy(&s, &t, 8);
+  z = c0 * r + c1;
+  const double r2 = r * r;
+  double y = c2 * r + 1;
+  y = z * r2 + y;
+  y = y * s;
+  return (float)y;
+}
+
+static const float k_atanhi[4] = { 4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f };
+static const float k_atanlo[4] = { 5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f };
+static const float k_aT[11] = { 3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f,
+                                9.0908870101e-02f, -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f,
+                                4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f };
+
+float sco_atanf(float x)
+{
+  float w, s1, s2, z;
+  int32_t id;
+  const int32_t hx = (int32_t)tr_fbits(x);
+  const int32_t ix = hx & 0x7fffffff;
+  if (ix >= 0x4c000000) /* |x| >= 2^25 */
+  {
+    if (ix > 0x7f800000) return x + x;
+    if (hx > 0) return k_atanhi[3] + k_atanlo[3];
+    return -k_atanhi[3] - k_atanlo[3];
+  }
+  if (ix < 0x3ee00000) /* |x| < 0.4375 */
+  {
+    if (ix < 0x31000000) return x; /* |x| < 2^-29 */
+    id = -1;
+  }
+  else
+  {
+    x = fabsf(x);
+    if (ix < 0x3f980000) /* |x| < 1.1875 */
+    {
+      if (ix < 0x3f300000) { id = 0; x = (2.0f * x - 1.0f) / (2.0f + x); }
+      else                 { id = 1; x = (x - 1.0f) / (x + 1.0f); }
+    }
+    else
+    {
+      if (ix < 0x401c0000) { id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x); }
+      else                 { id = 3; x = -1.0f / x; }
+    }
+  }
+  z = x * x;
+  w = z * z;
+  s1 = z * (k_aT[0] + w * (k_aT[2] + w * (k_aT[4] + w * (k_aT[6] + w * (k_aT[8] + w * k_aT[10])))));
+  s2 = w * (k_aT[1] + w * (k_aT[3] + w * (k_aT[5] + w * (k_aT[7] + w * k_aT[9]))));
+  if (id < 0) return x - x * (s1 + s2);
+  z = k_atanhi[id] - ((x * (s1 + s2) - k_atanlo[id]) - x);
+  return (hx < 0) ? -z : z;
+}
+
+float sco_atan2f(float y, float x)
+{
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  float z;
+  const int32_t hx = (int32_t)tr_fbits(x), hy = (int32_t)tr_fbits(y);
+  const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+  if (hx == 0x3f800000) return sco_atanf(y);
+  const int32_t m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0)
+  {
+    switch (m)
+    {
+      case 0: case 1: return y;
+      case 2: return pi + tiny;
+      default: return -pi - tiny;
+    }
+  }
+  if (ix == 0) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  if (ix == 0x7f800000)
+  {
+    if (iy == 0x7f800000)
+    {
+      switch (m)
+      {
+        case 0: return pi_o_4 + tiny;
+        case 1: return -pi_o_4 - tiny;
+        case 2: return 3.0f * pi_o_4 + tiny;
+        default: return -3.0f * pi_o_4 - tiny;
+      }
+    }
+    switch (m)
+    {
+      case 0: return 0.0f;
+      case 1: return -0.0f;
+      case 2: return pi + tiny;
+      default: return -pi - tiny;
+    }
+  }
+  if (iy == 0x7f800000) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  const int32_t k = (iy - ix) >> 23;
+  if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+  else if (hx < 0 && k < -60) z = 0.0f;
+  else z = sco_atanf(fabsf(y / x));
+  switch (m)
+  {
+    case 0: return z;
+    case 1: return tr_bitsf(tr_fbits(z) ^ 0x80000000u);
+    case 2: return pi - (z - pi_lo);
+    default: return (z - pi_lo) - pi;
+  }
+}
+
+static int tr_same(float a, float b) { return tr_fbits(a) == tr_fbits(b) || (a != a && b != b); }
+
+uint64_t sco_unary_sweep(int which, uint32_t first, uint64_t count, uint32_t stride, float (*ref)(float))
+{
+  uint64_t bad = 0;
+  uint32_t bits = first;
+  for (uint64_t i = 0; i < count; ++i, bits += stride)
+  {
+    const float x = tr_bitsf(bits);
+    const float mine = which == 0 ? sco_expf(x) : sco_atanf(x);
+    bad += tr_same(mine, ref(x)) ? 0 : 1;
+  }
+  return bad;
+}
+
+uint64_t sco_atan2_sweep(uint32_t seed, uint64_t count, float (*ref)(float, float))
+{
+  uint64_t bad = 0;
+  uint32_t r = seed ? seed : 1u;
+#define TR_NEXT() (r ^= r << 13, r ^= r >> 17, r ^= r << 5, r)
+  for (uint64_t i = 0; i < count; ++i)
+  {
+    const uint32_t a = TR_NEXT(), b = TR_NEXT();
+    float y = tr_bitsf(a), x = tr_bitsf(b);
+    if ((i & 3) == 1)
+    { /* directions as the lane graph holds them */
+      const float ang = (float)(TR_NEXT() & 0xffffff) * 3.7e-7f;
+      y = sco_sinf(ang);
+      x = sco_cosf(ang);
+      if (i & 4) y *= 0.5f;
+    }
+    else if ((i & 3) == 2)
+    { /* exponents within +-16 of each other */
+      x = tr_bitsf((b & 0x807fffffu) | ((a & 0x0f800000u) + 0x38000000u));
+      y = tr_bitsf((a & 0x807fffffu) | (((b >> 3) & 0x0f800000u) + 0x38000000u));
+    }
+    bad += tr_same(sco_atan2f(y, x), ref(y, x)) ? 0 : 1;
+  }
+#undef TR_NEXT
+  return bad;
+}
+
+/* chooseNextSegment, src/engine/traffic/sc_traffic_lanes.cpp:150-169 */
+static uint32_t tr_choose_next(const ScoLaneGraph* g, const float* dir, uint32_t node)
+{
+  uint32_t best = 0xFFFFFFFFu;
+  float bestDot = -1.0f;
+  for (uint32_t k = g->nodeConnOffset[node]; k < g->nodeConnOffset[node + 1]; ++k)
+  {
+    const uint32_t segId = g->nodeConn[k];
+    if (segId >= g->nSegments) continue;
+    if (!g->segActive[segId]) continue;
+    const float* sd = g->segDir + (size_t)segId * 3;
+    const float d = dir[0] * sd[0] + dir[1] * sd[1] + dir[2] * sd[2];
+    if (d > bestDot)
+    {
+      bestDot = d;
+      best = segId;
+    }
+  }
+  return best;
+}
+
+int sco_lane_advance(const ScoLaneGraph* g, uint32_t* laneId, float* s, float distance, float* outPos, float* outDir)
+{
+  if (*laneId == 0xFFFFFFFFu || *laneId >= g->nSegments) return 0;
+  float remaining = distance;
+  uint32_t current = *laneId;
+  float currentS = *s;
+  for (uint32_t guard = 0; guard < 8; ++guard)
+  {
+    if (!g->segActive[current]) return 0;
+    const float len = g->segLength[current];
+    if (len <= 1e-5f) return 0;
+    const float* dir = g->segDir + (size_t)current * 3;
+    const float available = len - currentS;
+    if (remaining <= available)
+    {
+      currentS += remaining;
+      const float* a = g->nodePos + (size_t)g->segNodes[(size_t)current * 2] * 3;
+      outPos[0] = a[0] + dir[0] * currentS;
+      outPos[1] = a[1] + dir[1] * currentS;
+      outPos[2] = a[2] + dir[2] * currentS;
+      outDir[0] = dir[0]; outDir[1] = dir[1]; outDir[2] = dir[2];
+      *laneId = current;
+      *s = currentS;
+      return 1;
+    }
+    remaining -= available;
+    currentS = 0.0f;
+    const uint32_t endNode = g->segNodes[(size_t)current * 2 + 1];
+    const uint32_t next = tr_choose_next(g, dir, endNode);
+    if (next == 0xFFFFFFFFu)
+    {
+      const float* e = g->nodePos + (size_t)endNode * 3;
+      outPos[0] = e[0]; outPos[1] = e[1]; outPos[2] = e[2];
+      outDir[0] = dir[0]; outDir[1] = dir[1]; outDir[2] = dir[2];
+      *laneId = current;
+      *s = len;
+      return 1;
+    }
+    current = next;
+  }
+  return 0;
+}
+
+uint32_t sco_lane_query_nearest(const ScoLaneGraph* g, const float* pos, float* outS)
+{
+  uint32_t best = 0xFFFFFFFFu;
+  float bestDist = 0.0f;
+  int hasBest = 0;
+  for (uint32_t i = 0; i < g->nSegments; ++i)
+  {
+    if (!g->segActive[i] || g->segLength[i] <= 1e-5f) continue;
+    const float* a = g->nodePos + (size_t)g->segNodes[(size_t)i * 2] * 3;
+    const float* dir = g->segDir + (size_t)i * 3;
+    const float toP[3] = { pos[0] - a[0], pos[1] - a[1], pos[2] - a[2] };
+    const float proj = toP[0] * dir[0] + toP[1] * dir[1] + toP[2] * dir[2];
+    const float mn = (proj < g->segLength[i]) ? proj : g->segLength[i]; /* std::min(seg.length, proj) */
+    const float s = (0.0f < mn) ? mn : 0.0f;                             /* std::max(0.0f, .) */
+    const float dx = pos[0] - (a[0] + dir[0] * s);
+    const float dy = pos[1] - (a[1] + dir[1] * s);
+    const float dz = pos[2] - (a[2] + dir[2] * s);
+    const float distSq = dx * dx + dy * dy + dz * dz;
+    if (!hasBest || distSq < bestDist)
+    {
+      hasBest = 1;
+      bestDist = distSq;
+      best = i;
+      *outS = s;
+    }
+  }
+  return best;
+}
+
+/* laneSpeedLimit, src/engine/traffic/sc_traffic_lanes.cpp:392-400 */
+static float tr_speed_limit(const ScoLaneGraph* g, uint32_t laneId)
+{
+  if (laneId == 0xFFFFFFFFu || laneId >= g->nSegments) return g->defaultSpeedLimit;
+  const uint32_t a = g->segNodes[(size_t)laneId * 2];
+  if (a >= g->nNodes) return g->defaultSpeedLimit;
+  return g->nodeSpeedLimit[a];
+}
+
+void sco_traffic_ai_on_rails(const ScoLaneGraph* g, uint32_t n, uint32_t* laneId, float* laneS, float* targetSpeed,
+                             float* lookAheadDist, float* trs9, const float* obstacleBrake, const uint8_t* skip, float dt,
+                             int hasDebug, float dbgLookAheadDist, float dbgSpeedMultiplier, uint8_t* outMoved)
+{
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    float* tr = trs9 + (size_t)i * 9; /* localPos 0..2, localRot 3..5, localScale 6..8 */
+    if (outMoved) outMoved[i] = 0;
+    if (skip && skip[i]) continue;                    /* sector not Active, :218-226 */
+    if (hasDebug) lookAheadDist[i] = dbgLookAheadDist; /* :237-238 */
+    if (laneId[i] == 0xFFFFFFFFu)                      /* :264-272 */
+    {
+      float qs = 0.0f;
+      const uint32_t q = sco_lane_query_nearest(g, tr, &qs);
+      if (q != 0xFFFFFFFFu)
+      {
+        laneId[i] = q;
+        laneS[i] = qs;
+      }
+    }
+    if (laneId[i] == 0xFFFFFFFFu || laneId[i] >= g->nSegments || !g->segActive[laneId[i]]) continue; /* :274-276 */
+
+    float target[3], dir[3];
+    {
+      uint32_t id = laneId[i];
+      float ss = laneS[i];
+      if (!sco_lane_advance(g, &id, &ss, lookAheadDist[i], target, dir)) continue; /* getLookAheadPoint :278-280 */
+    }
+    const float toTarget[3] = { target[0] - tr[0], 0.0f, target[2] - tr[2] };
+    if (sqrtf(toTarget[0] * toTarget[0] + toTarget[1] * toTarget[1] + toTarget[2] * toTarget[2]) < 1e-4f) continue;
+
+    float desiredSpeed = tr_speed_limit(g, laneId[i]); /* :295-298 */
+    if (hasDebug) desiredSpeed *= dbgSpeedMultiplier;
+    desiredSpeed = (0.0f < desiredSpeed) ? desiredSpeed : 0.0f;
+
+    const float brake = obstacleBrake ? obstacleBrake[i] : 0.0f;
+    /* on-rails branch :434-458 */
+    const float desired = desiredSpeed * (1.0f - brake);
+    const float t = 1.0f - sco_expf(-2.5f * dt); /* smoothExp(current, target, 2.5f, dt) */
+    targetSpeed[i] = targetSpeed[i] + (desired - targetSpeed[i]) * t;
+    const float travel = targetSpeed[i] * dt;
+    uint32_t id = laneId[i];
+    float ss = laneS[i];
+    float pos[3];
+    if (sco_lane_advance(g, &id, &ss, travel, pos, dir))
+    {
+      laneId[i] = id;
+      laneS[i] = ss;
+      tr[0] = pos[0];
+      tr[2] = pos[2];
+      tr[3] = 0.0f;
+      tr[4] = sco_atan2f(dir[0], dir[2]);
+      tr[5] = 0.0f;
+      if (outMoved) outMoved[i] = 1;
+    }
+  }
+}

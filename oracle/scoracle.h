@@ -73,6 +73,46 @@ int64_t sco_frame(uint32_t n, const uint32_t* entity, uint32_t* parent, float* t
 
 void sco_sincos_sweep(uint32_t first, uint64_t count, uint32_t stride, uint64_t* outSinHash, uint64_t* outCosHash);
 
+/* ---- traffic on rails ----------------------------------------------------------------------
+ * libm: glibc 2.39 expf (sysdeps/ieee754/flt-32/e_expf.c, e_exp2f_data.c), atanf (s_atanf.c) and atan2f
+ * (e_atan2f.c), generic variants: what std::exp / std::atan2 on float resolve to in
+ * src/engine/traffic/sc_traffic_ai.cpp:58-62, 72-75 on the oracle platform. */
+float sco_expf(float x);
+float sco_atanf(float x);
+float sco_atan2f(float y, float x);
+/* counts bit mismatches (NaN == NaN) of sco_expf / sco_atanf against the given functions over float bit patterns
+ * first, first+stride, ... (count of them) */
+uint64_t sco_unary_sweep(int which /*0 expf, 1 atanf*/, uint32_t first, uint64_t count, uint32_t stride, float (*ref)(float));
+/* same for sco_atan2f over count pseudo-random (y, x) pairs: raw bit patterns, unit directions and near-equal
+ * exponents in turn */
+uint64_t sco_atan2_sweep(uint32_t seed, uint64_t count, float (*ref)(float, float));
+
+/* Lane graph in flat arrays: LaneNode / LaneSegment, src/engine/traffic/sc_traffic_lanes.h:14-32 */
+typedef struct ScoLaneGraph
+{
+  uint32_t nNodes, nSegments;
+  const float* nodePos;           /* [nNodes*3] */
+  const float* nodeSpeedLimit;    /* [nNodes] */
+  const uint32_t* nodeConnOffset; /* [nNodes+1] CSR of LaneNode::connections */
+  const uint32_t* nodeConn;
+  const uint32_t* segNodes;       /* [nSegments*2] startNode, endNode */
+  const float* segDir;            /* [nSegments*3] */
+  const float* segLength;         /* [nSegments] */
+  const uint8_t* segActive;       /* [nSegments] */
+  float defaultSpeedLimit;
+} ScoLaneGraph;
+/* TrafficLaneGraph::advanceAlongLane, src/engine/traffic/sc_traffic_lanes.cpp:291-345 */
+int sco_lane_advance(const ScoLaneGraph* g, uint32_t* laneId, float* s, float distance, float* outPos3, float* outDir3);
+/* TrafficLaneGraph::queryNearestLane, src/engine/traffic/sc_traffic_lanes.cpp:239-278; returns the lane id */
+uint32_t sco_lane_query_nearest(const ScoLaneGraph* g, const float* pos3, float* outS);
+/* TrafficAISystem, src/engine/traffic/sc_traffic_ai.cpp:165-487, for n agents in OnRails mode without a physics
+ * world: per agent laneId / laneS / targetSpeed / lookAheadDist (TrafficAgent, sc_traffic_common.h:27-37) and the
+ * Transform's local TRS (9 floats; localPos.xz and localRot rewritten when the agent moves). obstacleBrake / skip
+ * may be NULL. outMoved[i] = 1 when the Transform was written (tr.dirty = true). */
+void sco_traffic_ai_on_rails(const ScoLaneGraph* g, uint32_t n, uint32_t* laneId, float* laneS, float* targetSpeed,
+                             float* lookAheadDist, float* trs9, const float* obstacleBrake, const uint8_t* skip, float dt,
+                             int hasDebug, float dbgLookAheadDist, float dbgSpeedMultiplier, uint8_t* outMoved);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 #include "scgpu_kernels.cuh"
 #include "scgpu_draws.cuh"
 #include "scgpu_peer.cuh"
+#include "scgpu_traffic.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -140,6 +141,14 @@ struct ScGpuScene
   uint32_t* dSortCounters = nullptr;  // kept, nRuns
   uint32_t hSortCounters[2] = {0, 0};
   bool sortedValid = false;
+
+  // traffic on rails (scgpu_traffic.cuh): lane graph records and the agent set
+  DeviceBuffer laneNodePos, laneNodeConn, laneConn, laneSegDirLen, laneSegNodes;
+  DeviceBuffer trafficAgents, trafficLook, trafficInputs;
+  uint32_t nLaneNodes = 0, nLaneSegs = 0, nTrafficAgents = 0;
+  float laneDefaultSpeed = 12.0f;
+  bool lanesSet = false;
+  uint32_t* dTrafficMoved = nullptr;
 
   std::vector<uint32_t> hEntity;  // dense handles (ComponentPool::m_denseEntities)
   std::vector<uint32_t> hSparse;  // index -> slot+1 (ComponentPool::m_sparse)
@@ -278,6 +287,9 @@ void freeAll(ScGpuScene* c)
   cudaFree(c->staging.ptr); cudaFree(c->scratch.ptr); cudaFree(c->drawItems.ptr);
   cudaFree(c->sortWork.ptr); cudaFree(c->sortedDraws.ptr); cudaFree(c->drawRuns.ptr); cudaFree(c->matPipe.ptr); cudaFree(c->dSortCounters);
   cudaFree(c->dAllCounts);
+  cudaFree(c->laneNodePos.ptr); cudaFree(c->laneNodeConn.ptr); cudaFree(c->laneConn.ptr); cudaFree(c->laneSegDirLen.ptr);
+  cudaFree(c->laneSegNodes.ptr); cudaFree(c->trafficAgents.ptr); cudaFree(c->trafficLook.ptr); cudaFree(c->trafficInputs.ptr);
+  cudaFree(c->dTrafficMoved);
   if (c->peerBox.base) { if (c->peerMapped) cudaIpcCloseMemHandle(c->peerBox.base); else cudaFree(c->peerBox.base); }
   cudaFree(c->dPeerState);
   if (c->hTotals) cudaFreeHost(c->hTotals);
@@ -692,6 +704,179 @@ int scgpuBuildEditorDraws(ScGpuScene* c, uint32_t n, const float* trs9, const ui
     SC_CUDA(c, cudaMemcpyAsync(out, s + oOut, (size_t)m * 88, cudaMemcpyDeviceToHost, c->stream));
     SC_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  return 1;
+}
+
+// ---- traffic on rails (scgpu_traffic.cuh) --------------------------------------------------------
+int scgpuTrafficSetLanes(ScGpuScene* c, const ScGpuLaneGraph* gph)
+{
+  if (!enter(c)) return 0;
+  if (!gph) return (int)fail(c, "scgpuTrafficSetLanes: graph is NULL");
+  if (gph->struct_size != sizeof(ScGpuLaneGraph)) return (int)fail(c, "scgpuTrafficSetLanes: struct_size %u != %zu", gph->struct_size, sizeof(ScGpuLaneGraph));
+  const uint32_t nN = gph->nNodes, nS = gph->nSegments, nC = gph->nConnections;
+  if ((nN && (!gph->nodePos || !gph->nodeSpeedLimit || !gph->nodeConnOffset)) || (nC && !gph->nodeConn) ||
+      (nS && (!gph->segNodes || !gph->segDir || !gph->segLength)))
+    return (int)fail(c, "scgpuTrafficSetLanes: NULL array");
+  std::vector<float4> nodePos(nN), segDirLen(nS);
+  std::vector<uint2> nodeConn(nN);
+  std::vector<uint4> segNodes(nS);
+  for (uint32_t i = 0; i < nN; ++i)
+  {
+    const uint32_t o0 = gph->nodeConnOffset[i], o1 = gph->nodeConnOffset[i + 1];
+    if (o1 < o0 || o1 > nC) return (int)fail(c, "scgpuTrafficSetLanes: nodeConnOffset[%u..] = %u, %u is not a CSR of %u connections", i, o0, o1, nC);
+    nodePos[i] = make_float4(gph->nodePos[3 * i], gph->nodePos[3 * i + 1], gph->nodePos[3 * i + 2], gph->nodeSpeedLimit[i]);
+    nodeConn[i] = make_uint2(o0, o1 - o0);
+  }
+  for (uint32_t i = 0; i < nS; ++i)
+  {
+    const uint32_t a = gph->segNodes[2 * i], b = gph->segNodes[2 * i + 1];
+    if (a >= nN || b >= nN) return (int)fail(c, "scgpuTrafficSetLanes: segment %u references node %u / %u of %u", i, a, b, nN);
+    segDirLen[i] = make_float4(gph->segDir[3 * i], gph->segDir[3 * i + 1], gph->segDir[3 * i + 2], gph->segLength[i]);
+    segNodes[i] = make_uint4(a, b, (!gph->segActive || gph->segActive[i]) ? 1u : 0u, 0u);
+  }
+  if (!ensure(c, c->laneNodePos, (size_t)nN * 16) || !ensure(c, c->laneNodeConn, (size_t)nN * 8) || !ensure(c, c->laneConn, (size_t)nC * 4) ||
+      !ensure(c, c->laneSegDirLen, (size_t)nS * 16) || !ensure(c, c->laneSegNodes, (size_t)nS * 16))
+    return 0;
+  // pageable sources: cudaMemcpyAsync returns after staging them, the vectors may die at scope exit
+  if (nN && (!uploadTo(c, c->laneNodePos.ptr, nodePos.data(), (size_t)nN * 16) || !uploadTo(c, c->laneNodeConn.ptr, nodeConn.data(), (size_t)nN * 8))) return 0;
+  if (nC && !uploadTo(c, c->laneConn.ptr, gph->nodeConn, (size_t)nC * 4)) return 0;
+  if (nS && (!uploadTo(c, c->laneSegDirLen.ptr, segDirLen.data(), (size_t)nS * 16) || !uploadTo(c, c->laneSegNodes.ptr, segNodes.data(), (size_t)nS * 16))) return 0;
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->nLaneNodes = nN;
+  c->nLaneSegs = nS;
+  c->laneDefaultSpeed = gph->defaultSpeedLimit;
+  c->lanesSet = true;
+  return 1;
+}
+
+int scgpuTrafficSetLaneActive(ScGpuScene* c, uint32_t n, const uint32_t* segment, const uint8_t* active)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!segment || !active) return (int)fail(c, "scgpuTrafficSetLaneActive: NULL argument");
+  if (!c->lanesSet) return (int)fail(c, "scgpuTrafficSetLaneActive: no lane graph (scgpuTrafficSetLanes)");
+  for (uint32_t i = 0; i < n; ++i)
+    if (segment[i] >= c->nLaneSegs) return (int)fail(c, "scgpuTrafficSetLaneActive: segment %u of %u", segment[i], c->nLaneSegs);
+  const size_t oAct = ((size_t)n * 4 + 255) & ~(size_t)255;
+  if (!ensure(c, c->staging, oAct + n)) return 0;
+  char* s = (char*)c->staging.ptr;
+  if (!uploadTo(c, s, segment, (size_t)n * 4) || !uploadTo(c, s + oAct, active, n)) return 0;
+  k_lane_set_active<<<blocksFor(n), kBlock, 0, c->stream>>>((uint4*)c->laneSegNodes.ptr, n, (const uint32_t*)s, (const uint8_t*)(s + oAct));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  return 1;
+}
+
+int scgpuTrafficSetAgents(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* laneId, const float* laneS,
+                          const float* targetSpeed, const float* lookAheadDist)
+{
+  if (!enter(c)) return 0;
+  if (n && (!entity || !laneId || !laneS || !targetSpeed || !lookAheadDist)) return (int)fail(c, "scgpuTrafficSetAgents: NULL argument");
+  if (!c->dTrafficMoved && !devAlloc(c, &c->dTrafficMoved, 1, true)) return 0;
+  std::vector<uint4> rec(n);
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    uint32_t sBits, vBits;
+    std::memcpy(&sBits, laneS + i, 4);
+    std::memcpy(&vBits, targetSpeed + i, 4);
+    rec[i] = make_uint4(entity[i], laneId[i], sBits, vBits);
+  }
+  if (!ensure(c, c->trafficAgents, (size_t)n * 16) || !ensure(c, c->trafficLook, (size_t)n * 4)) return 0;
+  if (n && (!uploadTo(c, c->trafficAgents.ptr, rec.data(), (size_t)n * 16) || !uploadTo(c, c->trafficLook.ptr, lookAheadDist, (size_t)n * 4))) return 0;
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->nTrafficAgents = n;
+  return 1;
+}
+
+int scgpuTrafficAdvance(ScGpuScene* c, const ScGpuTrafficStep* st, uint32_t* outMoved)
+{
+  if (!enter(c)) return 0;
+  if (outMoved) *outMoved = 0;
+  if (!st) return (int)fail(c, "scgpuTrafficAdvance: step is NULL");
+  if (st->struct_size != sizeof(ScGpuTrafficStep)) return (int)fail(c, "scgpuTrafficAdvance: struct_size %u != %zu", st->struct_size, sizeof(ScGpuTrafficStep));
+  if (!c->lanesSet) return (int)fail(c, "scgpuTrafficAdvance: no lane graph (scgpuTrafficSetLanes)");  // TrafficAIState::lanes == nullptr
+  const uint32_t n = c->nTrafficAgents;
+  if (n == 0) return 1;
+  const float* dBrake = nullptr;
+  const uint8_t* dSkip = nullptr;
+  if (st->obstacleBrake || st->skip)
+  {
+    const size_t oSkip = ((size_t)n * 4 + 255) & ~(size_t)255;
+    if (!ensure(c, c->trafficInputs, oSkip + n)) return 0;
+    char* s = (char*)c->trafficInputs.ptr;
+    if (st->obstacleBrake) { if (!uploadTo(c, s, st->obstacleBrake, (size_t)n * 4)) return 0; dBrake = (const float*)s; }
+    if (st->skip) { if (!uploadTo(c, s + oSkip, st->skip, n)) return 0; dSkip = (const uint8_t*)(s + oSkip); }
+  }
+  LaneGraphView g{};
+  g.nodePos = (const float4*)c->laneNodePos.ptr;
+  g.nodeConn = (const uint2*)c->laneNodeConn.ptr;
+  g.conn = (const uint32_t*)c->laneConn.ptr;
+  g.segDirLen = (const float4*)c->laneSegDirLen.ptr;
+  g.segNodes = (const uint4*)c->laneSegNodes.ptr;
+  g.nNodes = c->nLaneNodes;
+  g.nSegs = c->nLaneSegs;
+  g.defaultSpeedLimit = c->laneDefaultSpeed;
+  TrafficStepParams p{};
+  p.dt = st->dt;
+  p.speedMultiplier = st->speedMultiplier;
+  p.lookAheadDist = st->lookAheadDist;
+  p.hasDebug = st->hasDebug ? 1u : 0u;
+  SC_CUDA(c, cudaMemsetAsync(c->dTrafficMoved, 0, 4, c->stream));
+  k_traffic_advance<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, g, p, n, (uint4*)c->trafficAgents.ptr, (float*)c->trafficLook.ptr, dBrake,
+                                                            dSkip, stampOf(c->frame), c->dTrafficMoved);
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  if (outMoved)
+  {
+    SC_CUDA(c, cudaMemcpyAsync(outMoved, c->dTrafficMoved, 4, cudaMemcpyDeviceToHost, c->stream));
+    SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return 1;
+}
+
+int scgpuTrafficReadAgents(ScGpuScene* c, uint32_t cap, uint32_t* outLaneId, float* outLaneS, float* outTargetSpeed,
+                           float* outLookAheadDist, uint32_t* outCount)
+{
+  if (!enter(c)) return 0;
+  const uint32_t n = c->nTrafficAgents;
+  if (outCount) *outCount = n;
+  const uint32_t m = std::min(n, cap);
+  if (m == 0) return 1;
+  std::vector<uint4> rec(m);
+  std::vector<float> look(m);
+  SC_CUDA(c, cudaMemcpyAsync(rec.data(), c->trafficAgents.ptr, (size_t)m * 16, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaMemcpyAsync(look.data(), c->trafficLook.ptr, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (uint32_t i = 0; i < m; ++i)
+  {
+    if (outLaneId) outLaneId[i] = rec[i].y;
+    if (outLaneS) std::memcpy(outLaneS + i, &rec[i].z, 4);
+    if (outTargetSpeed) std::memcpy(outTargetSpeed + i, &rec[i].w, 4);
+    if (outLookAheadDist) outLookAheadDist[i] = look[i];
+  }
+  return 1;
+}
+
+int scgpuReadLocal(ScGpuScene* c, uint32_t n, const uint32_t* entity, float* outTrs9)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity || !outTrs9) return (int)fail(c, "scgpuReadLocal: NULL argument");
+  const size_t oOut = (((size_t)n * 4 + 255) & ~(size_t)255);
+  if (!ensure(c, c->scratch, oOut + (size_t)n * 36 + 32)) return 0;
+  char* s = (char*)c->scratch.ptr;
+  uint32_t* dMissing = (uint32_t*)(s + oOut + (((size_t)n * 36 + 15) & ~(size_t)15));
+  SC_CUDA(c, cudaMemcpyAsync(s, entity, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+  SC_CUDA(c, cudaMemsetAsync(dMissing, 0, 4, c->stream));
+  k_gather_local<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, (const uint32_t*)s, (float*)(s + oOut), dMissing);
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  uint32_t missing = 0;
+  SC_CUDA(c, cudaMemcpyAsync(outTrs9, s + oOut, (size_t)n * 36, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaMemcpyAsync(&missing, dMissing, 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (missing) return (int)fail(c, "scgpuReadLocal: %u of %u handles own no Transform (zeros returned for them)", missing, n);
   return 1;
 }
 

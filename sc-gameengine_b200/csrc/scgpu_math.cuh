@@ -470,4 +470,145 @@ __device__ __forceinline__ bool sphere_in_frustum(const float4* __restrict__ pla
   return inside;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// glibc 2.39 expf / atanf / atan2f (generic variants) for the traffic on-rails producer (scgpu_traffic.cuh):
+//   smoothExp   src/engine/traffic/sc_traffic_ai.cpp:58-62  1.0f - std::exp(-response * dt)
+//   yawFromDir  src/engine/traffic/sc_traffic_ai.cpp:72-75  std::atan2(dir[0], dir[2])
+// expf: sysdeps/ieee754/flt-32/e_expf.c + e_exp2f_data.c (ARM optimized-routines: N = 32 table, degree-3
+// polynomial in double, one rounding to float). atanf / atan2f: sysdeps/ieee754/flt-32/s_atanf.c, e_atan2f.c
+// (fdlibm, float arithmetic). Checked against the host libm (hwcaps=-FMA,-AVX2): expf and atanf over all 2^32
+// inputs, atan2f over 4e8 pairs, 0 mismatches (oracle/scoracle.c header; tests/test_traffic_oracle.py repeats
+// strided sweeps).
+// ---------------------------------------------------------------------------------------------------
+
+// e_exp2f_data.c: tab[i] = asuint64(2^(i/32)) - (i << 47)
+__constant__ uint64_t kExp2fTab[32] = {
+  0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+  0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+  0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+  0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+  0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+  0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+  0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+  0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull
+};
+
+__device__ __forceinline__ float expf_glibc(float x)
+{
+  const uint32_t xi = __float_as_uint(x);
+  const uint32_t abstop = (xi >> 20) & 0x7ffu;
+  if (abstop >= 0x42bu)  // |x| >= 88.0f or NaN
+  {
+    if (xi == 0xff800000u) return 0.0f;
+    if (abstop >= 0x7f8u) return __fadd_rn(x, x);
+    if (x > 0x1.62e42ep6f) return __int_as_float(0x7f800000);  // __math_oflowf
+    if (x < -0x1.9fe368p6f) return 0.0f;                        // __math_uflowf
+  }
+  // x * N/ln2 = k + r, r in [-1/2, 1/2]; the poly_scaled coefficients carry the powers of 1/N (exact)
+  const double z = __dmul_rn(0x1.71547652b82fep+5, (double)x);
+  double kd = __dadd_rn(z, 0x1.8p+52);
+  const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, 0x1.8p+52);
+  const double r = __dsub_rn(z, kd);
+  const uint64_t t = kExp2fTab[ki & 31u] + (ki << 47);
+  const double s = __longlong_as_double((long long)t);
+  const double p = __dadd_rn(__dmul_rn(0x1.c6af84b912394p-20, r), 0x1.ebfce50fac4f3p-13);
+  const double r2 = __dmul_rn(r, r);
+  double y = __dadd_rn(__dmul_rn(0x1.62e42ff0c52d6p-6, r), 1.0);
+  y = __dadd_rn(__dmul_rn(p, r2), y);
+  return __double2float_rn(__dmul_rn(y, s));
+}
+
+__device__ __forceinline__ float atanf_glibc(float x)
+{
+  // atanhi/atanlo for 0.5, 1.0, 1.5, inf and the 11 polynomial coefficients of s_atanf.c
+  const float hi0 = 4.6364760399e-01f, hi1 = 7.8539812565e-01f, hi2 = 9.8279368877e-01f, hi3 = 1.5707962513e+00f;
+  const float lo0 = 5.0121582440e-09f, lo1 = 3.7748947079e-08f, lo2 = 3.4473217170e-08f, lo3 = 7.5497894159e-08f;
+  const float a0 = 3.3333334327e-01f, a1 = -2.0000000298e-01f, a2 = 1.4285714924e-01f, a3 = -1.1111110449e-01f,
+              a4 = 9.0908870101e-02f, a5 = -7.6918758452e-02f, a6 = 6.6610731184e-02f, a7 = -5.8335702866e-02f,
+              a8 = 4.9768779427e-02f, a9 = -3.6531571299e-02f, a10 = 1.6285819933e-02f;
+  const int32_t hx = (int32_t)__float_as_uint(x);
+  const int32_t ix = hx & 0x7fffffff;
+  if (ix >= 0x4c000000)  // |x| >= 2^25
+  {
+    if (ix > 0x7f800000) return __fadd_rn(x, x);
+    return (hx > 0) ? __fadd_rn(hi3, lo3) : __fsub_rn(-hi3, lo3);
+  }
+  int id = -1;
+  float hi = 0.0f, lo = 0.0f;
+  if (ix < 0x3ee00000)  // |x| < 0.4375
+  {
+    if (ix < 0x31000000) return x;  // |x| < 2^-29
+  }
+  else
+  {
+    x = fabsf(x);
+    if (ix < 0x3f980000)
+    {
+      if (ix < 0x3f300000) { id = 0; hi = hi0; lo = lo0; x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x)); }
+      else                 { id = 1; hi = hi1; lo = lo1; x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f)); }
+    }
+    else
+    {
+      if (ix < 0x401c0000) { id = 2; hi = hi2; lo = lo2; x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x))); }
+      else                 { id = 3; hi = hi3; lo = lo3; x = __fdiv_rn(-1.0f, x); }
+    }
+  }
+  const float z = __fmul_rn(x, x);
+  const float w = __fmul_rn(z, z);
+  float e = __fadd_rn(a8, __fmul_rn(w, a10));
+  e = __fadd_rn(a6, __fmul_rn(w, e));
+  e = __fadd_rn(a4, __fmul_rn(w, e));
+  e = __fadd_rn(a2, __fmul_rn(w, e));
+  e = __fadd_rn(a0, __fmul_rn(w, e));
+  const float s1 = __fmul_rn(z, e);
+  float o = __fadd_rn(a7, __fmul_rn(w, a9));
+  o = __fadd_rn(a5, __fmul_rn(w, o));
+  o = __fadd_rn(a3, __fmul_rn(w, o));
+  o = __fadd_rn(a1, __fmul_rn(w, o));
+  const float s2 = __fmul_rn(w, o);
+  const float xs = __fmul_rn(x, __fadd_rn(s1, s2));
+  if (id < 0) return __fsub_rn(x, xs);
+  const float r = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), x));
+  return (hx < 0) ? -r : r;
+}
+
+__device__ __forceinline__ float atan2f_glibc(float y, float x)
+{
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  const int32_t hx = (int32_t)__float_as_uint(x), hy = (int32_t)__float_as_uint(y);
+  const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+  if (hx == 0x3f800000) return atanf_glibc(y);
+  const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);  // 2*sign(x) + sign(y)
+  const float piT = __fadd_rn(pi, tiny), hpiT = __fadd_rn(pi_o_2, tiny);
+  if (iy == 0) return (m < 2) ? y : ((m == 2) ? piT : __fsub_rn(-pi, tiny));
+  if (ix == 0) return (hy < 0) ? __fsub_rn(-pi_o_2, tiny) : hpiT;
+  if (ix == 0x7f800000)
+  {
+    if (iy == 0x7f800000)
+    {
+      if (m == 0) return __fadd_rn(pi_o_4, tiny);
+      if (m == 1) return __fsub_rn(-pi_o_4, tiny);
+      if (m == 2) return __fadd_rn(__fmul_rn(3.0f, pi_o_4), tiny);
+      return __fsub_rn(__fmul_rn(-3.0f, pi_o_4), tiny);
+    }
+    if (m == 0) return 0.0f;
+    if (m == 1) return -0.0f;
+    if (m == 2) return piT;
+    return __fsub_rn(-pi, tiny);
+  }
+  if (iy == 0x7f800000) return (hy < 0) ? __fsub_rn(-pi_o_2, tiny) : hpiT;
+  const int k = (iy - ix) >> 23;
+  float z;
+  if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+  else if (hx < 0 && k < -60) z = 0.0f;
+  else z = atanf_glibc(fabsf(__fdiv_rn(y, x)));
+  if (m == 0) return z;
+  if (m == 1) return __uint_as_float(__float_as_uint(z) ^ 0x80000000u);
+  if (m == 2) return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+  return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+}
+
 }  // namespace scgpu

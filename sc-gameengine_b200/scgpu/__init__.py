@@ -93,6 +93,20 @@ class SectorGen(C.Structure):
         super().__init__(struct_size=C.sizeof(SectorGen), **kw)
 
 
+class LaneGraph(C.Structure):
+    """ScGpuLaneGraph (include/scgpu.h)"""
+    _fields_ = [("struct_size", C.c_uint32), ("nNodes", C.c_uint32), ("nSegments", C.c_uint32), ("nConnections", C.c_uint32),
+                ("nodePos", C.c_void_p), ("nodeSpeedLimit", C.c_void_p), ("nodeConnOffset", C.c_void_p), ("nodeConn", C.c_void_p),
+                ("segNodes", C.c_void_p), ("segDir", C.c_void_p), ("segLength", C.c_void_p), ("segActive", C.c_void_p),
+                ("defaultSpeedLimit", C.c_float)]
+
+
+class TrafficStep(C.Structure):
+    """ScGpuTrafficStep (include/scgpu.h)"""
+    _fields_ = [("struct_size", C.c_uint32), ("dt", C.c_float), ("hasDebug", C.c_uint32), ("lookAheadDist", C.c_float),
+                ("speedMultiplier", C.c_float), ("obstacleBrake", C.c_void_p), ("skip", C.c_void_p)]
+
+
 EDITOR_DRAW_DTYPE = np.dtype([("mesh", "<u8"), ("material", "<u8"), ("model", "<f4", (16,)), ("flags", "<u4"), ("_pad", "<u4")])
 assert EDITOR_DRAW_DTYPE.itemsize == 88
 DRAW_RUN_DTYPE = np.dtype([("pipelineId", "<u4"), ("materialId", "<u4"), ("meshId", "<u4"), ("first", "<u4"), ("count", "<u4")])
@@ -139,6 +153,12 @@ SYMBOLS = {
     "scgpuBuildSortedDraws": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp), _u32p,
                                         C.POINTER(_vp), _u32p]),
     "scgpuReadSortedDraws": (C.c_int, [_vp, _vp, C.c_uint32, _vp, C.c_uint32]),
+    "scgpuTrafficSetLanes": (C.c_int, [_vp, C.POINTER(LaneGraph)]),
+    "scgpuTrafficSetLaneActive": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "scgpuTrafficSetAgents": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "scgpuTrafficAdvance": (C.c_int, [_vp, C.POINTER(TrafficStep), _u32p]),
+    "scgpuTrafficReadAgents": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _u32p]),
+    "scgpuReadLocal": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "scgpuCommGetUniqueId": (C.c_int, [_vp]),
     "scgpuCommInit": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "scgpuCommEnablePeerGather": (C.c_int, [_vp, C.c_uint32, C.c_uint32]),
@@ -254,6 +274,48 @@ class Scene:
         self._ck(self.lib.scgpuBuildEditorDraws(self.ctx, t.shape[0], _ptr(t), _ptr(m), _ptr(a), _ptr(out), out.shape[0], C.byref(n)),
                  "scgpuBuildEditorDraws")
         return out[: n.value]
+
+    # -- traffic on rails
+    def traffic_set_lanes(self, node_pos, node_speed, conn_offset, conn, seg_nodes, seg_dir, seg_len, seg_active=None,
+                          default_speed=12.0):
+        a = [_arr(node_pos, np.float32), _arr(node_speed, np.float32), _arr(conn_offset, np.uint32), _arr(conn, np.uint32),
+             _arr(seg_nodes, np.uint32), _arr(seg_dir, np.float32), _arr(seg_len, np.float32), _arr(seg_active, np.uint8)]
+        g = LaneGraph(C.sizeof(LaneGraph), a[1].shape[0], a[6].shape[0], a[3].shape[0], *[_ptr(x) for x in a], float(default_speed))
+        self._ck(self.lib.scgpuTrafficSetLanes(self.ctx, C.byref(g)), "scgpuTrafficSetLanes")
+
+    def traffic_set_lane_active(self, segment, active):
+        sg, ac = _arr(segment, np.uint32), _arr(active, np.uint8)
+        self._ck(self.lib.scgpuTrafficSetLaneActive(self.ctx, sg.shape[0], _ptr(sg), _ptr(ac)), "scgpuTrafficSetLaneActive")
+
+    def traffic_set_agents(self, entity, lane, s, speed, look):
+        e = _arr(entity, np.uint32)
+        self._ck(self.lib.scgpuTrafficSetAgents(self.ctx, e.shape[0], _ptr(e), _ptr(_arr(lane, np.uint32)), _ptr(_arr(s, np.float32)),
+                                                _ptr(_arr(speed, np.float32)), _ptr(_arr(look, np.float32))), "scgpuTrafficSetAgents")
+        self._n_agents = e.shape[0]
+
+    def traffic_advance(self, dt, brake=None, skip=None, debug=None, want_moved=True):
+        """one TrafficAISystem pass over the on-rails agents; debug = (lookAheadDist, speedMultiplier) or None"""
+        b, k = _arr(brake, np.float32), _arr(skip, np.uint8)
+        st = TrafficStep(C.sizeof(TrafficStep), dt, 1 if debug else 0, debug[0] if debug else 0.0, debug[1] if debug else 0.0,
+                         _ptr(b), _ptr(k))
+        moved = C.c_uint32(0)
+        self._ck(self.lib.scgpuTrafficAdvance(self.ctx, C.byref(st), C.byref(moved) if want_moved else None), "scgpuTrafficAdvance")
+        return moved.value
+
+    def traffic_read_agents(self):
+        n = getattr(self, "_n_agents", 0)
+        lane, s, v, look = np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        cnt = C.c_uint32(0)
+        self._ck(self.lib.scgpuTrafficReadAgents(self.ctx, n, _ptr(lane), _ptr(s), _ptr(v), _ptr(look), C.byref(cnt)),
+                 "scgpuTrafficReadAgents")
+        assert cnt.value == n
+        return lane, s, v, look
+
+    def read_local(self, entity):
+        e = _arr(entity, np.uint32)
+        out = np.zeros((e.shape[0], 9), np.float32)
+        self._ck(self.lib.scgpuReadLocal(self.ctx, e.shape[0], _ptr(e), _ptr(out)), "scgpuReadLocal")
+        return out
 
     def despawn(self, entity):
         e = _arr(entity, np.uint32)

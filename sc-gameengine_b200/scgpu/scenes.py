@@ -259,3 +259,117 @@ def shard_by_sector(sector, n_ranks):
     mid = cum - counts / 2.0
     sec_rank = np.minimum((mid * n_ranks / total).astype(np.int64), n_ranks - 1)
     return sec_rank[inv].astype(np.int32)
+
+
+# ---- lane graphs and on-rails agents for the traffic producer ---------------------------------
+
+def _quant(v, scale):
+    """quantPos / quantDir, src/engine/traffic/sc_traffic_lanes.cpp:34-44: round half away from zero"""
+    s = np.float32(v) * np.float32(scale)
+    return int(np.floor(np.float32(s + np.float32(0.5 if s >= 0 else -0.5))))
+
+
+def lane_grid(nx, nz, sector=SECTOR_SIZE, lane_width=3.5, speed=12.0, x0=0, z0=0):
+    """The lane graph TrafficLaneGraph::buildProceduralForSector (src/engine/traffic/sc_traffic_lanes.cpp:171-237)
+    builds for the sectors [x0, x0+nx) x [z0, z0+nz), visited x-major: per sector one east/west and one north/south
+    road of two opposite lanes, nodes shared between neighbouring sectors through the quantised (pos, dir) key of
+    addNode (:70-97), so that lanes continue across sector borders. Returns the flat arrays of ScGpuLaneGraph."""
+    f = np.float32
+    nodes, key2node, conns, segs = [], {}, [], []
+
+    def add_node(pos, d):
+        k = (_quant(pos[0], 100), _quant(pos[1], 100), _quant(pos[2], 100), _quant(d[0], 1000), _quant(d[1], 1000), _quant(d[2], 1000))
+        if k not in key2node:
+            key2node[k] = len(nodes)
+            nodes.append((f(pos[0]), f(pos[1]), f(pos[2])))
+            conns.append([])
+        return key2node[k]
+
+    def add_segment(a, b):
+        d = [f(nodes[b][i] - nodes[a][i]) for i in range(3)]
+        ln = f(np.sqrt(f(f(f(d[0] * d[0]) + f(d[1] * d[1])) + f(d[2] * d[2]))))
+        inv = f(f(1.0) / ln)
+        conns[a].append(len(segs))
+        segs.append((a, b, f(d[0] * inv), f(d[1] * inv), f(d[2] * inv), ln))
+
+    off = f(f(lane_width) * f(0.5))
+    for sx in range(x0, x0 + nx):
+        for sz in range(z0, z0 + nz):
+            mnx, mxx = f(f(sx) * f(sector)), f(f(sx + 1) * f(sector))
+            mnz, mxz = f(f(sz) * f(sector)), f(f(sz + 1) * f(sector))
+            cx, cz = f(f(mnx + mxx) * f(0.5)), f(f(mnz + mxz) * f(0.5))
+            add_segment(add_node((mnx, 0, f(cz - off)), (1, 0, 0)), add_node((mxx, 0, f(cz - off)), (1, 0, 0)))
+            add_segment(add_node((mxx, 0, f(cz + off)), (-1, 0, 0)), add_node((mnx, 0, f(cz + off)), (-1, 0, 0)))
+            add_segment(add_node((f(cx + off), 0, mnz), (0, 0, 1)), add_node((f(cx + off), 0, mxz), (0, 0, 1)))
+            add_segment(add_node((f(cx - off), 0, mxz), (0, 0, -1)), add_node((f(cx - off), 0, mnz), (0, 0, -1)))
+    off_arr = np.zeros(len(nodes) + 1, np.uint32)
+    off_arr[1:] = np.cumsum([len(c) for c in conns])
+    sg = np.array(segs, np.float64).reshape(-1, 6)
+    return dict(node_pos=np.array(nodes, np.float32).reshape(-1, 3), node_speed=np.full(len(nodes), speed, np.float32),
+                conn_offset=off_arr, conn=np.array([s for c in conns for s in c], np.uint32),
+                seg_nodes=np.ascontiguousarray(sg[:, :2].astype(np.uint32)), seg_dir=np.ascontiguousarray(sg[:, 2:5].astype(np.float32)),
+                seg_len=np.ascontiguousarray(sg[:, 5].astype(np.float32)), seg_active=np.ones(len(segs), np.uint8),
+                default_speed=np.float32(speed))
+
+
+def lane_random(n_nodes, n_segs, seed=7, extent=400.0, hostile=True):
+    """An arbitrary lane graph (curved roads, junctions with several exits, dead ends): random nodes, random directed
+    segments with dir = (b - a) / |b - a|. With hostile=True some segments are inactive, some shorter than the 1e-5
+    cut-off, some connection entries point past the segment array (skipped like sc_traffic_lanes.cpp:156-157) and
+    speed limits include 0 and negative values."""
+    rng = np.random.default_rng(seed)
+    pos = (rng.random((n_nodes, 3), np.float32) * np.float32(extent)).astype(np.float32)
+    pos[:, 1] = (rng.random(n_nodes, np.float32) * 3).astype(np.float32)
+    a = rng.integers(0, n_nodes, n_segs).astype(np.uint32)
+    b = rng.integers(0, n_nodes, n_segs).astype(np.uint32)
+    d = pos[b] - pos[a]
+    ln = np.sqrt((d * d).sum(1, dtype=np.float32)).astype(np.float32)
+    sdir = np.where(ln[:, None] > 1e-6, d / np.maximum(ln, np.float32(1e-30))[:, None], np.float32([0, 0, 1])).astype(np.float32)
+    active = np.ones(n_segs, np.uint8)
+    speed = (4 + rng.random(n_nodes) * 20).astype(np.float32)
+    conns = [[] for _ in range(n_nodes)]
+    for s in range(n_segs):
+        conns[a[s]].append(s)
+    if hostile:
+        active[rng.random(n_segs) < 0.08] = 0
+        ln[rng.random(n_segs) < 0.03] = np.float32(5e-6)
+        speed[rng.random(n_nodes) < 0.05] = 0
+        speed[rng.random(n_nodes) < 0.03] = -3
+        for c in conns:
+            if rng.random() < 0.05:
+                c.insert(int(rng.integers(0, len(c) + 1)), n_segs + int(rng.integers(0, 5)))
+    off = np.zeros(n_nodes + 1, np.uint32)
+    off[1:] = np.cumsum([len(c) for c in conns])
+    return dict(node_pos=pos, node_speed=speed, conn_offset=off, conn=np.array([s for c in conns for s in c], np.uint32),
+                seg_nodes=np.ascontiguousarray(np.stack([a, b], 1)), seg_dir=np.ascontiguousarray(sdir), seg_len=ln,
+                seg_active=active, default_speed=np.float32(12.0))
+
+
+def traffic_agents(graph, n, seed=11, hostile=True):
+    """n on-rails agents placed on random segments of `graph` (what sc_traffic_spawner.cpp:283-316 produces): returns
+    (agents dict lane/s/speed/look, trs9 [n, 9]). hostile adds agents without a lane, with lane ids past the array,
+    off-lane positions and s beyond the segment end."""
+    rng = np.random.default_rng(seed)
+    ns = len(graph["seg_len"])
+    lane = rng.integers(0, ns, n).astype(np.uint32)
+    s = (rng.random(n, np.float32) * graph["seg_len"][lane]).astype(np.float32)
+    a = graph["node_pos"][graph["seg_nodes"][lane, 0]]
+    pos = (a + graph["seg_dir"][lane] * s[:, None]).astype(np.float32)
+    pos[:, 1] = np.float32(0.9)
+    yaw = np.arctan2(graph["seg_dir"][lane, 0], graph["seg_dir"][lane, 2]).astype(np.float32)
+    speed = (rng.random(n, np.float32) * 14).astype(np.float32)
+    look = np.full(n, 12.0, np.float32)
+    if hostile:
+        lane[rng.random(n) < 0.05] = 0xFFFFFFFF
+        lane[rng.random(n) < 0.02] = ns + 3
+        far = rng.random(n) < 0.05
+        pos[far] += (rng.normal(size=(int(far.sum()), 3)) * 30).astype(np.float32)
+        s[rng.random(n) < 0.03] += np.float32(500.0)
+        look[rng.random(n) < 0.1] = np.float32(0.0)
+        look[rng.random(n) < 0.1] = np.float32(150.0)
+    trs = np.zeros((n, 9), np.float32)
+    trs[:, 0:3] = pos
+    trs[:, 3] = (rng.random(n) * 0.1).astype(np.float32)  # a vehicle that was tilted by the physics tier before
+    trs[:, 4] = yaw
+    trs[:, 6:9] = np.float32([1.8, 1.4, 4.2])
+    return dict(lane=lane, s=s, speed=speed, look=look), trs

@@ -193,12 +193,55 @@ def forest_scene(seed):
     return out
 
 
+def traffic_golden(L):
+    """the reference's TrafficAISystem over its own procedural lanes + a junction-rich random graph"""
+    from oracle_bind import LANE_KEYS, RefLanes, ref_traffic_frames
+    g0 = scenes.lane_random(120, 320, seed=77, hostile=False)
+    lanes = RefLanes(3.5, 12.0)
+    for i in range(len(g0["node_speed"])):
+        d = np.array([(i % 1000 - 500) / 1000.0, 0.1, 0.25], np.float32)
+        assert lanes.add_node(g0["node_pos"][i], d, float(g0["node_speed"][i])) == i
+    for s in range(len(g0["seg_len"])):
+        lanes.add_segment(int(g0["seg_nodes"][s, 0]), int(g0["seg_nodes"][s, 1]), g0["seg_dir"][s])
+    for sx in range(3):
+        for sz in range(3):
+            lanes.build_sector(sx + 10, sz + 10, 64.0)
+    lanes.remove_sector(11, 11)
+    for s in (5, 17, 100, 211):
+        lanes.set_active(s, False)
+    g = lanes.export()
+    agents, trs = scenes.traffic_agents(g, 400, seed=9)
+    dts = np.array([1 / 60] * 12 + [0.0, 0.5, 2.5, 1 / 144, 1 / 30, 1 / 60], np.float32)
+    frames = ref_traffic_frames(lanes, agents, trs, [float(x) for x in dts])
+    lanes.close()
+    out = {"g_" + k: g[k] for k in LANE_KEYS}
+    out["g_default_speed"] = g["default_speed"]
+    out.update(a_lane=agents["lane"], a_s=agents["s"], a_speed=agents["speed"], a_look=agents["look"], trs=trs, dts=dts)
+    for i, k in enumerate(("lane", "s", "speed", "look", "trs", "dirty")):
+        out["f_" + k] = np.stack([fr[i] for fr in frames])
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.normal(size=300) * 10.0 ** rng.integers(-6, 3, 300), [0, -0.0, 88, 89, -104, -87.4, 1e-30, np.inf, -np.inf, np.nan,
+                        0.4375, 0.6875, 1.1875, 2.4375, 2.0 ** 25, 1.0, -1.0]]).astype(np.float32)
+    out["kat_x"] = x
+    out["kat_expf"] = np.array([L.screfExpf(float(v)) for v in x], np.float32)
+    out["kat_atanf"] = np.array([L.screfAtanf(float(v)) for v in x], np.float32)
+    y2 = np.concatenate([rng.normal(size=300), [0, -0.0, 1, -1, np.inf, -np.inf, 0, 1e-40, 1e30, 3]]).astype(np.float32)
+    x2 = np.concatenate([rng.normal(size=300), [-1, -2, 0, -0.0, np.inf, -np.inf, 0, 1e30, 1e-40, 1]]).astype(np.float32)
+    out["kat_y2"], out["kat_x2"] = y2, x2
+    out["kat_atan2f"] = np.array([L.screfAtan2f(float(a), float(b)) for a, b in zip(y2, x2)], np.float32)
+    return out
+
+
 def main():
     if "hwcaps=-FMA" not in os.environ.get("GLIBC_TUNABLES", ""):
         env = dict(os.environ, GLIBC_TUNABLES="glibc.cpu.hwcaps=-FMA,-AVX2")
         os.execve(sys.executable, [sys.executable] + sys.argv, env)
     assert oracle_bind.ref_available(), "build oracle/_ref first: make -C oracle ref"
     L = oracle_bind.ref_lib()
+    if sys.argv[1:] == ["traffic"]:  # only the traffic fixture (the others are unchanged)
+        np.savez_compressed(HERE / "traffic.npz", **traffic_golden(L))
+        return
+    np.savez_compressed(HERE / "traffic.npz", **traffic_golden(L))
     np.savez_compressed(HERE / "kats.npz", **kats(L))
     np.savez_compressed(HERE / "default_scene.npz", **default_scene(L))
     np.savez_compressed(HERE / "forest_scene.npz", **forest_scene(4242))

@@ -13,6 +13,10 @@
 #define __restrict__
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { return float2{ x, y }; }
+struct uint2 { uint32_t x, y; };
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{ x, y }; }
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{ x, y, z, w }; }
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{ x, y, z, w }; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
@@ -29,3 +33,5 @@ static inline double __ll2double_rn(long long a) { return (double)a; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline long long __double_as_longlong(double d) { long long u; std::memcpy(&u, &d, 8); return u; }
+static inline double __longlong_as_double(long long u) { double d; std::memcpy(&d, &u, 8); return d; }

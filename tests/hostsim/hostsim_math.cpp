@@ -1,6 +1,8 @@
 // Host build of the device math header, exported for ctypes (tests only).
 #include "cuda_runtime.h"
 #include "../../sc-gameengine_b200/csrc/scgpu_math.cuh"
+#include "../../sc-gameengine_b200/csrc/scgpu_traffic.cuh"
+#include <vector>
 using namespace scgpu;
 extern "C" {
 void hs_sincos(float y, float* s, float* c) { sincosf_glibc(y, *s, *c); }
@@ -52,5 +54,65 @@ uint64_t hs_sincos_sweep(uint32_t first, uint64_t count, uint32_t stride, float 
     bad += (okS ? 0 : 1) + (okC ? 0 : 1);
   }
   return bad;
+}
+
+// ---- traffic on rails (scgpu_traffic.cuh) -------------------------------------------------------------------
+float hs_expf(float x) { return expf_glibc(x); }
+float hs_atanf(float x) { return atanf_glibc(x); }
+float hs_atan2f(float y, float x) { return atan2f_glibc(y, x); }
+static bool hs_same(float a, float b) { return __float_as_uint(a) == __float_as_uint(b) || (a != a && b != b); }
+uint64_t hs_unary_sweep(int which, uint32_t first, uint64_t count, uint32_t stride, float (*ref)(float))
+{
+  uint64_t bad = 0;
+  uint32_t bits = first;
+  for (uint64_t i = 0; i < count; ++i, bits += stride)
+  {
+    const float x = __uint_as_float(bits);
+    bad += hs_same(which == 0 ? expf_glibc(x) : atanf_glibc(x), ref(x)) ? 0 : 1;
+  }
+  return bad;
+}
+uint64_t hs_atan2_pairs(uint64_t n, const float* y, const float* x, float (*ref)(float, float))
+{
+  uint64_t bad = 0;
+  for (uint64_t i = 0; i < n; ++i) bad += hs_same(atan2f_glibc(y[i], x[i]), ref(y[i], x[i])) ? 0 : 1;
+  return bad;
+}
+// the per-agent device routine over the flat arrays of ScGpuLaneGraph, packed like scgpuTrafficSetLanes packs them
+void hs_traffic_on_rails(uint32_t nNodes, uint32_t nSegs, const float* nodePos3, const float* nodeSpeed, const uint32_t* connOffset,
+                         const uint32_t* conn, const uint32_t* segNodes2, const float* segDir3, const float* segLen,
+                         const uint8_t* segActive, float defaultSpeed, uint32_t n, uint32_t* laneId, float* laneS,
+                         float* targetSpeed, float* look, float* trs9, const float* brake, const uint8_t* skip, float dt,
+                         int hasDebug, float dbgLook, float dbgMul, uint8_t* outMoved)
+{
+  std::vector<float4> np(nNodes), sd(nSegs);
+  std::vector<uint2> nc(nNodes);
+  std::vector<uint4> sn(nSegs);
+  for (uint32_t i = 0; i < nNodes; ++i)
+  {
+    np[i] = make_float4(nodePos3[3 * i], nodePos3[3 * i + 1], nodePos3[3 * i + 2], nodeSpeed[i]);
+    nc[i] = make_uint2(connOffset[i], connOffset[i + 1] - connOffset[i]);
+  }
+  for (uint32_t i = 0; i < nSegs; ++i)
+  {
+    sd[i] = make_float4(segDir3[3 * i], segDir3[3 * i + 1], segDir3[3 * i + 2], segLen[i]);
+    sn[i] = make_uint4(segNodes2[2 * i], segNodes2[2 * i + 1], segActive[i] ? 1u : 0u, 0u);
+  }
+  LaneGraphView g{ np.data(), nc.data(), conn, sd.data(), sn.data(), nNodes, nSegs, defaultSpeed };
+  TrafficStepParams st{ dt, dbgMul, dbgLook, hasDebug ? 1u : 0u };
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    outMoved[i] = 0;
+    if (skip && skip[i]) continue;
+    float* t = trs9 + (size_t)i * 9;
+    float pos[3] = { t[0], t[1], t[2] };
+    float yaw = 0.0f;
+    if (traffic_agent_on_rails(g, st, brake ? brake[i] : 0.0f, laneId[i], laneS[i], targetSpeed[i], look[i], pos, yaw))
+    {
+      t[0] = pos[0]; t[1] = pos[1]; t[2] = pos[2];
+      t[3] = 0.0f; t[4] = yaw; t[5] = 0.0f;
+      outMoved[i] = 1;
+    }
+  }
 }
 }

@@ -60,6 +60,23 @@ def port_lib():
         L.sco_mat4_perspective_rh_zo.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _vp]
         L.sco_mat4_rotation_xyz.argtypes = [C.c_float, C.c_float, C.c_float, _vp]
         L.sco_sincos_sweep.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.sco_expf.restype = C.c_float
+        L.sco_expf.argtypes = [C.c_float]
+        L.sco_atanf.restype = C.c_float
+        L.sco_atanf.argtypes = [C.c_float]
+        L.sco_atan2f.restype = C.c_float
+        L.sco_atan2f.argtypes = [C.c_float, C.c_float]
+        L.sco_unary_sweep.restype = C.c_uint64
+        L.sco_unary_sweep.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, _vp]
+        L.sco_atan2_sweep.restype = C.c_uint64
+        L.sco_atan2_sweep.argtypes = [C.c_uint32, C.c_uint64, _vp]
+        L.sco_lane_advance.restype = C.c_int
+        L.sco_lane_advance.argtypes = [_vp, _u32p, C.POINTER(C.c_float), C.c_float, _vp, _vp]
+        L.sco_lane_query_nearest.restype = C.c_uint32
+        L.sco_lane_query_nearest.argtypes = [_vp, _vp, C.POINTER(C.c_float)]
+        L.sco_traffic_ai_on_rails.restype = None
+        L.sco_traffic_ai_on_rails.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int, C.c_float,
+                                              C.c_float, _vp]
         _port = L
     return _port
 
@@ -119,6 +136,31 @@ def ref_lib():
         L.screfCosf.argtypes = [C.c_float]
         L.screfSinCosSweep.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.screfJobWorkers.restype = C.c_uint32
+        L.screfLanesCreate.restype = _vp
+        L.screfLanesCreate.argtypes = [C.c_float, C.c_float]
+        L.screfLanesDestroy.argtypes = [_vp]
+        L.screfLanesAddNode.restype = C.c_uint32
+        L.screfLanesAddNode.argtypes = [_vp, _vp, _vp, C.c_float]
+        L.screfLanesAddSegment.restype = C.c_uint32
+        L.screfLanesAddSegment.argtypes = [_vp, C.c_uint32, C.c_uint32, _vp, C.c_int32, C.c_int32]
+        L.screfLanesBuildSector.argtypes = [_vp, C.c_int32, C.c_int32, C.c_float]
+        L.screfLanesRemoveSector.argtypes = [_vp, C.c_int32, C.c_int32]
+        L.screfLanesSetActive.argtypes = [_vp, C.c_uint32, C.c_int]
+        L.screfLanesCounts.argtypes = [_vp, _u32p, _u32p, _u32p]
+        L.screfLanesExport.argtypes = [_vp] * 9 + [C.POINTER(C.c_float)]
+        L.screfLaneAdvance.restype = C.c_int
+        L.screfLaneAdvance.argtypes = [_vp, _u32p, C.POINTER(C.c_float), C.c_float, _vp, _vp]
+        L.screfLaneQueryNearest.restype = C.c_uint32
+        L.screfLaneQueryNearest.argtypes = [_vp, _vp, C.POINTER(C.c_float)]
+        L.screfTrafficAddAgents.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]
+        L.screfTrafficSetPlayer.argtypes = [_vp, C.c_uint32]
+        L.screfRunTrafficAI.argtypes = [_vp, _vp, C.c_float, C.c_int, C.c_float, C.c_float]
+        L.screfTrafficReadAgents.argtypes = [_vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]
+        for name in ("screfExpf", "screfAtanf"):
+            getattr(L, name).restype = C.c_float
+            getattr(L, name).argtypes = [C.c_float]
+        L.screfAtan2f.restype = C.c_float
+        L.screfAtan2f.argtypes = [C.c_float, C.c_float]
         _ref = L
     return _ref
 
@@ -381,3 +423,101 @@ def renderer_sorted_draws(draws, material_pipeline, mesh_count):
         else:
             runs.append([k[0], k[1], k[2], pos, 1])
     return order, [tuple(r) for r in runs]
+
+
+# ---- traffic on rails -----------------------------------------------------------------------
+
+class ScoLaneGraph(C.Structure):
+    _fields_ = [("nNodes", C.c_uint32), ("nSegments", C.c_uint32), ("nodePos", _vp), ("nodeSpeedLimit", _vp),
+                ("nodeConnOffset", _vp), ("nodeConn", _vp), ("segNodes", _vp), ("segDir", _vp), ("segLength", _vp),
+                ("segActive", _vp), ("defaultSpeedLimit", C.c_float)]
+
+
+LANE_KEYS = ("node_pos", "node_speed", "conn_offset", "conn", "seg_nodes", "seg_dir", "seg_len", "seg_active")
+
+
+def sco_graph(g):
+    """ScoLaneGraph over the arrays of a lane-graph dict (keys LANE_KEYS + default_speed); the dict must outlive it."""
+    return ScoLaneGraph(len(g["node_speed"]), len(g["seg_len"]), _p(g["node_pos"]), _p(g["node_speed"]), _p(g["conn_offset"]),
+                        _p(g["conn"]), _p(g["seg_nodes"]), _p(g["seg_dir"]), _p(g["seg_len"]), _p(g["seg_active"]),
+                        float(g["default_speed"]))
+
+
+def port_traffic_step(g, agents, trs9, dt, brake=None, skip=None, debug=None):
+    """sco_traffic_ai_on_rails in place on agents = dict(lane u32, s f32, speed f32, look f32) and trs9 [n,9].
+    debug = (lookAheadDist, speedMultiplier) or None. Returns the moved mask."""
+    L = port_lib()
+    n = len(agents["lane"])
+    moved = np.zeros(n, np.uint8)
+    sg = sco_graph(g)
+    L.sco_traffic_ai_on_rails(C.byref(sg), n, _p(agents["lane"]), _p(agents["s"]), _p(agents["speed"]), _p(agents["look"]),
+                              _p(trs9), _p(brake), _p(skip), dt, 1 if debug else 0, debug[0] if debug else 0.0,
+                              debug[1] if debug else 0.0, _p(moved))
+    return moved
+
+
+class RefLanes:
+    """The reference's TrafficLaneGraph (oracle/_ref), built through its own addNode / addSegment /
+    buildProceduralForSector, exported as the flat arrays every implementation consumes."""
+
+    def __init__(self, lane_width=3.5, speed_limit=12.0):
+        self.L = ref_lib()
+        self.h = self.L.screfLanesCreate(lane_width, speed_limit)
+
+    def close(self):
+        if self.h:
+            self.L.screfLanesDestroy(self.h)
+            self.h = None
+
+    def add_node(self, pos, direction, speed):
+        return self.L.screfLanesAddNode(self.h, _p(np.asarray(pos, np.float32)), _p(np.asarray(direction, np.float32)), speed)
+
+    def add_segment(self, a, b, direction, owner=(0, 0)):
+        return self.L.screfLanesAddSegment(self.h, a, b, _p(np.asarray(direction, np.float32)), owner[0], owner[1])
+
+    def build_sector(self, x, z, size=64.0):
+        self.L.screfLanesBuildSector(self.h, x, z, size)
+
+    def remove_sector(self, x, z):
+        self.L.screfLanesRemoveSector(self.h, x, z)
+
+    def set_active(self, seg, active):
+        self.L.screfLanesSetActive(self.h, seg, 1 if active else 0)
+
+    def export(self):
+        nn, ns, nc = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        self.L.screfLanesCounts(self.h, C.byref(nn), C.byref(ns), C.byref(nc))
+        g = dict(node_pos=np.zeros((nn.value, 3), np.float32), node_speed=np.zeros(nn.value, np.float32),
+                 conn_offset=np.zeros(nn.value + 1, np.uint32), conn=np.zeros(max(nc.value, 1), np.uint32)[: nc.value],
+                 seg_nodes=np.zeros((ns.value, 2), np.uint32), seg_dir=np.zeros((ns.value, 3), np.float32),
+                 seg_len=np.zeros(ns.value, np.float32), seg_active=np.zeros(ns.value, np.uint8))
+        d = C.c_float(0)
+        self.L.screfLanesExport(self.h, *[_p(g[k]) for k in LANE_KEYS], C.byref(d))
+        g["default_speed"] = np.float32(d.value)
+        return g
+
+
+def ref_traffic_frames(lanes, agents, trs9, dts, debug=None):
+    """Runs the reference's own TrafficAISystem (physics == nullptr, streaming == nullptr) over a World holding one
+    PlayerVehicle and the given on-rails agents for every dt in dts. Returns per frame (lane, s, speed, look, trs9)."""
+    R = RefScene(1)
+    L = R.L
+    n = len(agents["lane"])
+    e = R.create_entities(n + 1)
+    player, ag = e[:1], np.ascontiguousarray(e[1:])
+    R.spawn(player, np.array([[0, 0, 0, 0, 0, 0, 1, 1, 1]], np.float32))
+    R.spawn(ag, trs9)
+    L.screfTrafficSetPlayer(R.w, int(player[0]))
+    L.screfTrafficAddAgents(R.w, n, _p(ag), _p(agents["lane"]), _p(agents["s"]), _p(agents["speed"]), _p(agents["look"]))
+    out = []
+    for dt in dts:
+        L.screfRunTransform(R.w)  # clears Transform::dirty, so that after the AI pass dirty == "moved this frame"
+        L.screfRunTrafficAI(R.w, lanes.h, dt, 1 if debug else 0, debug[0] if debug else 0.0, debug[1] if debug else 0.0)
+        lane, s, v, look = np.zeros(n, np.uint32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        L.screfTrafficReadAgents(R.w, n, _p(ag), _p(lane), _p(s), _p(v), _p(look))
+        t = np.zeros((n, 9), np.float32)
+        dirty = np.zeros(n, np.uint8)
+        L.screfReadTransform(R.w, n, _p(ag), None, _p(t), _p(dirty))
+        out.append((lane, s, v, look, t, dirty))
+    R.close()
+    return out
