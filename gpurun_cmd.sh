@@ -1,2 +1,3 @@
-timeout 600 python -m pytest tests/test_gpu_traffic.py -x -q > gpurun_out/tests_traffic.log 2>&1; tail -15 gpurun_out/tests_traffic.log
-timeout 300 python tools/bench_traffic.py > gpurun_out/traffic.json 2> gpurun_out/traffic.err; tail -3 gpurun_out/traffic.err; cat gpurun_out/traffic.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; tail -4 gpurun_out/tests_full.log
+python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/b_skew.json 2> gpurun_out/b_skew.err; python -c "
+import json; d=json.load(open('gpurun_out/b_skew.json')); print(d['ms_per_step'], d['roofline']['kernel_ms_avg'], d['roofline']['frac'])"

@@ -865,7 +865,13 @@ constexpr uint32_t kWinChunk = SCGPU_WIN_CHUNK;                        // consec
 // that every address is "lane base + constant" and folds into the instruction's immediate offset.
 constexpr uint32_t kWsBuf = 4 * 512 + 128;              // one prefetch buffer: 4 record planes + 32 slotInfo words
 constexpr uint32_t kWwMat = 2 * kWsBuf;                 // [4][32] float4: matrix columns of the level loop
-constexpr uint32_t kWwSched = kWwMat + 4 * 512;         // [32] u16: children of the current level
+// Byte offsets of the four column planes inside kWwMat. Columns 2 and 3 are skewed by 64 B: in a level product the even
+// lane of a pair reads / writes columns 0, 1 of its child and the odd lane columns 2, 3 of the SAME child; with plain
+// 512-byte planes both halves of every pair hit the same banks (a 2-way conflict on every LDS.128 / STS.128 of the
+// level loop, 7.7 wavefronts per instruction instead of 3 in ncu). With the skew the four pairs of a quarter warp,
+// which work on consecutive children, cover 128 distinct bytes.
+constexpr uint32_t kMatC1 = 512, kMatC2 = 1024 + 64, kMatC3 = 1536 + 64;
+constexpr uint32_t kWwSched = kWwMat + 4 * 512 + 64;    // [32] u16: children of the current level
 constexpr uint32_t kWwList = kWwSched + 64;             // 2 x [kWinChunk+1] u32 (64 B each): window starts of the current
                                                         // and of the next claimed chunk
 constexpr uint32_t kWwSize = kWwList + 128;             // per-warp block
@@ -1136,34 +1142,33 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
       if (maxL != 0u && dirtyM != 0u)
       {
         const uint32_t own = laneBase + kWwMat;
-        sts128(own, W.c0); sts128(own + 512, W.c1); sts128(own + 1024, W.c2); sts128(own + 1536, W.c3);
+        sts128(own, W.c0); sts128(own + kMatC1, W.c1); sts128(own + kMatC2, W.c2); sts128(own + kMatC3, W.c3);
         __syncwarp();
         // one product: this lane computes columns 2h, 2h+1 (h = lane & 1) of child = parent * child, in place
         auto level_item = [&](uint32_t child, uint32_t par)
         {
-          const uint32_t cAddr = warpBase + child * 16u + (lane & 1u) * 1024u;
+          const uint32_t cAddr = warpBase + child * 16u + (lane & 1u) * kMatC2;
           const uint32_t pAddr = warpBase + par * 16u;
-          const float4 P0 = lds128(pAddr + kWwMat), P1 = lds128(pAddr + kWwMat + 512), P2 = lds128(pAddr + kWwMat + 1024);
+          const float4 P0 = lds128(pAddr + kWwMat), P1 = lds128(pAddr + kWwMat + kMatC1), P2 = lds128(pAddr + kWwMat + kMatC2);
           const float4 La = lds128(cAddr + kWwMat), Lb = lds128(cAddr + kWwMat + 512);
           float4 oa, ob;
           {
-            const float2 m0 = fmul2_rn(P0.x, P0.y, La.x), m1 = fmul2_rn(P1.x, P1.y, La.y), m2 = fmul2_rn(P2.x, P2.y, La.z);
-            oa.x = __fadd_rn(__fadd_rn(m0.x, m1.x), m2.x);
-            oa.y = __fadd_rn(__fadd_rn(m0.y, m1.y), m2.y);
-            oa.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, La.x), __fmul_rn(P1.z, La.y)), __fmul_rn(P2.z, La.z));
-            oa.w = La.w;
-          }
-          {
-            const float2 m0 = fmul2_rn(P0.x, P0.y, Lb.x), m1 = fmul2_rn(P1.x, P1.y, Lb.y), m2 = fmul2_rn(P2.x, P2.y, Lb.z);
-            ob.x = __fadd_rn(__fadd_rn(m0.x, m1.x), m2.x);
-            ob.y = __fadd_rn(__fadd_rn(m0.y, m1.y), m2.y);
-            ob.z = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, Lb.x), __fmul_rn(P1.z, Lb.y)), __fmul_rn(P2.z, Lb.z));
-            ob.w = Lb.w;
-          }
-          if (lane & 1u)
-          {
-            const float4 P3 = lds128(pAddr + kWwMat + 1536);  // column 3: + parent translation (p[r][3] * 1)
-            ob.x = __fadd_rn(ob.x, P3.x); ob.y = __fadd_rn(ob.y, P3.y); ob.z = __fadd_rn(ob.z, P3.z);
+            // rows x, y of both columns as lane pairs; row z of column a and of column b paired with each other.
+            // Every sum is (p0 + p1) + p2 per element like sum3_ref, two elements per FFMA2 (fadd2_rn)
+            const float2 a0 = fmul2_rn(P0.x, P0.y, La.x), a1 = fmul2_rn(P1.x, P1.y, La.y), a2 = fmul2_rn(P2.x, P2.y, La.z);
+            const float2 b0 = fmul2_rn(P0.x, P0.y, Lb.x), b1 = fmul2_rn(P1.x, P1.y, Lb.y), b2 = fmul2_rn(P2.x, P2.y, Lb.z);
+            const float2 z0 = fmul2_rn(La.x, Lb.x, P0.z), z1 = fmul2_rn(La.y, Lb.y, P1.z), z2 = fmul2_rn(La.z, Lb.z, P2.z);
+            const float2 sa = fadd2_rn(fadd2_rn(a0, a1), a2);
+            float2 sb = fadd2_rn(fadd2_rn(b0, b1), b2);
+            float2 sz = fadd2_rn(fadd2_rn(z0, z1), z2);
+            if (lane & 1u)
+            {
+              const float4 P3 = lds128(pAddr + kWwMat + kMatC3);  // column 3: + parent translation (p[r][3] * 1)
+              sb = fadd2_rn(sb, make_float2(P3.x, P3.y));
+              sz.y = __fadd_rn(sz.y, P3.z);
+            }
+            oa = make_float4(sa.x, sa.y, sz.x, La.w);
+            ob = make_float4(sb.x, sb.y, sz.y, Lb.w);
           }
           sts128(cAddr + kWwMat, oa);
           sts128(cAddr + kWwMat + 512, ob);
@@ -1212,7 +1217,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
             }
           }
         }
-        W.c0 = lds128(own); W.c1 = lds128(own + 512); W.c2 = lds128(own + 1024); W.c3 = lds128(own + 1536);
+        W.c0 = lds128(own); W.c1 = lds128(own + kMatC1); W.c2 = lds128(own + kMatC2); W.c3 = lds128(own + kMatC3);
         // the structured products are value-exact iff every parent translation was finite; a non-finite one
         // propagates into the translation of all its descendants, so one test of the results covers all levels
         const float mag = fabsf(W.c3.x) + fabsf(W.c3.y) + fabsf(W.c3.z);

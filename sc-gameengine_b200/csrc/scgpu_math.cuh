@@ -164,6 +164,27 @@ __device__ __forceinline__ float2 fmul2_rn(float ax, float ay, float b)
   return make_float2(__fmul_rn(ax, b), __fmul_rn(ay, b));
 #endif
 }
+// Two IEEE single-precision SUMS in one instruction: fma.rn.f32x2(a, 1.0, b). a * 1.0 is exact, so the single
+// rounding of the fused operation is the rounding of a + b: bit-identical to add.rn.f32 per lane (signed zeros, NaN,
+// Inf and denormals included). The pair of ones comes from constant memory on purpose: with a literal 1.0 ptxas
+// simplifies the fma to an add and then contracts it with the mul.f32x2 that produced its operand (a real FMA,
+// which breaks parity); a value it cannot see through leaves 3 x FMUL2 + 2 x FFMA2(UR) for a 3-term dot-product
+// pair. The ones live in a uniform register pair, no general register is spent.
+__constant__ unsigned long long kOnes2 = 0x3f8000003f800000ull;
+__device__ __forceinline__ float2 fadd2_rn(float2 a, float2 b)
+{
+#if defined(__CUDA_ARCH__)
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(kOnes2), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+#else
+  return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+#endif
+}
 // (ax*bx, ay*by)
 __device__ __forceinline__ float2 fmul2_rn(float ax, float ay, float bx, float by)
 {
@@ -289,9 +310,11 @@ __device__ __forceinline__ Mat4 mat4_trs_from_sincos(float px, float py, float p
   // R = A*Rx : col0 = A.col0 ; col1 = A.col1*cx + A.col2*sx ; col2 = A.col1*(-sx) + A.col2*cx
   const float nsx = -sx;
   const float2 p1 = fmul2_rn(a01, a11, cx), q1 = fmul2_rn(a2.x, a2.y, sx);
-  const float r01 = __fadd_rn(p1.x, q1.x), r11 = __fadd_rn(p1.y, q1.y);
+  const float2 r1 = fadd2_rn(p1, q1);
+  const float r01 = r1.x, r11 = r1.y;
   const float2 p2 = fmul2_rn(a01, a11, nsx), q2 = fmul2_rn(a2.x, a2.y, cx);
-  const float r02 = __fadd_rn(p2.x, q2.x), r12 = __fadd_rn(p2.y, q2.y);
+  const float2 r2_ = fadd2_rn(p2, q2);
+  const float r02 = r2_.x, r12 = r2_.y;
   const float2 r2 = fmul2_rn(sx, cx, a22);         // r21, r22
   Mat4 m;
   const float2 c0 = fmul2_rn(a0.x, a0.y, sx_), c1 = fmul2_rn(r01, r11, sy_), c2 = fmul2_rn(r02, r12, sz_);
@@ -410,8 +433,9 @@ __device__ __forceinline__ void world_bounds_centre(const Mat4& m, float bminx, 
   ez = __fmul_rn(__fsub_rn(bmaxz, bminz), 0.5f);
   // products in pairs (x, y) per column; the sums keep the reference's order and stay scalar
   const float2 a0 = fmul2_rn(m.c0.x, m.c0.y, cx), a1 = fmul2_rn(m.c1.x, m.c1.y, cy), a2 = fmul2_rn(m.c2.x, m.c2.y, cz);
-  ox = __fadd_rn(sum3_ref(a0.x, a1.x, a2.x), m.c3.x);
-  oy = __fadd_rn(sum3_ref(a0.y, a1.y, a2.y), m.c3.y);
+  const float2 oxy = fadd2_rn(fadd2_rn(fadd2_rn(a0, a1), a2), make_float2(m.c3.x, m.c3.y));  // sum3_ref per lane, + c3
+  ox = oxy.x;
+  oy = oxy.y;
   oz = __fadd_rn(sum3_ref(__fmul_rn(m.c0.z, cx), __fmul_rn(m.c1.z, cy), __fmul_rn(m.c2.z, cz)), m.c3.z);
 }
 
