@@ -1153,14 +1153,16 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
           const float4 La = lds128(cAddr + kWwMat), Lb = lds128(cAddr + kWwMat + 512);
           float4 oa, ob;
           {
-            // rows x, y of both columns as lane pairs; row z of column a and of column b paired with each other.
-            // Every sum is (p0 + p1) + p2 per element like sum3_ref, two elements per FFMA2 (fadd2_rn)
+            // rows x, y of both columns as register pairs (FMUL2 products, FFMA2 sums: fadd2_rn); row z stays scalar
+            // (pairing it across the two columns costs more register moves than it saves). Every sum is
+            // (p0 + p1) + p2 per element like sum3_ref
             const float2 a0 = fmul2_rn(P0.x, P0.y, La.x), a1 = fmul2_rn(P1.x, P1.y, La.y), a2 = fmul2_rn(P2.x, P2.y, La.z);
             const float2 b0 = fmul2_rn(P0.x, P0.y, Lb.x), b1 = fmul2_rn(P1.x, P1.y, Lb.y), b2 = fmul2_rn(P2.x, P2.y, Lb.z);
-            const float2 z0 = fmul2_rn(La.x, Lb.x, P0.z), z1 = fmul2_rn(La.y, Lb.y, P1.z), z2 = fmul2_rn(La.z, Lb.z, P2.z);
             const float2 sa = fadd2_rn(fadd2_rn(a0, a1), a2);
             float2 sb = fadd2_rn(fadd2_rn(b0, b1), b2);
-            float2 sz = fadd2_rn(fadd2_rn(z0, z1), z2);
+            float2 sz;
+            sz.x = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, La.x), __fmul_rn(P1.z, La.y)), __fmul_rn(P2.z, La.z));
+            sz.y = __fadd_rn(__fadd_rn(__fmul_rn(P0.z, Lb.x), __fmul_rn(P1.z, Lb.y)), __fmul_rn(P2.z, Lb.z));
             if (lane & 1u)
             {
               const float4 P3 = lds128(pAddr + kWwMat + kMatC3);  // column 3: + parent translation (p[r][3] * 1)
