@@ -653,14 +653,26 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
   __syncthreads();
   // static schedule of the level loop (used by k_update_win when every node of the window is recomputed): in
   // level l, lanes 2j and 2j+1 of the window take the j-th node of that level. First every node writes its lane at
-  // its rank among the nodes of its level, then every lane looks up the node it helps with.
+  // its position in the order of its level, then every lane looks up the node it helps with.
   for (uint32_t k = (beg - tileBase) + tid; k < end - tileBase; k += kBlock)
   {
     const uint32_t d = sInfo[k] & kInfoDepthMask;
     if (d >= 1u && d <= 3u && !(sInfo[k] & kInfoUnreachable))
     {
+      // Order of the nodes of one level: by (rank inside the residue class of the lane index mod 4, class), not by
+      // lane index. The four lane pairs of a quarter warp then work on children from different classes wherever the
+      // level has them, and two children collide in the shared-memory banks of the matrix planes exactly when they
+      // are in the same class (plane rows are 16 B per lane; the odd lane of a pair is skewed by 64 B, kMatC2).
       const uint32_t w = sWinOf[k], h = k - sStart[w];
-      const uint32_t j = __popc(sLvl[w][d - 1u] & ((1u << h) - 1u));
+      const uint32_t M = sLvl[w][d - 1u], r = h & 3u;
+      const uint32_t t = __popc(M & (0x11111111u << r) & ((1u << h) - 1u));
+      uint32_t j = 0;
+#pragma unroll
+      for (uint32_t q = 0; q < 4u; ++q)
+      {
+        const uint32_t c = __popc(M & (0x11111111u << q));
+        j += min(c, t) + ((q < r && c > t) ? 1u : 0u);
+      }
       if (j < 16u) sChild[w][d - 1u][j] = (uint8_t)h;
     }
   }
