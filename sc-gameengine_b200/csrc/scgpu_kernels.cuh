@@ -897,12 +897,26 @@ __device__ __forceinline__ void red_global_add(uint32_t* p, uint32_t v)
 {
   asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q red.global.add.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v) : "memory");
 }
-// claim of kWinChunk windows: issue now (one elected lane), read the answer later
+// claim of one chunk of windows: issue now (one elected lane), read the answer later. The queue counts CLAIMS;
+// claim_to_chunk maps a claim index to its windows.
 __device__ __forceinline__ void queue_claim_issue(uint32_t* queue, uint32_t& old)
 {
   old = 0;
-  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q atom.global.add.u32 %0, [%1], %2;\n\t}"
-               : "+r"(old) : "l"(queue), "n"(kWinChunk) : "memory");
+  asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q atom.global.add.u32 %0, [%1], 1;\n\t}"
+               : "+r"(old) : "l"(queue) : "memory");
+}
+// Guided schedule: the first k1 claims are chunks of kWinChunk windows, the rest of the list is handed out in chunks
+// of kWinFine. A warp works ~3.6 us per window and owns up to three chunks at a time (current, staged, in flight),
+// so with coarse chunks only the warps finish up to a chunk (~29 us of a 450 us launch) apart; the fine region is long
+// enough (24 windows per resident warp) for every warp to reach it before the list ends. kWinFine >= 3: the list of
+// the next chunk is staged while window 1 of the current chunk is processed and must have landed (wait at the loop
+// top) before the last window of the chunk fetches from it.
+constexpr uint32_t kWinFine = 3;
+__device__ __forceinline__ void claim_to_chunk(uint32_t k, uint32_t total, uint32_t k1, uint32_t& cs, uint32_t& cnt)
+{
+  const bool coarse = k < k1;
+  cs = coarse ? k * kWinChunk : k1 * kWinChunk + (k - k1) * kWinFine;
+  cnt = cs < total ? min(coarse ? kWinChunk : kWinFine, total - cs) : 0u;
 }
 __device__ __forceinline__ uint32_t queue_claim_result(uint32_t old)
 {
@@ -1050,8 +1064,10 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   // ---- prologue: first chunk (its list is waited for), second chunk claimed and staged, third claim in flight ----
   uint32_t claimOld;
   queue_claim_issue(queue, claimOld);
-  uint32_t cs = queue_claim_result(claimOld);
-  uint32_t cnt = cs < total ? min(kWinChunk, total - cs) : 0u;  // windows in the current chunk
+  const uint32_t fineWindows = gridDim.x * kWinWarps * 24u;
+  const uint32_t k1 = total > fineWindows ? (total - fineWindows) / kWinChunk : 0u;  // claims below k1 are coarse
+  uint32_t cs, cnt;  // first window and number of windows of the current chunk
+  claim_to_chunk(queue_claim_result(claimOld), total, k1, cs, cnt);
   uint32_t pos = 0;                                             // index of the current window in it
   uint32_t cntNext = 0;                                         // windows in the staged next chunk
   uint32_t listAddr = warpBase + kWwList;                       // shared address of the current window's list entry
@@ -1133,8 +1149,8 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     {
       // the other list slot is dead since the previous chunk's last window finished: take the claim that has been
       // in flight for a whole chunk, stage that chunk's window starts there, and put the next claim in flight
-      const uint32_t csNext = queue_claim_result(claimOld);
-      cntNext = csNext < total ? min(kWinChunk, total - csNext) : 0u;
+      uint32_t csNext;
+      claim_to_chunk(queue_claim_result(claimOld), total, k1, csNext, cntNext);
       if (cntNext) stage_list(csNext, ((listAddr - warpBase - kWwList) < 64u) ? 1u : 0u);
       queue_claim_issue(queue, claimOld);
     }
