@@ -15,6 +15,7 @@ ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "profiles"
 SRC = ROOT / "gpurun_out"
 ROUND = "r01"
+VER = "v6"  # bumps when the profiled kernel changed (v5: persistent queue; v6: conflict-free matrix planes, FFMA2 sums)
 
 KEEP = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -28,6 +29,11 @@ KEEP = [
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed.sum.pct_of_peak_sustained_elapsed",
     "lts__t_sector_hit_rate.pct",
 ]
 
@@ -59,15 +65,16 @@ def gb(m, key):
 
 def main():
     n, views = 16773120, 5
-    win = summarise(SRC / f"{ROUND}_k_update_win.ncu-rep", f"{ROUND}_k_update_win_v5_ncu_raw.csv",
+    win = summarise(SRC / f"{ROUND}_k_update_win.ncu-rep", f"{ROUND}_k_update_win_{VER}_ncu_raw.csv",
                     f"k_update_win<5>, {n} instances in depth-4 groups, {views} views, all dirty (bench.py default workload)")
-    summarise(SRC / f"{ROUND}_k_update_flat.ncu-rep", f"{ROUND}_k_update_flat_v5_ncu_raw.csv",
-              f"k_update_flat<5>, {n} flat instances, {views} views, all dirty (SCGPU_BENCH_WORKLOAD=flat)")
+    if "--flat" in sys.argv:  # the flat kernel's capture is only refreshed when it was re-profiled
+        summarise(SRC / f"{ROUND}_k_update_flat.ncu-rep", f"{ROUND}_k_update_flat_{VER}_ncu_raw.csv",
+                  f"k_update_flat<5>, {n} flat instances, {views} views, all dirty (SCGPU_BENCH_WORKLOAD=flat)")
     rd, wr = gb(win, "dram__bytes_read.sum"), gb(win, "dram__bytes_write.sum")
     (OUT / "traffic.json").write_text(json.dumps({
         "kernel": "k_update_win<5 views>", "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
         "algorithmic_bytes_per_launch": 132 * n,
-        "source": f"profiles/{ROUND}_k_update_win_v5_ncu_raw.csv (ncu --set full, one launch, {n} instances x {views} views, all dirty)",
+        "source": f"profiles/{ROUND}_k_update_win_{VER}_ncu_raw.csv (ncu --set full, one launch, {n} instances x {views} views, all dirty)",
     }, indent=1))
     # launch list
     rows = list(csv.reader(open(SRC / f"launches_{ROUND}.csv", errors="replace")))
