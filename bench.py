@@ -259,6 +259,12 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 
+    # Libraries chat on stdout (NCCL prints "NCCL version ..." there at init): everything written to fd 1 until the
+    # result line goes to stderr instead, so that stdout carries exactly ONE JSON line.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     import scgpu
@@ -410,7 +416,10 @@ def main():
                 line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res.get("threads", res["cores"]),
                                         "kind": res["kind"], "sample": res["sample"], "host_cpus": res["cores"],
                                         "stages_ms": {k: res[k] for k in ("transform_ms", "cull_ms", "prep_ms") if k in res}}
+        sys.stdout.flush()
+        os.dup2(result_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
 
     scene.close()
     if world > 1:
