@@ -19,6 +19,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace scgpu;
@@ -231,6 +232,24 @@ int ensure(ScGpuScene* c, DeviceBuffer& b, size_t bytes)
 }
 
 inline uint32_t blocksFor(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
+
+// Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the stream still
+// runs; it calls pdl_wait() before touching anything the predecessor writes (scgpu_kernels.cuh).
+template <typename... KArgs, typename... Args>
+cudaError_t launchPdl(void (*kern)(KArgs...), uint32_t grid, uint32_t block, cudaStream_t st, Args&&... args)
+{
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 template <typename T>
 int devAlloc(ScGpuScene* c, T** p, size_t n, bool zero)
@@ -1110,8 +1129,9 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     {                                                                                                                    \
       k_update_win<V><<<c->numSMs * SCGPU_WIN_MINBLOCKS, kWinBlock, 0, c->stream>>>(                                     \
         p, c->planes, c->slotInfo, c->winList, c->tileWinBase + numTiles, c->totals + kQueueNext, c->slowList);          \
-      k_update_win_slow<V><<<c->numSMs * 4u, kWinBlock, 0, c->stream>>>(p, c->planes, c->slotInfo, c->totals + kQueueSlow, \
-                                                                   c->slowList);                                         \
+      SC_CUDA(c, launchPdl(k_update_win_slow<V>, c->numSMs * 4u, kWinBlock, c->stream, p, c->planes,                     \
+                           (const uint32_t*)c->slotInfo, (const uint32_t*)(c->totals + kQueueSlow),                      \
+                           (const uint32_t*)c->slowList));                                                               \
       ++c->launches;                                                                                                     \
     }                                                                                                                    \
     else                                                                                                                 \
@@ -1128,17 +1148,16 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     SC_CUDA(c, cudaGetLastError());
     if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK1[tslot], c->stream));
 
-    k_scan_tiles<<<c->nViews + 1, 1024, 0, c->stream>>>(c->tileCounts, c->tileOffsets, c->totals, numTiles);
+    SC_CUDA(c, launchPdl(k_scan_tiles, c->nViews + 1, 1024u, c->stream, (const uint32_t*)c->tileCounts, c->tileOffsets, c->totals,
+                         numTiles));
     ++c->launches;
-    SC_CUDA(c, cudaGetLastError());
 
     ScatterParams sp{};
     sp.vismask = c->vismask; sp.entity = c->a.entity; sp.tileCounts = c->tileCounts; sp.tileOffsets = c->tileOffsets;
     for (uint32_t v = 0; v < kMaxViews; ++v) { sp.outEntity[v] = c->visEntity[v]; sp.outSlot[v] = c->visSlot[v]; }
     sp.count = c->count; sp.numTiles = numTiles; sp.nViews = c->nViews;
-    k_scatter_visible<<<std::min(numTiles, c->numSMs * 8u), kBlock, 0, c->stream>>>(sp);
+    SC_CUDA(c, launchPdl(k_scatter_visible, std::min(numTiles, c->numSMs * 8u), kBlock, c->stream, sp));
     ++c->launches;
-    SC_CUDA(c, cudaGetLastError());
 
     if (flags & SCGPU_UPDATE_CULLED_LISTS)
     {

@@ -893,6 +893,13 @@ constexpr uint32_t kUpdateSmemWin = kWsRecomputed + 16;
 // windows handed to k_update_win_slow (both zeroed with the totals before every launch)
 constexpr uint32_t kQueueNext = kMaxViews + 2, kQueueSlow = kMaxViews + 3, kTotalsWords = kMaxViews + 4;
 
+// Programmatic dependent launch (the chain k_update_win -> k_update_win_slow -> k_scan_tiles -> k_scatter_visible of
+// one frame): pdl_trigger() lets the NEXT kernel of the stream be scheduled while this one still runs, pdl_wait() at
+// the top of that kernel blocks until this one has completed and its writes are visible. Launch latency and CTA
+// ramp-up then overlap the predecessor's tail. Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void red_global_add(uint32_t* p, uint32_t v)
 {
   asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q red.global.add.u32 [%0], %1;\n\t}" ::"l"(p), "r"(v) : "memory");
@@ -1031,6 +1038,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   asm volatile("shr.u32 %0, %1, 5;" : "=r"(warp) : "r"(tid));
   if (tid == 0) *reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed) = 0u;  // (also keeps the symbol referenced)
   __syncthreads();
+  pdl_trigger();
   const uint32_t total = *totalWindows;
 
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
@@ -1290,6 +1298,8 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid == 0) *reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed) = 0u;  // (also keeps the symbol referenced)
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();  // the list and its length are written by k_update_win
   const uint32_t nSlow = *slowCount;
   const uint32_t laneBase = sBase + warp * kWwSize + lane * 16;
   uint32_t order = 0, nRecomputed = 0, accTile = 0, accCand = 0;
@@ -1386,6 +1396,8 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict_
   __shared__ uint32_t sCarry;
   const uint32_t row = blockIdx.x;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t* in = tileCounts + (size_t)row * numTiles;
   uint32_t* out = tileOffsets + (size_t)row * numTiles;
   if (tid == 0) sCarry = 0;
@@ -1486,6 +1498,7 @@ __global__ void __launch_bounds__(kBlock) k_scatter_visible(const __grid_constan
   __shared__ uint32_t sCnt[kMaxViews];
   __shared__ uint64_t sWarp[kBlock / 32];
   const uint32_t tid = threadIdx.x;
+  pdl_wait();
   // grid-stride over the tiles: most tiles of an open world are fully culled, and 16 Ki CTAs that only read their
   // counts and exit cost more in launch overhead than the compaction itself
 #pragma unroll 1
