@@ -8,6 +8,7 @@
 #include "scgpu_draws.cuh"
 #include "scgpu_peer.cuh"
 #include "scgpu_traffic.cuh"
+#include "scgpu_pool.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -477,20 +478,14 @@ static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, cons
 {
   if ((uint64_t)c->count + n > c->capacity) return (int)fail(c, "%s: %u + %u instances exceed max_instances %u", who, c->count, n, c->capacity);
   if (c->hSparse.size() < c->sparseSize) c->hSparse.resize(c->sparseSize, 0u);
-  for (uint32_t j = 0; j < n; ++j)
+  uint32_t at = 0;
+  switch (poolRegisterSpawn(c->hEntity, c->hSparse, c->count, n, entity, &at))
   {
-    const uint32_t idx = entity[j] & 0xFFFFFFu;
-    if (entity[j] == SCGPU_INVALID_ENTITY) { for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u; return (int)fail(c, "%s: entity[%u] is the invalid handle", who, j); }
-    if (idx >= c->sparseSize) { for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u; return (int)fail(c, "%s: entity index %u >= max_entity_index %u", who, idx, c->sparseSize); }
-    if (c->hSparse[idx] != 0u)
-    {
-      for (uint32_t k = 0; k < j; ++k) c->hSparse[entity[k] & 0xFFFFFFu] = 0u;
-      return (int)fail(c, "%s: entity index %u already owns a Transform", who, idx);
-    }
-    c->hSparse[idx] = c->count + j + 1u;
+    case 0: return 1;
+    case 1: return (int)fail(c, "%s: entity[%u] is the invalid handle", who, at);
+    case 2: return (int)fail(c, "%s: entity index %u >= max_entity_index %u", who, entity[at] & 0xFFFFFFu, c->sparseSize);
+    default: return (int)fail(c, "%s: entity index %u already owns a Transform", who, entity[at] & 0xFFFFFFu);
   }
-  c->hEntity.insert(c->hEntity.end(), entity, entity + n);
-  return 1;
 }
 
 int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* parent, const float* trs9,
@@ -904,53 +899,11 @@ int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
   if (!enter(c)) return 0;
   if (n == 0) return 1;
   if (!entity) return (int)fail(c, "scgpuDespawn: entity is NULL");
-  if (c->hOrigin.size() < c->count)
-  {
-    const size_t old = c->hOrigin.size();
-    c->hOrigin.resize(c->count);
-    for (size_t i = old; i < c->hOrigin.size(); ++i) c->hOrigin[i] = (uint32_t)i;
-  }
-  std::vector<uint32_t> touched;
+  // replay of ComponentPool::remove on the host mirror (scgpu_pool.h) -> net slot moves + sparse entries to clear
+  static_assert(sizeof(PoolMove) == sizeof(uint2), "k_despawn_apply reads the moves as uint2");
+  std::vector<PoolMove> moves;
   std::vector<uint32_t> removedIdx;
-  touched.reserve(n);
-  removedIdx.reserve(n);
-  const uint32_t count0 = c->count;
-  uint32_t cnt = c->count;
-  for (uint32_t j = 0; j < n; ++j)
-  {
-    const uint32_t e = entity[j];
-    const uint32_t idx = e & 0xFFFFFFu;
-    if (e == SCGPU_INVALID_ENTITY || idx >= c->hSparse.size()) continue;
-    const uint32_t sp = c->hSparse[idx];
-    if (sp == 0u || c->hEntity[sp - 1u] != e) continue;  // stale or unknown handle: World::destroy returns false
-    const uint32_t s = sp - 1u, last = cnt - 1u;
-    if (s != last)
-    {
-      const uint32_t moved = c->hEntity[last];
-      c->hEntity[s] = moved;
-      c->hSparse[moved & 0xFFFFFFu] = s + 1u;
-      c->hOrigin[s] = c->hOrigin[last];
-      touched.push_back(s);
-    }
-    c->hSparse[idx] = 0u;
-    removedIdx.push_back(idx);
-    --cnt;
-  }
-  c->hEntity.resize(cnt);
-  // net moves: final content of every touched slot that survived
-  std::vector<uint2> moves;
-  moves.reserve(touched.size());
-  for (uint32_t s : touched)
-  {
-    if (s < cnt && c->hOrigin[s] != s)
-    {
-      moves.push_back(make_uint2(s, c->hOrigin[s]));
-      c->hOrigin[s] = s;  // also dedups slots touched more than once
-    }
-  }
-  for (uint32_t s : touched) if (s < c->hOrigin.size()) c->hOrigin[s] = s;
-  for (uint32_t s = cnt; s < count0; ++s) c->hOrigin[s] = s;
-  c->count = cnt;
+  poolReplayDespawn(c->hEntity, c->hSparse, c->hOrigin, c->count, n, entity, moves, removedIdx);
 
   const uint32_t nMoves = (uint32_t)moves.size(), nRem = (uint32_t)removedIdx.size();
   if (nMoves + nRem > 0)
