@@ -20,6 +20,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -154,7 +155,10 @@ struct ScGpuScene
 
   std::vector<uint32_t> hEntity;  // dense handles (ComponentPool::m_denseEntities)
   std::vector<uint32_t> hSparse;  // index -> slot+1 (ComponentPool::m_sparse)
-  std::vector<uint32_t> hOrigin;  // scratch for despawn batches: slot -> slot its content came from
+  std::vector<PoolMove> hMoves;   // results and work arrays of the last despawn batch (kept: no fresh pages per frame)
+  std::vector<uint32_t> hRemoved;
+  PoolScratch hPoolScratch;
+  uint32_t hostThreads = 1;       // host threads for the pool replay's gather / scatter passes (SCGPU_HOST_THREADS)
 
   uint64_t launches = 0;
   std::string err;
@@ -430,6 +434,13 @@ ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc)
   if (desc->max_instances == 0 || desc->max_instances > (1u << 24)) { fail(nullptr, "scgpuCreate: max_instances must be 1..%u (24-bit entity index, sc_ecs.h:18-20)", 1u << 24); return nullptr; }
   ScGpuScene* c = new (std::nothrow) ScGpuScene();
   if (!c) { fail(nullptr, "out of host memory"); return nullptr; }
+  {
+    // host threads for the pool bookkeeping of large despawn batches: SCGPU_HOST_THREADS, else half the cores up to 4 (the sequential middle pass bounds the gain)
+    const char* ht = getenv("SCGPU_HOST_THREADS");
+    const unsigned hw = std::thread::hardware_concurrency();
+    long want = ht ? strtol(ht, nullptr, 10) : (long)std::min(4u, std::max(1u, hw / 2u));
+    c->hostThreads = (uint32_t)std::min(64l, std::max(1l, want));
+  }
   if (!createImpl(c, desc))
   {
     g_createError = c->err;
@@ -901,9 +912,9 @@ int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
   if (!entity) return (int)fail(c, "scgpuDespawn: entity is NULL");
   // replay of ComponentPool::remove on the host mirror (scgpu_pool.h) -> net slot moves + sparse entries to clear
   static_assert(sizeof(PoolMove) == sizeof(uint2), "k_despawn_apply reads the moves as uint2");
-  std::vector<PoolMove> moves;
-  std::vector<uint32_t> removedIdx;
-  poolReplayDespawn(c->hEntity, c->hSparse, c->hOrigin, c->count, n, entity, moves, removedIdx);
+  std::vector<PoolMove>& moves = c->hMoves;
+  std::vector<uint32_t>& removedIdx = c->hRemoved;
+  poolReplayDespawn(c->hEntity, c->hSparse, c->count, n, entity, moves, removedIdx, c->hPoolScratch, c->hostThreads);
 
   const uint32_t nMoves = (uint32_t)moves.size(), nRem = (uint32_t)removedIdx.size();
   if (nMoves + nRem > 0)

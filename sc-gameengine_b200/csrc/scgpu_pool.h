@@ -4,16 +4,30 @@
 // replay and against the reference's own pool. The device keeps the same two arrays (entity[slot], sparse[index] ->
 // slot + 1); the mirror exists because ComponentPool::remove is order dependent: destroying entities one after the
 // other swaps the LAST dense element into each hole (sc_ecs.h:228-247), so the final dense order depends on the
-// sequence. A batch of despawns is replayed here handle by handle and reduced to the net `dst <- src` slot moves the
-// device has to apply (k_despawn_apply).
+// sequence. A batch of despawns is reduced here to the net `dst <- src` slot moves the device has to apply
+// (k_despawn_apply).
 //
-// The replay is a chain of dependent random accesses into arrays of tens of megabytes (sparse[index] -> slot ->
-// entity[slot], then sparse[index of the moved tail element]): unassisted it costs ~45 ns per handle, all of it
-// cache misses. The loop therefore runs a two-stage software prefetch pipeline over the batch. Prefetches are
-// hints computed from possibly stale values; the replay itself is unchanged, so the result is independent of them.
+// A literal handle-by-handle replay is a chain of dependent cache misses into arrays of tens of megabytes (sparse[index]
+// -> slot -> entity[slot] -> sparse[index of the moved tail element]; ~45 ns per handle). poolReplayDespawn computes
+// the SAME final state in three passes whose misses are independent of each other:
+//   A  gather   every handle's slot (sparse, then entity for the liveness check); iterations do not depend on each
+//               other: software prefetch keeps many misses in flight and the range can be cut across host threads;
+//   B  simulate the swap-with-last sequence on the vacated tail only. With k valid victims the pool shrinks from
+//               count to base = count - k, and three facts make the tail [base, count) self-contained:
+//                 - the element moved by a removal is the current last one, and last >= base throughout;
+//                 - so only elements that START in the tail ever move, and every one of them that survives ends up
+//                   in a slot below base (the tail is exactly what gets vacated);
+//                 - a victim that starts below base is removed from the slot it started in.
+//               The state is two k-sized arrays (which tail element sits in a tail slot / where a tail element is
+//               now), walked sequentially and cache resident;
+//   C  scatter  the surviving tail elements to their final slots (entity and sparse writes, again independent and
+//               cut across host threads).
 #pragma once
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
+#include <thread>
 #include <vector>
 
 namespace scgpu
@@ -27,99 +41,187 @@ struct PoolMove
 constexpr uint32_t kPoolInvalidEntity = 0xFFFFFFFFu;  // SCGPU_INVALID_ENTITY / sc::kInvalidEntity (sc_ecs.h:22)
 constexpr uint32_t kPoolIndexMask = 0xFFFFFFu;        // 24-bit entity index (sc_ecs.h:18-20)
 
-// Replays ComponentPool::remove for entity[0..n) in order.
+// Work arrays of poolReplayDespawn, kept between calls: a batch needs ~25 bytes per handle, and taking megabytes from
+// the allocator per call means fresh pages (one fault per 4 KiB) every frame.
+struct PoolScratch
+{
+  std::vector<uint32_t> raw, slot0, content, where;
+  std::vector<uint8_t> dead;
+  std::vector<uint64_t> seen;  // one bit per slot, all zero between calls
+  std::vector<uint32_t> chunkMoves;
+};
+
+// Runs fn(part, begin, end) over [0, n) cut into `parts` contiguous ranges, part 0 on the calling thread.
+template <class Fn>
+inline void poolParallelFor(uint32_t parts, uint32_t n, Fn fn)
+{
+  if (parts <= 1u || n < 32768u) { fn(0u, 0u, n); return; }
+  const uint32_t per = (n + parts - 1u) / parts;
+  std::vector<std::thread> th;
+  th.reserve(parts - 1u);
+  for (uint32_t p = 1; p < parts; ++p)
+  {
+    const uint32_t b = std::min(n, p * per), e = std::min(n, b + per);
+    th.emplace_back([=] { fn(p, b, e); });
+  }
+  fn(0u, 0u, std::min(n, per));
+  for (std::thread& t : th) t.join();
+}
+
+// Final state of ComponentPool::remove applied to entity[0..n) in order.
 //   dense   : handles in pool order (size == count on entry, shrunk on return)
 //   sparse  : entity index -> slot + 1, 0 = no component
-//   origin  : scratch, slot -> slot its content came from; identity outside a call (grown on demand)
-//   moves   : out, net moves for the surviving slots (sources always lie in the vacated tail [count_out, count_in),
-//             so no source is also a destination and the moves can be applied in parallel)
-//   removed : out, entity indices whose sparse entry must be cleared on the device
+//   moves   : out, one `dst <- src` per surviving element of the vacated tail: src in [count_out, count_in)
+//             ascending, dst < count_out, all dst distinct — they can be applied in parallel and in any order
+//   removed : out, entity indices whose sparse entry must be cleared on the device, in batch order
+//   threads : host threads for the gather and scatter passes (their iterations are independent; each is a chain of
+//             two cache misses, so this is latency hiding more than arithmetic); 1 = the calling thread only. The
+//             result does not depend on it.
 // Stale, unknown, repeated and invalid handles are skipped, like World::destroy returning false.
-inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t>& sparse, std::vector<uint32_t>& origin,
-                              uint32_t& count, uint32_t n, const uint32_t* entity, std::vector<PoolMove>& moves,
-                              std::vector<uint32_t>& removed)
+inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t>& sparse, uint32_t& count, uint32_t n,
+                              const uint32_t* entity, std::vector<PoolMove>& moves, std::vector<uint32_t>& removed,
+                              PoolScratch& scratch, uint32_t threads = 1)
 {
   moves.clear();
   removed.clear();
-  if (origin.size() < count)
-  {
-    const size_t old = origin.size();
-    origin.resize(count);
-    for (size_t i = old; i < origin.size(); ++i) origin[i] = (uint32_t)i;
-  }
-  std::vector<uint32_t> touched;
-  touched.reserve(n);
-  removed.reserve(n);
+  if (n == 0) return;
+  if (removed.capacity() < n) removed.reserve(n + n / 4);
   const uint32_t count0 = count;
-  uint32_t cnt = count;
   const size_t sparseSize = sparse.size();
   uint32_t* const pd = dense.data();
   uint32_t* const ps = sparse.data();
-  uint32_t* const po = origin.data();
+  threads = std::max(1u, std::min(threads, 64u));
 
-  constexpr uint32_t kFar = 24, kNear = 12;  // prefetch distances in handles
-  for (uint32_t j = 0; j < n; ++j)
-  {
-    // stage 1: the sparse entry of a handle far ahead
-    if (j + kFar < n)
+  // ---- A1 (parallel, read only): slot + 1 of every handle that names a live element, else 0
+  if (scratch.raw.size() < n) scratch.raw.resize(n + n / 4);
+  uint32_t* const raw = scratch.raw.data();
+  poolParallelFor(threads, n, [=](uint32_t, uint32_t b, uint32_t e_) {
+    constexpr uint32_t kFar = 32, kNear = 16;  // prefetch distances in handles: sparse entry, then the dense slot
+    for (uint32_t j = b; j < e_; ++j)
     {
-      const uint32_t i2 = entity[j + kFar] & kPoolIndexMask;
-      if (i2 < sparseSize) __builtin_prefetch(ps + i2, 1);
-    }
-    // stage 2: its dense slot (sparse entry has arrived by now), the tail element that will probably fill the hole,
-    // and that element's sparse entry
-    if (j + kNear < n)
-    {
-      const uint32_t i1 = entity[j + kNear] & kPoolIndexMask;
-      if (i1 < sparseSize)
+      if (j + kFar < e_)
       {
-        const uint32_t sp1 = ps[i1];
-        if (sp1 != 0u && sp1 <= cnt)
+        const uint32_t i2 = entity[j + kFar] & kPoolIndexMask;
+        if (i2 < sparseSize) __builtin_prefetch(ps + i2, 0);
+      }
+      if (j + kNear < e_)
+      {
+        const uint32_t i1 = entity[j + kNear] & kPoolIndexMask;
+        if (i1 < sparseSize)
         {
-          __builtin_prefetch(pd + (sp1 - 1u), 1);
-          __builtin_prefetch(po + (sp1 - 1u), 1);
+          const uint32_t sp1 = ps[i1];
+          if (sp1 != 0u && sp1 <= count0) __builtin_prefetch(pd + (sp1 - 1u), 0);
         }
       }
-      if (cnt > kNear)
+      const uint32_t e = entity[j];
+      const uint32_t idx = e & kPoolIndexMask;
+      uint32_t r = 0u;
+      if (e != kPoolInvalidEntity && idx < sparseSize)
       {
-        const uint32_t tail = pd[cnt - 1u - kNear] & kPoolIndexMask;  // sequential, cached
-        if (tail < sparseSize) __builtin_prefetch(ps + tail, 1);
+        const uint32_t sp = ps[idx];
+        if (sp != 0u && sp <= count0 && pd[sp - 1u] == e) r = sp;
       }
+      raw[j] = r;
     }
+  });
 
-    const uint32_t e = entity[j];
-    const uint32_t idx = e & kPoolIndexMask;
-    if (e == kPoolInvalidEntity || idx >= sparseSize) continue;
-    const uint32_t sp = ps[idx];
-    if (sp == 0u || pd[sp - 1u] != e) continue;  // stale or unknown handle
-    const uint32_t s = sp - 1u, last = cnt - 1u;
+  // ---- A2 (sequential, cache resident): victims in batch order; a handle repeated in the batch names a slot that
+  // was seen before (one bit per slot) and is skipped like the stale handle it would be by then
+  std::vector<uint32_t>& slot0 = scratch.slot0;
+  slot0.clear();
+  if (slot0.capacity() < n) slot0.reserve(n + n / 4);
+  if (scratch.seen.size() < ((size_t)count0 + 63u) / 64u) scratch.seen.resize(((size_t)count0 + 63u) / 64u + 1024u, 0ull);
+  uint64_t* const seen = scratch.seen.data();
+  for (uint32_t j = 0; j < n; ++j)
+  {
+    if (raw[j] == 0u) continue;
+    const uint32_t s = raw[j] - 1u;
+    const uint64_t bit = 1ull << (s & 63u);
+    if (seen[s >> 6] & bit) continue;
+    seen[s >> 6] |= bit;
+    slot0.push_back(s);
+    removed.push_back(entity[j] & kPoolIndexMask);
+  }
+  const uint32_t k = (uint32_t)slot0.size();
+  if (k == 0) return;
+  const uint32_t base = count0 - k;
+
+  // ---- B (sequential, cache resident): the swap-with-last sequence on the tail [base, count0) only.
+  // content: tail slot -> tail element in it; where: tail element -> its current slot; dead: tail element is a victim
+  if (scratch.content.size() < k)
+  {
+    scratch.content.resize(k + k / 4);
+    scratch.where.resize(k + k / 4);
+    scratch.dead.resize(k + k / 4);
+  }
+  uint32_t* const content = scratch.content.data();
+  uint32_t* const where = scratch.where.data();
+  uint8_t* const dead = scratch.dead.data();
+  for (uint32_t t = 0; t < k; ++t) { content[t] = where[t] = base + t; dead[t] = 0; }
+  for (uint32_t v = 0; v < k; ++v)
+  {
+    const uint32_t s0 = slot0[v];
+    seen[s0 >> 6] = 0ull;  // leaves the bitmap clean for the next call
+    if (s0 >= base) dead[s0 - base] = 1;
+  }
+  uint32_t cnt = count0;
+  for (uint32_t v = 0; v < k; ++v)
+  {
+    const uint32_t s0 = slot0[v];
+    const uint32_t s = s0 >= base ? where[s0 - base] : s0;
+    const uint32_t last = cnt - 1u;
     if (s != last)
     {
-      const uint32_t moved = pd[last];
-      pd[s] = moved;
-      ps[moved & kPoolIndexMask] = s + 1u;
-      po[s] = po[last];
-      touched.push_back(s);
+      const uint32_t o = content[last - base];  // the live element in the last slot (always a tail element)
+      if (s >= base) content[s - base] = o;
+      where[o - base] = s;
     }
-    ps[idx] = 0u;
-    removed.push_back(idx);
     --cnt;
   }
-  dense.resize(cnt);
 
-  // net moves: final content of every touched slot that survived
-  moves.reserve(touched.size());
-  for (uint32_t s : touched)
-  {
-    if (s < cnt && po[s] != s)
+  // ---- C (parallel): the victims' sparse entries are cleared, surviving tail elements go to their final slots.
+  // Writes are disjoint: cleared indices belong to victims, set indices to survivors, dst slots are distinct and
+  // below base, sources at or above it. Moves are collected per range and concatenated in range order.
+  const uint32_t parts = (threads <= 1u || k < 32768u) ? 1u : threads;
+  if (moves.capacity() < k) moves.reserve(k + k / 4);
+  moves.resize(k);
+  PoolMove* const mv = moves.data();
+  scratch.chunkMoves.assign(parts, 0u);
+  uint32_t* const chunkMoves = scratch.chunkMoves.data();
+  const uint32_t* const rem = removed.data();
+  poolParallelFor(parts, k, [=](uint32_t part, uint32_t b, uint32_t e_) {
+    for (uint32_t v = b; v < e_; ++v)
     {
-      moves.push_back(PoolMove{s, po[s]});
-      po[s] = s;  // also dedups slots touched more than once
+      if (v + 16u < e_) __builtin_prefetch(ps + rem[v + 16u], 1);
+      ps[rem[v]] = 0u;
+    }
+    uint32_t m = b;  // range-local output position: at most e_ - b moves, written in place at [b, ...)
+    for (uint32_t t = b; t < e_; ++t)
+    {
+      if (t + 16u < e_ && !dead[t + 16u]) __builtin_prefetch(pd + where[t + 16u], 1);
+      if (dead[t]) continue;
+      const uint32_t dst = where[t], h = pd[base + t];
+      pd[dst] = h;
+      ps[h & kPoolIndexMask] = dst + 1u;
+      mv[m++] = PoolMove{dst, base + t};
+    }
+    chunkMoves[part] = m - b;
+  });
+  // close the gaps between the ranges' move lists
+  uint32_t total = chunkMoves[0];
+  if (parts > 1u)
+  {
+    const uint32_t per = (k + parts - 1u) / parts;
+    for (uint32_t p = 1; p < parts; ++p)
+    {
+      const uint32_t b = std::min(k, p * per);
+      if (total != b) std::memmove(mv + total, mv + b, (size_t)chunkMoves[p] * sizeof(PoolMove));
+      total += chunkMoves[p];
     }
   }
-  for (uint32_t s : touched) po[s] = s;
-  for (uint32_t s = cnt; s < count0; ++s) po[s] = s;
-  count = cnt;
+  moves.resize(total);
+  dense.resize(base);
+  count = base;
 }
 
 // Host mirror of World::create + add<Transform> for a batch: validates every handle first so that a failed call

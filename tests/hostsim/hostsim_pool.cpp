@@ -6,10 +6,12 @@ using namespace scgpu;
 
 struct HsPool
 {
-  std::vector<uint32_t> dense, sparse, origin;
+  std::vector<uint32_t> dense, sparse;
   uint32_t count = 0;
   std::vector<PoolMove> moves;
   std::vector<uint32_t> removed;
+  PoolScratch scratch;
+  uint32_t threads = 1;
 };
 
 extern "C" {
@@ -20,6 +22,7 @@ HsPool* hs_pool_create(uint32_t sparseSize)
   return p;
 }
 void hs_pool_destroy(HsPool* p) { delete p; }
+void hs_pool_set_threads(HsPool* p, uint32_t threads) { p->threads = threads; }
 // 0 = ok, else 1 + reason (scgpu_pool.h), *badAt = offending position
 int hs_pool_spawn(HsPool* p, uint32_t n, const uint32_t* entity, uint32_t* badAt)
 {
@@ -31,7 +34,7 @@ int hs_pool_spawn(HsPool* p, uint32_t n, const uint32_t* entity, uint32_t* badAt
 double hs_pool_despawn(HsPool* p, uint32_t n, const uint32_t* entity)
 {
   const auto t0 = std::chrono::steady_clock::now();
-  poolReplayDespawn(p->dense, p->sparse, p->origin, p->count, n, entity, p->moves, p->removed);
+  poolReplayDespawn(p->dense, p->sparse, p->count, n, entity, p->moves, p->removed, p->scratch, p->threads);
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 uint32_t hs_pool_count(const HsPool* p) { return p->count; }
@@ -43,11 +46,5 @@ void hs_pool_read(const HsPool* p, uint32_t* dense, uint32_t* sparse, uint32_t* 
   if (sparse) std::memcpy(sparse, p->sparse.data(), p->sparse.size() * 4);
   if (moves2) std::memcpy(moves2, p->moves.data(), p->moves.size() * 8);
   if (removed) std::memcpy(removed, p->removed.data(), p->removed.size() * 4);
-}
-// 1 when the scratch origin table is the identity over [0, size) (the invariant between calls)
-int hs_pool_origin_is_identity(const HsPool* p)
-{
-  for (size_t i = 0; i < p->origin.size(); ++i) if (p->origin[i] != (uint32_t)i) return 0;
-  return 1;
 }
 }

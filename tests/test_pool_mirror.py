@@ -25,6 +25,7 @@ def hs():
     L.hs_pool_create.restype = C.c_void_p
     L.hs_pool_create.argtypes = [C.c_uint32]
     L.hs_pool_destroy.argtypes = [C.c_void_p]
+    L.hs_pool_set_threads.argtypes = [C.c_void_p, C.c_uint32]
     L.hs_pool_spawn.restype = C.c_int
     L.hs_pool_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.hs_pool_despawn.restype = C.c_double
@@ -33,15 +34,14 @@ def hs():
         getattr(L, f).restype = C.c_uint32
         getattr(L, f).argtypes = [C.c_void_p]
     L.hs_pool_read.argtypes = [C.c_void_p] + [C.c_void_p] * 4
-    L.hs_pool_origin_is_identity.restype = C.c_int
-    L.hs_pool_origin_is_identity.argtypes = [C.c_void_p]
     return L
 
 
 class Pool:
-    def __init__(self, L, sparse_size):
+    def __init__(self, L, sparse_size, threads=1):
         self.L, self.sparse_size = L, sparse_size
         self.p = L.hs_pool_create(sparse_size)
+        L.hs_pool_set_threads(self.p, threads)
 
     def close(self):
         self.L.hs_pool_destroy(self.p)
@@ -98,14 +98,13 @@ def check_batch(pool, victims):
     assert np.array_equal(sparse, expect)
     # the net moves reproduce the new order from the old one, in any application order
     if len(moves):
-        assert len(np.unique(moves[:, 0])) == len(moves)
+        assert len(np.unique(moves[:, 0])) == len(moves) == len(np.unique(moves[:, 1]))
         assert moves[:, 0].max() < len(after) <= moves[:, 1].min()
         assert moves[:, 1].max() < len(before)
     replay = before.copy()
     for d, s in moves[::-1]:
         replay[d] = before[s]
     assert np.array_equal(replay[: len(after)], after)
-    assert pool.L.hs_pool_origin_is_identity(pool.p) == 1
 
 
 def handles(idx, gen=0):
@@ -169,6 +168,25 @@ def test_random_churn_against_naive(hs, seed):
             i = h & 0xFFFFFF
             gen[i] = (gen[i] + 1) & 0xFF
             free.append(i)
+    p.close()
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_large_batches_threaded_gather_and_scatter(hs, threads):
+    """batches above the threading threshold (32 Ki handles): the result must not depend on the thread count"""
+    rng = np.random.default_rng(7)
+    n = 150_000
+    p = Pool(hs, 1 << 18, threads)
+    assert p.spawn(handles(rng.permutation(n))) == (0, 0)
+    for it in range(3):
+        dense, _ = p.state()
+        victims = rng.choice(dense, 50_000 - 7000 * it, replace=False)
+        if it == 1:   # mostly tail elements, in pool order: long move chains
+            victims = dense[-45_000:].copy()
+        batch = np.concatenate([victims, victims[:3000], rng.integers(0, 1 << 32, 500, dtype=np.uint64).astype(np.uint32)])
+        if it == 2:
+            rng.shuffle(batch)
+        check_batch(p, batch)
     p.close()
 
 

@@ -37,6 +37,18 @@ def main():
     pool = scenes.city_hier(n // 10 + 64, seed=99)   # template for the spawned groups
     next_id = n
     wall, dev, upd = [], [], []
+    # the pool replay alone (scgpu_pool.h through tests/hostsim), on a second mirror fed the same batches: tells how much
+    # of scgpuDespawn / scgpuSpawn is host bookkeeping and how much is upload + launch
+    import ctypes as C
+    hs = C.CDLL(str(ROOT / "tests" / "hostsim" / "libhostsim.so"))
+    hs.hs_pool_create.restype = C.c_void_p
+    hs.hs_pool_create.argtypes = [C.c_uint32]
+    hs.hs_pool_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    hs.hs_pool_despawn.restype = C.c_double
+    hs.hs_pool_despawn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    mirror = hs.hs_pool_create(1 << 24)
+    hs.hs_pool_spawn(mirror, n, e.ctypes.data, None)
+    replay_ms, register_ms = [], []
     for f in range(warm + frames):
         # victims: random whole groups worth ~10 % of the instances
         cand = np.nonzero(alive_group)[0]
@@ -51,6 +63,10 @@ def main():
         moved = rng.choice(live, (3 * len(live)) // 10, replace=False).astype(np.uint32)
         trs = sc["trs9"][moved % n].copy()
         trs[:, 0] += np.float32(0.25)
+        replay_ms.append(hs.hs_pool_despawn(mirror, len(dead), dead.ctypes.data) * 1e3)
+        tr = time.perf_counter()
+        hs.hs_pool_spawn(mirror, m, fresh_e.ctypes.data, None)   # fails exactly when s.spawn below does, pool untouched
+        register_ms.append((time.perf_counter() - tr) * 1e3)
         t0 = time.perf_counter()
         s.despawn(dead)
         t1 = time.perf_counter()
@@ -74,7 +90,8 @@ def main():
                 "recomputed": int(c.recomputed)}
     med = {k: statistics.median(w[k] for w in wall) for k in wall[0]}
     out = {"workload": "BASELINE configs[4] per-GPU share: 8 Mi instances, depth-4 groups, 5 views, per frame 10% despawn + 10% spawn + 30% setLocal",
-           "frames": frames, "host_ms_median": med, "device_update_ms_median": statistics.median(upd),
+           "frames": frames, "host_ms_median": med,
+           "pool_replay_alone_ms_median": {"despawn": statistics.median(replay_ms[warm:]), "spawn": statistics.median(register_ms[warm:] or [0.0])}, "device_update_ms_median": statistics.median(upd),
            "device_fused_kernel_ms_median": statistics.median(dev), "device_fused_kernel_ms_per_frame": dev, "last_frame": last,
            "instances_per_s_e2e": last["transforms"] / (med["frame_ms"] * 1e-3)}
     print(json.dumps(out, indent=1))
