@@ -1,5 +1,5 @@
-timeout 100 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "churn or forest or empty" > gpurun_out/tests_churn.log 2>&1; echo "parity rc=$?"; tail -2 gpurun_out/tests_churn.log
-for t in 1 4 8 16; do
-SCGPU_HOST_THREADS=$t timeout 70 python tools/bench_churn.py > gpurun_out/churn_t$t.json 2> gpurun_out/churn.err; echo "churn threads=$t rc=$?"; tail -3 gpurun_out/churn.err; python -c "
-import json; d=json.load(open('gpurun_out/churn_t$t.json')); print(d['host_ms_median'], d['pool_replay_alone_ms_median'], d['device_update_ms_median'])"
-done
+timeout 80 python tools/bench_next_rows.py > gpurun_out/next_rows.json 2> gpurun_out/next_rows.err; echo "next rows rc=$?"; tail -2 gpurun_out/next_rows.err; python -c "
+import json; d=json.load(open('gpurun_out/next_rows.json'))
+for k,v in d.items(): print(k, v.get('ms'))"
+timeout 70 python tools/bench_churn.py > gpurun_out/churn_final.json 2> gpurun_out/churn.err; echo "churn rc=$?"; tail -3 gpurun_out/churn.err; python -c "
+import json; d=json.load(open('gpurun_out/churn_final.json')); print(d['host_ms_median'], d['pool_replay_alone_ms_median'], d['device_update_ms_median'])"

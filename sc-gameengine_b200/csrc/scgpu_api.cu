@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -158,6 +159,14 @@ struct ScGpuScene
   std::vector<PoolMove> hMoves;   // results and work arrays of the last despawn batch (kept: no fresh pages per frame)
   std::vector<uint32_t> hRemoved;
   PoolScratch hPoolScratch;
+  // pinned staging ring for large uploads from pageable memory (uploadStaged): two chunks per host thread
+  static constexpr uint32_t kUpSlots = 8;
+  static constexpr size_t kUpChunk = 2u << 20, kUpStagedMin = 1u << 20;
+  struct UpPiece { char* dst; const char* src; size_t len; };
+  std::vector<UpPiece> upPieces;
+  void* upBuf[kUpSlots] = {};
+  cudaEvent_t upEv[kUpSlots] = {};
+  bool upPending[kUpSlots] = {};
   uint32_t hostThreads = 1;       // host threads for the pool replay's gather / scatter passes (SCGPU_HOST_THREADS)
 
   uint64_t launches = 0;
@@ -317,6 +326,11 @@ void freeAll(ScGpuScene* c)
   if (c->peerBox.base) { if (c->peerMapped) cudaIpcCloseMemHandle(c->peerBox.base); else cudaFree(c->peerBox.base); }
   cudaFree(c->dPeerState);
   if (c->hTotals) cudaFreeHost(c->hTotals);
+  for (uint32_t i = 0; i < ScGpuScene::kUpSlots; ++i)
+  {
+    if (c->upEv[i]) cudaEventDestroy(c->upEv[i]);
+  }
+  if (c->upBuf[0]) cudaFreeHost(c->upBuf[0]);
   if (c->hAllCounts) cudaFreeHost(c->hAllCounts);
   if (c->evDone) cudaEventDestroy(c->evDone);
   for (uint32_t i = 0; i < ScGpuScene::kTimingRing; ++i)
@@ -401,10 +415,94 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   return 1;
 }
 
+// Large uploads from PAGEABLE caller memory go through a ring of pinned chunks filled by several host threads: every
+// thread owns two chunks, copies its share of the sources into them and queues the DMA of each on the context stream
+// (the driver's own pageable path is one thread deep: 7-18 GB/s measured on the box against ~50 GB/s for the link).
+// A call with several arrays (scgpuSpawn: six) hands them over together so that the threads start once. The sources are
+// consumed when the call returns, as for every host pointer of the ABI.
+struct UpSeg
+{
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+
+int ensureUploadRing(ScGpuScene* c)
+{
+  if (c->upBuf[0]) return 1;
+  // one pinned block for the whole ring (pinning costs ~1-2 ms per call whatever the size)
+  void* block = nullptr;
+  SC_CUDA(c, cudaHostAlloc(&block, ScGpuScene::kUpChunk * ScGpuScene::kUpSlots, cudaHostAllocDefault));
+  for (uint32_t i = 0; i < ScGpuScene::kUpSlots; ++i)
+  {
+    c->upBuf[i] = (char*)block + ScGpuScene::kUpChunk * i;
+    SC_CUDA(c, cudaEventCreateWithFlags(&c->upEv[i], cudaEventDisableTiming));
+  }
+  return 1;
+}
+
+int uploadSegs(ScGpuScene* c, const UpSeg* segs, uint32_t nSegs)
+{
+  typedef ScGpuScene::UpPiece Piece;
+  std::vector<Piece>& pieces = c->upPieces;
+  pieces.clear();
+  const size_t chunk = ScGpuScene::kUpChunk;
+  size_t pageable = 0;
+  bool isPageable[16] = {};
+  for (uint32_t i = 0; i < nSegs && i < 16u && c->hostThreads > 1u; ++i)
+  {
+    if (!segs[i].src || segs[i].bytes < 65536u) continue;  // small ones are cheaper through the driver
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, segs[i].src) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+    if (at.type == cudaMemoryTypeUnregistered) { isPageable[i] = true; pageable += segs[i].bytes; }
+  }
+  const bool staged = pageable >= ScGpuScene::kUpStagedMin;
+  for (uint32_t i = 0; i < nSegs; ++i)
+  {
+    if (!segs[i].src || segs[i].bytes == 0) continue;
+    if (staged && i < 16u && isPageable[i])
+    {
+      for (size_t off = 0; off < segs[i].bytes; off += chunk)
+        pieces.push_back(Piece{(char*)segs[i].dst + off, (const char*)segs[i].src + off, std::min(chunk, segs[i].bytes - off)});
+    }
+    else
+      SC_CUDA(c, cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (pieces.empty()) return 1;
+
+  const uint32_t nPieces = (uint32_t)pieces.size();
+  const uint32_t T = std::min(std::min(c->hostThreads, ScGpuScene::kUpSlots / 2u), nPieces);
+  if (!ensureUploadRing(c)) return 0;
+  std::atomic<int> err{(int)cudaSuccess};
+  const Piece* const pc = pieces.data();
+  auto work = [&](uint32_t t) {
+    cudaError_t e = cudaSetDevice(c->device);
+    for (uint32_t i = t, round = 0; i < nPieces && e == cudaSuccess; i += T, ++round)
+    {
+      const uint32_t slot = 2u * t + (round & 1u);
+      if (c->upPending[slot]) e = cudaEventSynchronize(c->upEv[slot]);  // the DMA that last read this chunk
+      if (e != cudaSuccess) break;
+      memcpy(c->upBuf[slot], pc[i].src, pc[i].len);
+      e = cudaMemcpyAsync(pc[i].dst, c->upBuf[slot], pc[i].len, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(c->upEv[slot], c->stream);
+      c->upPending[slot] = true;
+    }
+    if (e != cudaSuccess) err.store((int)e);
+  };
+  std::vector<std::thread> th;
+  th.reserve(T - 1u);
+  for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t);
+  work(0u);
+  for (std::thread& t : th) t.join();
+  if (err.load() != (int)cudaSuccess)
+    return (int)fail(c, "staged upload failed: %s", cudaGetErrorString((cudaError_t)err.load()));
+  return 1;
+}
+
 int uploadTo(ScGpuScene* c, void* dst, const void* src, size_t bytes)
 {
-  SC_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
-  return 1;
+  const UpSeg seg{dst, src, bytes};
+  return uploadSegs(c, &seg, 1);
 }
 
 // stamps are 24 bits wide and 0 means "never"
@@ -441,7 +539,7 @@ ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc)
     long want = ht ? strtol(ht, nullptr, 10) : (long)std::min(4u, std::max(1u, hw / 2u));
     c->hostThreads = (uint32_t)std::min(64l, std::max(1l, want));
   }
-  if (!createImpl(c, desc))
+  if (!createImpl(c, desc) || (c->hostThreads > 1u && !ensureUploadRing(c)))  // ring up front: no first-upload hiccup
   {
     g_createError = c->err;
     freeAll(c);
@@ -520,12 +618,14 @@ int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t
     const size_t oFlags = bytes; bytes += flags ? (size_t)m * 4 : 0;
     if (!ensure(c, c->staging, bytes)) return 0;
     char* s = (char*)c->staging.ptr;
-    if (!uploadTo(c, s + oEntity, entity + off, (size_t)m * 4)) return 0;
-    if (parent && !uploadTo(c, s + oParent, parent + off, (size_t)m * 4)) return 0;
-    if (!uploadTo(c, s + oTrs, trs9 + (size_t)off * 9, (size_t)m * 36)) return 0;
-    if (aabb6 && !uploadTo(c, s + oAabb, aabb6 + (size_t)off * 6, (size_t)m * 24)) return 0;
-    if (meshMat2 && !uploadTo(c, s + oMm, meshMat2 + (size_t)off * 2, (size_t)m * 8)) return 0;
-    if (flags && !uploadTo(c, s + oFlags, flags + off, (size_t)m * 4)) return 0;
+    const UpSeg segs[6] = {
+      {s + oEntity, entity + off, (size_t)m * 4},
+      {s + oParent, parent ? parent + off : nullptr, (size_t)m * 4},
+      {s + oTrs, trs9 + (size_t)off * 9, (size_t)m * 36},
+      {s + oAabb, aabb6 ? aabb6 + (size_t)off * 6 : nullptr, (size_t)m * 24},
+      {s + oMm, meshMat2 ? meshMat2 + (size_t)off * 2 : nullptr, (size_t)m * 8},
+      {s + oFlags, flags ? flags + off : nullptr, (size_t)m * 4}};
+    if (!uploadSegs(c, segs, 6)) return 0;
     k_spawn<<<blocksFor(m), kBlock, 0, c->stream>>>(
       c->a, c->count + off, m, (const uint32_t*)(s + oEntity), parent ? (const uint32_t*)(s + oParent) : nullptr,
       (const float*)(s + oTrs), aabb6 ? (const float*)(s + oAabb) : nullptr,
@@ -922,9 +1022,8 @@ int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
     const size_t bytes = (size_t)nMoves * 8 + (size_t)nRem * 4;
     if (!ensure(c, c->staging, bytes)) return 0;
     char* s = (char*)c->staging.ptr;
-    if (nMoves && !uploadTo(c, s, moves.data(), (size_t)nMoves * 8)) return 0;
-    if (nRem && !uploadTo(c, s + (size_t)nMoves * 8, removedIdx.data(), (size_t)nRem * 4)) return 0;
-    // moves/removedIdx are pageable host vectors: the copies above are complete (staged) when the calls return
+    const UpSeg segs[2] = {{s, moves.data(), (size_t)nMoves * 8}, {s + (size_t)nMoves * 8, removedIdx.data(), (size_t)nRem * 4}};
+    if (!uploadSegs(c, segs, 2)) return 0;
     k_despawn_apply<<<blocksFor((uint64_t)nMoves + nRem), kBlock, 0, c->stream>>>(
       c->a, nMoves, (const uint2*)s, nRem, (const uint32_t*)(s + (size_t)nMoves * 8));
     ++c->launches;
@@ -940,8 +1039,8 @@ static int uploadEntityBatch(ScGpuScene* c, uint32_t n, const uint32_t* entity, 
   const size_t bytes = (size_t)n * 4 + (size_t)n * payloadBytesPer;
   if (!ensure(c, c->staging, bytes)) return 0;
   char* s = (char*)c->staging.ptr;
-  if (!uploadTo(c, s, entity, (size_t)n * 4)) return 0;
-  if (payload && !uploadTo(c, s + (size_t)n * 4, payload, (size_t)n * payloadBytesPer)) return 0;
+  const UpSeg segs[2] = {{s, entity, (size_t)n * 4}, {s + (size_t)n * 4, payload, (size_t)n * payloadBytesPer}};
+  if (!uploadSegs(c, segs, 2)) return 0;
   *dEntity = (const uint32_t*)s;
   if (dPayload) *dPayload = s + (size_t)n * 4;
   return 1;

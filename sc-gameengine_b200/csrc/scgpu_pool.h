@@ -237,12 +237,14 @@ inline int poolRegisterSpawn(std::vector<uint32_t>& dense, std::vector<uint32_t>
   uint32_t j = 0;
   for (; j < n; ++j)
   {
+    const uint32_t idx = entity[j] & kPoolIndexMask;
     if (j + kAhead < n)
     {
+      // scattered handles (a recycled free list) only: for runs of consecutive indices the hardware prefetcher does
+      // the work and the extra instruction costs more than the loop body
       const uint32_t ia = entity[j + kAhead] & kPoolIndexMask;
-      if (ia < sparseSize) __builtin_prefetch(ps + ia, 1);
+      if (ia - idx > 4u * kAhead && ia < sparseSize) __builtin_prefetch(ps + ia, 1);
     }
-    const uint32_t idx = entity[j] & kPoolIndexMask;
     if (entity[j] == kPoolInvalidEntity) { why = 1; break; }
     if (idx >= sparseSize) { why = 2; break; }
     if (ps[idx] != 0u) { why = 3; break; }
