@@ -14,6 +14,11 @@
  * host pointer it passes and may reuse it as soon as the call returns. One context is not re-entrant; calls
  * may come from any thread (the device is selected on entry).
  *
+ * Host pointers may be pageable or pinned. Large pageable arrays are copied through a pinned ring inside the library
+ * by up to SCGPU_HOST_THREADS (environment, default min(4, cores / 2)) short-lived host threads, which also share the
+ * pool bookkeeping of large scgpuDespawn batches; SCGPU_HOST_THREADS=1 keeps every call on the calling thread.
+ * Results never depend on the thread count.
+ *
  * There is no CPU fallback: without a CUDA device scgpuCreate() fails.
  */
 #ifndef SCGPU_H
