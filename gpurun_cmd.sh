@@ -1,1 +1,1 @@
-timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench2 rc=$?"; tail -2 gpurun_out/bench_n2.err; cut -c1-400 gpurun_out/bench_n2.json
+timeout 100 python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/tests_full.log
