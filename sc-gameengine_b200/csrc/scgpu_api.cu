@@ -491,8 +491,14 @@ int uploadSegs(ScGpuScene* c, const UpSeg* segs, uint32_t nSegs)
   };
   std::vector<std::thread> th;
   th.reserve(T - 1u);
-  for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t);
+  uint32_t started = 1;
+  for (; started < T; ++started)
+  {
+    try { th.emplace_back(work, started); }
+    catch (...) { break; }  // thread limit reached: the calling thread takes the remaining shares (no exception across the ABI)
+  }
   work(0u);
+  for (uint32_t t = started; t < T; ++t) work(t);
   for (std::thread& t : th) t.join();
   if (err.load() != (int)cudaSuccess)
     return (int)fail(c, "staged upload failed: %s", cudaGetErrorString((cudaError_t)err.load()));

@@ -59,12 +59,19 @@ inline void poolParallelFor(uint32_t parts, uint32_t n, Fn fn)
   const uint32_t per = (n + parts - 1u) / parts;
   std::vector<std::thread> th;
   th.reserve(parts - 1u);
-  for (uint32_t p = 1; p < parts; ++p)
+  uint32_t started = 1;  // ranges [0, started) have an owner; a thread that cannot be created leaves its range to the caller
+  for (; started < parts; ++started)
   {
-    const uint32_t b = std::min(n, p * per), e = std::min(n, b + per);
-    th.emplace_back([=] { fn(p, b, e); });
+    const uint32_t p = started, b = std::min(n, p * per), e = std::min(n, b + per);
+    try { th.emplace_back([=] { fn(p, b, e); }); }
+    catch (...) { break; }  // no exception may cross the C ABI: the rest runs on the calling thread
   }
   fn(0u, 0u, std::min(n, per));
+  for (uint32_t p = started; p < parts; ++p)
+  {
+    const uint32_t b = std::min(n, p * per), e = std::min(n, b + per);
+    fn(p, b, e);
+  }
   for (std::thread& t : th) t.join();
 }
 
