@@ -103,3 +103,194 @@ def test_shard_by_sector_keeps_cells_and_groups_together():
         assert np.array_equal(owner[child], owner[sc["parent"][child]])  # a hierarchy group lives in its root's cell
         share = np.bincount(owner, minlength=world) / len(owner)
         assert share.max() < 1.5 / world                           # balanced by instance count
+
+
+# ---- churn across shards (SURVEY.md §8e "Churn"): ShardRouter replicated on every rank ---------------------------------
+
+CHURN_FRAMES = 4
+
+
+def _churn_batches():
+    """Deterministic per-frame deltas, identical on every rank and in the unsharded run: whole groups despawn (plus a
+    few stale and repeated handles), fresh groups spawn — half of them in cells nobody has seen, beyond the rim of the
+    initial city — and random live instances get a new local TRS."""
+    from scgpu import scenes
+    sc, e, par, vps = _scene()
+    rng = np.random.default_rng(123)
+    roots = np.nonzero(sc["parent"] < 0)[0]
+    ends = np.append(roots[1:], N)
+    alive = np.ones(len(roots), bool)
+    fresh_alive = []          # (entity handles) of spawned groups still alive
+    next_index = N
+    frames = []
+    for f in range(CHURN_FRAMES):
+        pick = rng.choice(np.nonzero(alive)[0], 60, replace=False)
+        alive[pick] = False
+        dead = np.concatenate([np.arange(roots[g], ends[g], dtype=np.uint32) for g in pick])
+        if fresh_alive and f % 2 == 1:      # also drop a group spawned earlier
+            dead = np.concatenate([dead, fresh_alive.pop(0)])
+        dead = np.concatenate([dead, dead[:5], np.array([0x00FFFFF0, 0x07000001], np.uint32)])  # repeats + stale handles
+        m = 400
+        tmpl = scenes.city_hier(m, seed=900 + f)
+        ent = np.arange(next_index, next_index + m, dtype=np.uint32)
+        next_index += m
+        troots = tmpl["parent"] < 0
+        trs = tmpl["trs9"].copy()
+        sector = tmpl["sector"].copy()
+        # every second group moves out beyond the rim: cells no rank has seen yet
+        gid = np.cumsum(troots) - 1
+        far = (gid % 2 == 1)
+        shift = np.int32(40 + 3 * f)
+        trs[troots & far, 0] += np.float32(shift * 64.0)
+        sector[far, 0] += shift
+        spawn = dict(entity=ent, trs9=trs, parent=scenes.parent_handles(tmpl["parent"], ent), aabb6=tmpl["aabb6"],
+                     mesh_mat=tmpl["mesh_mat"], flags=tmpl["flags"], sector=sector)
+        tr = np.nonzero(troots)[0]
+        tend = np.append(tr[1:], m)
+        for a, b in list(zip(tr, tend))[:3]:
+            fresh_alive.append(ent[a:b].copy())
+        live = np.concatenate([np.repeat(alive, ends - roots).nonzero()[0].astype(np.uint32)] + [ent])
+        moved = rng.choice(live, len(live) // 5, replace=False).astype(np.uint32)
+        mtrs = np.tile(np.array([0, 0, 0, 0, 0, 0, 1, 1, 1], np.float32), (len(moved), 1))
+        mtrs[:, 0:3] = rng.uniform(-300, 300, (len(moved), 3)).astype(np.float32)
+        mtrs[:, 4] = rng.uniform(0, 6.28, len(moved)).astype(np.float32)
+        frames.append(dict(dead=dead, spawn=spawn, moved=moved, mtrs=mtrs))
+    return frames
+
+
+def _apply(scene, fr, keep_dead=None, keep_spawn=None, keep_moved=None):
+    d = fr["dead"] if keep_dead is None else fr["dead"][keep_dead]
+    if len(d):
+        scene.despawn(d)
+    sp = fr["spawn"]
+    k = slice(None) if keep_spawn is None else keep_spawn
+    if len(sp["entity"][k]):
+        scene.spawn(sp["entity"][k], sp["trs9"][k], sp["parent"][k], sp["aabb6"][k], sp["mesh_mat"][k], sp["flags"][k])
+    k = slice(None) if keep_moved is None else keep_moved
+    if len(fr["moved"][k]):
+        scene.set_local(fr["moved"][k], fr["mtrs"][k])
+
+
+def _churn_worker(rank, world, port, q):
+    try:
+        _churn_worker_body(rank, world, port, q)
+    except BaseException as ex:   # surface the failure at once instead of letting the parent wait for its timeout
+        import traceback
+        q.put("rank %d: %s\n%s" % (rank, ex, traceback.format_exc()))
+        raise
+
+
+def _churn_worker_body(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle_bind import PortScene
+    from scgpu import scenes
+    from scgpu.sharding import ShardRouter, NOWHERE
+    sc, e, par, vps = _scene()
+    owner = scenes.shard_by_sector(sc["sector"], world)
+    router = ShardRouter(world, e, sc["sector"], owner, max_entity_index=1 << 16)
+    mine = np.nonzero(owner == rank)[0]
+    s = PortScene()
+    s.spawn(e[mine], sc["trs9"][mine], par[mine], sc["aabb6"][mine], sc["mesh_mat"][mine], sc["flags"][mine])
+    s.update(vps)
+    per_frame = []
+    for fr in _churn_batches():
+        # every rank routes the whole batch (replicated router) and applies its share; the order of the three calls is
+        # the unsharded one: despawn, spawn, edits
+        r_dead = router.route_despawn(fr["dead"])
+        r_spawn = router.route_spawn(fr["spawn"]["entity"], fr["spawn"]["sector"])
+        r_moved = router.rank_of(fr["moved"])
+        assert not np.any(r_moved == NOWHERE)
+        _apply(s, fr, r_dead == rank, r_spawn == rank, r_moved == rank)
+        s.update(vps)
+        counts = torch.tensor([len(v) for v in s.visible] + [len(s.entity)], dtype=torch.int64)
+        all_counts = [torch.zeros(VIEWS + 1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(all_counts, counts)
+        gathered = []
+        for v in range(VIEWS):
+            mx = int(max(c[v] for c in all_counts))
+            buf = torch.zeros(max(mx, 1), dtype=torch.int64)
+            buf[: len(s.visible[v])] = torch.from_numpy(s.visible[v].astype(np.int64))
+            outs = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+            dist.gather(buf, outs, dst=0)
+            if rank == 0:
+                gathered.append(np.concatenate([outs[r][: int(all_counts[r][v])].numpy() for r in range(world)]).astype(np.uint32))
+        if rank == 0:
+            per_frame.append(dict(gathered=gathered, counts=torch.stack(all_counts).numpy(), router_counts=router.counts()))
+    if rank == 0:
+        q.put(per_frame)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_churn_routed_by_cell_equals_unsharded_world_size_2():
+    """Spawns follow their root's cell (new cells join the neighbouring block), despawns and edits follow the entity:
+    after every frame the union of the ranks' visible lists equals the unsharded world's, counts included, and every
+    rank's instance count is what the replicated router says it is."""
+    from oracle_bind import PortScene
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_churn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=500)
+    if isinstance(res, str):
+        for p in procs:
+            p.kill()
+        pytest.fail(res)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sc, e, par, vps = _scene()
+    ref = PortScene()
+    ref.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+    ref.update(vps)
+    seen_visible = 0
+    for f, fr in enumerate(_churn_batches()):
+        _apply(ref, fr)
+        ref.update(vps)
+        got = res[f]
+        assert got["counts"][:, VIEWS].sum() == len(ref.entity), f"frame {f}: instances"
+        assert np.array_equal(got["counts"][:, VIEWS], got["router_counts"]), f"frame {f}: router bookkeeping"
+        assert got["counts"][:, VIEWS].min() > 0
+        for v in range(VIEWS):
+            assert got["counts"][:, v].sum() == len(ref.visible[v]), f"frame {f} view {v}: count"
+            assert np.array_equal(np.sort(got["gathered"][v]), np.sort(ref.visible[v])), f"frame {f} view {v}"
+            seen_visible += len(ref.visible[v])
+    assert seen_visible > 0
+
+
+def test_router_cells_handles_and_rim_growth():
+    from scgpu import scenes
+    from scgpu.sharding import ShardRouter, NOWHERE
+    sc = scenes.city_hier(6000, seed=3)
+    e = (np.arange(6000, dtype=np.uint32) | np.uint32(2 << 24))
+    owner = scenes.shard_by_sector(sc["sector"], 4)
+    r = ShardRouter(4, e, sc["sector"], owner, max_entity_index=1 << 15)
+    assert np.array_equal(r.rank_of(e), owner)
+    assert np.array_equal(r.counts(), np.bincount(owner, minlength=4))
+    # wrong generation / never spawned -> nowhere
+    assert np.all(r.rank_of(np.array([5 | (3 << 24), 7000], np.uint32)) == NOWHERE)
+    # known cells keep their owner, cells beyond the rim join the outer blocks and are remembered
+    assert np.array_equal(r.rank_of_cell(sc["sector"][::97]), owner[::97])
+    zmax, zmin = sc["sector"][:, 1].max(), sc["sector"][:, 1].min()
+    assert r.rank_of_cell(np.array([[0, zmax + 5]], np.int32))[0] == 3
+    assert r.rank_of_cell(np.array([[0, zmin - 5]], np.int32))[0] == 0
+    new = np.array([9000 | (1 << 24), 9001 | (1 << 24)], np.uint32)
+    got = r.route_spawn(new, np.array([[2, zmax + 5], [2, zmax + 5]], np.int32))
+    assert list(got) == [3, 3] and list(r.rank_of(new)) == [3, 3]
+    with pytest.raises(ValueError):
+        r.route_spawn(new[:1], np.array([[0, 0]], np.int32))          # index still owned
+    d = r.route_despawn(np.array([new[0], new[0], e[10]], np.uint32))
+    assert list(d) == [3, NOWHERE, owner[10]]
+    assert r.rank_of(new[:1])[0] == NOWHERE
+    # a split cell is refused
+    bad = owner.copy()
+    k = np.nonzero((sc["sector"] == sc["sector"][0]).all(axis=1))[0]
+    if len(k) > 1:
+        bad[k[0]] = (bad[k[0]] + 1) % 4
+        with pytest.raises(ValueError):
+            ShardRouter(4, e, sc["sector"], bad, max_entity_index=1 << 15)
