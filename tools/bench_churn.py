@@ -1,6 +1,11 @@
 #!/usr/bin/env python
 """BASELINE.json configs[4] per-GPU share on one B200: 8 Mi instances in depth-4 groups, 5 views; every frame 10 % of
 the instances despawn, as many spawn, 30 % get a new local TRS (python tools/bench_churn.py > gpurun_out/churn.json).
+Under torchrun (WORLD_SIZE > 1, e.g. `python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1
+tools/bench_churn.py`) every rank churns its own block of world cells (8 x 8 Mi = configs[4]'s 64 M instances; each rank
+generates only its share of the deltas, which is what the replicated ShardRouter of scgpu/sharding.py leaves it with),
+the visible lists are gathered to rank 0 every frame, and the frame time is the maximum over the ranks. (The torchrun
+mode was written after round 1's GPU budget was spent: single-GPU numbers are measured, the N > 1 mode is not yet.)
 
 Everything goes through the C ABI from HOST buffers (pinned): the frame time is wall clock from the first delta call
 to the counts being on the host; the device share comes from the library's CUDA-event timings. The despawn victims
@@ -20,15 +25,33 @@ from scgpu import scenes  # noqa: E402
 
 
 def main():
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = 8 * 1024 * 1024
     views, frames, warm = 5, 8, 2
-    rng = np.random.default_rng(5)
-    sc = scenes.city_hier(n)
+    rng = np.random.default_rng(5 + rank)
+    sc = scenes.city_hier(n, seed=424242 + 7919 * rank)
+    if rank:  # rank r owns the block of world cells shifted by r grid sides along +x (as in bench.py)
+        sc["trs9"][sc["parent"] < 0, 0] += np.float32(rank * sc["side"] * scenes.SECTOR_SIZE)
     e = np.arange(n, dtype=np.uint32)
     par = scenes.parent_handles(sc["parent"], e)
-    s = scgpu.Scene(n + n // 4, max_views=views, max_entity_index=1 << 24)
+    s = scgpu.Scene(n + n // 4, max_views=views, device=local_rank, max_entity_index=1 << 24)
     s.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
     s.set_views(scenes.standard_views(views))
+    if world > 1:
+        uid = [scgpu.Scene.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        s.comm_init(world, rank, uid[0])
+        if os.environ.get("SCGPU_GATHER", "peer") == "peer":
+            s.enable_peer_gather(0)
     s.update(); s.counts()
     s.enable_timings(True)
     roots = np.nonzero(sc["parent"] < 0)[0]
@@ -64,6 +87,8 @@ def main():
         trs = sc["trs9"][moved % n].copy()
         trs[:, 0] += np.float32(0.25)
         replay_ms.append(hs.hs_pool_despawn(mirror, len(dead), dead.ctypes.data) * 1e3)
+        if world > 1:
+            dist.barrier()
         tr = time.perf_counter()
         hs.hs_pool_spawn(mirror, m, fresh_e.ctypes.data, None)   # fails exactly when s.spawn below does, pool untouched
         register_ms.append((time.perf_counter() - tr) * 1e3)
@@ -79,7 +104,11 @@ def main():
         s.set_local(moved, trs)
         t3 = time.perf_counter()
         s.update()
+        if world > 1:
+            s.gather_visible(0)
         c = s.counts()
+        if world > 1:
+            s.synchronize()   # the gather of this frame has landed on rank 0
         t4 = time.perf_counter()
         k, u = s.last_timings()
         if f >= warm:
@@ -88,14 +117,24 @@ def main():
             dev.append(k); upd.append(u)
         last = {"despawned": int(len(dead)), "spawned": int(spawned), "moved": int(len(moved)), "transforms": int(c.transforms),
                 "recomputed": int(c.recomputed)}
+    if world > 1:   # a frame is as slow as its slowest rank
+        import torch
+        t = torch.tensor([[w[k] for k in sorted(w)] for w in wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        keys = sorted(wall[0])
+        wall = [dict(zip(keys, row)) for row in t.cpu().tolist()]
     med = {k: statistics.median(w[k] for w in wall) for k in wall[0]}
     out = {"workload": "BASELINE configs[4] per-GPU share: 8 Mi instances, depth-4 groups, 5 views, per frame 10% despawn + 10% spawn + 30% setLocal",
            "frames": frames, "host_ms_median": med,
            "pool_replay_alone_ms_median": {"despawn": statistics.median(replay_ms[warm:]), "spawn": statistics.median(register_ms[warm:] or [0.0])}, "device_update_ms_median": statistics.median(upd),
            "device_fused_kernel_ms_median": statistics.median(dev), "device_fused_kernel_ms_per_frame": dev, "last_frame": last,
-           "instances_per_s_e2e": last["transforms"] / (med["frame_ms"] * 1e-3)}
-    print(json.dumps(out, indent=1))
+           "n_gpus": world, "instances_per_s_e2e": world * last["transforms"] / (med["frame_ms"] * 1e-3)}
+    if rank == 0:
+        print(json.dumps(out, indent=1))
     s.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
