@@ -294,3 +294,96 @@ def test_router_cells_handles_and_rim_growth():
         bad[k[0]] = (bad[k[0]] + 1) % 4
         with pytest.raises(ValueError):
             ShardRouter(4, e, sc["sector"], bad, max_entity_index=1 << 15)
+
+
+def test_cpp_router_agrees_with_the_harness_router():
+    """sc-gameengine_b200/host/sc_gpu_shard_router.h (what an engine process links) against scgpu/sharding.py over random
+    spawn / despawn / lookup batches with known cells, unseen cells, stale, repeated and out-of-range handles."""
+    import ctypes as C
+    import subprocess
+    from scgpu import scenes
+    from scgpu.sharding import ShardRouter
+    hs_dir = ROOT / "tests" / "hostsim"
+    subprocess.run(["make", "-C", str(hs_dir)], check=True, capture_output=True)
+    L = C.CDLL(str(hs_dir / "libhostsim.so"))
+    L.hs_router_create.restype = C.c_void_p
+    L.hs_router_create.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    for f in ("hs_router_rank_of_cell", "hs_router_rank_of", "hs_router_despawn"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.hs_router_spawn.restype = C.c_int
+    L.hs_router_spawn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hs_router_counts.argtypes = [C.c_void_p, C.c_void_p]
+    L.hs_router_destroy.argtypes = [C.c_void_p]
+
+    world, cap = 4, 1 << 15
+    sc = scenes.city_hier(8000, seed=21)
+    e = np.arange(8000, dtype=np.uint32) | np.uint32(1 << 24)
+    owner = scenes.shard_by_sector(sc["sector"], world)
+    py = ShardRouter(world, e, sc["sector"], owner, max_entity_index=cap)
+    cells, first = np.unique(sc["sector"], axis=0, return_index=True)
+    cells = np.ascontiguousarray(cells, np.int32)
+    cown = np.ascontiguousarray(owner[first], np.int32)
+    cpp = L.hs_router_create(world, len(cells), cells.ctypes.data, cown.ctypes.data, cap)
+    assert cpp
+    # a split cell is refused by both
+    bad = np.concatenate([cells, cells[:1]])
+    bown = np.concatenate([cown, (cown[:1] + 1) % world]).astype(np.int32)
+    assert not L.hs_router_create(world, len(bad), np.ascontiguousarray(bad).ctypes.data, bown.ctypes.data, cap)
+
+    def cpp_call(fn, ent):
+        ent = np.ascontiguousarray(ent, np.uint32)
+        out = np.zeros(len(ent), np.int32)
+        fn(cpp, len(ent), ent.ctypes.data, out.ctypes.data)
+        return out
+
+    def cpp_spawn(ent, sect):
+        ent = np.ascontiguousarray(ent, np.uint32)
+        sect = np.ascontiguousarray(sect, np.int32)
+        out = np.zeros(len(ent), np.int32)
+        ok = L.hs_router_spawn(cpp, len(ent), ent.ctypes.data, sect.ctypes.data, out.ctypes.data)
+        return ok, out
+
+    ok, got = cpp_spawn(e, sc["sector"])          # the initial scene, registered through the spawn path
+    assert ok and np.array_equal(got, owner)
+    rng = np.random.default_rng(8)
+    live = list(e)
+    next_index = 8000
+    lo, hi = sc["sector"].min() - 6, sc["sector"].max() + 6
+    for it in range(25):
+        m = int(rng.integers(1, 300))
+        ent = (np.arange(next_index, next_index + m, dtype=np.uint32) | np.uint32((it % 200) << 24))
+        next_index += m
+        sect = rng.integers(lo, hi, (m, 2)).astype(np.int32)      # known cells, holes inside the city, cells beyond the rim
+        sect[m // 2:] = sect[m // 2]                              # several spawns share one (possibly new) cell
+        want = py.route_spawn(ent, sect)
+        ok, got = cpp_spawn(ent, sect)
+        assert ok and np.array_equal(got, want), f"spawn batch {it}"
+        live.extend(ent)
+        probe = rng.integers(lo - 3, hi + 3, (200, 2)).astype(np.int32)
+        out = np.zeros(200, np.int32)
+        L.hs_router_rank_of_cell(cpp, 200, probe.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, py.rank_of_cell(probe)), f"cells after batch {it}"
+        k = int(rng.integers(1, 400))
+        pick = rng.choice(len(live), min(k, len(live)), replace=False)
+        victims = np.array([live[i] for i in pick], np.uint32)
+        noise = np.array([0x00FFFFF0, 7 | (250 << 24), int(victims[0]), 40000], np.uint32)
+        batch = np.concatenate([victims, noise])
+        rng.shuffle(batch)
+        assert np.array_equal(cpp_call(L.hs_router_rank_of, batch), py.rank_of(batch)), f"lookup {it}"
+        assert np.array_equal(cpp_call(L.hs_router_despawn, batch), py.route_despawn(batch)), f"despawn {it}"
+        gone = set(int(v) for v in victims)
+        live = [h for h in live if int(h) not in gone]
+        cnt = np.zeros(world, np.uint64)
+        L.hs_router_counts(cpp, cnt.ctypes.data)
+        assert np.array_equal(cnt.astype(np.int64), py.counts())
+    # a spawn onto a live index or a repeat inside the batch fails and changes nothing
+    before = cpp_call(L.hs_router_rank_of, np.array(live[:50], np.uint32))
+    ok, _ = cpp_spawn(np.array([live[0], 30000], np.uint32), np.zeros((2, 2), np.int32))
+    assert not ok
+    ok, _ = cpp_spawn(np.array([30001, 30001], np.uint32), np.zeros((2, 2), np.int32))
+    assert not ok
+    ok, _ = cpp_spawn(np.array([30002, cap + 5], np.uint32), np.zeros((2, 2), np.int32))
+    assert not ok
+    assert np.array_equal(cpp_call(L.hs_router_rank_of, np.array(live[:50], np.uint32)), before)
+    assert list(cpp_call(L.hs_router_rank_of, np.array([30000, 30001, 30002], np.uint32))) == [-1, -1, -1]
+    L.hs_router_destroy(cpp)
