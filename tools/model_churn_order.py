@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""CPU model of what streaming churn does to the Transform-pool ORDER (no GPU needed): the bench_churn.py pattern (4 % of
+the instances despawn per frame as whole groups, as many spawn) replayed on the real pool mirror (scgpu_pool.h through
+tests/hostsim, i.e. the reference's swap-with-last order), reporting per frame how many children end up more than a
+hierarchy window (32 slots) away from their parent, or BEFORE it. Those are the instances k_update_win cannot resolve
+inside a warp. Result (1 Mi instances, depth-4 groups): 3 % after one frame, 21 % after 8, 40 % after 20, 54 % after 40 —
+see DESIGN.md §9."""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / 'sc-gameengine_b200'))
+from scgpu import scenes
+hs = C.CDLL(str(ROOT / 'tests' / 'hostsim' / 'libhostsim.so'))
+hs.hs_pool_create.restype = C.c_void_p; hs.hs_pool_create.argtypes=[C.c_uint32]
+hs.hs_pool_spawn.argtypes=[C.c_void_p,C.c_uint32,C.c_void_p,C.c_void_p]
+hs.hs_pool_despawn.restype=C.c_double; hs.hs_pool_despawn.argtypes=[C.c_void_p,C.c_uint32,C.c_void_p]
+hs.hs_pool_count.restype=C.c_uint32; hs.hs_pool_count.argtypes=[C.c_void_p]
+hs.hs_pool_read.argtypes=[C.c_void_p]+[C.c_void_p]*4
+n = 1<<20
+sc = scenes.city_hier(n)
+e = np.arange(n, dtype=np.uint32)
+IDX = 1<<24
+parent_of = np.full(IDX, -1, np.int64)      # entity index -> parent entity index
+parent_of[:n] = sc["parent"]
+pool = hs.hs_pool_create(IDX); hs.hs_pool_spawn(pool, n, e.ctypes.data, None)
+rng = np.random.default_rng(5)
+roots = np.nonzero(sc["parent"] < 0)[0]; group_end = np.append(roots[1:], n)
+groups = [(int(a),int(b)) for a,b in zip(roots, group_end)]   # entity id ranges
+alive = np.ones(len(groups), bool)
+tmpl = scenes.city_hier(n//10+64, seed=99)
+next_id = n
+for f in range(40):
+    cand = np.nonzero(alive)[0]
+    pick = rng.choice(cand, max(1,len(cand)//25), replace=False)   # ~4 % like the bench
+    alive[pick] = False
+    dead = np.concatenate([np.arange(groups[g][0], groups[g][1], dtype=np.uint32) for g in pick])
+    hs.hs_pool_despawn(pool, len(dead), dead.ctypes.data)
+    m = len(dead)
+    fresh = np.arange(next_id, next_id+m, dtype=np.uint32)
+    tp = tmpl["parent"][:m]; tp = np.where(tp < m, tp, -1)
+    parent_of[fresh] = np.where(tp>=0, tp+next_id, -1)
+    # register fresh groups as alive groups
+    tr = np.nonzero(tp<0)[0]; te = np.append(tr[1:], m)
+    for a,b in zip(tr,te): groups.append((next_id+int(a), next_id+int(b)))
+    alive = np.concatenate([alive, np.ones(len(tr), bool)])
+    hs.hs_pool_spawn(pool, m, fresh.ctypes.data, None)
+    next_id += m
+    cnt = hs.hs_pool_count(pool)
+    dense = np.zeros(cnt, np.uint32); hs.hs_pool_read(pool, dense.ctypes.data, None, None, None)
+    slot_of = np.full(IDX, -1, np.int64); slot_of[dense] = np.arange(cnt)
+    par = parent_of[dense]; has = par >= 0
+    ps = np.where(has, slot_of[np.where(has, par, 0)], -1)
+    dist = np.where(has, np.arange(cnt) - ps, 0)
+    far = has & ((dist > 31) | (dist < 0))
+    fwd = has & (dist < 0)
+    if f % 4 == 3 or f < 4:
+        print(f"frame {f+1:2d}: instances {cnt}, children with parent > 31 slots away or behind: {far.sum()} ({100*far.mean():.2f} %), parent AFTER child: {fwd.sum()}")
