@@ -11,7 +11,9 @@
 // -> slot -> entity[slot] -> sparse[index of the moved tail element]; ~45 ns per handle). poolReplayDespawn computes
 // the SAME final state in three passes whose misses are independent of each other:
 //   A  gather   every handle's slot (sparse, then entity for the liveness check); iterations do not depend on each
-//               other: software prefetch keeps many misses in flight and the range can be cut across host threads;
+//               other: software prefetch keeps many misses in flight and the range can be cut across host threads.
+//               A bitmap over the slots tells whether the batch names an element twice; if not (the normal case) the
+//               victims are compacted in parallel too, else one sequential walk lets the first occurrence win;
 //   B  simulate the swap-with-last sequence on the vacated tail only. With k valid victims the pool shrinks from
 //               count to base = count - k, and three facts make the tail [base, count) self-contained:
 //                 - the element moved by a removal is the current last one, and last >= base throughout;
@@ -24,6 +26,7 @@
 //               cut across host threads).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -48,7 +51,7 @@ struct PoolScratch
   std::vector<uint32_t> raw, slot0, content, where;
   std::vector<uint8_t> dead;
   std::vector<uint64_t> seen;  // one bit per slot, all zero between calls
-  std::vector<uint32_t> chunkMoves;
+  std::vector<uint32_t> chunkMoves, partCount;
 };
 
 // Runs fn(part, begin, end) over [0, n) cut into `parts` contiguous ranges, part 0 on the calling thread.
@@ -99,11 +102,19 @@ inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t
   uint32_t* const ps = sparse.data();
   threads = std::max(1u, std::min(threads, 64u));
 
-  // ---- A1 (parallel, read only): slot + 1 of every handle that names a live element, else 0
+  // ---- A1 (parallel): slot + 1 of every handle that names a live element, else 0. Every live slot named is also
+  // marked in a bitmap (one bit per slot); finding the bit already set means the batch names an element twice.
   if (scratch.raw.size() < n) scratch.raw.resize(n + n / 4);
   uint32_t* const raw = scratch.raw.data();
-  poolParallelFor(threads, n, [=](uint32_t, uint32_t b, uint32_t e_) {
+  if (scratch.seen.size() < ((size_t)count0 + 63u) / 64u) scratch.seen.resize(((size_t)count0 + 63u) / 64u + 1024u, 0ull);
+  uint64_t* const seen = scratch.seen.data();
+  const uint32_t partsA = (threads <= 1u || n < 32768u) ? 1u : threads;
+  scratch.partCount.assign(partsA + 1u, 0u);
+  uint32_t* const partCount = scratch.partCount.data();
+  std::atomic<uint32_t> repeats{0u};
+  poolParallelFor(partsA, n, [=, &repeats](uint32_t part, uint32_t b, uint32_t e_) {
     constexpr uint32_t kFar = 32, kNear = 16;  // prefetch distances in handles: sparse entry, then the dense slot
+    uint32_t valid = 0, again = 0;
     for (uint32_t j = b; j < e_; ++j)
     {
       if (j + kFar < e_)
@@ -129,25 +140,59 @@ inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t
         if (sp != 0u && sp <= count0 && pd[sp - 1u] == e) r = sp;
       }
       raw[j] = r;
+      if (r)
+      {
+        const uint32_t s = r - 1u;
+        const uint64_t bit = 1ull << (s & 63u);
+        uint64_t old;
+        if (partsA == 1u) { old = seen[s >> 6]; seen[s >> 6] = old | bit; }
+        else old = __atomic_fetch_or(seen + (s >> 6), bit, __ATOMIC_RELAXED);
+        again += (old & bit) ? 1u : 0u;
+        ++valid;
+      }
     }
+    partCount[part + 1u] = valid;
+    if (again) repeats.fetch_add(again, std::memory_order_relaxed);
   });
 
-  // ---- A2 (sequential, cache resident): victims in batch order; a handle repeated in the batch names a slot that
-  // was seen before (one bit per slot) and is skipped like the stale handle it would be by then
+  // ---- A2: the victims in batch order (slot0) and their entity indices (removed)
   std::vector<uint32_t>& slot0 = scratch.slot0;
-  slot0.clear();
-  if (slot0.capacity() < n) slot0.reserve(n + n / 4);
-  if (scratch.seen.size() < ((size_t)count0 + 63u) / 64u) scratch.seen.resize(((size_t)count0 + 63u) / 64u + 1024u, 0ull);
-  uint64_t* const seen = scratch.seen.data();
-  for (uint32_t j = 0; j < n; ++j)
+  if (repeats.load() == 0u)
   {
-    if (raw[j] == 0u) continue;
-    const uint32_t s = raw[j] - 1u;
-    const uint64_t bit = 1ull << (s & 63u);
-    if (seen[s >> 6] & bit) continue;
-    seen[s >> 6] |= bit;
-    slot0.push_back(s);
-    removed.push_back(entity[j] & kPoolIndexMask);
+    // no element is named twice: every non-zero raw entry is a victim, and the ranges compact in parallel
+    for (uint32_t p = 0; p < partsA; ++p) partCount[p + 1u] += partCount[p];
+    const uint32_t kAll = partCount[partsA];
+    slot0.resize(kAll);
+    removed.resize(kAll);
+    uint32_t* const s0 = slot0.data();
+    uint32_t* const rm = removed.data();
+    poolParallelFor(partsA, n, [=](uint32_t part, uint32_t b, uint32_t e_) {
+      uint32_t w = partCount[part];
+      for (uint32_t j = b; j < e_; ++j)
+      {
+        if (raw[j] == 0u) continue;
+        s0[w] = raw[j] - 1u;
+        rm[w] = entity[j] & kPoolIndexMask;
+        ++w;
+      }
+    });
+  }
+  else
+  {
+    // a handle repeated in the batch is stale the second time: walk the batch in order, first occurrence wins
+    for (uint32_t j = 0; j < n; ++j) if (raw[j]) seen[(raw[j] - 1u) >> 6] = 0ull;  // every set bit is this batch's
+    slot0.clear();
+    if (slot0.capacity() < n) slot0.reserve(n + n / 4);
+    for (uint32_t j = 0; j < n; ++j)
+    {
+      if (raw[j] == 0u) continue;
+      const uint32_t s = raw[j] - 1u;
+      const uint64_t bit = 1ull << (s & 63u);
+      if (seen[s >> 6] & bit) continue;
+      seen[s >> 6] |= bit;
+      slot0.push_back(s);
+      removed.push_back(entity[j] & kPoolIndexMask);
+    }
   }
   const uint32_t k = (uint32_t)slot0.size();
   if (k == 0) return;

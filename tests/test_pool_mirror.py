@@ -175,16 +175,18 @@ def test_random_churn_against_naive(hs, seed):
 def test_large_batches_threaded_gather_and_scatter(hs, threads):
     """batches above the threading threshold (32 Ki handles): the result must not depend on the thread count"""
     rng = np.random.default_rng(7)
-    n = 150_000
+    n = 200_000
     p = Pool(hs, 1 << 18, threads)
     assert p.spawn(handles(rng.permutation(n))) == (0, 0)
-    for it in range(3):
+    for it in range(4):
         dense, _ = p.state()
         victims = rng.choice(dense, 50_000 - 7000 * it, replace=False)
         if it == 1:   # mostly tail elements, in pool order: long move chains
             victims = dense[-45_000:].copy()
-        batch = np.concatenate([victims, victims[:3000], rng.integers(0, 1 << 32, 500, dtype=np.uint64).astype(np.uint32)])
-        if it == 2:
+        # frame 0 names no element twice (victims compacted in parallel), the others do (sequential walk, first wins)
+        batch = np.concatenate([victims, victims[:3000] if it else victims[:0],
+                                rng.integers(1 << 30, 1 << 32, 500, dtype=np.uint64).astype(np.uint32)])
+        if it >= 2:
             rng.shuffle(batch)
         check_batch(p, batch)
     p.close()
