@@ -159,7 +159,7 @@ struct ScGpuScene
   std::vector<PoolMove> hMoves;   // results and work arrays of the last despawn batch (kept: no fresh pages per frame)
   std::vector<uint32_t> hRemoved;
   PoolScratch hPoolScratch;
-  // pinned staging ring for large uploads from pageable memory (uploadStaged): two chunks per host thread
+  // pinned staging ring for large uploads from pageable memory (uploadSegs): two chunks per host thread
   static constexpr uint32_t kUpSlots = 8;
   static constexpr size_t kUpChunk = 2u << 20, kUpStagedMin = 1u << 20;
   struct UpPiece { char* dst; const char* src; size_t len; };
@@ -167,7 +167,7 @@ struct ScGpuScene
   void* upBuf[kUpSlots] = {};
   cudaEvent_t upEv[kUpSlots] = {};
   bool upPending[kUpSlots] = {};
-  uint32_t hostThreads = 1;       // host threads for the pool replay's gather / scatter passes (SCGPU_HOST_THREADS)
+  uint32_t hostThreads = 1;       // host threads for the pool replay and for staged uploads (SCGPU_HOST_THREADS)
 
   uint64_t launches = 0;
   std::string err;
