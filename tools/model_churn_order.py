@@ -4,7 +4,8 @@ the instances despawn per frame as whole groups, as many spawn) replayed on the 
 tests/hostsim, i.e. the reference's swap-with-last order), reporting per frame how many instances end up 32 or more slots away from their parent (a
 link no hierarchy window can hold: k_update_win hands those windows to the generic path) and how many have their parent
 AFTER them. Result (1 Mi instances, depth-4 groups): far links 1.2 % after one frame, 8.8 % after 8, 20 % after 20,
-33 % after 40 — see DESIGN.md §9."""
+33 % after 40; windows (the greedy cut of k_build_windows replayed) holding at least one far
+child: 11 %, 59 %, 86 %, 94 % — see DESIGN.md §9."""
 import ctypes as C
 import sys
 from pathlib import Path
@@ -56,5 +57,28 @@ for f in range(40):
     dist = np.where(has, np.arange(cnt) - ps, 0)
     far = has & (np.abs(dist) > 31)      # k_build_windows: a link of 32 slots or more can never sit inside one window
     fwd = has & (dist < 0)
+    # the greedy window cut of k_build_windows (largest position within 32 slots that no near link crosses) and the
+    # share of windows that hold at least one far child, i.e. that k_update_win hands to the generic path
+    slots = np.arange(cnt)
+    near = has & ~far
+    lo = np.minimum(slots, ps)[near]; hi = np.maximum(slots, ps)[near]
+    diff = np.zeros(cnt + 2, np.int64)
+    np.add.at(diff, lo + 1, 1); np.add.at(diff, hi + 1, -1)
+    crossed = np.cumsum(diff)[: cnt + 1] > 0          # crossed[c]: a near link crosses the cut position c
+    far_prefix = np.concatenate([[0], np.cumsum(far)])
+    start, n_win, n_slow, inst_slow = 0, 0, 0, 0
+    while start < cnt:
+        end = min(start + 32, cnt)
+        c = end
+        while c > start + 1 and c < cnt and crossed[c]:
+            c -= 1
+        if c <= start:
+            c = end
+        n_win += 1
+        if far_prefix[c] - far_prefix[start] > 0:
+            n_slow += 1; inst_slow += c - start
+        start = c
+    if f % 4 == 3 or f < 4:
+        print(f"          windows {n_win} (mean {cnt / n_win:.1f} slots), with a far child: {n_slow} ({100 * n_slow / n_win:.1f} %) holding {100 * inst_slow / cnt:.1f} % of the instances")
     if f % 4 == 3 or f < 4:
         print(f"frame {f+1:2d}: instances {cnt}, children more than 31 slots from their parent: {far.sum()} ({100*far.mean():.2f} %); parent AFTER child (any distance): {fwd.sum()} ({100*fwd.mean():.2f} %)")
