@@ -129,3 +129,53 @@ def test_math_kats_port_equals_reference(ref, port):
     ref.screfMat4Perspective(C.c_float(1.0471975), C.c_float(16 / 9), C.c_float(0.1), C.c_float(1000.0), 1, f(o1))
     port.sco_mat4_perspective_rh_zo(C.c_float(1.0471975), C.c_float(16 / 9), C.c_float(0.1), C.c_float(1000.0), 1, f(o2))
     assert_same_bits(o1, o2, "perspective")
+
+
+def test_long_streaming_churn_port_equals_reference():
+    """30 frames of group-wise churn on a depth-4 city (the pattern of tools/bench_churn.py in miniature): whole groups
+    despawn, fresh groups spawn, a fifth of the live instances get a new local TRS. Swap-with-last scrambles the pool
+    frame by frame (tools/model_churn_order.py: after 30 frames a quarter of the children sit 32 or more slots from their
+    parent, a third of the parents FOLLOW their children) — the regime the GPU path's window builder and generic path
+    live in. Pool order, ordered lists and world matrices of the oracle against the reference's own systems."""
+    rng = np.random.default_rng(77)
+    r, p = _mk()
+    n = 3000
+    sc = scenes.city_hier(n, seed=31)
+    e = r.create_entities(n)
+    par = scenes.parent_handles(sc["parent"], e)
+    vps = scenes.standard_views(5)
+    for s in (r, p):
+        s.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+        s.update(vps)
+    compare_frame(r, p, e, 5, "churn frame 0")
+    roots = np.nonzero(sc["parent"] < 0)[0]
+    groups = [e[a:b] for a, b in zip(roots, np.append(roots[1:], n))]
+    far_seen = 0
+    for frame in range(1, 31):
+        pick = rng.choice(len(groups), max(1, len(groups) // 12), replace=False)
+        dead = np.concatenate([groups[g] for g in pick])
+        groups = [g for i, g in enumerate(groups) if i not in set(pick.tolist())]
+        m = len(dead)
+        tmpl = scenes.city_hier(m + 8, seed=500 + frame)
+        tp = np.where(tmpl["parent"][:m] < m, tmpl["parent"][:m], -1)
+        fe = r.create_entities(m)                      # the reference recycles freed indices with a new generation
+        fpar = scenes.parent_handles(tp, fe)
+        tr = np.nonzero(tp < 0)[0]
+        groups += [fe[a:b] for a, b in zip(tr, np.append(tr[1:], m))]
+        live = np.concatenate(groups)
+        moved = rng.choice(live, len(live) // 5, replace=False)
+        trs = random_trs(rng, len(moved), spread=300.0)
+        for s in (r, p):
+            s.despawn(dead)
+            s.spawn(fe, tmpl["trs9"][:m], fpar, tmpl["aabb6"][:m], tmpl["mesh_mat"][:m], tmpl["flags"][:m])
+            s.set_local(moved, trs)
+            s.update(vps)
+        dense = r.dense_entities()
+        assert np.array_equal(dense, p.entity), f"pool order differs in frame {frame}"
+        compare_frame(r, p, dense, 5, f"churn frame {frame}")
+        if frame % 10 == 0:
+            compare_draws(r, p, 0, f"churn frame {frame}")
+            slot = {int(h): i for i, h in enumerate(dense)}
+            ph = r.read_parents(dense)
+            far_seen = sum(1 for i, h in enumerate(ph) if int(h) in slot and abs(slot[int(h)] - i) >= 32)
+    assert far_seen > n // 20, "the scene did not get scrambled: the test does not reach the regime it is about"
