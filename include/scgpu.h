@@ -11,10 +11,13 @@
  * Conventions (style of src/engine/include/sc_engine_render.h:22-63,130-163): opaque context, POD structs,
  * int 1 = ok / 0 = failure, null-tolerant, no exceptions or aborts across the boundary; the failure text is
  * available from scgpuLastError(). The context owns every device buffer and its stream; the caller owns every
- * host pointer it passes and may reuse it as soon as the call returns. One context is not re-entrant; calls
- * may come from any thread (the device is selected on entry).
+ * host pointer it passes. One context is not re-entrant; calls may come from any thread (the device is selected on
+ * entry).
  *
- * Host pointers may be pageable or pinned. Large pageable arrays are copied through a pinned ring inside the library
+ * Host pointers may be pageable or pinned. PAGEABLE memory is consumed before the call returns and may be reused at
+ * once. PINNED or registered memory (cudaHostAlloc / cudaHostRegister) is read by the copy engine asynchronously and
+ * without an intermediate copy: it must stay untouched until the next call that waits for the stream — any result
+ * call, or scgpuSynchronize — has returned. Large pageable arrays are copied through a pinned ring inside the library
  * by up to SCGPU_HOST_THREADS (environment, default min(4, cores / 2)) short-lived host threads, which also share the
  * pool bookkeeping of large scgpuDespawn batches; SCGPU_HOST_THREADS=1 keeps every call on the calling thread.
  * Results never depend on the thread count.
@@ -37,7 +40,7 @@ extern "C" {
 #define SCGPU_API __attribute__((visibility("default")))
 #endif
 
-#define SCGPU_API_VERSION 1u
+#define SCGPU_API_VERSION 2u
 #define SCGPU_MAX_VIEWS 8u
 #define SCGPU_INVALID_ENTITY 0xFFFFFFFFu /* sc::kInvalidEntity, src/core/include/sc_ecs.h:36 */
 
@@ -47,7 +50,8 @@ extern "C" {
 
 /* scgpuUpdate flags */
 #define SCGPU_UPDATE_FREEZE_CULLING 1u /* CullingState::freezeCulling (.cpp:1227-1233): every candidate visible */
-#define SCGPU_UPDATE_SKIP_TRANSFORM 2u /* cull/compact only (views changed, transforms did not) */
+#define SCGPU_UPDATE_SKIP_TRANSFORM 2u /* cull/compact only (views changed, transforms did not). Consumes no dirty state:
+                                        * instances dirtied before it are recomputed by the next update without the flag */
 #define SCGPU_UPDATE_CULLED_LISTS   4u /* also build CullingState::culled (.cpp:1273-1280) for every view */
 
 typedef struct ScGpuScene ScGpuScene;
@@ -103,6 +107,25 @@ SCGPU_API int scgpuSpawn(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, co
  * handles are skipped like the reference does. */
 SCGPU_API int scgpuDespawn(ScGpuScene* ctx, uint32_t n, const uint32_t* entity);
 SCGPU_API int scgpuSetLocal(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const float* trs9);
+/* Delta-sized forms of setLocal. The engine's per-frame writers change position and rotation only — the physics sync
+ * (src/engine/physics/sc_physics.cpp:1178-1184) and the traffic tiers (src/engine/traffic/sc_traffic_ai.cpp:449-457) —
+ * or the position alone (setLocalPosition, sc_ecs.h:92-96); the scale stays as it is. 28 / 16 bytes per instance over
+ * PCIe instead of 40. posRot6: localPos.xyz, localRot.xyz. Both mark the instance dirty. */
+SCGPU_API int scgpuSetLocalPosRot(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const float* posRot6);
+SCGPU_API int scgpuSetLocalPosition(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const float* pos3);
+/* The same for a RANGE of the Transform pool in its dense order (ComponentPool::denseEntities, what ForEach<Transform>
+ * walks): element j is the Transform at dense index firstDense + j. No handles cross PCIe and nothing is looked up.
+ * floatsPerInstance selects the fields: SCGPU_LOCAL_POS, SCGPU_LOCAL_POS_ROT or SCGPU_LOCAL_TRS. */
+#define SCGPU_LOCAL_POS 3u
+#define SCGPU_LOCAL_POS_ROT 6u
+#define SCGPU_LOCAL_TRS 9u
+SCGPU_API int scgpuSetLocalRange(ScGpuScene* ctx, uint32_t firstDense, uint32_t n, uint32_t floatsPerInstance, const float* data);
+/* RenderMesh / Bounds of entities that already own a Transform: World::add<RenderMesh / Bounds> after the fact and
+ * edits of meshId, materialId or the AABB (src/engine/traffic/sc_traffic_lod.cpp:47-70, src/engine/src/sc_imgui.cpp:720).
+ * Each array may be NULL (that component field is left alone); flags = the new SCGPU_HAS_* bits. Does not dirty the
+ * Transform. Unknown handles are skipped. */
+SCGPU_API int scgpuSetRender(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const uint32_t* meshMat2, const float* aabb6,
+                             const uint32_t* flags);
 SCGPU_API int scgpuSetParent(ScGpuScene* ctx, uint32_t n, const uint32_t* entity, const uint32_t* parent);
 SCGPU_API int scgpuMarkDirty(ScGpuScene* ctx, uint32_t n, const uint32_t* entity);
 /* Same as scgpuSetLocal but entity/trs9 are DEVICE pointers (producers that already live in HBM). */
@@ -142,10 +165,13 @@ typedef struct ScGpuDeviceViews
 {
   const uint32_t* visibleEntity[SCGPU_MAX_VIEWS]; /* device, compacted entity handles per view */
   const uint32_t* visibleSlot[SCGPU_MAX_VIEWS];   /* device, the matching Transform-pool slots */
-  const uint32_t* visibleCount;                   /* device, [max_views+1]; last = renderablesTotal */
+  const uint32_t* visibleCount;                   /* device, [nViews] visible per view, [nViews] = renderablesTotal */
   const float* worldCol[4];                       /* device, world matrix column planes (float4 per slot) */
-  const uint32_t* entity;                         /* device, slot -> entity handle */
-  uint32_t count;                                 /* live slots */
+  const uint32_t* entity;                         /* device, slot -> entity handle (SCGPU_INVALID_ENTITY: a hole) */
+  uint32_t count;                                 /* live Transforms (size of the reference's pool) */
+  uint32_t extent;                                /* device slots in use: live Transforms + holes left by despawns */
+  const uint32_t* rank;                           /* device, slot -> dense index in the reference's Transform pool */
+  const uint32_t* perm;                           /* device, dense index -> slot */
 } ScGpuDeviceViews;
 SCGPU_API int scgpuGetDeviceViews(ScGpuScene* ctx, ScGpuDeviceViews* out);
 SCGPU_API void* scgpuGetStream(ScGpuScene* ctx);

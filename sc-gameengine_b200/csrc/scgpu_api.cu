@@ -2,13 +2,15 @@
 //
 // Host-side state is deliberately small: an entity mirror (dense handles + sparse index, the two arrays of the
 // reference's ComponentPool<Transform>, src/core/include/sc_ecs.h:199-277) so that despawns replay the
-// reference's swap-with-last order exactly, plus device buffer bookkeeping. All arithmetic runs on the GPU.
+// reference's swap-with-last ORDER exactly, the slot layout (scgpu_layout.h: which device slot a Transform lives in,
+// independent of that order), plus device buffer bookkeeping. All arithmetic runs on the GPU.
 #include "../../include/scgpu.h"
 #include "scgpu_kernels.cuh"
 #include "scgpu_draws.cuh"
 #include "scgpu_peer.cuh"
 #include "scgpu_traffic.cuh"
 #include "scgpu_pool.h"
+#include "scgpu_layout.h"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -97,15 +99,17 @@ struct ScGpuScene
   uint32_t sparseSize = 0;
   uint32_t maxViews = 1;
   uint32_t nViews = 0;
-  uint32_t count = 0;
+  uint32_t count = 0;        // live Transforms (size of the reference's pool)
   uint32_t frame = 1;        // id of the NEXT update; instances dirtied now carry this stamp
   bool topologyDirty = false;
   bool anyParentEver = false;
   bool forceAllDirty = false;
   bool updatedOnce = false;
+  bool poisoned = false;     // a device step failed after the host mirror was committed: the two no longer agree
   uint32_t lastUpdateFlags = 0;
   uint32_t lastNumTiles = 0;
   bool culledListsValid = false;
+  SlotLayout layout;         // device slots: extent, holes (scgpu_layout.h)
 
   SceneArrays a{};
   // hierarchy windows (k_build_windows -> k_scan_tiles -> k_flatten_windows, on topology changes only)
@@ -116,10 +120,13 @@ struct ScGpuScene
   uint32_t* winList = nullptr;       // [total+1] absolute start slot of every window (bit 31: generic path)
   uint32_t* slowList = nullptr;      // windows k_update_win hands to k_update_win_slow (start | len << 24)
   uint32_t numSMs = 148;
-  uint8_t* vismask = nullptr;
-  uint32_t* tileCounts = nullptr;
-  uint32_t* tileOffsets = nullptr;
-  uint32_t* totals = nullptr;  // [maxViews+1] + recomputed at [maxViews+1]
+  uint32_t* visBits = nullptr;   // [maxViews + 1][bitWords]: visible per (view, pool rank); last plane: culling candidates
+  uint32_t bitWords = 0;
+  uint32_t* acc = nullptr;       // kAccWords frame accumulators + the window queue, zero between frames
+  uint32_t* totals = nullptr;    // frame totals written by k_compact: [0..nViews) visible, [nViews] candidates, [kMaxViews+1] recomputed
+  uint32_t* compactPub = nullptr;   // [numSMs][kPubStride] per-segment counts + flags of k_compact
+  uint32_t* compactTicket = nullptr;
+  uint32_t compactTicketBase = 0, compactSeq = 0;
   uint32_t* visEntity[kMaxViews] = {};
   uint32_t* visSlot[kMaxViews] = {};
   uint32_t* culledEntity[kMaxViews] = {};
@@ -155,7 +162,9 @@ struct ScGpuScene
   uint32_t* dTrafficMoved = nullptr;
 
   std::vector<uint32_t> hEntity;  // dense handles (ComponentPool::m_denseEntities)
-  std::vector<uint32_t> hSparse;  // index -> slot+1 (ComponentPool::m_sparse)
+  std::vector<uint32_t> hSparse;  // index -> dense index + 1 (ComponentPool::m_sparse)
+  std::vector<uint32_t> hSlotOf;  // index -> device slot of the Transform it owns
+  std::vector<uint32_t> hSlotScratch;  // slots of the current spawn batch / of the victims of the current despawn batch
   std::vector<PoolMove> hMoves;   // results and work arrays of the last despawn batch (kept: no fresh pages per frame)
   std::vector<uint32_t> hRemoved;
   PoolScratch hPoolScratch;
@@ -212,6 +221,19 @@ bool fail(ScGpuScene* c, const char* fmt, ...)
       return (int)fail((c), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// for device steps that follow a committed change of the host mirror: a failure leaves the two out of step for good
+#define SC_CUDA_P(c, call)                                                                       \
+  do                                                                                             \
+  {                                                                                              \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+    {                                                                                            \
+      fail((c), "%s failed: %s (%s:%d); the context is unusable from here on", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      (c)->poisoned = true;                                                                      \
+      return 0;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
 #define SC_NCCL(c, call)                                                                          \
   do                                                                                              \
   {                                                                                               \
@@ -223,6 +245,7 @@ bool fail(ScGpuScene* c, const char* fmt, ...)
 bool enter(ScGpuScene* c)
 {
   if (!c) return false;
+  if (c->poisoned) return false;  // the message of the failure that poisoned the context stays in place
   c->err.clear();
   if (cudaSetDevice(c->device) != cudaSuccess) return fail(c, "cudaSetDevice(%d) failed", c->device);
   return true;
@@ -312,7 +335,8 @@ void freeAll(ScGpuScene* c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
-  cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->slowList); cudaFree(c->vismask); cudaFree(c->tileCounts); cudaFree(c->tileOffsets); cudaFree(c->totals);
+  cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->slowList); cudaFree(c->visBits); cudaFree(c->acc); cudaFree(c->compactPub); cudaFree(c->compactTicket); cudaFree(c->totals);
+  cudaFree(c->a.rank); cudaFree(c->a.perm);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
@@ -392,15 +416,19 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   if (!devAlloc(c, &c->a.meshMat, n, true)) return 0;
   if (!devAlloc(c, &c->a.sparse, (size_t)c->sparseSize, true)) return 0;
   c->a.sparseSize = c->sparseSize;
-  if (!devAlloc(c, &c->vismask, n, true)) return 0;
+  if (!devAlloc(c, &c->a.rank, n, true)) return 0;
+  if (!devAlloc(c, &c->a.perm, n, true)) return 0;
+  c->bitWords = (uint32_t)(n / 32);  // n is a multiple of kTile: planes are 16-byte multiples
+  if (!devAlloc(c, &c->visBits, (size_t)(c->maxViews + 1) * c->bitWords, true)) return 0;
+  if (!devAlloc(c, &c->acc, (size_t)kAccWords, true)) return 0;
+  if (!devAlloc(c, &c->compactPub, (size_t)c->numSMs * kPubStride, true)) return 0;
+  if (!devAlloc(c, &c->compactTicket, 1, true)) return 0;
   if (!devAlloc(c, &c->slotInfo, n, true)) return 0;
   if (!devAlloc(c, &c->winLocal, (size_t)c->maxTiles * (kMaxWin + 1), true)) return 0;
   if (!devAlloc(c, &c->tileWinCount, (size_t)c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->tileWinBase, (size_t)c->maxTiles + 1, true)) return 0;
   if (!devAlloc(c, &c->winList, (size_t)c->maxTiles * kMaxWin + 1, true)) return 0;
   if (!devAlloc(c, &c->slowList, (size_t)c->maxTiles * kMaxWin + 1, true)) return 0;
-  if (!devAlloc(c, &c->tileCounts, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
-  if (!devAlloc(c, &c->tileOffsets, (size_t)(kMaxViews + 1) * c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->totals, (size_t)kTotalsWords, true)) return 0;
   for (uint32_t v = 0; v < c->maxViews; ++v)
   {
@@ -412,6 +440,7 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   SC_CUDA(c, cudaEventCreateWithFlags(&c->evDone, cudaEventDisableTiming));
   SC_CUDA(c, cudaStreamSynchronize(c->stream));
   c->hEntity.reserve(c->capacity);
+  c->layout.reset(c->capacity);
   return 1;
 }
 
@@ -582,25 +611,61 @@ int scgpuSynchronize(ScGpuScene* ctx)
 {
   if (!enter(ctx)) return 0;
   SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->peerEnabled && ctx->lastGatherPeer && ctx->gatheredValid && ctx->rank != ctx->peerRoot)
+  {
+    // a producer that could not deliver learns it here (the root learns it from its read-back calls)
+    uint32_t err = 0;
+    SC_CUDA(ctx, cudaMemcpy(&err, ctx->dPeerState + 1, 4, cudaMemcpyDeviceToHost));
+    if (err & 1u) return (int)fail(ctx, "peer gather: the root did not release this rank's mailbox within the time limit; the last frame's lists were not delivered");
+  }
   return 1;
 }
 
 // ---- deltas -------------------------------------------------------------------------------------------
 
-// Host mirror of World::create + add<Transform>: validates the handles against the pool mirror first, so that a failed
-// call leaves the scene untouched, then appends them in pool order.
-static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const char* who)
+static int poison(ScGpuScene* c)
+{
+  c->poisoned = true;
+  c->err += " (host mirror already updated: the context is unusable from here on)";
+  return 0;
+}
+
+// Host half of a spawn batch: World::create + add<Transform> on the pool mirror (every handle is validated first, so a
+// refused batch leaves the scene untouched), then a device slot for every element (scgpu_layout.h). *slotOf == nullptr:
+// the batch got the run of fresh slots starting at *slot0; else slotOf[j] (host array, valid until the next call).
+// Call it after every fallible allocation: a device failure behind it poisons the context.
+static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* parent, const char* who,
+                         uint32_t* slot0, const uint32_t** slotOf)
 {
   if ((uint64_t)c->count + n > c->capacity) return (int)fail(c, "%s: %u + %u instances exceed max_instances %u", who, c->count, n, c->capacity);
   if (c->hSparse.size() < c->sparseSize) c->hSparse.resize(c->sparseSize, 0u);
+  if (c->hSlotOf.size() < c->sparseSize) c->hSlotOf.resize(c->sparseSize, 0u);
   uint32_t at = 0;
   switch (poolRegisterSpawn(c->hEntity, c->hSparse, c->count, n, entity, &at))
   {
-    case 0: return 1;
+    case 0: break;
     case 1: return (int)fail(c, "%s: entity[%u] is the invalid handle", who, at);
     case 2: return (int)fail(c, "%s: entity index %u >= max_entity_index %u", who, entity[at] & 0xFFFFFFu, c->sparseSize);
     default: return (int)fail(c, "%s: entity index %u already owns a Transform", who, entity[at] & 0xFFFFFFu);
   }
+  uint32_t* const so = c->hSlotOf.data();
+  if (!c->layout.hasHoles())
+  {
+    const uint32_t s0 = c->layout.appendRun(n);  // cannot fail: without holes the extent is the pool size
+    for (uint32_t j = 0; j < n; ++j) so[entity[j] & 0xFFFFFFu] = s0 + j;
+    *slot0 = s0;
+    *slotOf = nullptr;
+  }
+  else
+  {
+    if (c->hSlotScratch.size() < n) c->hSlotScratch.resize(n + n / 4);
+    uint32_t* const sl = c->hSlotScratch.data();
+    c->layout.placeBatch(n, entity, parent, sl);  // cannot fail: holes + tail room >= capacity - count >= n
+    for (uint32_t j = 0; j < n; ++j) so[entity[j] & 0xFFFFFFu] = sl[j];
+    *slot0 = 0;
+    *slotOf = sl;
+  }
+  return 1;
 }
 
 int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* parent, const float* trs9,
@@ -609,35 +674,42 @@ int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t
   if (!enter(c)) return 0;
   if (n == 0) return 1;
   if (!entity || !trs9) return (int)fail(c, "scgpuSpawn: entity and trs9 are required");
-  if (!registerSpawn(c, n, entity, "scgpuSpawn")) return 0;
-
   const uint32_t chunkMax = 1u << 20;
+  {
+    const size_t m = std::min(chunkMax, n);
+    if (!ensure(c, c->staging, m * (4 + 4 + 4 + 36 + 24 + 8 + 4))) return 0;  // before the mirror changes
+  }
+  uint32_t slot0 = 0;
+  const uint32_t* slotOf = nullptr;
+  if (!registerSpawn(c, n, entity, parent, "scgpuSpawn", &slot0, &slotOf)) return 0;
+
   for (uint32_t off = 0; off < n; off += chunkMax)
   {
     const uint32_t m = std::min(chunkMax, n - off);
     size_t bytes = 0;
     const size_t oEntity = bytes; bytes += (size_t)m * 4;
     const size_t oParent = bytes; bytes += parent ? (size_t)m * 4 : 0;
+    const size_t oSlot = bytes; bytes += slotOf ? (size_t)m * 4 : 0;
     const size_t oTrs = bytes; bytes += (size_t)m * 36;
     const size_t oAabb = bytes; bytes += aabb6 ? (size_t)m * 24 : 0;
     const size_t oMm = bytes; bytes += meshMat2 ? (size_t)m * 8 : 0;
     const size_t oFlags = bytes; bytes += flags ? (size_t)m * 4 : 0;
-    if (!ensure(c, c->staging, bytes)) return 0;
     char* s = (char*)c->staging.ptr;
-    const UpSeg segs[6] = {
+    const UpSeg segs[7] = {
       {s + oEntity, entity + off, (size_t)m * 4},
       {s + oParent, parent ? parent + off : nullptr, (size_t)m * 4},
+      {s + oSlot, slotOf ? slotOf + off : nullptr, (size_t)m * 4},
       {s + oTrs, trs9 + (size_t)off * 9, (size_t)m * 36},
       {s + oAabb, aabb6 ? aabb6 + (size_t)off * 6 : nullptr, (size_t)m * 24},
       {s + oMm, meshMat2 ? meshMat2 + (size_t)off * 2 : nullptr, (size_t)m * 8},
       {s + oFlags, flags ? flags + off : nullptr, (size_t)m * 4}};
-    if (!uploadSegs(c, segs, 6)) return 0;
+    if (!uploadSegs(c, segs, 7)) return poison(c);
     k_spawn<<<blocksFor(m), kBlock, 0, c->stream>>>(
-      c->a, c->count + off, m, (const uint32_t*)(s + oEntity), parent ? (const uint32_t*)(s + oParent) : nullptr,
-      (const float*)(s + oTrs), aabb6 ? (const float*)(s + oAabb) : nullptr,
+      c->a, slot0 + off, slotOf ? (const uint32_t*)(s + oSlot) : nullptr, c->count + off, m, (const uint32_t*)(s + oEntity),
+      parent ? (const uint32_t*)(s + oParent) : nullptr, (const float*)(s + oTrs), aabb6 ? (const float*)(s + oAabb) : nullptr,
       meshMat2 ? (const uint32_t*)(s + oMm) : nullptr, flags ? (const uint32_t*)(s + oFlags) : nullptr, stampOf(c->frame));
     ++c->launches;
-    SC_CUDA(c, cudaGetLastError());
+    SC_CUDA_P(c, cudaGetLastError());
   }
   if (parent)
   {
@@ -645,7 +717,8 @@ int scgpuSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t
     for (uint32_t j = 0; j < n && !any; ++j) any = parent[j] != SCGPU_INVALID_ENTITY;
     if (any) { c->anyParentEver = true; c->topologyDirty = true; }
   }
-  // a new Transform can turn a dangling parent handle valid (and shifts nothing else): re-resolve if any hierarchy exists
+  // a new Transform can turn a dangling parent handle valid, and a reused hole changes the windows around it:
+  // re-resolve if any hierarchy exists
   if (c->anyParentEver) c->topologyDirty = true;
   c->count += n;
   return 1;
@@ -683,19 +756,24 @@ int scgpuSpawnSectors(ScGpuScene* c, const ScGpuSectorGen* gen, uint32_t nSector
   const uint32_t n = first[nSectors];
   if (n != nEntities)
     return (int)fail(c, "scgpuSpawnSectors: the sectors yield %u spawn records but %u entity handles were passed", n, nEntities);
-  if (!registerSpawn(c, n, entity, "scgpuSpawnSectors")) return 0;
   const size_t oCoord = 0, oFirst = (size_t)nSectors * 8, oEntity = oFirst + ((size_t)nSectors + 1) * 4;
-  const size_t bytes = oEntity + (size_t)n * 4;
+  const size_t oSlot = oEntity + (size_t)n * 4;
+  const size_t bytes = oSlot + (size_t)n * 4;
   if (!ensure(c, c->staging, bytes)) return 0;
+  uint32_t slot0 = 0;
+  const uint32_t* slotOf = nullptr;
+  if (!registerSpawn(c, n, entity, nullptr, "scgpuSpawnSectors", &slot0, &slotOf)) return 0;
   char* s = (char*)c->staging.ptr;
-  if (!uploadTo(c, s + oCoord, coordXZ, (size_t)nSectors * 8)) return 0;
-  if (!uploadTo(c, s + oFirst, first.data(), ((size_t)nSectors + 1) * 4)) return 0;
-  if (!uploadTo(c, s + oEntity, entity, (size_t)n * 4)) return 0;
-  k_spawn_sectors<<<nSectors, 64, 0, c->stream>>>(c->a, g, c->count, (const int32_t*)(s + oCoord), (const uint32_t*)(s + oFirst),
+  if (!uploadTo(c, s + oCoord, coordXZ, (size_t)nSectors * 8)) return poison(c);
+  if (!uploadTo(c, s + oFirst, first.data(), ((size_t)nSectors + 1) * 4)) return poison(c);
+  if (!uploadTo(c, s + oEntity, entity, (size_t)n * 4)) return poison(c);
+  if (slotOf && !uploadTo(c, s + oSlot, slotOf, (size_t)n * 4)) return poison(c);
+  k_spawn_sectors<<<nSectors, 64, 0, c->stream>>>(c->a, g, slot0, slotOf ? (const uint32_t*)(s + oSlot) : nullptr, c->count,
+                                                  (const int32_t*)(s + oCoord), (const uint32_t*)(s + oFirst),
                                                   (const uint32_t*)(s + oEntity), stampOf(c->frame));
   ++c->launches;
-  SC_CUDA(c, cudaGetLastError());
-  SC_CUDA(c, cudaStreamSynchronize(c->stream));  // `first` is a local: the pageable upload must have left it
+  SC_CUDA_P(c, cudaGetLastError());
+  SC_CUDA_P(c, cudaStreamSynchronize(c->stream));  // `first` is a local: the pageable upload must have left it
   if (c->anyParentEver) c->topologyDirty = true;
   c->count += n;
   return 1;
@@ -779,23 +857,27 @@ int scgpuSpawnSectorFile(ScGpuScene* c, const void* bytes, size_t nBytes, const 
   if ((f.payload | f.recordSize | f.meshOffset) & 3u) return (int)fail(c, "scgpuSpawnSectorFile: INST records are not 4-byte aligned");
   if ((assets->nMeshes && !assets->meshes) || (assets->nMaterials && !assets->materials))
     return (int)fail(c, "scgpuSpawnSectorFile: asset table pointer is NULL");
-  if (!registerSpawn(c, f.count, entity, "scgpuSpawnSectorFile")) return 0;
   const size_t payloadBytes = (size_t)f.count * f.recordSize;
   const size_t oPay = 0, oEnt = (payloadBytes + 255) & ~(size_t)255, oMesh = oEnt + (((size_t)f.count * 4 + 255) & ~(size_t)255);
   const size_t oMat = oMesh + (((size_t)assets->nMeshes * 16 + 255) & ~(size_t)255);
-  const size_t total = oMat + (size_t)assets->nMaterials * 16 + 16;
+  const size_t oSlot = (oMat + (size_t)assets->nMaterials * 16 + 16 + 255) & ~(size_t)255;
+  const size_t total = oSlot + (size_t)f.count * 4;
   if (!ensure(c, c->staging, total)) return 0;
+  uint32_t slot0 = 0;
+  const uint32_t* slotOf = nullptr;
+  if (!registerSpawn(c, f.count, entity, nullptr, "scgpuSpawnSectorFile", &slot0, &slotOf)) return 0;
   char* s = (char*)c->staging.ptr;
-  if (!uploadTo(c, s + oPay, (const char*)bytes + f.payload, payloadBytes)) return 0;
-  if (!uploadTo(c, s + oEnt, entity, (size_t)f.count * 4)) return 0;
-  if (assets->nMeshes && !uploadTo(c, s + oMesh, assets->meshes, (size_t)assets->nMeshes * 16)) return 0;
-  if (assets->nMaterials && !uploadTo(c, s + oMat, assets->materials, (size_t)assets->nMaterials * 16)) return 0;
+  if (!uploadTo(c, s + oPay, (const char*)bytes + f.payload, payloadBytes)) return poison(c);
+  if (!uploadTo(c, s + oEnt, entity, (size_t)f.count * 4)) return poison(c);
+  if (assets->nMeshes && !uploadTo(c, s + oMesh, assets->meshes, (size_t)assets->nMeshes * 16)) return poison(c);
+  if (assets->nMaterials && !uploadTo(c, s + oMat, assets->materials, (size_t)assets->nMaterials * 16)) return poison(c);
+  if (slotOf && !uploadTo(c, s + oSlot, slotOf, (size_t)f.count * 4)) return poison(c);
   k_spawn_sector_file<<<blocksFor(f.count), kBlock, 0, c->stream>>>(
-    c->a, c->count, f.count, (const uint32_t*)(s + oPay), f.recordSize / 4u, f.meshOffset / 4u, (const uint32_t*)(s + oEnt),
-    (const AssetBinding*)(s + oMesh), assets->nMeshes, assets->defaultMesh, (const AssetBinding*)(s + oMat), assets->nMaterials,
-    assets->defaultMaterial, stampOf(c->frame));
+    c->a, slot0, slotOf ? (const uint32_t*)(s + oSlot) : nullptr, c->count, f.count, (const uint32_t*)(s + oPay), f.recordSize / 4u,
+    f.meshOffset / 4u, (const uint32_t*)(s + oEnt), (const AssetBinding*)(s + oMesh), assets->nMeshes, assets->defaultMesh,
+    (const AssetBinding*)(s + oMat), assets->nMaterials, assets->defaultMaterial, stampOf(c->frame));
   ++c->launches;
-  SC_CUDA(c, cudaGetLastError());
+  SC_CUDA_P(c, cudaGetLastError());
   if (c->anyParentEver) c->topologyDirty = true;
   c->count += f.count;
   return 1;
@@ -1016,24 +1098,33 @@ int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
   if (!enter(c)) return 0;
   if (n == 0) return 1;
   if (!entity) return (int)fail(c, "scgpuDespawn: entity is NULL");
-  // replay of ComponentPool::remove on the host mirror (scgpu_pool.h) -> net slot moves + sparse entries to clear
+  if (!ensure(c, c->staging, (size_t)n * 12)) return 0;  // before the mirror changes: at most n moves + n victims
+  // replay of ComponentPool::remove on the host mirror (scgpu_pool.h) -> net moves in rank space + the victims
   static_assert(sizeof(PoolMove) == sizeof(uint2), "k_despawn_apply reads the moves as uint2");
   std::vector<PoolMove>& moves = c->hMoves;
   std::vector<uint32_t>& removedIdx = c->hRemoved;
   poolReplayDespawn(c->hEntity, c->hSparse, c->count, n, entity, moves, removedIdx, c->hPoolScratch, c->hostThreads);
 
   const uint32_t nMoves = (uint32_t)moves.size(), nRem = (uint32_t)removedIdx.size();
-  if (nMoves + nRem > 0)
+  if (nRem > 0)
   {
-    const size_t bytes = (size_t)nMoves * 8 + (size_t)nRem * 4;
-    if (!ensure(c, c->staging, bytes)) return 0;
+    // the victims' device slots become holes (in batch order: a group destroyed as a whole is one run)
+    if (c->hSlotScratch.size() < nRem) c->hSlotScratch.resize(nRem + nRem / 4);
+    uint32_t* const sl = c->hSlotScratch.data();
+    const uint32_t* const so = c->hSlotOf.data();
+    for (uint32_t v = 0; v < nRem; ++v)
+    {
+      if (v + 16u < nRem) __builtin_prefetch(so + removedIdx[v + 16u], 0);
+      sl[v] = so[removedIdx[v]];
+    }
+    c->layout.release(nRem, sl);
     char* s = (char*)c->staging.ptr;
-    const UpSeg segs[2] = {{s, moves.data(), (size_t)nMoves * 8}, {s + (size_t)nMoves * 8, removedIdx.data(), (size_t)nRem * 4}};
-    if (!uploadSegs(c, segs, 2)) return 0;
+    const UpSeg segs[2] = {{s, moves.data(), (size_t)nMoves * 8}, {s + (size_t)nMoves * 8, sl, (size_t)nRem * 4}};
+    if (!uploadSegs(c, segs, 2)) return poison(c);
     k_despawn_apply<<<blocksFor((uint64_t)nMoves + nRem), kBlock, 0, c->stream>>>(
       c->a, nMoves, (const uint2*)s, nRem, (const uint32_t*)(s + (size_t)nMoves * 8));
     ++c->launches;
-    SC_CUDA(c, cudaGetLastError());
+    SC_CUDA_P(c, cudaGetLastError());
     if (c->anyParentEver) c->topologyDirty = true;
   }
   return 1;
@@ -1052,14 +1143,86 @@ static int uploadEntityBatch(ScGpuScene* c, uint32_t n, const uint32_t* entity, 
   return 1;
 }
 
-int scgpuSetLocal(ScGpuScene* c, uint32_t n, const uint32_t* entity, const float* trs9)
+}  // extern "C" (a template cannot have C linkage)
+
+// the setLocal family: kFloats floats per instance, addressed by handle or (entity == nullptr) by dense index
+template <int kFloats>
+static int setLocalImpl(ScGpuScene* c, const char* who, uint32_t n, const uint32_t* entity, uint32_t firstDense, const float* data)
 {
   if (!enter(c)) return 0;
   if (n == 0) return 1;
-  if (!entity || !trs9) return (int)fail(c, "scgpuSetLocal: NULL argument");
-  const uint32_t* dE; const void* dT;
-  if (!uploadEntityBatch(c, n, entity, trs9, 36, &dE, &dT)) return 0;
-  k_set_local<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, (const float*)dT, stampOf(c->frame));
+  if (!data) return (int)fail(c, "%s: NULL argument", who);
+  if (!entity && ((uint64_t)firstDense + n > c->count))
+    return (int)fail(c, "%s: dense range [%u, %u + %u) exceeds the %u live Transforms", who, firstDense, firstDense, n, c->count);
+  const uint32_t* dE = nullptr;
+  const void* dT = nullptr;
+  if (entity)
+  {
+    if (!uploadEntityBatch(c, n, entity, data, kFloats * 4, &dE, &dT)) return 0;
+  }
+  else
+  {
+    if (!ensure(c, c->staging, (size_t)n * kFloats * 4)) return 0;
+    if (!uploadTo(c, c->staging.ptr, data, (size_t)n * kFloats * 4)) return 0;
+    dT = c->staging.ptr;
+  }
+  k_set_local<kFloats><<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, firstDense, (const float*)dT, stampOf(c->frame));
+  ++c->launches;
+  SC_CUDA(c, cudaGetLastError());
+  return 1;
+}
+
+extern "C" {
+
+int scgpuSetLocal(ScGpuScene* c, uint32_t n, const uint32_t* entity, const float* trs9)
+{
+  if (c && n && !entity) { if (enter(c)) fail(c, "scgpuSetLocal: NULL argument"); return 0; }
+  return setLocalImpl<9>(c, "scgpuSetLocal", n, entity, 0, trs9);
+}
+
+int scgpuSetLocalPosRot(ScGpuScene* c, uint32_t n, const uint32_t* entity, const float* posRot6)
+{
+  if (c && n && !entity) { if (enter(c)) fail(c, "scgpuSetLocalPosRot: NULL argument"); return 0; }
+  return setLocalImpl<6>(c, "scgpuSetLocalPosRot", n, entity, 0, posRot6);
+}
+
+int scgpuSetLocalPosition(ScGpuScene* c, uint32_t n, const uint32_t* entity, const float* pos3)
+{
+  if (c && n && !entity) { if (enter(c)) fail(c, "scgpuSetLocalPosition: NULL argument"); return 0; }
+  return setLocalImpl<3>(c, "scgpuSetLocalPosition", n, entity, 0, pos3);
+}
+
+int scgpuSetLocalRange(ScGpuScene* c, uint32_t firstDense, uint32_t n, uint32_t floatsPerInstance, const float* data)
+{
+  switch (floatsPerInstance)
+  {
+    case SCGPU_LOCAL_POS: return setLocalImpl<3>(c, "scgpuSetLocalRange", n, nullptr, firstDense, data);
+    case SCGPU_LOCAL_POS_ROT: return setLocalImpl<6>(c, "scgpuSetLocalRange", n, nullptr, firstDense, data);
+    case SCGPU_LOCAL_TRS: return setLocalImpl<9>(c, "scgpuSetLocalRange", n, nullptr, firstDense, data);
+    default: break;
+  }
+  if (enter(c)) fail(c, "scgpuSetLocalRange: floatsPerInstance must be 3 (position), 6 (position, rotation) or 9 (position, rotation, scale), not %u", floatsPerInstance);
+  return 0;
+}
+
+int scgpuSetRender(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint32_t* meshMat2, const float* aabb6, const uint32_t* flags)
+{
+  if (!enter(c)) return 0;
+  if (n == 0) return 1;
+  if (!entity) return (int)fail(c, "scgpuSetRender: entity is NULL");
+  if (!meshMat2 && !aabb6 && !flags) return 1;
+  size_t bytes = 0;
+  const size_t oE = bytes; bytes += (size_t)n * 4;
+  const size_t oM = bytes; bytes += meshMat2 ? (size_t)n * 8 : 0;
+  const size_t oB = bytes; bytes += aabb6 ? (size_t)n * 24 : 0;
+  const size_t oF = bytes; bytes += flags ? (size_t)n * 4 : 0;
+  if (!ensure(c, c->staging, bytes)) return 0;
+  char* s = (char*)c->staging.ptr;
+  const UpSeg segs[4] = {{s + oE, entity, (size_t)n * 4}, {s + oM, meshMat2, (size_t)n * 8}, {s + oB, aabb6, (size_t)n * 24},
+                         {s + oF, flags, (size_t)n * 4}};
+  if (!uploadSegs(c, segs, 4)) return 0;
+  k_set_render<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, (const uint32_t*)(s + oE), meshMat2 ? (const uint32_t*)(s + oM) : nullptr,
+                                                       aabb6 ? (const float*)(s + oB) : nullptr, flags ? (const uint32_t*)(s + oF) : nullptr);
   ++c->launches;
   SC_CUDA(c, cudaGetLastError());
   return 1;
@@ -1070,7 +1233,7 @@ int scgpuSetLocalDevice(ScGpuScene* c, uint32_t n, const uint32_t* d_entity, con
   if (!enter(c)) return 0;
   if (n == 0) return 1;
   if (!d_entity || !d_trs9) return (int)fail(c, "scgpuSetLocalDevice: NULL argument");
-  k_set_local<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, d_entity, d_trs9, stampOf(c->frame));
+  k_set_local<9><<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, d_entity, 0u, d_trs9, stampOf(c->frame));
   ++c->launches;
   SC_CUDA(c, cudaGetLastError());
   return 1;
@@ -1153,53 +1316,56 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
   if (!enter(c)) return 0;
   if (c->nViews == 0) return (int)fail(c, "scgpuUpdate: no views set (scgpuSetViews)");
   const uint32_t stamp = stampOf(c->frame);
-  const uint32_t numTiles = (c->count + kTile - 1) / kTile;
+  const uint32_t extent = c->layout.extent();  // slots the frame kernels walk: live Transforms + holes
+  const uint32_t numTiles = (extent + kTile - 1) / kTile;
   const uint32_t tslot = c->timedUpdates % ScGpuScene::kTimingRing;
+  const bool wantCulled = (flags & SCGPU_UPDATE_CULLED_LISTS) != 0;
+  const bool skipTransform = (flags & SCGPU_UPDATE_SKIP_TRANSFORM) != 0;
+  if (wantCulled)
+    for (uint32_t v = 0; v < c->nViews; ++v)
+      if (!c->culledEntity[v] && !devAlloc(c, &c->culledEntity[v], (size_t)c->capacityPad, false)) return 0;
   if (c->timings) SC_CUDA(c, cudaEventRecord(c->evU0[tslot], c->stream));
 
-  if (c->topologyDirty && c->count)
+  if (c->topologyDirty && extent)
   {
-    k_resolve_parents<<<blocksFor(c->count), kBlock, 0, c->stream>>>(c->a, c->count, stamp);
+    k_resolve_parents<<<blocksFor(extent), kBlock, 0, c->stream>>>(c->a, extent, stamp);
     ++c->launches;
     SC_CUDA(c, cudaGetLastError());
     if (c->anyParentEver)
     {
-      k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winLocal, c->tileWinCount, c->count);
+      k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winLocal, c->tileWinCount, extent);
       k_scan_tiles<<<1, 1024, 0, c->stream>>>(c->tileWinCount, c->tileWinBase, c->tileWinBase + numTiles, numTiles);
-      k_flatten_windows<<<numTiles, 128, 0, c->stream>>>(c->winLocal, c->tileWinCount, c->tileWinBase, c->winList, numTiles, c->count);
+      k_flatten_windows<<<numTiles, 128, 0, c->stream>>>(c->winLocal, c->tileWinCount, c->tileWinBase, c->winList, numTiles, extent);
       c->launches += 3;
       SC_CUDA(c, cudaGetLastError());
     }
   }
   c->topologyDirty = false;
 
-  SC_CUDA(c, cudaMemsetAsync(c->totals, 0, sizeof(uint32_t) * kTotalsWords, c->stream));
   if (numTiles)
   {
     UpdateParams p{};
     p.rec0 = c->a.rec[0]; p.rec1 = c->a.rec[1]; p.rec2 = c->a.rec[2]; p.rec3 = c->a.rec[3];
     p.w0 = c->a.world[0]; p.w1 = c->a.world[1]; p.w2 = c->a.world[2]; p.w3 = c->a.world[3];
     p.parentSlot = c->a.parentSlot;
-    p.vismask = c->vismask;
-    p.tileCounts = c->tileCounts;
-    p.recomputed = c->totals + kMaxViews + 1;
-    p.count = c->count;
-    p.numTiles = numTiles;
+    p.rank = c->a.rank;
+    p.visBits = c->visBits;
+    p.acc = c->acc;
+    p.count = extent;
+    p.bitWords = c->bitWords;
     p.stamp = stamp;
     p.nViews = c->nViews;
     p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
-              ((flags & SCGPU_UPDATE_SKIP_TRANSFORM) ? kUpdSkipTransform : 0u);
-    if (c->anyParentEver)  // the window kernel accumulates its per-tile counts with atomics
-      SC_CUDA(c, cudaMemsetAsync(c->tileCounts, 0, sizeof(uint32_t) * (size_t)(c->nViews + 1) * numTiles, c->stream));
+              (skipTransform ? kUpdSkipTransform : 0u) | (wantCulled ? kUpdCandBits : 0u);
     if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
 #define SC_LAUNCH_UPDATE(V)                                                                                              \
   case V:                                                                                                                \
     if (c->anyParentEver)                                                                                                \
     {                                                                                                                    \
       k_update_win<V><<<c->numSMs * SCGPU_WIN_MINBLOCKS, kWinBlock, 0, c->stream>>>(                                     \
-        p, c->planes, c->slotInfo, c->winList, c->tileWinBase + numTiles, c->totals + kQueueNext, c->slowList);          \
+        p, c->planes, c->slotInfo, c->winList, c->tileWinBase + numTiles, c->acc + kAccQueueNext, c->slowList);          \
       SC_CUDA(c, launchPdl(k_update_win_slow<V>, c->numSMs * 4u, kWinBlock, c->stream, p, c->planes,                     \
-                           (const uint32_t*)c->slotInfo, (const uint32_t*)(c->totals + kQueueSlow),                      \
+                           (const uint32_t*)c->slotInfo, (const uint32_t*)(c->acc + kAccQueueSlow),                      \
                            (const uint32_t*)c->slowList));                                                               \
       ++c->launches;                                                                                                     \
     }                                                                                                                    \
@@ -1216,45 +1382,55 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     ++c->launches;
     SC_CUDA(c, cudaGetLastError());
     if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK1[tslot], c->stream));
-
-    SC_CUDA(c, launchPdl(k_scan_tiles, c->nViews + 1, 1024u, c->stream, (const uint32_t*)c->tileCounts, c->tileOffsets, c->totals,
-                         numTiles));
-    ++c->launches;
-
-    ScatterParams sp{};
-    sp.vismask = c->vismask; sp.entity = c->a.entity; sp.tileCounts = c->tileCounts; sp.tileOffsets = c->tileOffsets;
-    for (uint32_t v = 0; v < kMaxViews; ++v) { sp.outEntity[v] = c->visEntity[v]; sp.outSlot[v] = c->visSlot[v]; }
-    sp.count = c->count; sp.numTiles = numTiles; sp.nViews = c->nViews;
-    SC_CUDA(c, launchPdl(k_scatter_visible, std::min(numTiles, c->numSMs * 8u), kBlock, c->stream, sp));
-    ++c->launches;
-
-    if (flags & SCGPU_UPDATE_CULLED_LISTS)
-    {
-      for (uint32_t v = 0; v < c->nViews; ++v)
-        if (!c->culledEntity[v] && !devAlloc(c, &c->culledEntity[v], (size_t)c->capacityPad, false)) return 0;
-      CulledParams cp{};
-      cp.vismask = c->vismask; cp.rec3 = c->a.rec[3]; cp.entity = c->a.entity; cp.tileOffsets = c->tileOffsets;
-      for (uint32_t v = 0; v < kMaxViews; ++v) cp.outEntity[v] = c->culledEntity[v];
-      cp.count = c->count; cp.numTiles = numTiles; cp.nViews = c->nViews;
-      k_scatter_culled<<<numTiles, kBlock, 0, c->stream>>>(cp);
-      ++c->launches;
-      SC_CUDA(c, cudaGetLastError());
-    }
   }
-  c->culledListsValid = (flags & SCGPU_UPDATE_CULLED_LISTS) != 0;
-  // totals layout: [0..nViews) visible per view, [nViews] candidates, [kMaxViews+1] recomputed
+
+  // compaction in pool order, totals, and clean bitmaps / counters / queue for the next frame: one launch
+  {
+    CompactParams q{};
+    q.bits = c->visBits; q.perm = c->a.perm; q.entity = c->a.entity;
+    for (uint32_t v = 0; v < kMaxViews; ++v) { q.outEntity[v] = c->visEntity[v]; q.outSlot[v] = c->visSlot[v]; q.culledEntity[v] = c->culledEntity[v]; }
+    q.acc = c->acc; q.totals = c->totals; q.pub = c->compactPub; q.ticket = c->compactTicket;
+    q.nWords = std::min(c->bitWords, (((c->count + 31u) / 32u) + 3u) & ~3u);
+    const uint32_t grid = std::max(1u, std::min(c->numSMs, (q.nWords + kCompactChunkWords - 1u) / kCompactChunkWords));
+    q.segWords = (((q.nWords + grid - 1u) / grid) + 3u) & ~3u;
+    q.bitWords = c->bitWords;
+    q.nViews = c->nViews;
+    q.culled = wantCulled ? 1u : 0u;
+    q.ticketBase = c->compactTicketBase;
+    if (++c->compactSeq == 0u) ++c->compactSeq;  // 0 is what a never-written flag holds
+    q.seq = c->compactSeq;
+    c->compactTicketBase += grid;
+    SC_CUDA(c, launchPdl(k_compact, grid, kCompactThreads, c->stream, q));
+    ++c->launches;
+  }
+  c->culledListsValid = wantCulled;
   SC_CUDA(c, cudaMemcpyAsync(c->hTotals, c->totals, sizeof(uint32_t) * (kMaxViews + 2), cudaMemcpyDeviceToHost, c->stream));
   if (c->timings) { SC_CUDA(c, cudaEventRecord(c->evU1[tslot], c->stream)); ++c->timedUpdates; }
   SC_CUDA(c, cudaEventRecord(c->evDone, c->stream));
 
   c->lastUpdateFlags = flags;
   c->lastNumTiles = numTiles;
-  c->forceAllDirty = false;
   c->updatedOnce = true;
   c->gatheredValid = false;
   c->sortedValid = false;
-  ++c->frame;
-  if (stampOf(c->frame) == 0u) ++c->frame;  // stamp 0 is reserved for "never dirty"
+  if (!skipTransform)
+  {
+    // A cull-only update consumes no dirty stamp: whatever was dirtied before it is still recomputed by the next
+    // transforming update, like the reference's t.dirty, which stays set until TransformSystem has seen the node.
+    c->forceAllDirty = false;
+    ++c->frame;
+    if (stampOf(c->frame) == 0u)
+    {
+      // the 24-bit stamp wraps: forget every stored stamp (all older than this update) so that none aliases a future id
+      if (extent)
+      {
+        k_clear_stamps<<<blocksFor(extent), kBlock, 0, c->stream>>>(c->a, extent);
+        ++c->launches;
+        SC_CUDA(c, cudaGetLastError());
+      }
+      c->frame += 1u;  // stamp 0 is reserved for "never dirty"
+    }
+  }
   return 1;
 }
 
@@ -1522,8 +1698,13 @@ int scgpuReadDenseEntities(ScGpuScene* c, uint32_t* outEntity, uint32_t cap, uin
   const uint32_t m = std::min(c->count, cap);
   if (m && outEntity)
   {
-    // read from the device copy (not the host mirror) so tests can check that the two agree
-    SC_CUDA(c, cudaMemcpyAsync(outEntity, c->a.entity, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
+    // gathered from the device arrays (entity[perm[rank]]), not copied from the host mirror, so that tests can check
+    // that the two agree
+    if (!ensure(c, c->scratch, (size_t)m * 4)) return 0;
+    k_gather_dense<<<blocksFor(m), kBlock, 0, c->stream>>>(c->a, m, (uint32_t*)c->scratch.ptr);
+    ++c->launches;
+    SC_CUDA(c, cudaGetLastError());
+    SC_CUDA(c, cudaMemcpyAsync(outEntity, c->scratch.ptr, (size_t)m * 4, cudaMemcpyDeviceToHost, c->stream));
     SC_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   return 1;
@@ -1539,6 +1720,9 @@ int scgpuGetDeviceViews(ScGpuScene* c, ScGpuDeviceViews* out)
   for (int k = 0; k < 4; ++k) out->worldCol[k] = (const float*)c->a.world[k];
   out->entity = c->a.entity;
   out->count = c->count;
+  out->extent = c->layout.extent();
+  out->rank = c->a.rank;
+  out->perm = c->a.perm;
   return 1;
 }
 
@@ -1630,6 +1814,8 @@ int scgpuGatherVisible(ScGpuScene* c, uint32_t root)
     q.rank = c->rank;
     q.nViews = c->nViews;
     q.isRoot = (c->rank == root) ? 1u : 0u;
+    // the error word describes ONE gather: a slow or overflowing frame must not fail every later one
+    SC_CUDA(c, cudaMemsetAsync(c->dPeerState + 1, 0, 4, c->stream));
     k_peer_pack<<<32, kBlock, 0, c->stream>>>(q);
     ++c->launches;
     if (c->rank == root)
@@ -1711,6 +1897,7 @@ static int peerFetchCounts(ScGpuScene* c)
   SC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (err & 2u) return (int)fail(c, "peer gather: a rank did not deliver within the time limit");
   if (err & 4u) return (int)fail(c, "peer gather: a rank's visible lists exceed the mailbox capacity (scgpuCommEnablePeerGather capEntries)");
+  if (err & 8u) return (int)fail(c, "peer gather: a rank could not deliver this frame (the root had not released its mailbox in time)");
   return 1;
 }
 

@@ -1,24 +1,30 @@
 // scgpu_kernels.cuh — sm_100a kernels of the scene-update hot path.
 //
-// HBM layout (one "slot" per Transform, slot order == the reference's Transform-pool dense order, so every
-// output list comes out in the reference's order without a sort):
+// HBM layout. One device SLOT per Transform, given out when the Transform is spawned and kept until it is despawned
+// (scgpu_layout.h): a hierarchy group stays contiguous for as long as it lives, whatever swap-with-last does to the
+// ORDER of the reference's Transform pool. That order (the dense index, "rank") is carried beside the data:
 //   rec0[slot] = { pos.x, pos.y, pos.z, rot.x }            float4 planes: one 128-bit load per thread, a warp
 //   rec1[slot] = { rot.y, rot.z, scale.x, scale.y }        reads 512 contiguous bytes per instruction.
 //   rec2[slot] = { scale.z, aabbMin.x, aabbMin.y, aabbMin.z }   64 B per instance = TRS 36 + AABB 24 + flags 4,
 //   rec3[slot] = { aabbMax.x, aabbMax.y, aabbMax.z, flags }     exactly SURVEY.md §8(d)'s read set.
 //   world0..3[slot] = world matrix columns (float4 planes, coalesced 128-bit stores)
+//   rank[slot] = dense index of the Transform in the reference's pool; perm[rank] = slot   (k_spawn, k_despawn_apply)
 //   parentSlot[slot] = resolved parent slot or kNone (maintained by k_resolve_parents on topology changes)
 //   slotInfo[slot]   = depth + parent lane of the slot inside its hierarchy window, flags, 3-level work schedule;
 //   winList[w]       = start slot of window w (+ flags): hierarchical scenes are cut into windows of <= 32 consecutive
 //                      slots that no parent link crosses; one warp resolves one window (k_build_windows ->
 //                      k_scan_tiles -> k_flatten_windows on topology changes; k_update_win every frame).
-//   flags: bit0 HAS_BOUNDS, bit1 HAS_MESH, bits 8..31 = dirty stamp (id of the update that must recompute
-//          the instance). A stamp instead of a dirty bit means the frame kernel never writes the records.
+//   flags: bit0 HAS_BOUNDS, bit1 HAS_MESH, bit2 LIVE (clear: a hole left by a despawn), bits 8..31 = dirty stamp (id of
+//          the update that must recompute the instance). A stamp instead of a dirty bit means the frame kernel never
+//          writes the records.
+//   visBits[view][rank / 32] = one bit per pool rank: the instance is visible in that view (+ one plane of culling
+//          candidates when the culled lists are wanted). Written by the frame kernels for the ~1 % of instances that
+//          survive the plane tests, read AND cleared by k_compact.
 //
-// Frame = k_update_flat | k_update_win + k_update_win_slow (transform + sphere + V-view plane tests + per-tile
-//         counts, one pass over the instances)
-//         -> k_scan_tiles (exclusive scan of the per-tile counts, V+1 rows)
-//         -> k_scatter_visible (stable per-view compaction of entity handles / slots)
+// Frame = k_update_flat | k_update_win + k_update_win_slow (transform + sphere + V-view plane tests, one pass over the
+//         slots; visible instances set their bit)
+//         -> k_compact (one pass over the bitmaps in rank order = the reference's pool order: per-view lists of entity
+//            handles and slots, totals; leaves bitmaps, counters and the work queue zeroed for the next frame)
 #pragma once
 #include "scgpu_math.cuh"
 
@@ -30,10 +36,12 @@ constexpr uint32_t kMaxViews = 8;
 constexpr uint32_t kBlock = 256;       // threads per CTA
 constexpr uint32_t kSubTiles = 4;      // sub-tiles of kBlock slots per CTA
 constexpr uint32_t kTile = kBlock * kSubTiles;
-constexpr uint32_t kFlagBounds = 1u, kFlagMesh = 2u;
+constexpr uint32_t kFlagBounds = 1u, kFlagMesh = 2u, kFlagLive = 4u;
 constexpr uint32_t kStampShift = 8;
 constexpr uint32_t kUpdateSmemFlat = 3 * 4 * kBlock * 16;  // dynamic shared memory of k_update_flat
-constexpr uint32_t kUpdForceDirty = 1u, kUpdFreeze = 2u, kUpdSkipTransform = 4u;
+constexpr uint32_t kUpdForceDirty = 1u, kUpdFreeze = 2u, kUpdSkipTransform = 4u, kUpdCandBits = 8u;
+// accumulators of one frame (ScGpuScene::acc), all zero between frames (k_compact leaves them so)
+constexpr uint32_t kAccCand = 0, kAccRecomputed = 1, kAccQueueNext = 2, kAccQueueSlow = 3, kAccWords = 4;
 
 struct ViewPlanes
 {
@@ -51,11 +59,11 @@ struct UpdateParams
   float4* w2;
   float4* w3;
   const uint32_t* parentSlot;
-  uint8_t* vismask;
-  uint32_t* tileCounts;  // [(nViews+1)][numTiles]; row nViews = culling candidates
-  uint32_t* recomputed;  // single counter
-  uint32_t count;
-  uint32_t numTiles;
+  const uint32_t* rank;  // slot -> dense index in the reference's pool
+  uint32_t* visBits;     // [nViews (+1 with kUpdCandBits)][bitWords], indexed by rank
+  uint32_t* acc;         // kAcc* counters
+  uint32_t count;        // slots in use (extent): live Transforms + holes
+  uint32_t bitWords;     // words per bitmap plane
   uint32_t stamp;
   uint32_t nViews;
   uint32_t flags;
@@ -139,8 +147,9 @@ __device__ __forceinline__ Mat4 compose_any(const Mat4& pw, const Mat4& l, bool 
 __device__ __forceinline__ bool slot_dirty(const UpdateParams& p, uint32_t s)
 {
   if (p.flags & kUpdSkipTransform) return false;
-  if (p.flags & kUpdForceDirty) return true;
-  return (__float_as_uint(p.rec3[s].w) >> kStampShift) == p.stamp;
+  const uint32_t fl = __float_as_uint(p.rec3[s].w);
+  if (p.flags & kUpdForceDirty) return (fl & kFlagLive) != 0u;
+  return (fl >> kStampShift) == p.stamp;
 }
 
 // ---- ancestor walk for a parent outside the CTA's sub-tile --------------------------------------------
@@ -352,6 +361,53 @@ __device__ __forceinline__ uint32_t sphere_cull_warp(const ViewPlanes& vp, bool 
   return cull_views_warp<kViews>(vp, test, ox, oy, oz, -world_bounds_radius(W, ex, ey, ez), order);
 }
 
+// ---- visible bits -> the per-view bitmaps, indexed by POOL RANK (the reference's order) ------------------------------
+// Called by a whole warp when at least one of its lanes has something to report (~1 % of the warps of an open world).
+// Only those lanes read their rank. When the ranks are the lane numbers plus a common base — the layout of a scene that
+// has seen no churn, and of most groups in one that has — the warp's 32 bits per view are two word-sized ORs by two
+// lanes; otherwise every lane sets its own bits.
+__device__ __forceinline__ void red_global_or(uint32_t* p, uint32_t v)
+{
+  asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int kViews>
+__device__ __forceinline__ void emit_visible_warp(const UpdateParams& p, uint32_t s, uint32_t lane, uint32_t mask, bool cand)
+{
+  const bool wantCand = (p.flags & kUpdCandBits) != 0;
+  const bool need = mask != 0u || (wantCand && cand);
+  const uint32_t needM = __ballot_sync(0xffffffffu, need);
+  if (needM == 0u) return;
+  const uint32_t r = need ? p.rank[s] : 0u;
+  const uint32_t first = __ffs(needM) - 1u;
+  const uint32_t rFirst = __shfl_sync(0xffffffffu, r, first);
+  const uint32_t base = rFirst - first;  // rank lane 0 would have
+  const bool consecutive = __all_sync(0xffffffffu, !need || r == base + lane) && rFirst >= first;
+  if (consecutive)
+  {
+    const uint32_t word = base >> 5, sh = base & 31u;
+#pragma unroll
+    for (int v = 0; v <= kViews; ++v)
+    {
+      if (v == kViews && !wantCand) break;
+      const uint32_t m = __ballot_sync(0xffffffffu, v < kViews ? ((mask >> v) & 1u) != 0u : cand);
+      if (m == 0u) continue;
+      const uint32_t part = lane == 0u ? (m << sh) : (sh ? (m >> (32u - sh)) : 0u);
+      if (lane < 2u && part) red_global_or(p.visBits + (size_t)v * p.bitWords + word + lane, part);
+    }
+  }
+  else if (need)
+  {
+    const uint32_t bit = 1u << (r & 31u);
+    uint32_t* w = p.visBits + (r >> 5);
+#pragma unroll
+    for (int v = 0; v < kViews; ++v)
+      if ((mask >> v) & 1u) red_global_or(w + (size_t)v * p.bitWords, bit);
+    if (wantCand && cand) red_global_or(w + (size_t)kViews * p.bitWords, bit);
+  }
+}
+
+
 // ---- K1+K2, flat scenes: fused transform + cull, all views in one pass ------------------------------------------------
 // No instance has a parent: pure streaming. One thread per slot, kSubTiles sub-tiles of kBlock consecutive slots per
 // CTA; the four record planes of a sub-tile are staged in shared memory by TMA bulk copies two sub-tiles ahead, so the
@@ -361,7 +417,7 @@ template <int kViews>
 __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant__ UpdateParams p,
                                                            const __grid_constant__ ViewPlanes vp)
 {
-  __shared__ uint32_t sCounts[kMaxViews + 2];
+  __shared__ uint32_t sCounts[2];  // candidates, recomputed
   __shared__ __align__(8) uint64_t sFull[2];
   // dynamic shared memory (kUpdateSmemFlat bytes, opted in by the host):
   //   sRec[2][4][kBlock]  TMA staging, double buffered
@@ -372,7 +428,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
 
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
-  if (tid < kMaxViews + 2) sCounts[tid] = 0;
+  if (tid < 2) sCounts[tid] = 0;
   const uint32_t tileBase = blockIdx.x * kTile;
   const uint32_t nSub = min(kSubTiles, (p.count - tileBase + kBlock - 1) / kBlock);
   // the arrays are padded to a multiple of kTile, so a partial last sub-tile is still copied whole
@@ -405,9 +461,6 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
   const bool freeze = (p.flags & kUpdFreeze) != 0;
   uint32_t nRecomputed = 0, nCand = 0;
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
-  uint32_t nVis[kViews];
-#pragma unroll
-  for (int v = 0; v < kViews; ++v) nVis[v] = 0;
 
 #pragma unroll 1
   for (uint32_t sub = 0; sub < nSub; ++sub)
@@ -433,7 +486,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
     if (tid == 0 && sub + 2 < nSub) stage(sub + 2);
 
     const uint32_t fl = __float_as_uint(r3.w);
-    const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+    // (a hole left by a despawn has flags == 0: stamp 0 is never the current one, and it owns no LIVE bit)
+    const bool ownDirty = live && !skip && ((force && (fl & kFlagLive)) || ((fl >> kStampShift) == p.stamp));
     const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x);
     float sx, cx, sy, cy, sz, cz;
     sincos3_warp(ownDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
@@ -463,31 +517,19 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
       mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
     }
     if (cand && !test) mask = allMask;  // frozen culling or no Bounds component: always visible
-    if (live) p.vismask[s] = (uint8_t)mask;
-    if (__any_sync(0xffffffffu, mask != 0u))
-    {
-#pragma unroll
-      for (int v = 0; v < kViews; ++v) nVis[v] += (mask >> v) & 1u;
-    }
+    emit_visible_warp<kViews>(p, s, lane, mask, cand);
     nCand += cand ? 1u : 0u;
   }
 
-  // per-tile counts: one warp reduction (REDUX) per counter, one shared atomic per warp
-#pragma unroll
-  for (int v = 0; v < kViews; ++v)
-  {
-    const uint32_t r = __reduce_add_sync(0xffffffffu, nVis[v]);
-    if (lane == 0 && r) atomicAdd(&sCounts[v], r);
-  }
+  // frame totals: one warp reduction (REDUX) per counter, one shared atomic per warp, one global atomic per CTA
   {
     const uint32_t r = __reduce_add_sync(0xffffffffu, nCand);
-    if (lane == 0 && r) atomicAdd(&sCounts[kViews], r);
+    if (lane == 0 && r) atomicAdd(&sCounts[0], r);
     const uint32_t q = __reduce_add_sync(0xffffffffu, nRecomputed);
-    if (lane == 0 && q) atomicAdd(&sCounts[kMaxViews + 1], q);
+    if (lane == 0 && q) atomicAdd(&sCounts[1], q);
   }
   __syncthreads();
-  if (tid <= (uint32_t)kViews) p.tileCounts[tid * p.numTiles + blockIdx.x] = sCounts[tid];
-  if (tid == 0 && sCounts[kMaxViews + 1]) atomicAdd(p.recomputed, sCounts[kMaxViews + 1]);
+  if (tid < 2 && sCounts[tid]) atomicAdd(p.acc + (tid == 0 ? kAccCand : kAccRecomputed), sCounts[tid]);
 }
 
 // ---- hierarchy windows ------------------------------------------------------------------------------------------
@@ -728,7 +770,7 @@ __device__ __noinline__ uint32_t window_slow(const UpdateParams& p, uint32_t a, 
   r0 = r1 = r2 = r3 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (live) { r0 = p.rec0[s]; r1 = p.rec1[s]; r2 = p.rec2[s]; r3 = p.rec3[s]; }
   const uint32_t fl = __float_as_uint(r3.w);
-  const bool ownDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+  const bool ownDirty = live && !skip && ((force && (fl & kFlagLive)) || ((fl >> kStampShift) == p.stamp));
   const uint32_t wl = info & kInfoDepthMask;
   const bool external = (info & kInfoExternal) != 0;
   bool dead = !live || (info & kInfoUnreachable);  // never visited by the DFS: world matrix stays as stored
@@ -887,11 +929,11 @@ constexpr uint32_t kWwSched = kWwMat + 4 * 512 + 64;    // [32] u16: children of
 constexpr uint32_t kWwList = kWwSched + 64;             // 2 x [kWinChunk+1] u32 (64 B each): window starts of the current
                                                         // and of the next claimed chunk
 constexpr uint32_t kWwSize = kWwList + 128;             // per-warp block
-constexpr uint32_t kWsRecomputed = kWinWarps * kWwSize; // u32: world matrices rewritten by this CTA
+constexpr uint32_t kWsRecomputed = kWinWarps * kWwSize; // u32: world matrices rewritten by this CTA; +4: its candidates
 constexpr uint32_t kUpdateSmemWin = kWsRecomputed + 16;
-// device-side work queue of k_update_win: totals[kQueueNext] = next unclaimed window, totals[kQueueSlow] = number of
-// windows handed to k_update_win_slow (both zeroed with the totals before every launch)
-constexpr uint32_t kQueueNext = kMaxViews + 2, kQueueSlow = kMaxViews + 3, kTotalsWords = kMaxViews + 4;
+// device-side work queue of k_update_win: acc[kAccQueueNext] = next unclaimed chunk, acc[kAccQueueSlow] = number of
+// windows handed to k_update_win_slow (k_compact leaves both zeroed for the next frame)
+constexpr uint32_t kTotalsWords = kMaxViews + 2;  // frame totals: [0..nViews) visible, [nViews] candidates, [kMaxViews+1] recomputed
 
 // Programmatic dependent launch (the chain k_update_win -> k_update_win_slow -> k_scan_tiles -> k_scatter_visible of
 // one frame): pdl_trigger() lets the NEXT kernel of the stream be scheduled while this one still runs, pdl_wait() at
@@ -932,11 +974,12 @@ __device__ __forceinline__ uint32_t queue_claim_result(uint32_t old)
   return __shfl_sync(0xffffffffu, old, leader);
 }
 
-// store + bounding sphere + plane tests + per-tile counts of one resolved window (records in shared memory at recAddr)
+// store + bounding sphere + plane tests of one resolved window (records in shared memory at recAddr); visible lanes set
+// their bits in the rank-indexed bitmaps, candidates are counted warp-uniformly and flushed once per warp
 template <int kViews>
 __device__ __forceinline__ void finish_window(const UpdateParams& p, const ViewPlanes& vp, uint32_t a, uint32_t lane, uint32_t recAddr,
                                               bool live, bool nodeDirty, const Mat4& W, uint32_t& order, uint32_t& nRecomputed,
-                                              uint32_t& accTile, uint32_t& accCand)
+                                              uint32_t& accCand)
 {
   constexpr uint32_t allMask = (1u << kViews) - 1u;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
@@ -955,55 +998,8 @@ __device__ __forceinline__ void finish_window(const UpdateParams& p, const ViewP
     mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
   }
   if (cand && !test) mask = allMask;
-  if (live) p.vismask[a + lane] = (uint8_t)mask;
-  // per-tile counts (zeroed by the host before the launch). Candidates: consecutive windows of a warp mostly lie in
-  // the same tile, so their count is accumulated warp-uniformly (accTile / accCand) and written with one global
-  // reduction when the tile changes; a window that straddles a tile boundary is written at once, per part. Visible
-  // counts (rare in an open world) go out per window.
-  const uint32_t candM = __ballot_sync(0xffffffffu, cand);
-  if (candM)
-  {
-    const uint32_t tile = a / kTile;
-    const uint32_t room = (tile + 1u) * kTile - a;  // slots left in the window's first tile
-    uint32_t lowMask = 0xffffffffu;
-    if (room >= 32u)
-    {
-      if (tile != accTile)
-      {
-        if (accCand) red_global_add(p.tileCounts + (size_t)kViews * p.numTiles + accTile, accCand);
-        accTile = tile;
-        accCand = 0u;
-      }
-      accCand += __popc(candM);
-    }
-    else
-    {
-      lowMask = (1u << room) - 1u;
-      uint32_t* cc = p.tileCounts + (size_t)kViews * p.numTiles + tile;
-      if (candM & lowMask) red_global_add(cc, __popc(candM & lowMask));
-      if (candM & ~lowMask) red_global_add(cc + 1, __popc(candM & ~lowMask));
-    }
-    if (__any_sync(0xffffffffu, mask != 0u))
-    {
-      uint32_t* cnt = p.tileCounts + tile;
-#pragma unroll
-      for (int v = 0; v < kViews; ++v)
-      {
-        const uint32_t m = __ballot_sync(0xffffffffu, (mask >> v) & 1u);
-        if (m)
-        {
-          if (m & lowMask) red_global_add(cnt + (size_t)v * p.numTiles, __popc(m & lowMask));
-          if (m & ~lowMask) red_global_add(cnt + (size_t)v * p.numTiles + 1, __popc(m & ~lowMask));
-        }
-      }
-    }
-  }
-}
-
-// the candidates accumulated by finish_window and not yet written
-__device__ __forceinline__ void flush_window_counts(const UpdateParams& p, uint32_t kViews, uint32_t accTile, uint32_t accCand)
-{
-  if (accCand) red_global_add(p.tileCounts + (size_t)kViews * p.numTiles + accTile, accCand);
+  accCand += __popc(__ballot_sync(0xffffffffu, cand));
+  emit_visible_warp<kViews>(p, a + lane, lane, mask, cand);
 }
 
 }  // namespace scgpu
@@ -1024,7 +1020,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
                                                           const uint32_t* __restrict__ slotInfo,
                                                           const uint32_t* __restrict__ winList,
                                                           const uint32_t* __restrict__ totalWindows,
-                                                          uint32_t* __restrict__ queue,  // &totals[kQueueNext], [1] = slow count
+                                                          uint32_t* __restrict__ queue,  // &acc[kAccQueueNext], [1] = slow count
                                                           uint32_t* __restrict__ slowList)
 {
   uint32_t sBase;
@@ -1036,7 +1032,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   uint32_t lane, warp;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
   asm volatile("shr.u32 %0, %1, 5;" : "=r"(warp) : "r"(tid));
-  if (tid == 0) *reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed) = 0u;  // (also keeps the symbol referenced)
+  if (tid < 2) reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed)[tid] = 0u;  // (also keeps the symbol referenced)
   __syncthreads();
   pdl_trigger();
   const uint32_t total = *totalWindows;
@@ -1044,7 +1040,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
-  uint32_t nRecomputed = 0, accTile = 0, accCand = 0;
+  uint32_t nRecomputed = 0, accCand = 0;
   const uint32_t warpBase = sBase + warp * kWwSize;
   const uint32_t laneBase = warpBase + lane * 16;  // this lane's float4 of plane 0, buffer 0
 
@@ -1119,7 +1115,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         r0 = lds128(recAddr); r1 = lds128(recAddr + 512); sclZ = __uint_as_float(lds32(recAddr + 1024));
         fl = lds32(recAddr + 1536 + 12);
       }
-      nodeDirty = live && !skip && (force || ((fl >> kStampShift) == p.stamp));
+      nodeDirty = live && !skip && ((force && (fl & kFlagLive)) || ((fl >> kStampShift) == p.stamp));
       parentLane = (info >> kInfoParentShift) & 31u;
       // ---- 1. children inherit dirtiness level by level ----
       liveMask = __ballot_sync(0xffffffffu, live);
@@ -1262,7 +1258,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
       }
     }
-    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed, accTile, accCand);
+    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed, accCand);
     else
     {
       // redone by k_update_win_slow (generic path), which also culls and counts it
@@ -1273,13 +1269,13 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     listAddr = nextList;
     bufOff ^= kWsBuf;
   }
-  flush_window_counts(p, kViews, accTile, accCand);
   if (nRecomputed) warp_reds_add(sBase + kWsRecomputed, nRecomputed);
+  if (accCand) warp_reds_add(sBase + kWsRecomputed + 4, accCand);
   __syncthreads();
-  if (tid == 0)
+  if (tid < 2)
   {
-    const uint32_t r = lds32(sBase + kWsRecomputed);
-    if (r) atomicAdd(p.recomputed, r);
+    const uint32_t r = lds32(sBase + kWsRecomputed + 4 * tid);
+    if (r) atomicAdd(p.acc + (tid == 0 ? kAccRecomputed : kAccCand), r);
   }
 }
 
@@ -1296,13 +1292,13 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
   asm("mov.u32 %0, scgpu_win_smem;" : "=r"(sBase));
   asm volatile("" ::"l"(scgpu_win_smem));  // keeps the array emitted: every other access goes through sBase
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  if (tid == 0) *reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed) = 0u;  // (also keeps the symbol referenced)
+  if (tid < 2) reinterpret_cast<uint32_t*>(scgpu_win_smem + kWsRecomputed)[tid] = 0u;  // (also keeps the symbol referenced)
   __syncthreads();
   pdl_trigger();
   pdl_wait();  // the list and its length are written by k_update_win
   const uint32_t nSlow = *slowCount;
   const uint32_t laneBase = sBase + warp * kWwSize + lane * 16;
-  uint32_t order = 0, nRecomputed = 0, accTile = 0, accCand = 0;
+  uint32_t order = 0, nRecomputed = 0, accCand = 0;
 #pragma unroll 1
   for (uint32_t k = blockIdx.x * kWinWarps + warp; k < nSlow; k += gridDim.x * kWinWarps)
   {
@@ -1318,15 +1314,15 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
     const uint32_t info = live ? slotInfo[a + lane] : 0u;
     float4 wb[4];
     const bool nodeDirty = window_slow(p, a, len, info, wb) != 0u;
-    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, nRecomputed, accTile, accCand);
+    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, nRecomputed, accCand);
   }
-  flush_window_counts(p, kViews, accTile, accCand);
   if (nRecomputed) warp_reds_add(sBase + kWsRecomputed, nRecomputed);
+  if (accCand) warp_reds_add(sBase + kWsRecomputed + 4, accCand);
   __syncthreads();
-  if (tid == 0)
+  if (tid < 2)
   {
-    const uint32_t r = lds32(sBase + kWsRecomputed);
-    if (r) atomicAdd(p.recomputed, r);
+    const uint32_t r = lds32(sBase + kWsRecomputed + 4 * tid);
+    if (r) atomicAdd(p.acc + (tid == 0 ? kAccRecomputed : kAccCand), r);
   }
 }
 
@@ -1448,23 +1444,58 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict_
   if (tid == 0) totals[row] = sCarry;
 }
 
-// ---- K3b: stable compaction of the visible sets (CullingState::visible, .cpp:1273-1280) --------------------
-// One CTA per tile, thread t owns slots base+4t..base+4t+3 (their 4 mask bytes are one 32-bit load). Up to five
-// views share one 64-bit block scan (12 bits per view, a tile holds at most 1024 instances).
-struct ScatterParams
+// ---- K3: compaction of the visible sets in POOL ORDER (CullingState::visible / ::culled, .cpp:1273-1280) ----------
+// The frame kernels left one bit per (view, pool rank). One pass over those bitmaps in rank order yields the
+// reference's lists whatever the device layout is: rank -> perm[rank] = slot -> entity[slot]. A single launch of at
+// most one CTA per SM; CTA k owns the k-th contiguous segment of every plane:
+//   1. popcount of its segment per row (row = view, + one culled row per view when the candidate plane is present),
+//   2. publishes the counts (store, fence, flag = this launch's sequence number) and adds up the counts of the
+//      segments before it — a chained wait that cannot deadlock: segment numbers are tickets taken at run time, so
+//      every segment a CTA waits for belongs to a CTA that is already running,
+//   3. second pass over the segment (L1/L2 resident): block scan of the per-thread counts, entity handles and slots
+//      written at prefix + rank-ordered position,
+//   4. clears the words it found set, so the next frame starts from clean bitmaps without a memset; the CTA of the
+//      last segment also writes the frame totals and zeroes the accumulators and the work queue of k_update_win.
+// Replaces round 1's per-tile counts + k_scan_tiles + k_scatter_visible + k_scatter_culled + two memsets.
+constexpr uint32_t kCompactThreads = 1024;
+constexpr uint32_t kCompactRows = 2 * kMaxViews;
+constexpr uint32_t kPubStride = 32;                    // words per segment in the publication area: counts[16], flag at [16]
+constexpr uint32_t kPubFlag = kCompactRows;
+constexpr uint32_t kCompactChunkWords = kCompactThreads * 4;  // one uint4 per thread and row per chunk
+
+struct CompactParams
 {
-  const uint8_t* vismask;
-  const uint32_t* entity;
-  const uint32_t* tileCounts;
-  const uint32_t* tileOffsets;
+  uint32_t* bits;                        // [nViews (+1)][bitWords]
+  const uint32_t* perm;                  // rank -> slot
+  const uint32_t* entity;                // slot -> handle
   uint32_t* outEntity[kMaxViews];
   uint32_t* outSlot[kMaxViews];
-  uint32_t count;
-  uint32_t numTiles;
-  uint32_t nViews;
+  uint32_t* culledEntity[kMaxViews];     // valid when culled != 0
+  uint32_t* acc;                         // kAcc*
+  uint32_t* totals;                      // out, kTotalsWords
+  uint32_t* pub;                         // [gridDim.x][kPubStride]
+  uint32_t* ticket;                      // running CTA ticket (never reset; ticketBase = its value before this launch)
+  uint32_t ticketBase, seq;
+  uint32_t bitWords, segWords;           // words per plane / per segment (a multiple of 4)
+  uint32_t nWords;                       // words that can hold a set bit: ceil(live count / 32), rounded up to 4
+  uint32_t nViews, culled;
 };
 
-__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* sWarp, uint32_t tid)
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t popc4(uint4 w) { return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w); }
+__device__ __forceinline__ uint4 andn4(uint4 a, uint4 b) { return make_uint4(a.x & ~b.x, a.y & ~b.y, a.z & ~b.z, a.w & ~b.w); }
+
+// exclusive scan of one 64-bit value per thread over the CTA (1024 threads); *total = sum over the CTA
+__device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* sWarp, uint32_t tid, uint64_t* total)
 {
   const uint32_t lane = tid & 31u, warp = tid >> 5;
   uint64_t x = v;
@@ -1478,130 +1509,169 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_
   __syncthreads();
   if (warp == 0)
   {
-    uint64_t w = lane < (kBlock / 32) ? sWarp[lane] : 0ull;
+    uint64_t w = sWarp[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
       const uint64_t y = __shfl_up_sync(0xffffffffu, w, o);
       if ((int)lane >= o) w += y;
     }
-    if (lane < (kBlock / 32)) sWarp[lane] = w;
+    sWarp[lane] = w;  // inclusive over warps
   }
   __syncthreads();
   const uint64_t r = (warp ? sWarp[warp - 1] : 0ull) + x - v;
-  __syncthreads();  // sWarp is reused by the caller's next scan
+  *total = sWarp[31];
+  __syncthreads();  // sWarp is reused by the next scan
   return r;
 }
 
-__global__ void __launch_bounds__(kBlock) k_scatter_visible(const __grid_constant__ ScatterParams p)
+__global__ void __launch_bounds__(kCompactThreads, 1) k_compact(const __grid_constant__ CompactParams p)
 {
-  __shared__ uint32_t sCnt[kMaxViews];
-  __shared__ uint64_t sWarp[kBlock / 32];
-  const uint32_t tid = threadIdx.x;
-  pdl_wait();
-  // grid-stride over the tiles: most tiles of an open world are fully culled, and 16 Ki CTAs that only read their
-  // counts and exit cost more in launch overhead than the compaction itself
-#pragma unroll 1
-  for (uint32_t tile = blockIdx.x; tile < p.numTiles; tile += gridDim.x)
-  {
-  __syncthreads();  // sCnt of the previous tile is no longer read
-  if (tid < kMaxViews) sCnt[tid] = tid < p.nViews ? p.tileCounts[tid * p.numTiles + tile] : 0u;
+  __shared__ uint32_t sSeg;
+  __shared__ uint32_t sCount[kCompactRows];   // set bits of this segment per row
+  __shared__ uint32_t sBase[kCompactRows];    // output position of this segment's (then: this chunk's) first entry per row
+  __shared__ uint64_t sWarp[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  pdl_wait();  // the frame kernels' bits and counters are complete and visible
+  if (tid == 0) sSeg = atomicAdd(p.ticket, 1u) - p.ticketBase;
+  if (tid < kCompactRows) { sCount[tid] = 0u; sBase[tid] = 0u; }
   __syncthreads();
-  uint32_t anyVis = 0;
-#pragma unroll
-  for (uint32_t v = 0; v < kMaxViews; ++v) anyVis |= sCnt[v];
-  if (!anyVis) continue;  // block-uniform
+  const uint32_t seg = sSeg;
+  const uint32_t nRows = p.culled ? 2u * p.nViews : p.nViews;
+  const uint32_t w0 = min(p.nWords, seg * p.segWords), w1 = min(p.nWords, w0 + p.segWords);
+  const uint4* const candPlane = reinterpret_cast<const uint4*>(p.bits + (size_t)p.nViews * p.bitWords);
 
-  const uint32_t slot0 = tile * kTile + tid * 4u;
-  uint32_t m4 = 0;
-  if (slot0 < p.count) m4 = reinterpret_cast<const uint32_t*>(p.vismask)[slot0 >> 2];
-  // mask bytes of slots >= count are never written: drop them
-  if (slot0 + 3u >= p.count)
+  // ---- 1. counts of this segment
   {
+    uint32_t cnt[kCompactRows];
 #pragma unroll
-    for (uint32_t k = 0; k < 4; ++k)
-      if (slot0 + k >= p.count) m4 &= ~(0xFFu << (8u * k));
-  }
-
-  for (uint32_t v0 = 0; v0 < p.nViews; v0 += 5)
-  {
-    const uint32_t vEnd = min(p.nViews, v0 + 5u);
-    uint64_t packed = 0;
-    for (uint32_t v = v0; v < vEnd; ++v)
+    for (uint32_t r = 0; r < kCompactRows; ++r) cnt[r] = 0u;
+    for (uint32_t w = w0 + tid * 4u; w < w1; w += kCompactChunkWords)
     {
-      const uint32_t bits = (m4 >> v) & 0x01010101u;
-      const uint32_t c = __popc(bits);
-      packed |= (uint64_t)c << (12u * (v - v0));
-    }
-    const uint64_t excl = block_exclusive_scan_u64(packed, sWarp, tid);
-    for (uint32_t v = v0; v < vEnd; ++v)
-    {
-      if (sCnt[v] == 0) continue;
-      const uint32_t bits = (m4 >> v) & 0x01010101u;
-      if (!bits) continue;
-      uint32_t dst = p.tileOffsets[v * p.numTiles + tile] + (uint32_t)((excl >> (12u * (v - v0))) & 0xFFFu);
+      uint4 cand = make_uint4(0u, 0u, 0u, 0u);
+      if (p.culled) cand = candPlane[w >> 2];
 #pragma unroll
-      for (uint32_t k = 0; k < 4; ++k)
+      for (uint32_t v = 0; v < kMaxViews; ++v)
       {
-        if (bits & (1u << (8u * k)))
+        if (v < p.nViews)
         {
-          const uint32_t s = slot0 + k;
-          p.outSlot[v][dst] = s;
-          p.outEntity[v][dst] = p.entity[s];
-          ++dst;
+          const uint4 vis = reinterpret_cast<const uint4*>(p.bits + (size_t)v * p.bitWords)[w >> 2];
+          cnt[v] += popc4(vis);
+          if (p.culled) cnt[kMaxViews + v] += popc4(andn4(cand, vis));
         }
       }
     }
-  }
-  }
-}
-
-// culled lists (CullingState::culled): candidates whose view bit is clear. Offsets follow from the candidate and
-// visible offsets, so no second scan is needed.
-struct CulledParams
-{
-  const uint8_t* vismask;
-  const float4* rec3;
-  const uint32_t* entity;
-  const uint32_t* tileOffsets;  // rows 0..nViews-1 visible, row nViews candidates
-  uint32_t* outEntity[kMaxViews];
-  uint32_t count;
-  uint32_t numTiles;
-  uint32_t nViews;
-};
-
-__global__ void __launch_bounds__(kBlock) k_scatter_culled(const __grid_constant__ CulledParams p)
-{
-  __shared__ uint64_t sWarp[kBlock / 32];
-  const uint32_t tile = blockIdx.x, tid = threadIdx.x;
-  const uint32_t slot0 = tile * kTile + tid * 4u;
-  uint32_t m4 = 0, cand4 = 0;
-  if (slot0 < p.count)
-  {
-    m4 = reinterpret_cast<const uint32_t*>(p.vismask)[slot0 >> 2];
 #pragma unroll
-    for (uint32_t k = 0; k < 4; ++k)
-      if (slot0 + k < p.count && (__float_as_uint(p.rec3[slot0 + k].w) & kFlagMesh)) cand4 |= 1u << (8u * k);
-  }
-  for (uint32_t v0 = 0; v0 < p.nViews; v0 += 5)
-  {
-    const uint32_t vEnd = min(p.nViews, v0 + 5u);
-    uint64_t packed = 0;
-    for (uint32_t v = v0; v < vEnd; ++v)
+    for (uint32_t r = 0; r < kCompactRows; ++r)
     {
-      const uint32_t bits = cand4 & ~((m4 >> v) & 0x01010101u);
-      packed |= (uint64_t)__popc(bits) << (12u * (v - v0));
+      const uint32_t c = __reduce_add_sync(0xffffffffu, cnt[r]);
+      // rows are stored densely: visible rows 0..nViews-1, culled rows nViews..2 nViews-1
+      const uint32_t row = r < kMaxViews ? r : p.nViews + (r - kMaxViews);
+      if (lane == 0 && c) atomicAdd(&sCount[row], c);
     }
-    const uint64_t excl = block_exclusive_scan_u64(packed, sWarp, tid);
-    for (uint32_t v = v0; v < vEnd; ++v)
+  }
+  __syncthreads();
+
+  // ---- 2. publish, then add up the segments before this one
+  uint32_t* const myPub = p.pub + (size_t)seg * kPubStride;
+  if (tid < nRows) myPub[tid] = sCount[tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) st_release_gpu(myPub + kPubFlag, p.seq);
+  for (uint32_t t = tid; t < seg; t += kCompactThreads)
+  {
+    const uint32_t* q = p.pub + (size_t)t * kPubStride;
+    while (ld_acquire_gpu(q + kPubFlag) != p.seq) __nanosleep(40);
+    for (uint32_t r = 0; r < nRows; ++r)
     {
-      const uint32_t bits = cand4 & ~((m4 >> v) & 0x01010101u);
-      if (!bits) continue;
-      uint32_t dst = p.tileOffsets[p.nViews * p.numTiles + tile] - p.tileOffsets[v * p.numTiles + tile] +
-                     (uint32_t)((excl >> (12u * (v - v0))) & 0xFFFu);
+      const uint32_t c = q[r];
+      if (c) atomicAdd(&sBase[r], c);
+    }
+  }
+  __syncthreads();
+  if (seg == gridDim.x - 1u)
+  {
+    // frame totals; accumulators and the window queue are left zeroed for the next frame
+    if (tid < p.nViews) p.totals[tid] = sBase[tid] + sCount[tid];
+    if (tid == 32) { p.totals[p.nViews] = p.acc[kAccCand]; p.acc[kAccCand] = 0u; }
+    if (tid == 33) { p.totals[kMaxViews + 1] = p.acc[kAccRecomputed]; p.acc[kAccRecomputed] = 0u; }
+    if (tid == 34) { p.acc[kAccQueueNext] = 0u; p.acc[kAccQueueSlow] = 0u; }
+  }
+
+  // ---- 3 + 4. lists, then clean bitmaps
+  for (uint32_t c0 = w0; c0 < w1; c0 += kCompactChunkWords)
+  {
+    const uint32_t w = c0 + tid * 4u;
+    const bool mine = w < w1;
+    uint4 cand = make_uint4(0u, 0u, 0u, 0u);
+    if (p.culled && mine) cand = candPlane[w >> 2];
+    // three rows share one 64-bit block scan (21-bit fields: a chunk holds 2^17 ranks)
+    for (uint32_t r0 = 0; r0 < nRows; r0 += 3u)
+    {
+      const uint32_t rEnd = min(nRows, r0 + 3u);
+      uint32_t any = 0;
+      for (uint32_t r = r0; r < rEnd; ++r) any |= sCount[r];
+      if (!any) continue;  // block-uniform: nothing set in this segment for these rows
+      uint4 bitsOf[3];
+      uint64_t packed = 0;
 #pragma unroll
-      for (uint32_t k = 0; k < 4; ++k)
-        if (bits & (1u << (8u * k))) p.outEntity[v][dst++] = p.entity[slot0 + k];
+      for (uint32_t j = 0; j < 3u; ++j)
+      {
+        const uint32_t r = r0 + j;
+        uint4 b = make_uint4(0u, 0u, 0u, 0u);
+        if (mine && r < rEnd)
+        {
+          const uint32_t v = r < p.nViews ? r : r - p.nViews;
+          b = reinterpret_cast<const uint4*>(p.bits + (size_t)v * p.bitWords)[w >> 2];
+          if (r >= p.nViews) b = andn4(cand, b);
+        }
+        bitsOf[j] = b;
+        packed |= (uint64_t)popc4(b) << (21u * j);
+      }
+      uint64_t total;
+      const uint64_t excl = block_exclusive_scan_u64(packed, sWarp, tid, &total);
+#pragma unroll
+      for (uint32_t j = 0; j < 3u; ++j)
+      {
+        const uint32_t r = r0 + j;
+        const uint4 b = bitsOf[j];
+        if ((b.x | b.y | b.z | b.w) != 0u)  // implies r < rEnd
+        {
+          uint32_t pos = sBase[r] + (uint32_t)((excl >> (21u * j)) & 0x1FFFFFu);
+          const bool vis = r < p.nViews;
+          uint32_t* outE = vis ? p.outEntity[r] : p.culledEntity[r - p.nViews];
+          uint32_t* outS = vis ? p.outSlot[r] : nullptr;
+          const uint32_t word[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+          for (uint32_t k = 0; k < 4u; ++k)
+          {
+            uint32_t m = word[k];
+            while (m)
+            {
+              const uint32_t rank = (w + k) * 32u + (__ffs(m) - 1u);
+              m &= m - 1u;
+              const uint32_t slot = p.perm[rank];
+              outE[pos] = p.entity[slot];
+              if (outS) outS[pos] = slot;
+              ++pos;
+            }
+          }
+        }
+      }
+      __syncthreads();  // every thread has read sBase of these rows
+      if (tid < rEnd - r0) sBase[r0 + tid] += (uint32_t)((total >> (21u * tid)) & 0x1FFFFFu);
+    }
+    __syncthreads();
+    // clear what was set (all planes of this chunk); untouched words are not written
+    if (mine)
+    {
+      const uint32_t nPlanes = p.nViews + (p.culled ? 1u : 0u);
+      for (uint32_t v = 0; v < nPlanes; ++v)
+      {
+        uint4* q = reinterpret_cast<uint4*>(p.bits + (size_t)v * p.bitWords) + (w >> 2);
+        const uint4 b = *q;
+        if ((b.x | b.y | b.z | b.w) != 0u) *q = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   }
 }
@@ -1643,20 +1713,30 @@ struct SceneArrays
   uint32_t* parentSlot;  // resolved slot or kNone
   uint32_t* entity;      // slot -> handle
   uint2* meshMat;
-  uint32_t* sparse;      // Entity::index() -> slot+1 (ComponentPool sparse array, sc_ecs.h:199-277)
+  uint32_t* sparse;      // Entity::index() -> slot+1 (ComponentPool sparse array, sc_ecs.h:199-277; here: DEVICE slot)
   uint32_t sparseSize;
+  uint32_t* rank;        // slot -> dense index in the reference's Transform pool (ComponentPool::m_denseEntities)
+  uint32_t* perm;        // dense index -> slot
 };
 
+// slot of the j-th element of a spawn batch: a run of fresh slots, or wherever the host's layout put it (scgpu_layout.h)
+__device__ __forceinline__ uint32_t spawn_slot(uint32_t slot0, const uint32_t* __restrict__ slotOf, uint32_t j)
+{
+  return slotOf ? slotOf[j] : slot0 + j;
+}
+
 // World::add<Transform> + setLocal (+Bounds/RenderMesh) for n new slots [slot0, slot0+n)
-__global__ void __launch_bounds__(kBlock) k_spawn(SceneArrays a, uint32_t slot0, uint32_t n,
-                                                  const uint32_t* __restrict__ entity, const uint32_t* __restrict__ parent,
+__global__ void __launch_bounds__(kBlock) k_spawn(SceneArrays a, uint32_t slot0, const uint32_t* __restrict__ slotOf, uint32_t rank0,
+                                                  uint32_t n, const uint32_t* __restrict__ entity, const uint32_t* __restrict__ parent,
                                                   const float* __restrict__ trs9, const float* __restrict__ aabb6,
                                                   const uint32_t* __restrict__ meshMat2, const uint32_t* __restrict__ flags,
                                                   uint32_t stamp)
 {
   const uint32_t j = blockIdx.x * kBlock + threadIdx.x;
   if (j >= n) return;
-  const uint32_t s = slot0 + j;
+  const uint32_t s = spawn_slot(slot0, slotOf, j);
+  a.rank[s] = rank0 + j;
+  a.perm[rank0 + j] = s;
   const float* t = trs9 + (size_t)j * 9;
   float sx = t[6], sy = t[7], sz = t[8];
   // TransformSystem's zero-scale patch (sc_ecs.cpp:143-149); the instance is dirty anyway
@@ -1667,7 +1747,7 @@ __global__ void __launch_bounds__(kBlock) k_spawn(SceneArrays a, uint32_t slot0,
     const float* b = aabb6 + (size_t)j * 6;
     bmin[0] = b[0]; bmin[1] = b[1]; bmin[2] = b[2]; bmax[0] = b[3]; bmax[1] = b[4]; bmax[2] = b[5];
   }
-  const uint32_t f = (flags ? (flags[j] & 0xFFu) : (kFlagBounds | kFlagMesh)) | (stamp << kStampShift);
+  const uint32_t f = (flags ? (flags[j] & (kFlagBounds | kFlagMesh)) : (kFlagBounds | kFlagMesh)) | kFlagLive | (stamp << kStampShift);
   a.rec[0][s] = make_float4(t[0], t[1], t[2], t[3]);
   a.rec[1][s] = make_float4(t[4], t[5], sx, sy);
   a.rec[2][s] = make_float4(sz, bmin[0], bmin[1], bmin[2]);
@@ -1722,7 +1802,8 @@ __device__ __forceinline__ float sg_rand01(uint32_t& state)
 __device__ __forceinline__ float sg_lerp(float a, float b, float t) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t)); }
 
 // one CTA per sector, one thread per SpawnRecord (ground plane first, then the props in generation order)
-__global__ void __launch_bounds__(64) k_spawn_sectors(SceneArrays a, SectorGen g, uint32_t slot0, const int32_t* __restrict__ coordXZ,
+__global__ void __launch_bounds__(64) k_spawn_sectors(SceneArrays a, SectorGen g, uint32_t slot0, const uint32_t* __restrict__ slotOf,
+                                                      uint32_t rank0, const int32_t* __restrict__ coordXZ,
                                                       const uint32_t* __restrict__ first, const uint32_t* __restrict__ entity,
                                                       uint32_t stamp)
 {
@@ -1758,8 +1839,10 @@ __global__ void __launch_bounds__(64) k_spawn_sectors(SceneArrays a, SectorGen g
       mat = (m < 0.40f) ? g.matChecker : ((m < 0.80f) ? g.matTest : g.matUnlit);
       mesh = (sg_rand01(rng) < 0.90f) ? g.meshCube : g.meshTriangle;
     }
-    const uint32_t s = slot0 + base + i;
-    const uint32_t f = (kFlagBounds | kFlagMesh) | (stamp << kStampShift);
+    const uint32_t s = spawn_slot(slot0, slotOf, base + i);
+    a.rank[s] = rank0 + base + i;
+    a.perm[rank0 + base + i] = s;
+    const uint32_t f = (kFlagBounds | kFlagMesh | kFlagLive) | (stamp << kStampShift);
     a.rec[0][s] = make_float4(px, py, pz, 0.0f);
     a.rec[1][s] = make_float4(ry, 0.0f, sx, sy);
     a.rec[2][s] = make_float4(sz, -0.5f, -0.5f, -0.5f);
@@ -1797,7 +1880,8 @@ __device__ __forceinline__ uint32_t resolve_asset(const AssetBinding* __restrict
   return dflt;
 }
 
-__global__ void __launch_bounds__(kBlock) k_spawn_sector_file(SceneArrays a, uint32_t slot0, uint32_t n, const uint32_t* __restrict__ payload,
+__global__ void __launch_bounds__(kBlock) k_spawn_sector_file(SceneArrays a, uint32_t slot0, const uint32_t* __restrict__ slotOf, uint32_t rank0,
+                                                              uint32_t n, const uint32_t* __restrict__ payload,
                                                               uint32_t recordWords, uint32_t meshWord, const uint32_t* __restrict__ entity,
                                                               const AssetBinding* __restrict__ meshes, uint32_t nMeshes, uint32_t defaultMesh,
                                                               const AssetBinding* __restrict__ materials, uint32_t nMaterials,
@@ -1813,8 +1897,10 @@ __global__ void __launch_bounds__(kBlock) k_spawn_sector_file(SceneArrays a, uin
   for (int k = 0; k < 9; ++k) t[k] = __uint_as_float(r[4 + k]);
   float sx = t[6], sy = t[7], sz = t[8];
   if (sx == 0.0f && sy == 0.0f && sz == 0.0f) { sx = sy = sz = 1.0f; }  // TransformSystem's zero-scale patch, as k_spawn
-  const uint32_t s = slot0 + j;
-  const uint32_t f = (kFlagBounds | kFlagMesh) | (stamp << kStampShift);
+  const uint32_t s = spawn_slot(slot0, slotOf, j);
+  a.rank[s] = rank0 + j;
+  a.perm[rank0 + j] = s;
+  const uint32_t f = (kFlagBounds | kFlagMesh | kFlagLive) | (stamp << kStampShift);
   a.rec[0][s] = make_float4(t[0], t[1], t[2], t[3]);
   a.rec[1][s] = make_float4(t[4], t[5], sx, sy);
   a.rec[2][s] = make_float4(sz, -0.5f, -0.5f, -0.5f);  // kUnitCubeBounds (sc_world_partition.cpp:27, 725)
@@ -1842,22 +1928,74 @@ __device__ __forceinline__ uint32_t find_slot(const SceneArrays& a, uint32_t han
   return s - 1u;
 }
 
-// setLocal (sc_ecs.h:78-84) for n entities; unknown handles are skipped
-__global__ void __launch_bounds__(kBlock) k_set_local(SceneArrays a, uint32_t n, const uint32_t* __restrict__ entity,
-                                                      const float* __restrict__ trs9, uint32_t stamp)
+// The setLocal family, one thread per instance. kFloats = 9: setLocal (sc_ecs.h:78-84: position, rotation, scale);
+// 6: position + rotation, all that the physics sync and the traffic tiers write (sc_physics.cpp:1178-1184,
+// sc_traffic_ai.cpp:449-457); 3: setLocalPosition (sc_ecs.h:92-96). Addressed by entity handle (unknown handles are
+// skipped) or, with entity == nullptr, by position in the pool: element j is the Transform at dense index
+// firstRank + j — no handle crosses PCIe and no sparse lookup is made.
+template <int kFloats>
+__global__ void __launch_bounds__(kBlock) k_set_local(SceneArrays a, uint32_t n, const uint32_t* __restrict__ entity, uint32_t firstRank,
+                                                      const float* __restrict__ data, uint32_t stamp)
+{
+  const uint32_t j = blockIdx.x * kBlock + threadIdx.x;
+  if (j >= n) return;
+  uint32_t s;
+  if (entity)
+  {
+    s = find_slot(a, entity[j]);
+    if (s == kNone) return;
+  }
+  else
+    s = a.perm[firstRank + j];
+  const float* t = data + (size_t)j * kFloats;
+  if (kFloats == 3)
+  {
+    float* r0 = reinterpret_cast<float*>(a.rec[0] + s);
+    r0[0] = t[0]; r0[1] = t[1]; r0[2] = t[2];
+  }
+  else
+  {
+    a.rec[0][s] = make_float4(t[0], t[1], t[2], t[3]);
+    if (kFloats == 6)
+      *reinterpret_cast<float2*>(a.rec[1] + s) = make_float2(t[4], t[5]);
+    else
+    {
+      float sx = t[6], sy = t[7], sz = t[8];
+      if (sx == 0.0f && sy == 0.0f && sz == 0.0f) { sx = sy = sz = 1.0f; }  // TransformSystem's zero-scale patch (sc_ecs.cpp:143-149)
+      a.rec[1][s] = make_float4(t[4], t[5], sx, sy);
+      reinterpret_cast<float*>(a.rec[2] + s)[0] = sz;
+    }
+  }
+  uint32_t* fw = reinterpret_cast<uint32_t*>(a.rec[3] + s) + 3;
+  *fw = (*fw & 0xFFu) | (stamp << kStampShift);
+}
+
+// World::add / remove of RenderMesh or Bounds on an entity that already owns a Transform, and edits of their fields
+// (sc_traffic_lod.cpp:47-70 adds both late and rewrites meshId / materialId on every LOD change; sc_imgui.cpp:720 edits
+// materialId): mesh + material ids, local AABB and the HAS_* bits. Does not touch the dirty stamp — the reference's
+// culling reads these components every frame and they have nothing to do with Transform::dirty.
+__global__ void __launch_bounds__(kBlock) k_set_render(SceneArrays a, uint32_t n, const uint32_t* __restrict__ entity,
+                                                       const uint32_t* __restrict__ meshMat2, const float* __restrict__ aabb6,
+                                                       const uint32_t* __restrict__ flags)
 {
   const uint32_t j = blockIdx.x * kBlock + threadIdx.x;
   if (j >= n) return;
   const uint32_t s = find_slot(a, entity[j]);
   if (s == kNone) return;
-  const float* t = trs9 + (size_t)j * 9;
-  float sx = t[6], sy = t[7], sz = t[8];
-  if (sx == 0.0f && sy == 0.0f && sz == 0.0f) { sx = sy = sz = 1.0f; }
-  a.rec[0][s] = make_float4(t[0], t[1], t[2], t[3]);
-  a.rec[1][s] = make_float4(t[4], t[5], sx, sy);
-  reinterpret_cast<float*>(a.rec[2] + s)[0] = sz;
-  uint32_t* fw = reinterpret_cast<uint32_t*>(a.rec[3] + s) + 3;
-  *fw = (*fw & 0xFFu) | (stamp << kStampShift);
+  if (meshMat2) a.meshMat[s] = make_uint2(meshMat2[(size_t)j * 2], meshMat2[(size_t)j * 2 + 1]);
+  if (aabb6)
+  {
+    const float* b = aabb6 + (size_t)j * 6;
+    float* r2 = reinterpret_cast<float*>(a.rec[2] + s);
+    float* r3 = reinterpret_cast<float*>(a.rec[3] + s);
+    r2[1] = b[0]; r2[2] = b[1]; r2[3] = b[2];
+    r3[0] = b[3]; r3[1] = b[4]; r3[2] = b[5];
+  }
+  if (flags)
+  {
+    uint32_t* fw = reinterpret_cast<uint32_t*>(a.rec[3] + s) + 3;
+    *fw = (*fw & ~(kFlagBounds | kFlagMesh)) | (flags[j] & (kFlagBounds | kFlagMesh));
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) k_mark_dirty(SceneArrays a, uint32_t n, const uint32_t* __restrict__ entity,
@@ -1884,32 +2022,49 @@ __global__ void __launch_bounds__(kBlock) k_set_parent(SceneArrays a, uint32_t n
   *fw = (*fw & 0xFFu) | (stamp << kStampShift);
 }
 
-// World::destroy batches: the host replays ComponentPool::remove's swap-with-last (sc_ecs.h:240-262) on its
-// entity mirror and hands over the net result: slots to fill (dst <- src, src always in the vacated tail, so
-// sources and destinations never overlap) and the sparse entries to clear.
+// World::destroy batches. The host replays ComponentPool::remove's swap-with-last (sc_ecs.h:240-262) on its mirror of
+// the pool and hands over the net result in RANK space: `dst <- src` (the element at dense index src ends up at dst;
+// src always in the vacated tail, dst below it, so sources and destinations never overlap) and the device slots of
+// the destroyed Transforms. Nothing moves in HBM: a survivor only learns its new rank, a victim's slot becomes a hole
+// (flags 0: not live, not a candidate, never dirty) that scgpu_layout.h hands to a later spawn.
 __global__ void __launch_bounds__(kBlock) k_despawn_apply(SceneArrays a, uint32_t nMoves, const uint2* __restrict__ moves,
-                                                          uint32_t nRemoved, const uint32_t* __restrict__ removedIndex)
+                                                          uint32_t nRemoved, const uint32_t* __restrict__ removedSlot)
 {
   const uint32_t j = blockIdx.x * kBlock + threadIdx.x;
   if (j < nMoves)
   {
     const uint32_t dst = moves[j].x, src = moves[j].y;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-      a.rec[k][dst] = a.rec[k][src];
-      a.world[k][dst] = a.world[k][src];
-    }
-    const uint32_t e = a.entity[src];
-    a.entity[dst] = e;
-    a.parent[dst] = a.parent[src];
-    a.meshMat[dst] = a.meshMat[src];
-    a.sparse[e & 0xFFFFFFu] = dst + 1u;
+    const uint32_t s = a.perm[src];
+    a.perm[dst] = s;
+    a.rank[s] = dst;
   }
   else if (j < nMoves + nRemoved)
   {
-    a.sparse[removedIndex[j - nMoves]] = 0u;
+    const uint32_t s = removedSlot[j - nMoves];
+    const uint32_t e = a.entity[s];
+    a.sparse[e & 0xFFFFFFu] = 0u;
+    a.entity[s] = kNone;
+    a.parent[s] = kNone;
+    a.parentSlot[s] = kNone;
+    a.rec[3][s] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+
+// Dirty stamps are 24 bits wide. When the update counter wraps, every stamp still stored is older than 16.7 M updates
+// and would alias a future one: reset them all to 0 ("never") once, right after the update that used the last id.
+__global__ void __launch_bounds__(kBlock) k_clear_stamps(SceneArrays a, uint32_t extent)
+{
+  const uint32_t s = blockIdx.x * kBlock + threadIdx.x;
+  if (s >= extent) return;
+  uint32_t* fw = reinterpret_cast<uint32_t*>(a.rec[3] + s) + 3;
+  *fw &= 0xFFu;
+}
+
+// ComponentPool::denseEntities(): entity handles in pool order
+__global__ void __launch_bounds__(kBlock) k_gather_dense(SceneArrays a, uint32_t n, uint32_t* __restrict__ out)
+{
+  const uint32_t r = blockIdx.x * kBlock + threadIdx.x;
+  if (r < n) out[r] = a.entity[a.perm[r]];
 }
 
 // TransformSystem's per-frame parent validation (sc_ecs.cpp:151-164), run only when the topology changed:

@@ -24,6 +24,9 @@ namespace scgpu
 constexpr uint32_t kPeerHeaderWords = 16;  // 64 B
 constexpr uint32_t kPeerFlag = 0, kPeerCounts = 1, kPeerOverflow = kPeerCounts + kMaxViews + 2;
 constexpr long long kPeerSpinClocks = 4000000000ll;  // ~2 s at 1.9 GHz: a dead peer must not hang the box
+// error word of one gather (ScGpuScene::dPeerState[1], cleared at the start of every gather): 1 = this (non-root) rank
+// timed out waiting for the root's progress and delivered nothing; on the root: 2 = a rank's flag never came,
+// 4 = a rank's lists exceed the mailbox, 8 = a rank reported that it delivered nothing
 
 struct PeerBox
 {
@@ -70,10 +73,11 @@ struct PeerPackParams
 __global__ void __launch_bounds__(kBlock) k_peer_pack(const __grid_constant__ PeerPackParams q)
 {
   __shared__ uint32_t sOff[kMaxViews + 1];
-  __shared__ uint32_t sLast;
+  __shared__ uint32_t sLast, sStale;
   const uint32_t parity = q.seq & 1u;
   if (threadIdx.x == 0)
   {
+    sStale = 0u;
     if (q.isRoot)
     {
       // everything the root enqueued before this gather (the consumers of gather seq-1 included) has completed
@@ -85,7 +89,8 @@ __global__ void __launch_bounds__(kBlock) k_peer_pack(const __grid_constant__ Pe
       const long long t0 = clock64();
       while ((int32_t)(ld_acquire_sys(q.box.progress()) - (q.seq - 1u)) < 0)
       {
-        if (clock64() - t0 > kPeerSpinClocks) { *q.error = 1u; break; }
+        // the root may still be reading this buffer: write NOTHING into it, report the frame as failed instead
+        if (clock64() - t0 > kPeerSpinClocks) { atomicOr(q.error, 1u); sStale = 1u; break; }
         __nanosleep(200);
       }
     }
@@ -96,8 +101,9 @@ __global__ void __launch_bounds__(kBlock) k_peer_pack(const __grid_constant__ Pe
   __syncthreads();
   const uint32_t total = sOff[q.nViews];
   const bool overflow = total > q.box.cap;
+  const bool stale = sStale != 0u;
   uint32_t* dst = q.box.payload(q.rank, parity);
-  if (!overflow)
+  if (!overflow && !stale)
   {
     for (uint32_t v = 0; v < q.nViews; ++v)
     {
@@ -114,8 +120,9 @@ __global__ void __launch_bounds__(kBlock) k_peer_pack(const __grid_constant__ Pe
   if (sLast)
   {
     uint32_t* h = q.box.header(q.rank, parity);
+    // (the header is 64 B that the root reads only after the flag: safe to write even when the payload was not)
     if (threadIdx.x < kMaxViews + 2) h[kPeerCounts + threadIdx.x] = q.totals[threadIdx.x];
-    if (threadIdx.x == 0) h[kPeerOverflow] = overflow ? 1u : 0u;
+    if (threadIdx.x == 0) h[kPeerOverflow] = stale ? 2u : (overflow ? 1u : 0u);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0)
@@ -141,7 +148,8 @@ __global__ void __launch_bounds__(64) k_peer_wait(PeerBox box, uint32_t seq, uin
       __nanosleep(100);
     }
     if (!ok) atomicOr(error, 2u);
-    else if (h[kPeerOverflow]) atomicOr(error, 4u);
+    else if (h[kPeerOverflow] == 1u) atomicOr(error, 4u);
+    else if (h[kPeerOverflow] == 2u) { atomicOr(error, 8u); ok = false; }  // the producer gave up: its payload is not this frame's
     for (uint32_t k = 0; k < kMaxViews + 2; ++k) allCounts[r * (kMaxViews + 2) + k] = ok ? h[kPeerCounts + k] : 0u;
   }
 }

@@ -58,6 +58,9 @@ class DeviceViews(C.Structure):
         ("worldCol", C.c_void_p * 4),
         ("entity", C.c_void_p),
         ("count", C.c_uint32),
+        ("extent", C.c_uint32),
+        ("rank", C.c_void_p),
+        ("perm", C.c_void_p),
     ]
 
 
@@ -131,6 +134,10 @@ SYMBOLS = {
     "scgpuSectorSpawnCount": (C.c_uint32, [C.POINTER(SectorGen), C.c_int32, C.c_int32]),
     "scgpuSpawnSectors": (C.c_int, [_vp, C.POINTER(SectorGen), C.c_uint32, _vp, _vp, C.c_uint32]),
     "scgpuSetLocal": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "scgpuSetLocalPosRot": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "scgpuSetLocalPosition": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
+    "scgpuSetLocalRange": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
+    "scgpuSetRender": (C.c_int, [_vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "scgpuSetParent": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
     "scgpuMarkDirty": (C.c_int, [_vp, C.c_uint32, _vp]),
     "scgpuSetLocalDevice": (C.c_int, [_vp, C.c_uint32, _vp, _vp]),
@@ -325,6 +332,26 @@ class Scene:
         e = _arr(entity, np.uint32)
         t = _arr(trs9, np.float32, 9)
         self._ck(self.lib.scgpuSetLocal(self.ctx, e.shape[0], _ptr(e), _ptr(t)), "scgpuSetLocal")
+
+    def set_local_pos_rot(self, entity, pos_rot6):
+        e = _arr(entity, np.uint32)
+        t = _arr(pos_rot6, np.float32, 6)
+        self._ck(self.lib.scgpuSetLocalPosRot(self.ctx, e.shape[0], _ptr(e), _ptr(t)), "scgpuSetLocalPosRot")
+
+    def set_local_position(self, entity, pos3):
+        e = _arr(entity, np.uint32)
+        t = _arr(pos3, np.float32, 3)
+        self._ck(self.lib.scgpuSetLocalPosition(self.ctx, e.shape[0], _ptr(e), _ptr(t)), "scgpuSetLocalPosition")
+
+    def set_local_range(self, first_dense, data, floats_per_instance):
+        """fields of the Transforms at dense indices first_dense.. (pool order); 3 = pos, 6 = pos + rot, 9 = TRS"""
+        t = _arr(data, np.float32, floats_per_instance)
+        self._ck(self.lib.scgpuSetLocalRange(self.ctx, first_dense, t.shape[0], floats_per_instance, _ptr(t)), "scgpuSetLocalRange")
+
+    def set_render(self, entity, mesh_mat=None, aabb6=None, flags=None):
+        e = _arr(entity, np.uint32)
+        self._ck(self.lib.scgpuSetRender(self.ctx, e.shape[0], _ptr(e), _ptr(_arr(mesh_mat, np.uint32, 2)),
+                                         _ptr(_arr(aabb6, np.float32, 6)), _ptr(_arr(flags, np.uint32))), "scgpuSetRender")
 
     def set_local_device(self, n, d_entity_ptr, d_trs_ptr):
         self._ck(self.lib.scgpuSetLocalDevice(self.ctx, n, d_entity_ptr, d_trs_ptr), "scgpuSetLocalDevice")

@@ -38,7 +38,7 @@ def test_struct_layouts_match_the_reference_records():
     assert scgpu.DRAW_ITEM_DTYPE.itemsize == 80  # sc::DrawItem, sc_ecs.h:159-165
     assert scgpu.DRAW_ITEM_DTYPE.fields["model"][1] == 16
     lib = scgpu.load_library()
-    assert lib.scgpuGetApiVersion() == 1
+    assert lib.scgpuGetApiVersion() == 2
 
 
 def test_no_cpu_fallback():

@@ -30,7 +30,7 @@ def _entities(checkers, n):
 def test_create_reports_device():
     import scgpu
     s = scgpu.Scene(1024, max_views=2)
-    assert s.lib.scgpuGetApiVersion() == 1
+    assert s.lib.scgpuGetApiVersion() == 2
     s.close()
 
 
