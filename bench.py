@@ -9,6 +9,15 @@ re-transformed, culled against all views and compacted). Workload at any N: the 
 16 Mi instances per GPU in depth-4 groups, main camera + 4 shadow cascades (BASELINE.json configs[2]; 8 GPUs of
 it = configs[3], 128 Mi instances sharded by world cell). Weak scaling: every rank owns a contiguous block of
 world cells; the only exchange is the gather of the compacted lists to rank 0 (inside the timed step for N>1).
+
+Beside the headline numbers the same line carries
+  "partial_dirty"  the same scene with 30 % of the instances dirty per frame (TransformSystem only recomputes
+                   t.dirty || parentDirty, sc_ecs.cpp:178-210): device time and the mixed 132 / 96-byte roofline;
+  "churn"          BASELINE.json configs[4], the per-GPU share: 8 Mi instances, per frame 10 % despawn + 10 % spawn +
+                   30 % setLocal through the C ABI from host buffers, >= 100 timed frames, the fused kernel's time series
+                   (it must stay flat: the device layout no longer follows the pool's swap-with-last order);
+  "gather"         (N > 1) the gathered per-view totals on rank 0, checked against the sum of the ranks' own counts and
+                   the concatenation of their lists.
 """
 from __future__ import annotations
 
@@ -30,7 +39,11 @@ METRIC = "instances transformed+culled/sec"
 UNIT = "instances/s"
 DEFAULT_INSTANCES = 16 * 1024 * 1024 - 4096  # per GPU; < 2^24 entity indices per World shard (sc_ecs.h:18-20)
 ALG_BYTES_DIRTY = 132   # read TRS 36 + parent 4 + flags 4 + AABB 24, write world 64
-REF_SAMPLE = 2_000_000  # instances per step of the CPU reference arm (bounded sample)
+ALG_BYTES_CLEAN = 96    # read flags 4 + parent 4 + world 64 + AABB 24, no write
+REF_SAMPLE = 2_000_000  # instances per step of the bounded cpu_baseline sample (N = 1 line of our arm)
+REF_WORLD_MAX = 8_000_000  # the reference's job system is safe up to ~11 M entities per World: larger
+                           # scenes run as consecutive Worlds of at most this many instances, times summed
+CHURN_INSTANCES = 8 * 1024 * 1024
 
 
 def build_scene(n, rank, seed=424242):
@@ -130,9 +143,23 @@ def recorded_traffic():
 # CPU reference arm / cpu_baseline worker (runs in a subprocess with the libm variant pinned)
 # --------------------------------------------------------------------------------------------------------
 
+def _world_cuts(sc, n, limit):
+    """[a, b) ranges of at most `limit` instances cut at group boundaries (a group never straddles two Worlds)"""
+    roots = np.nonzero(sc["parent"] < 0)[0]
+    cuts, a = [], 0
+    while a < n:
+        b = min(n, a + limit)
+        if b < n:
+            b = int(roots[np.searchsorted(roots, b, side="right") - 1])
+        cuts.append((a, b))
+        a = b
+    return cuts
+
+
 def cpu_worker(args):
-    """Times the reference's own TransformSystem -> CullingSystem x V -> RenderPrepStreamingSystem on a bounded
-    sample of the bench workload. Prints one JSON object per step set."""
+    """Times the reference's own TransformSystem -> CullingSystem x V -> RenderPrepStreamingSystem over `--sample-instances`
+    instances of the bench workload, as consecutive Worlds of at most REF_WORLD_MAX instances whose times are summed.
+    Prints one JSON object."""
     sys.path.insert(0, str(ROOT / "tests"))
     import ctypes as C
     import oracle_bind
@@ -140,29 +167,37 @@ def cpu_worker(args):
     sc = build_scene(n, 0)
     vps = views_for(sc, args.views)
     from scgpu import scenes
-    out = {"cores": os.cpu_count(), "sample": f"{n} instances of the same depth-4 city, {args.views} views, all dirty, per step"}
+    out = {"cores": os.cpu_count()}
     if oracle_bind.ref_available():
-        r = oracle_bind.RefScene(0)
-        e = r.create_entities(n)
-        par = scenes.parent_handles(sc["parent"], e)
-        r.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
-        L = r.L
+        cuts = _world_cuts(sc, n, REF_WORLD_MAX)
+        worlds = []
+        for a, b in cuts:
+            r = oracle_bind.RefScene(0)
+            e = r.create_entities(b - a)
+            lp = np.where(sc["parent"][a:b] >= 0, sc["parent"][a:b] - a, -1)
+            r.spawn(e, sc["trs9"][a:b], scenes.parent_handles(lp, e), sc["aabb6"][a:b], sc["mesh_mat"][a:b], sc["flags"][a:b])
+            worlds.append((r, np.ascontiguousarray(e)))
+        L = worlds[0][0].L
         vp = np.ascontiguousarray(vps, np.float32)
-        ee = np.ascontiguousarray(e)
         tT, tC, tP = C.c_double(), C.c_double(), C.c_double()
         per_step = []
-        total = args.warmup + args.steps
-        for it in range(total):
-            L.screfTimeFrame(r.w, 1, args.views, vp.ctypes.data_as(C.c_void_p), n, ee.ctypes.data_as(C.c_void_p), 0,
-                             C.byref(tT), C.byref(tC), C.byref(tP))
+        for it in range(args.warmup + args.steps):
+            acc = np.zeros(3)
+            for r, ee in worlds:
+                L.screfTimeFrame(r.w, 1, args.views, vp.ctypes.data_as(C.c_void_p), len(ee), ee.ctypes.data_as(C.c_void_p), 0,
+                                 C.byref(tT), C.byref(tC), C.byref(tP))
+                acc += (tT.value, tC.value, tP.value)
             if it >= args.warmup:
-                per_step.append((tT.value, tC.value, tP.value))
+                per_step.append(acc)
         a = np.array(per_step)
         out.update(kind="reference", threads=int(L.screfJobWorkers()) + 1,
                    transform_ms=float(a[:, 0].mean() * 1e3), cull_ms=float(a[:, 1].mean() * 1e3),
-                   prep_ms=float(a[:, 2].mean() * 1e3))
+                   prep_ms=float(a[:, 2].mean() * 1e3), worlds=[int(b - a_) for a_, b in cuts])
         sec = float(a.sum(axis=1).mean())
-        r.close()
+        for r, _ in worlds:
+            r.close()
+        out["sample"] = (f"{n} instances of the same depth-4 city, {args.views} views, all dirty, per step; "
+                         f"{len(cuts)} consecutive World(s) of <= {REF_WORLD_MAX} instances, times summed")
     else:
         p = oracle_bind.PortScene()
         e = np.arange(n, dtype=np.uint32)
@@ -176,6 +211,7 @@ def cpu_worker(args):
                 times.append(time.perf_counter() - t0)
         out.update(kind="port", threads=1)
         sec = float(np.mean(times))
+        out["sample"] = f"{n} instances of the same depth-4 city, {args.views} views, all dirty, per step (plain-C oracle, 1 thread)"
     out.update(value=n / sec, unit=UNIT, ms_per_step=sec * 1e3, sample_instances=n)
     print(json.dumps(out), flush=True)
 
@@ -196,21 +232,26 @@ def run_cpu_worker(sample, views, steps, warmup, timeout=900):
 
 
 def reference_arm(args, rank, world):
+    """The reference's own CPU implementation on OUR arm's config: the whole per-GPU instance set (16.77 M), as
+    consecutive Worlds of <= 8 M. --quick falls back to the bounded 2 M sample."""
     if rank != 0:
         return
-    res = run_cpu_worker(args.ref_sample, args.views, args.steps, args.warmup, timeout=3000)
+    sample = args.ref_sample if args.quick else args.instances
+    steps = args.steps if args.quick else min(args.steps, 6)   # ~4 s per 16.77 M step: keep the run within minutes
+    warm = min(args.warmup, 1)
+    res = run_cpu_worker(sample, args.views, steps, warm, timeout=3000)
     if "error" in res:
         print(json.dumps({"impl": "reference", "unavailable": res["error"].replace("\n", " ")[:200]}))
         return
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, res["sample_instances"], sample=True),
         "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res.get("threads", res["cores"]),
                          "kind": res["kind"], "sample": res["sample"],
                          "stages_ms": {k: res[k] for k in ("transform_ms", "cull_ms", "prep_ms") if k in res},
-                         "host_cpus": res["cores"]},
+                         "host_cpus": res["cores"], "worlds": res.get("worlds")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -225,13 +266,246 @@ def workload_config(args, n_per_gpu, sample=False):
         "sharding": ("world cell blocks, one process per GPU; visible lists gathered to rank 0 through "
                      + ("NVLink peer memory" if os.environ.get("SCGPU_GATHER", "peer") == "peer" else "NCCL send/recv"))
         if args.gpus > 1 else "single GPU",
-        "l2": "inputs (>= 2 GB per step) exceed the 126 MB L2; no explicit flush" if not sample else "cpu sample",
+        "l2": "inputs (>= 2 GB per step) exceed the 126 MB L2; no explicit flush" if not sample else "cpu run",
     }
 
 
 # --------------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------------
+
+class Dist:
+    """torch.distributed when WORLD_SIZE > 1, no-ops otherwise"""
+
+    def __init__(self, world, local_rank):
+        self.world = world
+        self.dist = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        import torch
+        if self.dist:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max(self, x):
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_objects(self, obj):
+        if not self.dist:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.dist:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def comm_setup(scene, D, rank):
+    import scgpu
+    if D.world > 1:
+        uid = [scgpu.Scene.comm_unique_id() if rank == 0 else None]
+        D.dist.broadcast_object_list(uid, src=0)
+        scene.comm_init(D.world, rank, uid[0])
+        if os.environ.get("SCGPU_GATHER", "peer") == "peer":  # lists travel through NVLink peer memory, not NCCL
+            scene.enable_peer_gather(0)
+
+
+def check_gather(scene, D, rank, views):
+    """rank 0 reads what the gather delivered and compares it with what the ranks hold themselves"""
+    if D.world == 1:
+        return None
+    scene.update(0)
+    scene.gather_visible(0)
+    local_counts = [int(scene.counts().visible[v]) for v in range(views)]
+    local_lists = [scene.read_visible(v) for v in range(views)]
+    scene.synchronize()
+    import zlib
+    mine = {"counts": local_counts, "crc": [zlib.crc32(l.tobytes()) for l in local_lists]}
+    everyone = D.gather_objects(mine)
+    out = None
+    if rank == 0:
+        g = scene.gathered_counts()
+        ok = True
+        totals = []
+        for v in range(views):
+            per_rank = [everyone[r]["counts"][v] for r in range(D.world)]
+            ok &= [int(x) for x in g[:, v]] == per_rank
+            lst = scene.read_gathered_visible(v)
+            ok &= len(lst) == sum(per_rank)
+            off = 0
+            for r in range(D.world):   # concatenated in rank order: every rank's slice must be that rank's own list
+                ok &= zlib.crc32(lst[off:off + per_rank[r]].tobytes()) == everyone[r]["crc"][v]
+                off += per_rank[r]
+            totals.append(int(sum(per_rank)))
+        out = {"gather_checked": bool(ok), "gathered_visible_per_view": totals,
+               "rank0_local_visible_per_view": local_counts,
+               "check": "gathered counts == every rank's own counts; gathered lists == rank-ordered concatenation of the ranks' lists (crc32 per slice)"}
+        if not ok:
+            raise SystemExit("bench.py: the gathered visible lists differ from the ranks' own lists")
+    D.barrier()
+    return out
+
+
+def partial_dirty_leg(scene, sc, n, args, D, stream, torch):
+    """30 % of the instances get a new local TRS per frame from a DEVICE-resident producer (scgpuSetLocalDevice), then the
+    update: what TransformSystem's dirty test (sc_ecs.cpp:178-210) buys. Returns the dict for the JSON line."""
+    rng = np.random.default_rng(12345)
+    m = (3 * n) // 10
+    idx = np.sort(rng.choice(n, m, replace=False)).astype(np.uint32)
+    trs = sc["trs9"][idx].copy()
+    trs[:, 0] += np.float32(0.125)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    d_e = torch.from_numpy(idx.view(np.int32)).to(dev)
+    d_t = torch.from_numpy(trs).to(dev)
+    torch.cuda.synchronize()
+    steps = max(5, min(args.steps, 20))
+
+    def step():
+        scene.set_local_device(m, d_e.data_ptr(), d_t.data_ptr())
+        scene.update(0)
+        if D.world > 1:
+            scene.gather_visible(0)
+
+    for _ in range(3):
+        step()
+    D.barrier()
+    scene.enable_timings(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    D.barrier()
+    ms = D.max(ev0.elapsed_time(ev1) / steps)
+    k_ms, u_ms = scene.read_timings(steps)
+    rec = int(scene.counts().recomputed)
+    peak, _ = measured_peak()
+    alg = ALG_BYTES_DIRTY * rec + ALG_BYTES_CLEAN * (n - rec)
+    k = float(np.mean(k_ms))
+    return {"dirty_fraction_set": 0.3, "recomputed_per_frame": rec, "recomputed_fraction": rec / n, "steps": steps,
+            "ms_per_step": ms, "value": n * D.world / (ms * 1e-3), "unit": UNIT, "kernel_ms_avg": k,
+            "update_ms_avg": float(np.mean(u_ms)),
+            "roofline": {"bound": "hbm", "achieved": alg / (k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(alg),
+                         "formula": "132 B x recomputed + 96 B x clean (SURVEY.md 8d)"},
+            "note": "dirty instances chosen at random (every hierarchy window is partly dirty, children inherit); the step "
+                    "includes the device-side setLocal of the 30 % (k_set_local), kernel_ms is the fused kernel alone"}
+
+
+def churn_leg(args, D, rank, local_rank, torch):
+    """BASELINE.json configs[4], per-GPU share: 8 Mi instances in depth-4 groups, 5 views; per frame ~10 % of the instances
+    despawn as whole groups, as many spawn (same entity indices, next generation, like the reference's LIFO index
+    reuse), 30 % of the rest get a new local TRS — all through the C ABI from pinned HOST buffers. >= 100 timed frames."""
+    import scgpu
+    from scgpu import scenes
+    n = args.churn_instances
+    frames, warm = args.churn_frames, 4
+    cohorts = 10
+    sc = scenes.city_hier(n, seed=99 + 7919 * rank)
+    if rank:
+        sc["trs9"][sc["parent"] < 0, 0] += np.float32(rank * sc["side"] * scenes.SECTOR_SIZE)
+    rng = np.random.default_rng(5 + rank)
+    roots = np.nonzero(sc["parent"] < 0)[0]
+    glen = np.diff(np.append(roots, n))
+    gco = rng.integers(0, cohorts, size=len(roots))           # every group belongs to one of ten cohorts, at random
+    cohort_of = np.repeat(gco, glen).astype(np.uint8)
+    index = np.arange(n, dtype=np.uint32)                     # entity index == initial position, reused by every generation
+    gen = np.zeros(cohorts, np.uint32)
+    members = [np.nonzero(cohort_of == c)[0].astype(np.uint32) for c in range(cohorts)]   # group order kept
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    tmpl = []
+    for c in range(cohorts):
+        ix = members[c]
+        pos = np.full(n, -1, np.int64)
+        pos[ix] = np.arange(len(ix))
+        lp = np.where(sc["parent"][ix] >= 0, pos[np.maximum(sc["parent"][ix], 0)], -1)
+        tmpl.append(dict(ix=ix, parent=lp, trs=pin(sc["trs9"][ix]), aabb=pin(sc["aabb6"][ix]), mm=pin(sc["mesh_mat"][ix]),
+                         flags=pin(sc["flags"][ix])))
+    moved_pat = [np.sort(rng.choice(n, (3 * n) // 10, replace=False)).astype(np.uint32) for _ in range(4)]
+    moved_trs = [pin(sc["trs9"][p] + np.float32(0.25)) for p in moved_pat]
+
+    scene = scgpu.Scene(n + n // 8, max_views=args.views, device=local_rank, max_entity_index=n)
+    scene.spawn(index, sc["trs9"], scenes.parent_handles(sc["parent"], index), sc["aabb6"], sc["mesh_mat"], sc["flags"])
+    scene.set_views(scenes.standard_views(args.views))
+    comm_setup(scene, D, rank)
+    scene.update(0)
+    scene.counts()
+    scene.enable_timings(True)
+    calls = {"despawn_ms": [], "spawn_ms": [], "set_local_ms": [], "update_counts_ms": [], "frame_ms": []}
+    k_series, u_series, slow_series = [], [], []
+    rec = 0
+    for f in range(warm + frames):
+        c = f % cohorts
+        t = tmpl[c]
+        dead = pin(t["ix"] | (gen[c] << np.uint32(24)))
+        gen[c] = (gen[c] + 1) & 0xFF
+        fresh = pin(t["ix"] | (gen[c] << np.uint32(24)))
+        fpar = pin(scenes.parent_handles(t["parent"], fresh))
+        mp = moved_pat[f % 4]
+        keep = cohort_of[mp] != c                               # the cohort that was just replaced keeps its spawn TRS
+        moved = pin(mp[keep] | (gen[cohort_of[mp[keep]]] << np.uint32(24)))
+        mtrs = pin(moved_trs[f % 4][keep])
+        D.barrier()
+        t0 = time.perf_counter()
+        scene.despawn(dead)
+        t1 = time.perf_counter()
+        scene.spawn(fresh, t["trs"], fpar, t["aabb"], t["mm"], t["flags"])
+        t2 = time.perf_counter()
+        scene.set_local(moved, mtrs)
+        t3 = time.perf_counter()
+        scene.update(0)
+        if D.world > 1:
+            scene.gather_visible(0)
+        cnt = scene.counts()
+        if D.world > 1:
+            scene.synchronize()
+        t4 = time.perf_counter()
+        if f >= warm:
+            k, u = scene.last_timings()
+            k_series.append(k)
+            u_series.append(u)
+            slow_series.append(int(cnt.slowWindows))
+            for key, v in zip(calls, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t4 - t0)):
+                calls[key].append(v * 1e3)
+            rec = int(cnt.recomputed)
+    live, extent = int(cnt.transforms), int(cnt.extent)
+    frame_ms = D.max(float(np.median(calls["frame_ms"])))
+    k = np.array(k_series)
+    first, last = float(k[:10].mean()), float(k[-10:].mean())
+    peak, _ = measured_peak()
+    alg = ALG_BYTES_DIRTY * rec + ALG_BYTES_CLEAN * (live - rec)
+    out = {
+        "workload": "BASELINE.json configs[4], per-GPU share: %d instances in depth-4 groups, %d views; per frame ~10 %% despawn "
+                    "(whole groups, chosen at random at start-up) + as many spawn + 30 %% setLocal, through the C ABI from "
+                    "pinned host buffers" % (n, args.views),
+        "frames": frames, "n_gpus": D.world, "instances_per_gpu": live, "slots_walked": extent,
+        "e2e_frame_ms_median": frame_ms, "e2e_value": live * D.world / (frame_ms * 1e-3), "unit": UNIT,
+        "calls_ms_median": {k_: float(np.median(v)) for k_, v in calls.items()},
+        "device_update_ms_median": float(np.median(u_series)),
+        "fused_kernel_ms": {"first10_mean": first, "last10_mean": last, "drift": last / first - 1.0,
+                            "min": float(k.min()), "max": float(k.max()), "series": [round(float(x), 4) for x in k]},
+        "slow_windows": {"first": slow_series[0], "last": slow_series[-1], "max": max(slow_series)},
+        "recomputed_last_frame": rec,
+        "roofline": {"bound": "hbm", "achieved": alg / (last * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg / (last * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(alg),
+                     "formula": "132 B x recomputed + 96 B x clean (SURVEY.md 8d), fused kernel, mean of the last 10 frames"},
+        "per_frame_bytes_h2d": int(len(dead) * 4 + len(fresh) * (4 + 4 + 36 + 24 + 8 + 4) + len(moved) * 40),
+    }
+    scene.close()
+    return out
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -242,8 +516,13 @@ def main():
     ap.add_argument("--instances", type=int, default=DEFAULT_INSTANCES, help="instances per GPU")
     ap.add_argument("--views", type=int, default=5)
     ap.add_argument("--ref-sample", type=int, default=REF_SAMPLE)
+    ap.add_argument("--quick", action="store_true", help="reference arm: a bounded 2 M sample instead of the whole set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-churn", action="store_true")
+    ap.add_argument("--no-partial", action="store_true")
+    ap.add_argument("--churn-instances", type=int, default=CHURN_INSTANCES)
+    ap.add_argument("--churn-frames", type=int, default=100)
     ap.add_argument("--cpu-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--sample-instances", type=int, default=REF_SAMPLE, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -266,14 +545,12 @@ def main():
     os.dup2(2, 1)
 
     import torch
-    import torch.distributed as dist
     import scgpu
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the scene-update path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D = Dist(world, local_rank)
 
     n = args.instances
     sc = build_scene(n, rank)
@@ -283,12 +560,7 @@ def main():
     from scgpu import scenes
     scene.spawn(entity, sc["trs9"], scenes.parent_handles(sc["parent"], entity), sc["aabb6"], sc["mesh_mat"], sc["flags"])
     scene.set_views(vps)
-    if world > 1:
-        uid = [scgpu.Scene.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        scene.comm_init(world, rank, uid[0])
-        if os.environ.get("SCGPU_GATHER", "peer") == "peer":  # lists travel through NVLink peer memory, not NCCL
-            scene.enable_peer_gather(0)
+    comm_setup(scene, D, rank)
 
     stream = torch.cuda.ExternalStream(scene.stream, device=torch.device("cuda", local_rank))
 
@@ -298,17 +570,12 @@ def main():
         if world > 1:
             scene.gather_visible(0)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     sampler = ClockSampler(local_rank)  # nvmlInit takes tens of ms and differs per process: keep it out of the region
     sampler.start()
     scene.enable_timings(True)
     for _ in range(args.warmup):
         step()
-    barrier()
+    D.barrier()
 
     # ---- timed region: K steps, device-resident inputs, CUDA events on the context stream -----------------
     scene.enable_timings(True)  # events exist already: this only resets the ring
@@ -320,7 +587,7 @@ def main():
     for _ in range(args.steps):
         step()
     ev1.record(stream)
-    barrier()
+    D.barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     launches = scene.launches - launches0
@@ -330,57 +597,88 @@ def main():
     counts = scene.counts()
     vis_counts = [int(counts.visible[v]) for v in range(args.views)]
 
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     per_rank = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         # per-rank view of the same timed region (diagnostic: which rank sets the max, and is it its kernels or the gather)
         mine = {"rank": rank, "ms_per_step": dev_ms / args.steps, "kernel_ms": float(np.mean(k_ms)) if len(k_ms) else None,
                 "update_ms": float(np.mean(u_ms)) if len(u_ms) else None, "sm_mhz": clocks.get("sm_mhz")}
-        per_rank = [None] * world
-        dist.all_gather_object(per_rank, mine)
-    dev_ms_max = float(t.item())
-    ms_per_step = dev_ms_max / args.steps
+        per_rank = D.gather_objects(mine)
+    ms_per_step = D.max(dev_ms) / args.steps
     total_instances = n * world
     value = total_instances / (ms_per_step * 1e-3)
 
-    # ---- e2e: the same frame through the C ABI with HOST buffers: upload of every instance's TRS, update,
-    #      read-back of counts and of every view's visible list ---------------------------------------------
+    gather = check_gather(scene, D, rank, args.views)
+
+    # ---- e2e: the same frame through the C ABI with HOST buffers: upload of every instance's new local transform,
+    #      update, read-back of counts and of every view's visible list (N > 1: the GATHERED lists, on the root) -----
     e2e = None
     if not args.no_e2e:
         pin_e = torch.from_numpy(entity).pin_memory()
         pin_t = torch.from_numpy(sc["trs9"]).pin_memory()
-        pe, pt = pin_e.numpy(), pin_t.numpy()
-        out_lists = [torch.empty(n, dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(args.views)]
+        pin_pr = torch.from_numpy(np.ascontiguousarray(sc["trs9"][:, 0:6])).pin_memory()
+        pe, pt, ppr = pin_e.numpy(), pin_t.numpy(), pin_pr.numpy()
+        cap = n * (world if rank == 0 else 1)
+        out_lists = [torch.empty(min(cap, 1 << 26), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+                     for _ in range(args.views)]
 
-        def e2e_step():
-            scene.set_local(pe, pt)
-            scene.update(0)
-            if world > 1:
-                scene.gather_visible(0)
+        def read_back():
             scene.counts()
             got = 0
-            for v in range(args.views):
-                got += len(scene.read_visible(v, out_lists[v]))
+            if world > 1:
+                scene.gather_visible(0)
+                if rank == 0:
+                    for v in range(args.views):
+                        got += len(scene.read_gathered_visible(v, out_lists[v]))
+                else:
+                    scene.synchronize()   # this rank's lists have left for the root
+            else:
+                for v in range(args.views):
+                    got += len(scene.read_visible(v, out_lists[v]))
             return got
 
+        uploads = {
+            # what the engine's per-frame writers change: position + rotation (physics sync sc_physics.cpp:1178-1184, traffic
+            # sc_traffic_ai.cpp:449-457), whole pool in dense order, no handles: 24 B per instance
+            "pos_rot_range": (lambda: scene.set_local_range(0, ppr, 6), n * 24),
+            # every field of every Transform, dense order: 36 B per instance
+            "trs_range": (lambda: scene.set_local_range(0, pt, 9), n * 36),
+            # round 1's form: setLocal by entity handle, 4 + 36 B per instance
+            "trs_by_handle": (lambda: scene.set_local(pe, pt), n * 40),
+        }
         e2e_steps = max(3, min(args.steps, 10))
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        got = 0
-        for _ in range(e2e_steps):
-            got = e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-        e2e = {"value": total_instances / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * (4 + 36)),
-               "d2h_bytes_per_step": int(got * 4 + 4 * (scgpu.MAX_VIEWS + 2)), "ms_per_step": e2e_s * 1e3,
-               "steps": e2e_steps,
-               "path": "scgpuSetLocal(all, pinned host TRS) + scgpuUpdate + scgpuGetCounts + scgpuReadVisible x views"}
+        variants = {}
+        for name, (upload, h2d) in uploads.items():
+            def e2e_step():
+                upload()
+                scene.update(0)
+                return read_back()
+            e2e_step()
+            D.barrier()
+            t0 = time.perf_counter()
+            got = 0
+            for _ in range(e2e_steps):
+                got = e2e_step()
+            D.barrier()
+            sec = D.max((time.perf_counter() - t0) / e2e_steps)
+            variants[name] = {"value": total_instances / sec, "ms_per_step": sec * 1e3, "h2d_bytes_per_step": int(h2d),
+                              "d2h_bytes_per_step": int(got * 4 + 4 * (scgpu.MAX_VIEWS + 3))}
+        head = variants["pos_rot_range"]
+        e2e = {"value": head["value"], "unit": UNIT, "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": head["d2h_bytes_per_step"], "ms_per_step": head["ms_per_step"], "steps": e2e_steps,
+               "path": "scgpuSetLocalRange(whole pool, pinned host position+rotation: the fields the engine's per-frame writers "
+                       "change) + scgpuUpdate + scgpuGetCounts + " +
+                       ("scgpuGatherVisible + scgpuReadGatheredVisible x views on rank 0" if world > 1 else "scgpuReadVisible x views"),
+               "variants": variants}
+
+    partial = None
+    if not args.no_partial:
+        partial = partial_dirty_leg(scene, sc, n, args, D, stream, torch)
+    scene.close()
+    del scene
+
+    churn = None
+    if not args.no_churn:
+        churn = churn_leg(args, D, rank, local_rank, torch)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -394,17 +692,24 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, n),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {
-                "bound": "hbm", "kernel": "k_update_win<V> (fused transform + sphere + V-view cull + tile counts; hierarchy windows per warp)",
+                "bound": "hbm", "kernel": "k_update_win<V> (fused transform + sphere + V-view cull + visibility bits; hierarchy windows per warp)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_instance": ALG_BYTES_DIRTY, "kernel_ms_avg": k_avg_ms,
                 "kernel_share_of_step": (k_avg_ms / ms_per_step) if k_avg_ms else None,
                 "update_ms_avg": float(np.mean(u_ms)) if len(u_ms) else None,
+                "step_frac_of_peak": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                 "traffic": (traffic or {}).get("dram_bytes_per_launch"),
                 "traffic_source": (traffic or {}).get("source"),
             },
             "visible_per_view": vis_counts, "wall_ms_per_step": t_wall * 1e3 / args.steps,
         }
+        if gather:
+            line["gather"] = gather
+        if partial:
+            line["partial_dirty"] = partial
+        if churn:
+            line["churn"] = churn
         if per_rank:
             line["per_rank"] = per_rank
         if world == 1 and not args.no_cpu_baseline:
@@ -421,10 +726,7 @@ def main():
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
 
-    scene.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
 
 
 if __name__ == "__main__":

@@ -85,6 +85,9 @@ typedef struct ScGpuCounts
   uint32_t visible[SCGPU_MAX_VIEWS];
   uint32_t culled[SCGPU_MAX_VIEWS];
   uint32_t recomputed;                   /* world matrices rewritten by the last update */
+  uint32_t slowWindows;                  /* diagnostics: hierarchy windows (<= 32 slots) the last update resolved through the
+                                          * generic path (parent outside the window, cycle, non-affine or non-finite matrices) */
+  uint32_t extent;                       /* diagnostics: device slots the last update walked (transforms + holes) */
 } ScGpuCounts;
 
 /* ---- lifetime ------------------------------------------------------------------------------------- */
@@ -343,6 +346,8 @@ SCGPU_API int scgpuReadGatheredVisible(ScGpuScene* ctx, uint32_t view, uint32_t*
 SCGPU_API uint64_t scgpuKernelLaunchCount(ScGpuScene* ctx);
 /* device time of the main fused kernel and of the whole last update, from CUDA events on the context stream */
 SCGPU_API int scgpuLastUpdateTimings(ScGpuScene* ctx, float* outFusedKernelMs, float* outUpdateMs);
+/* enable: 0 = off, 1 = every update, n > 1 = every n-th update (the event pairs around the fused kernel keep the
+ * compaction from overlapping its tail, so a benchmark may sample them) */
 SCGPU_API int scgpuEnableTimings(ScGpuScene* ctx, int enable);
 /* per-launch device times (ms) of up to the last 256 updates since timings were enabled, oldest first */
 SCGPU_API int scgpuReadUpdateTimings(ScGpuScene* ctx, float* outFusedKernelMs, float* outUpdateMs, uint32_t cap,

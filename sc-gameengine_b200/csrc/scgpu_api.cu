@@ -108,6 +108,7 @@ struct ScGpuScene
   bool poisoned = false;     // a device step failed after the host mirror was committed: the two no longer agree
   uint32_t lastUpdateFlags = 0;
   uint32_t lastNumTiles = 0;
+  uint32_t lastExtent = 0;
   bool culledListsValid = false;
   SlotLayout layout;         // device slots: extent, holes (scgpu_layout.h)
 
@@ -124,16 +125,16 @@ struct ScGpuScene
   uint32_t bitWords = 0;
   uint32_t* acc = nullptr;       // kAccWords frame accumulators + the window queue, zero between frames
   uint32_t* totals = nullptr;    // frame totals written by k_compact: [0..nViews) visible, [nViews] candidates, [kMaxViews+1] recomputed
-  uint32_t* compactPub = nullptr;   // [numSMs][kPubStride] per-segment counts + flags of k_compact
-  uint32_t* compactTicket = nullptr;
-  uint32_t compactTicketBase = 0, compactSeq = 0;
+  uint32_t* chunkCounts = nullptr;  // [2 parities][kMaxViews + 1][chunkStride]: set bits per chunk of kChunkRanks ranks
+  uint32_t chunkStride = 0;
+  uint32_t chunkParity = 0;         // parity the NEXT update's kernels count into (the other one is all zero by then)
   uint32_t* visEntity[kMaxViews] = {};
   uint32_t* visSlot[kMaxViews] = {};
   uint32_t* culledEntity[kMaxViews] = {};
   uint32_t maxTiles = 0;
 
   ViewPlanes planes{};
-  uint32_t* hTotals = nullptr;  // pinned [maxViews+2]
+  uint32_t* hTotals = nullptr;  // pinned [kTotalsWords]
   cudaEvent_t evDone = nullptr;
   // ring of CUDA event pairs around the fused kernel / the whole update, so that a benchmark can read the
   // per-launch device times of many asynchronous updates after a single synchronise
@@ -141,6 +142,7 @@ struct ScGpuScene
   cudaEvent_t evK0[kTimingRing] = {}, evK1[kTimingRing] = {}, evU0[kTimingRing] = {}, evU1[kTimingRing] = {};
   uint32_t timedUpdates = 0;
   bool timings = false;
+  uint32_t timingEvery = 1, updateSerial = 0;
 
   DeviceBuffer staging;   // uploads
   DeviceBuffer scratch;   // read-back gathers / draw items
@@ -272,6 +274,7 @@ inline uint32_t blocksFor(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBl
 
 // Launch with programmatic stream serialisation: the kernel may be scheduled while its predecessor in the stream still
 // runs; it calls pdl_wait() before touching anything the predecessor writes (scgpu_kernels.cuh).
+int g_pdlLevel = 2;  // experiment knob (SCGPU_PDL): 0 = plain launches, 1 = only k_update_win_slow chained, 2 = whole frame chained
 template <typename... KArgs, typename... Args>
 cudaError_t launchPdl(void (*kern)(KArgs...), uint32_t grid, uint32_t block, cudaStream_t st, Args&&... args)
 {
@@ -284,7 +287,8 @@ cudaError_t launchPdl(void (*kern)(KArgs...), uint32_t grid, uint32_t block, cud
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  const bool isSlow = block == kWinBlock;
+  cfg.numAttrs = (g_pdlLevel >= 2 || (g_pdlLevel == 1 && isSlow)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
@@ -335,7 +339,7 @@ void freeAll(ScGpuScene* c)
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
-  cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->slowList); cudaFree(c->visBits); cudaFree(c->acc); cudaFree(c->compactPub); cudaFree(c->compactTicket); cudaFree(c->totals);
+  cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->slowList); cudaFree(c->visBits); cudaFree(c->acc); cudaFree(c->chunkCounts); cudaFree(c->totals);
   cudaFree(c->a.rank); cudaFree(c->a.perm);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
@@ -421,8 +425,8 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   c->bitWords = (uint32_t)(n / 32);  // n is a multiple of kTile: planes are 16-byte multiples
   if (!devAlloc(c, &c->visBits, (size_t)(c->maxViews + 1) * c->bitWords, true)) return 0;
   if (!devAlloc(c, &c->acc, (size_t)kAccWords, true)) return 0;
-  if (!devAlloc(c, &c->compactPub, (size_t)c->numSMs * kPubStride, true)) return 0;
-  if (!devAlloc(c, &c->compactTicket, 1, true)) return 0;
+  c->chunkStride = c->bitWords / kCompactChunkWords + 1u;
+  if (!devAlloc(c, &c->chunkCounts, (size_t)2 * (kMaxViews + 1) * c->chunkStride, true)) return 0;
   if (!devAlloc(c, &c->slotInfo, n, true)) return 0;
   if (!devAlloc(c, &c->winLocal, (size_t)c->maxTiles * (kMaxWin + 1), true)) return 0;
   if (!devAlloc(c, &c->tileWinCount, (size_t)c->maxTiles, true)) return 0;
@@ -435,8 +439,8 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
     if (!devAlloc(c, &c->visEntity[v], n, false)) return 0;
     if (!devAlloc(c, &c->visSlot[v], n, false)) return 0;
   }
-  SC_CUDA(c, cudaMallocHost((void**)&c->hTotals, sizeof(uint32_t) * (kMaxViews + 2)));
-  memset(c->hTotals, 0, sizeof(uint32_t) * (kMaxViews + 2));
+  SC_CUDA(c, cudaHostAlloc((void**)&c->hTotals, sizeof(uint32_t) * kTotalsWords, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(c->hTotals, 0, sizeof(uint32_t) * kTotalsWords);
   SC_CUDA(c, cudaEventCreateWithFlags(&c->evDone, cudaEventDisableTiming));
   SC_CUDA(c, cudaStreamSynchronize(c->stream));
   c->hEntity.reserve(c->capacity);
@@ -567,6 +571,7 @@ ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc)
   if (desc->max_instances == 0 || desc->max_instances > (1u << 24)) { fail(nullptr, "scgpuCreate: max_instances must be 1..%u (24-bit entity index, sc_ecs.h:18-20)", 1u << 24); return nullptr; }
   ScGpuScene* c = new (std::nothrow) ScGpuScene();
   if (!c) { fail(nullptr, "out of host memory"); return nullptr; }
+  if (const char* pl = getenv("SCGPU_PDL")) g_pdlLevel = atoi(pl);
   {
     // host threads for the pool bookkeeping of large despawn batches: SCGPU_HOST_THREADS, else half the cores up to 4 (the sequential middle pass bounds the gain)
     const char* ht = getenv("SCGPU_HOST_THREADS");
@@ -583,7 +588,28 @@ ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc)
   return c;
 }
 
-void scgpuDestroy(ScGpuScene* ctx) { freeAll(ctx); }
+void scgpuDestroy(ScGpuScene* ctx)
+{
+#ifdef SCGPU_COMPACT_TIMING
+  if (ctx)
+  {
+    // diagnostics build only: per-CTA phase timestamps of the last k_compact launch
+    static unsigned long long h[1024 * 8];
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (cudaMemcpyFromSymbol(h, g_compactStamps, sizeof(h)) == cudaSuccess)
+    {
+      unsigned long long t0 = ~0ull;
+      for (int b = 0; b < 1024; ++b) if (h[b * 8] && h[b * 8] < t0) t0 = h[b * 8];
+      for (int b = 0; b < 1024; ++b)
+        if (h[b * 8])
+          fprintf(stderr, "compact cta %4d: start %6llu wait %6llu prefix %6llu emit %6llu end %6llu ns\n", b, h[b * 8] - t0,
+                  h[b * 8 + 1] - t0, h[b * 8 + 2] - t0, h[b * 8 + 3] - t0, h[b * 8 + 4] - t0);
+    }
+  }
+#endif
+  freeAll(ctx);
+}
 
 void* scgpuGetStream(ScGpuScene* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
@@ -603,6 +629,8 @@ int scgpuEnableTimings(ScGpuScene* ctx, int enable)
     }
   }
   ctx->timings = enable != 0;
+  ctx->timingEvery = enable > 1 ? (uint32_t)enable : 1u;
+  ctx->updateSerial = 0;
   ctx->timedUpdates = 0;
   return 1;
 }
@@ -1324,7 +1352,10 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
   if (wantCulled)
     for (uint32_t v = 0; v < c->nViews; ++v)
       if (!c->culledEntity[v] && !devAlloc(c, &c->culledEntity[v], (size_t)c->capacityPad, false)) return 0;
-  if (c->timings) SC_CUDA(c, cudaEventRecord(c->evU0[tslot], c->stream));
+  // event pairs around the fused kernel cut the programmatic-dependent-launch chain: timings may be sampled (every
+  // n-th update) so that the other frames run undisturbed
+  const bool timed = c->timings && (c->updateSerial++ % c->timingEvery) == 0u;
+  if (timed) SC_CUDA(c, cudaEventRecord(c->evU0[tslot], c->stream));
 
   if (c->topologyDirty && extent)
   {
@@ -1350,6 +1381,8 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.parentSlot = c->a.parentSlot;
     p.rank = c->a.rank;
     p.visBits = c->visBits;
+    p.chunkCounts = c->chunkCounts + (size_t)c->chunkParity * (kMaxViews + 1) * c->chunkStride;
+    p.chunkStride = c->chunkStride;
     p.acc = c->acc;
     p.count = extent;
     p.bitWords = c->bitWords;
@@ -1357,7 +1390,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.nViews = c->nViews;
     p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
               (skipTransform ? kUpdSkipTransform : 0u) | (wantCulled ? kUpdCandBits : 0u);
-    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
+    if (timed) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
 #define SC_LAUNCH_UPDATE(V)                                                                                              \
   case V:                                                                                                                \
     if (c->anyParentEver)                                                                                                \
@@ -1381,35 +1414,48 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
 #undef SC_LAUNCH_UPDATE
     ++c->launches;
     SC_CUDA(c, cudaGetLastError());
-    if (c->timings) SC_CUDA(c, cudaEventRecord(c->evK1[tslot], c->stream));
+    if (timed) SC_CUDA(c, cudaEventRecord(c->evK1[tslot], c->stream));
   }
 
   // compaction in pool order, totals, and clean bitmaps / counters / queue for the next frame: one launch
   {
     CompactParams q{};
-    q.bits = c->visBits; q.perm = c->a.perm; q.entity = c->a.entity;
-    for (uint32_t v = 0; v < kMaxViews; ++v) { q.outEntity[v] = c->visEntity[v]; q.outSlot[v] = c->visSlot[v]; q.culledEntity[v] = c->culledEntity[v]; }
-    q.acc = c->acc; q.totals = c->totals; q.pub = c->compactPub; q.ticket = c->compactTicket;
+    q.bits = c->visBits;
+    for (uint32_t v = 0; v < kMaxViews; ++v) { q.outSlot[v] = c->visSlot[v]; q.culledEntity[v] = c->culledEntity[v]; }
+    q.acc = c->acc; q.totals = c->totals; q.totalsHost = c->hTotals;
+    q.chunkCounts = c->chunkCounts + (size_t)c->chunkParity * (kMaxViews + 1) * c->chunkStride;
+    q.chunkCountsNext = c->chunkCounts + (size_t)(c->chunkParity ^ 1u) * (kMaxViews + 1) * c->chunkStride;
+    q.chunkStride = c->chunkStride;
+    c->chunkParity ^= 1u;
     q.nWords = std::min(c->bitWords, (((c->count + 31u) / 32u) + 3u) & ~3u);
-    const uint32_t grid = std::max(1u, std::min(c->numSMs, (q.nWords + kCompactChunkWords - 1u) / kCompactChunkWords));
-    q.segWords = (((q.nWords + grid - 1u) / grid) + 3u) & ~3u;
+    const uint32_t grid = std::max(1u, (q.nWords + kCompactChunkWords - 1u) / kCompactChunkWords);  // one CTA per chunk
     q.bitWords = c->bitWords;
     q.nViews = c->nViews;
     q.culled = wantCulled ? 1u : 0u;
-    q.ticketBase = c->compactTicketBase;
-    if (++c->compactSeq == 0u) ++c->compactSeq;  // 0 is what a never-written flag holds
-    q.seq = c->compactSeq;
-    c->compactTicketBase += grid;
-    SC_CUDA(c, launchPdl(k_compact, grid, kCompactThreads, c->stream, q));
-    ++c->launches;
+    switch (c->nViews)
+    {
+#define SC_LAUNCH_COMPACT(V) case V: SC_CUDA(c, launchPdl(k_compact<V>, grid, kCompactThreads, c->stream, q)); break;
+      SC_LAUNCH_COMPACT(1) SC_LAUNCH_COMPACT(2) SC_LAUNCH_COMPACT(3) SC_LAUNCH_COMPACT(4)
+      SC_LAUNCH_COMPACT(5) SC_LAUNCH_COMPACT(6) SC_LAUNCH_COMPACT(7) SC_LAUNCH_COMPACT(8)
+#undef SC_LAUNCH_COMPACT
+      default: return (int)fail(c, "scgpuUpdate: unsupported view count %u", c->nViews);
+    }
+    ResolveParams rp{};
+    rp.perm = c->a.perm; rp.entity = c->a.entity; rp.totals = c->totals;
+    for (uint32_t v = 0; v < kMaxViews; ++v) { rp.outEntity[v] = c->visEntity[v]; rp.outSlot[v] = c->visSlot[v]; rp.culledEntity[v] = c->culledEntity[v]; }
+    rp.nViews = c->nViews;
+    rp.culled = q.culled;
+    SC_CUDA(c, launchPdl(k_resolve_lists, c->numSMs * 2u, kBlock, c->stream, rp));
+    c->launches += 2;
   }
   c->culledListsValid = wantCulled;
-  SC_CUDA(c, cudaMemcpyAsync(c->hTotals, c->totals, sizeof(uint32_t) * (kMaxViews + 2), cudaMemcpyDeviceToHost, c->stream));
-  if (c->timings) { SC_CUDA(c, cudaEventRecord(c->evU1[tslot], c->stream)); ++c->timedUpdates; }
+  // (the frame totals reach the pinned host copy from k_compact itself: no copy-engine operation in the chain)
+  if (timed) { SC_CUDA(c, cudaEventRecord(c->evU1[tslot], c->stream)); ++c->timedUpdates; }
   SC_CUDA(c, cudaEventRecord(c->evDone, c->stream));
 
   c->lastUpdateFlags = flags;
   c->lastNumTiles = numTiles;
+  c->lastExtent = extent;
   c->updatedOnce = true;
   c->gatheredValid = false;
   c->sortedValid = false;
@@ -1477,6 +1523,8 @@ int scgpuGetCounts(ScGpuScene* c, ScGpuCounts* out)
     out->culled[v] = out->renderablesTotal - c->hTotals[v];
   }
   out->recomputed = c->hTotals[kMaxViews + 1];
+  out->slowWindows = c->hTotals[kMaxViews + 2];
+  out->extent = c->lastExtent;
   return 1;
 }
 

@@ -40,6 +40,7 @@ constexpr uint32_t kFlagBounds = 1u, kFlagMesh = 2u, kFlagLive = 4u;
 constexpr uint32_t kStampShift = 8;
 constexpr uint32_t kUpdateSmemFlat = 3 * 4 * kBlock * 16;  // dynamic shared memory of k_update_flat
 constexpr uint32_t kUpdForceDirty = 1u, kUpdFreeze = 2u, kUpdSkipTransform = 4u, kUpdCandBits = 8u;
+constexpr uint32_t kChunkShift = 15, kChunkRanks = 1u << kChunkShift;  // compaction chunk: 32 Ki pool ranks = 1024 bitmap words
 // accumulators of one frame (ScGpuScene::acc), all zero between frames (k_compact leaves them so)
 constexpr uint32_t kAccCand = 0, kAccRecomputed = 1, kAccQueueNext = 2, kAccQueueSlow = 3, kAccWords = 4;
 
@@ -61,6 +62,8 @@ struct UpdateParams
   const uint32_t* parentSlot;
   const uint32_t* rank;  // slot -> dense index in the reference's pool
   uint32_t* visBits;     // [nViews (+1 with kUpdCandBits)][bitWords], indexed by rank
+  uint32_t* chunkCounts; // [nViews (+1)][chunkStride]: set bits per chunk of kChunkRanks ranks (this frame's parity)
+  uint32_t chunkStride;
   uint32_t* acc;         // kAcc* counters
   uint32_t count;        // slots in use (extent): live Transforms + holes
   uint32_t bitWords;     // words per bitmap plane
@@ -371,6 +374,11 @@ __device__ __forceinline__ void red_global_or(uint32_t* p, uint32_t v)
   asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void red_global_add_u32(uint32_t* p, uint32_t v)
+{
+  asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <int kViews>
 __device__ __forceinline__ void emit_visible_warp(const UpdateParams& p, uint32_t s, uint32_t lane, uint32_t mask, bool cand)
 {
@@ -385,28 +393,52 @@ __device__ __forceinline__ void emit_visible_warp(const UpdateParams& p, uint32_
   const bool consecutive = __all_sync(0xffffffffu, !need || r == base + lane) && rFirst >= first;
   if (consecutive)
   {
+    // lanes 0, 1: the two bitmap words the 32 ranks fall into; lanes 2, 3: the one or two chunks they fall into
     const uint32_t word = base >> 5, sh = base & 31u;
+    const uint32_t chunk = base >> kChunkShift;
+    const uint32_t room = ((chunk + 1u) << kChunkShift) - base;  // ranks left in the first chunk
+    const uint32_t lowMask = room >= 32u ? 0xffffffffu : ((1u << room) - 1u);
 #pragma unroll
     for (int v = 0; v <= kViews; ++v)
     {
       if (v == kViews && !wantCand) break;
       const uint32_t m = __ballot_sync(0xffffffffu, v < kViews ? ((mask >> v) & 1u) != 0u : cand);
       if (m == 0u) continue;
-      const uint32_t part = lane == 0u ? (m << sh) : (sh ? (m >> (32u - sh)) : 0u);
-      if (lane < 2u && part) red_global_or(p.visBits + (size_t)v * p.bitWords + word + lane, part);
+      uint32_t val = 0;
+      uint32_t* dst = nullptr;
+      if (lane < 2u)
+      {
+        val = lane == 0u ? (m << sh) : (sh ? (m >> (32u - sh)) : 0u);
+        dst = p.visBits + (size_t)v * p.bitWords + word + lane;
+        if (val) red_global_or(dst, val);
+      }
+      else if (lane < 4u)
+      {
+        val = __popc(lane == 2u ? (m & lowMask) : (m & ~lowMask));
+        dst = p.chunkCounts + (size_t)v * p.chunkStride + chunk + (lane - 2u);
+        if (val) red_global_add_u32(dst, val);
+      }
     }
   }
   else if (need)
   {
     const uint32_t bit = 1u << (r & 31u);
     uint32_t* w = p.visBits + (r >> 5);
+    uint32_t* cnt = p.chunkCounts + (r >> kChunkShift);
 #pragma unroll
     for (int v = 0; v < kViews; ++v)
-      if ((mask >> v) & 1u) red_global_or(w + (size_t)v * p.bitWords, bit);
-    if (wantCand && cand) red_global_or(w + (size_t)kViews * p.bitWords, bit);
+      if ((mask >> v) & 1u)
+      {
+        red_global_or(w + (size_t)v * p.bitWords, bit);
+        red_global_add_u32(cnt + (size_t)v * p.chunkStride, 1u);
+      }
+    if (wantCand && cand)
+    {
+      red_global_or(w + (size_t)kViews * p.bitWords, bit);
+      red_global_add_u32(cnt + (size_t)kViews * p.chunkStride, 1u);
+    }
   }
 }
-
 
 // ---- K1+K2, flat scenes: fused transform + cull, all views in one pass ------------------------------------------------
 // No instance has a parent: pure streaming. One thread per slot, kSubTiles sub-tiles of kBlock consecutive slots per
@@ -933,7 +965,8 @@ constexpr uint32_t kWsRecomputed = kWinWarps * kWwSize; // u32: world matrices r
 constexpr uint32_t kUpdateSmemWin = kWsRecomputed + 16;
 // device-side work queue of k_update_win: acc[kAccQueueNext] = next unclaimed chunk, acc[kAccQueueSlow] = number of
 // windows handed to k_update_win_slow (k_compact leaves both zeroed for the next frame)
-constexpr uint32_t kTotalsWords = kMaxViews + 2;  // frame totals: [0..nViews) visible, [nViews] candidates, [kMaxViews+1] recomputed
+// frame totals: [0..nViews) visible, [nViews] candidates, [kMaxViews+1] recomputed, [kMaxViews+2] windows that took the generic path
+constexpr uint32_t kTotalsWords = kMaxViews + 3;
 
 // Programmatic dependent launch (the chain k_update_win -> k_update_win_slow -> k_scan_tiles -> k_scatter_visible of
 // one frame): pdl_trigger() lets the NEXT kernel of the stream be scheduled while this one still runs, pdl_wait() at
@@ -1445,58 +1478,49 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* __restrict_
 }
 
 // ---- K3: compaction of the visible sets in POOL ORDER (CullingState::visible / ::culled, .cpp:1273-1280) ----------
-// The frame kernels left one bit per (view, pool rank). One pass over those bitmaps in rank order yields the
-// reference's lists whatever the device layout is: rank -> perm[rank] = slot -> entity[slot]. A single launch of at
-// most one CTA per SM; CTA k owns the k-th contiguous segment of every plane:
-//   1. popcount of its segment per row (row = view, + one culled row per view when the candidate plane is present),
-//   2. publishes the counts (store, fence, flag = this launch's sequence number) and adds up the counts of the
-//      segments before it — a chained wait that cannot deadlock: segment numbers are tickets taken at run time, so
-//      every segment a CTA waits for belongs to a CTA that is already running,
-//   3. second pass over the segment (L1/L2 resident): block scan of the per-thread counts, entity handles and slots
-//      written at prefix + rank-ordered position,
-//   4. clears the words it found set, so the next frame starts from clean bitmaps without a memset; the CTA of the
-//      last segment also writes the frame totals and zeroes the accumulators and the work queue of k_update_win.
+// The frame kernels left one bit per (view, pool rank) and, per CHUNK of 32 Ki ranks, the number of bits they set. One
+// pass over the bitmaps in rank order yields the reference's lists whatever the device layout is:
+// rank -> perm[rank] = slot -> entity[slot]. A single launch, one CTA per chunk (1024 words of every plane, one uint4
+// per thread and plane, held in registers from the load to the last use), no dependency between CTAs:
+//   1. output position of the chunk per row (row = view, + one culled row per view when the candidate plane is
+//      present) = sum of the chunk counts before it (<= 511 values per row, L2 resident),
+//   2. block scan of the per-thread popcounts; the set bit positions (= ranks) are written at chunk position + scan,
+//      one non-empty word per warp step with the 32 lanes taking its 32 bits (coalesced stores, and a dense word costs
+//      what a sparse one costs); k_resolve_lists then maps rank -> slot -> entity handle for all entries in parallel,
+//   3. the words found set are cleared and the chunk counts of the OTHER frame parity are zeroed, so the next frame
+//      starts clean without a memset; the CTA of the last chunk also writes the frame totals and zeroes the
+//      accumulators and the work queue of k_update_win.
+// Chunks of 32 Ki ranks (not one long segment per SM) because the visible instances cluster around the camera: the few
+// hundred thousand ranks that hold nearly all set bits spread over ten or more SMs this way.
 // Replaces round 1's per-tile counts + k_scan_tiles + k_scatter_visible + k_scatter_culled + two memsets.
-constexpr uint32_t kCompactThreads = 1024;
+constexpr uint32_t kCompactThreads = 256;
 constexpr uint32_t kCompactRows = 2 * kMaxViews;
-constexpr uint32_t kPubStride = 32;                    // words per segment in the publication area: counts[16], flag at [16]
-constexpr uint32_t kPubFlag = kCompactRows;
-constexpr uint32_t kCompactChunkWords = kCompactThreads * 4;  // one uint4 per thread and row per chunk
+constexpr uint32_t kCompactChunkWords = kCompactThreads * 4;  // one uint4 per thread and plane
+static_assert(kCompactChunkWords * 32u == kChunkRanks, "one CTA per chunk");
 
 struct CompactParams
 {
   uint32_t* bits;                        // [nViews (+1)][bitWords]
-  const uint32_t* perm;                  // rank -> slot
-  const uint32_t* entity;                // slot -> handle
-  uint32_t* outEntity[kMaxViews];
-  uint32_t* outSlot[kMaxViews];
-  uint32_t* culledEntity[kMaxViews];     // valid when culled != 0
+  const uint32_t* chunkCounts;           // [nViews (+1)][chunkStride], this frame's parity
+  uint32_t* chunkCountsNext;             // the other parity: zeroed here for the next frame
+  uint32_t* outSlot[kMaxViews];          // receives the visible RANKS in ascending order (k_resolve_lists makes slots of them)
+  uint32_t* culledEntity[kMaxViews];     // valid when culled != 0; receives ranks likewise
   uint32_t* acc;                         // kAcc*
   uint32_t* totals;                      // out, kTotalsWords
-  uint32_t* pub;                         // [gridDim.x][kPubStride]
-  uint32_t* ticket;                      // running CTA ticket (never reset; ticketBase = its value before this launch)
-  uint32_t ticketBase, seq;
-  uint32_t bitWords, segWords;           // words per plane / per segment (a multiple of 4)
+  uint32_t* totalsHost;                  // the same, in pinned host memory: written over PCIe by the last chunk's CTA, so
+                                         // that no copy-engine operation sits in the frame's kernel chain
+  uint32_t bitWords, chunkStride;        // words per plane / counts per row
   uint32_t nWords;                       // words that can hold a set bit: ceil(live count / 32), rounded up to 4
   uint32_t nViews, culled;
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
-{
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v)
-{
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint32_t popc4(uint4 w) { return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w); }
 __device__ __forceinline__ uint4 andn4(uint4 a, uint4 b) { return make_uint4(a.x & ~b.x, a.y & ~b.y, a.z & ~b.z, a.w & ~b.w); }
 
-// exclusive scan of one 64-bit value per thread over the CTA (1024 threads); *total = sum over the CTA
+// exclusive scan of one 64-bit value per thread over the CTA (kCompactThreads threads); *total = sum over the CTA
 __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_t* sWarp, uint32_t tid, uint64_t* total)
 {
+  constexpr uint32_t kWarps = kCompactThreads / 32;
   const uint32_t lane = tid & 31u, warp = tid >> 5;
   uint64_t x = v;
 #pragma unroll
@@ -1507,171 +1531,224 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_
   }
   if (lane == 31) sWarp[warp] = x;
   __syncthreads();
-  if (warp == 0)
-  {
-    uint64_t w = sWarp[lane];
+  uint64_t before = 0, all = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      const uint64_t y = __shfl_up_sync(0xffffffffu, w, o);
-      if ((int)lane >= o) w += y;
-    }
-    sWarp[lane] = w;  // inclusive over warps
+  for (uint32_t k = 0; k < kWarps; ++k)
+  {
+    const uint64_t t = sWarp[k];
+    if (k < warp) before += t;
+    all += t;
   }
-  __syncthreads();
-  const uint64_t r = (warp ? sWarp[warp - 1] : 0ull) + x - v;
-  *total = sWarp[31];
+  *total = all;
   __syncthreads();  // sWarp is reused by the next scan
-  return r;
+  return before + x - v;
 }
 
-__global__ void __launch_bounds__(kCompactThreads, 1) k_compact(const __grid_constant__ CompactParams p)
+// the set bits of one plane row held by this warp (4 words per lane, consecutive lanes = consecutive words) as ranks at
+// out[first position of the word + rank order inside the word]; one warp step per non-empty word
+__device__ __forceinline__ void emit_ranks_warp(uint32_t* __restrict__ out, uint4 b, uint32_t pos, uint32_t w, uint32_t lane)
 {
-  __shared__ uint32_t sSeg;
-  __shared__ uint32_t sCount[kCompactRows];   // set bits of this segment per row
-  __shared__ uint32_t sBase[kCompactRows];    // output position of this segment's (then: this chunk's) first entry per row
-  __shared__ uint64_t sWarp[32];
-  const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  pdl_wait();  // the frame kernels' bits and counters are complete and visible
-  if (tid == 0) sSeg = atomicAdd(p.ticket, 1u) - p.ticketBase;
-  if (tid < kCompactRows) { sCount[tid] = 0u; sBase[tid] = 0u; }
-  __syncthreads();
-  const uint32_t seg = sSeg;
-  const uint32_t nRows = p.culled ? 2u * p.nViews : p.nViews;
-  const uint32_t w0 = min(p.nWords, seg * p.segWords), w1 = min(p.nWords, w0 + p.segWords);
-  const uint4* const candPlane = reinterpret_cast<const uint4*>(p.bits + (size_t)p.nViews * p.bitWords);
-
-  // ---- 1. counts of this segment
+  const uint32_t word[4] = { b.x, b.y, b.z, b.w };
+  const uint32_t ltMask = (1u << lane) - 1u;
+#pragma unroll
+  for (uint32_t k = 0; k < 4u; ++k)
   {
-    uint32_t cnt[kCompactRows];
-#pragma unroll
-    for (uint32_t r = 0; r < kCompactRows; ++r) cnt[r] = 0u;
-    for (uint32_t w = w0 + tid * 4u; w < w1; w += kCompactChunkWords)
+    uint32_t nz = __ballot_sync(0xffffffffu, word[k] != 0u);
+    while (nz)
     {
-      uint4 cand = make_uint4(0u, 0u, 0u, 0u);
-      if (p.culled) cand = candPlane[w >> 2];
+      const uint32_t src = __ffs(nz) - 1u;
+      nz &= nz - 1u;
+      const uint32_t wv = __shfl_sync(0xffffffffu, word[k], src);
+      const uint32_t wp = __shfl_sync(0xffffffffu, pos, src);
+      const uint32_t wr = (__shfl_sync(0xffffffffu, w, src) + k) * 32u;
+      if ((wv >> lane) & 1u) out[wp + __popc(wv & ltMask)] = wr + lane;
+    }
+    pos += __popc(word[k]);
+  }
+}
+
+#ifdef SCGPU_COMPACT_TIMING
+__device__ unsigned long long g_compactStamps[1024 * 8];
+#define SC_STAMP(k)                                                                                                   \
+  do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_compactStamps[blockIdx.x * 8 + (k)] = t_; } } while (0)
+#else
+#define SC_STAMP(k) do { } while (0)
+#endif
+
+template <int kViews>
+__global__ void __launch_bounds__(kCompactThreads, 4) k_compact(const __grid_constant__ CompactParams p)
+{
+  constexpr uint32_t V = (uint32_t)kViews;
+  __shared__ uint32_t sBase[2 * V];    // output position of this chunk's first entry per row: visible rows 0..V-1, culled rows V..2V-1
+  __shared__ uint32_t sCount[2 * V];   // set bits of this chunk per row
+  __shared__ uint64_t sWarp[kCompactThreads / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t seg = blockIdx.x;
+  const bool culled = p.culled != 0u;
+  const uint32_t nRows = culled ? 2u * V : V;
+  const uint32_t w = seg * kCompactChunkWords + tid * 4u;
+  const bool mine = w < p.nWords;
+  if (tid < 2u * V) { sBase[tid] = 0u; sCount[tid] = 0u; }
+  SC_STAMP(0);
+  pdl_wait();  // the frame kernels' bits and counters are complete and visible
+  __syncthreads();
+  pdl_trigger();  // k_resolve_lists may take its place on the SMs once every CTA of this grid is running
+  SC_STAMP(1);
+
+  // ---- this thread's four words of every plane (in flight while the chunk positions are added up)
+  uint4 vis[V];
+  uint4 cand = make_uint4(0u, 0u, 0u, 0u);
+  if (culled && mine) cand = reinterpret_cast<const uint4*>(p.bits + (size_t)V * p.bitWords)[w >> 2];
 #pragma unroll
-      for (uint32_t v = 0; v < kMaxViews; ++v)
+  for (uint32_t v = 0; v < V; ++v)
+  {
+    vis[v] = make_uint4(0u, 0u, 0u, 0u);
+    if (mine) vis[v] = reinterpret_cast<const uint4*>(p.bits + (size_t)v * p.bitWords)[w >> 2];
+  }
+
+  // ---- 1. sum of the chunk counts before this chunk, per row (culled = candidates - visible; the candidates are row V
+  //         of the counts). A 16 Mi-slot context has 512 chunks: at most three counts per thread and row, all loads
+  //         independent. The thread that meets t == seg contributes the chunk's own counts.
+  {
+    static_assert((1u << 24) / kChunkRanks <= 3u * kCompactThreads, "three rounds cover every chunk");
+    uint32_t before[V + 1], own[V + 1];
+#pragma unroll
+    for (uint32_t v = 0; v <= V; ++v) { before[v] = 0u; own[v] = 0u; }
+#pragma unroll
+    for (uint32_t round = 0; round < 3u; ++round)
+    {
+      const uint32_t t = tid + round * kCompactThreads;
+#pragma unroll
+      for (uint32_t v = 0; v <= V; ++v)
       {
-        if (v < p.nViews)
+        if (t <= seg && (v < V || culled))
         {
-          const uint4 vis = reinterpret_cast<const uint4*>(p.bits + (size_t)v * p.bitWords)[w >> 2];
-          cnt[v] += popc4(vis);
-          if (p.culled) cnt[kMaxViews + v] += popc4(andn4(cand, vis));
+          const uint32_t c = p.chunkCounts[(size_t)v * p.chunkStride + t];
+          if (t < seg) before[v] += c; else own[v] = c;
         }
       }
     }
 #pragma unroll
-    for (uint32_t r = 0; r < kCompactRows; ++r)
+    for (uint32_t v = 0; v < V; ++v)
     {
-      const uint32_t c = __reduce_add_sync(0xffffffffu, cnt[r]);
-      // rows are stored densely: visible rows 0..nViews-1, culled rows nViews..2 nViews-1
-      const uint32_t row = r < kMaxViews ? r : p.nViews + (r - kMaxViews);
-      if (lane == 0 && c) atomicAdd(&sCount[row], c);
+      const uint32_t b = __reduce_add_sync(0xffffffffu, before[v]);
+      const uint32_t o = __reduce_add_sync(0xffffffffu, own[v]);
+      if (lane == 0 && b) atomicAdd(&sBase[v], b);
+      if (lane == 0 && o) atomicAdd(&sCount[v], o);
+      if (culled)
+      {
+        const uint32_t cb = __reduce_add_sync(0xffffffffu, before[V] - before[v]);
+        const uint32_t co = __reduce_add_sync(0xffffffffu, own[V] - own[v]);
+        if (lane == 0 && cb) atomicAdd(&sBase[V + v], cb);
+        if (lane == 0 && co) atomicAdd(&sCount[V + v], co);
+      }
     }
   }
   __syncthreads();
-
-  // ---- 2. publish, then add up the segments before this one
-  uint32_t* const myPub = p.pub + (size_t)seg * kPubStride;
-  if (tid < nRows) myPub[tid] = sCount[tid];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) st_release_gpu(myPub + kPubFlag, p.seq);
-  for (uint32_t t = tid; t < seg; t += kCompactThreads)
-  {
-    const uint32_t* q = p.pub + (size_t)t * kPubStride;
-    while (ld_acquire_gpu(q + kPubFlag) != p.seq) __nanosleep(40);
-    for (uint32_t r = 0; r < nRows; ++r)
-    {
-      const uint32_t c = q[r];
-      if (c) atomicAdd(&sBase[r], c);
-    }
-  }
-  __syncthreads();
+  SC_STAMP(2);
   if (seg == gridDim.x - 1u)
   {
     // frame totals; accumulators and the window queue are left zeroed for the next frame
-    if (tid < p.nViews) p.totals[tid] = sBase[tid] + sCount[tid];
-    if (tid == 32) { p.totals[p.nViews] = p.acc[kAccCand]; p.acc[kAccCand] = 0u; }
-    if (tid == 33) { p.totals[kMaxViews + 1] = p.acc[kAccRecomputed]; p.acc[kAccRecomputed] = 0u; }
-    if (tid == 34) { p.acc[kAccQueueNext] = 0u; p.acc[kAccQueueSlow] = 0u; }
+    uint32_t val = 0, at = 0xFFFFFFFFu;
+    if (tid < V) { at = tid; val = sBase[tid] + sCount[tid]; }
+    if (tid == 32) { at = V; val = p.acc[kAccCand]; p.acc[kAccCand] = 0u; }
+    if (tid == 33) { at = kMaxViews + 1; val = p.acc[kAccRecomputed]; p.acc[kAccRecomputed] = 0u; }
+    if (tid == 34) { at = kMaxViews + 2; val = p.acc[kAccQueueSlow]; p.acc[kAccQueueNext] = 0u; p.acc[kAccQueueSlow] = 0u; }
+    if (at != 0xFFFFFFFFu)
+    {
+      p.totals[at] = val;
+      p.totalsHost[at] = val;
+      __threadfence_system();
+    }
   }
 
-  // ---- 3 + 4. lists, then clean bitmaps
-  for (uint32_t c0 = w0; c0 < w1; c0 += kCompactChunkWords)
+  // ---- 2. ranks out: three rows share one 64-bit block scan (21-bit fields: a chunk holds 2^15 ranks)
+#pragma unroll
+  for (uint32_t r0 = 0; r0 < 2u * V; r0 += 3u)
   {
-    const uint32_t w = c0 + tid * 4u;
-    const bool mine = w < w1;
-    uint4 cand = make_uint4(0u, 0u, 0u, 0u);
-    if (p.culled && mine) cand = candPlane[w >> 2];
-    // three rows share one 64-bit block scan (21-bit fields: a chunk holds 2^17 ranks)
-    for (uint32_t r0 = 0; r0 < nRows; r0 += 3u)
+    if (r0 >= nRows) break;
+    uint32_t any = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 3u; ++j) any |= (r0 + j < nRows) ? sCount[r0 + j] : 0u;
+    if (!any) continue;  // block-uniform: nothing set in this chunk for these rows
+    uint4 bitsOf[3];
+    uint64_t packed = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 3u; ++j)
     {
-      const uint32_t rEnd = min(nRows, r0 + 3u);
-      uint32_t any = 0;
-      for (uint32_t r = r0; r < rEnd; ++r) any |= sCount[r];
-      if (!any) continue;  // block-uniform: nothing set in this segment for these rows
-      uint4 bitsOf[3];
-      uint64_t packed = 0;
-#pragma unroll
-      for (uint32_t j = 0; j < 3u; ++j)
-      {
-        const uint32_t r = r0 + j;
-        uint4 b = make_uint4(0u, 0u, 0u, 0u);
-        if (mine && r < rEnd)
-        {
-          const uint32_t v = r < p.nViews ? r : r - p.nViews;
-          b = reinterpret_cast<const uint4*>(p.bits + (size_t)v * p.bitWords)[w >> 2];
-          if (r >= p.nViews) b = andn4(cand, b);
-        }
-        bitsOf[j] = b;
-        packed |= (uint64_t)popc4(b) << (21u * j);
-      }
-      uint64_t total;
-      const uint64_t excl = block_exclusive_scan_u64(packed, sWarp, tid, &total);
-#pragma unroll
-      for (uint32_t j = 0; j < 3u; ++j)
-      {
-        const uint32_t r = r0 + j;
-        const uint4 b = bitsOf[j];
-        if ((b.x | b.y | b.z | b.w) != 0u)  // implies r < rEnd
-        {
-          uint32_t pos = sBase[r] + (uint32_t)((excl >> (21u * j)) & 0x1FFFFFu);
-          const bool vis = r < p.nViews;
-          uint32_t* outE = vis ? p.outEntity[r] : p.culledEntity[r - p.nViews];
-          uint32_t* outS = vis ? p.outSlot[r] : nullptr;
-          const uint32_t word[4] = { b.x, b.y, b.z, b.w };
-#pragma unroll
-          for (uint32_t k = 0; k < 4u; ++k)
-          {
-            uint32_t m = word[k];
-            while (m)
-            {
-              const uint32_t rank = (w + k) * 32u + (__ffs(m) - 1u);
-              m &= m - 1u;
-              const uint32_t slot = p.perm[rank];
-              outE[pos] = p.entity[slot];
-              if (outS) outS[pos] = slot;
-              ++pos;
-            }
-          }
-        }
-      }
-      __syncthreads();  // every thread has read sBase of these rows
-      if (tid < rEnd - r0) sBase[r0 + tid] += (uint32_t)((total >> (21u * tid)) & 0x1FFFFFu);
+      const uint32_t r = r0 + j;  // compile-time after unrolling: vis[] is indexed statically
+      uint4 b = make_uint4(0u, 0u, 0u, 0u);
+      if (r < 2u * V && r < nRows) b = r < V ? vis[r < V ? r : 0] : andn4(cand, vis[r >= V && r < 2u * V ? r - V : 0]);
+      bitsOf[j] = b;
+      packed |= (uint64_t)popc4(b) << (21u * j);
     }
-    __syncthreads();
-    // clear what was set (all planes of this chunk); untouched words are not written
-    if (mine)
+    uint64_t total;
+    const uint64_t excl = block_exclusive_scan_u64(packed, sWarp, tid, &total);
+#pragma unroll
+    for (uint32_t j = 0; j < 3u; ++j)
     {
-      const uint32_t nPlanes = p.nViews + (p.culled ? 1u : 0u);
-      for (uint32_t v = 0; v < nPlanes; ++v)
+      const uint32_t r = r0 + j;
+      if (r < nRows && ((total >> (21u * j)) & 0x1FFFFFu) != 0u)  // warp-uniform (block-uniform)
       {
-        uint4* q = reinterpret_cast<uint4*>(p.bits + (size_t)v * p.bitWords) + (w >> 2);
-        const uint4 b = *q;
-        if ((b.x | b.y | b.z | b.w) != 0u) *q = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t* out = r < V ? p.outSlot[r < V ? r : 0] : p.culledEntity[r >= V && r < 2u * V ? r - V : 0];
+        emit_ranks_warp(out, bitsOf[j], sBase[r] + (uint32_t)((excl >> (21u * j)) & 0x1FFFFFu), w, lane);
       }
+    }
+  }
+
+  SC_STAMP(3);
+  // ---- 3. clean bitmaps and chunk counts for the next frame: only words that were set are written
+  if (mine)
+  {
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (uint32_t v = 0; v < V; ++v)
+      if ((vis[v].x | vis[v].y | vis[v].z | vis[v].w) != 0u)
+        reinterpret_cast<uint4*>(p.bits + (size_t)v * p.bitWords)[w >> 2] = zero;
+    if (culled && (cand.x | cand.y | cand.z | cand.w) != 0u)
+      reinterpret_cast<uint4*>(p.bits + (size_t)V * p.bitWords)[w >> 2] = zero;
+  }
+  // the other parity was read by the previous frame's k_compact (complete) and is written by the next frame's kernels
+  // (not started): every row of it, ALL chunks (the pool may have been larger then than it is now, and another view count)
+  if (tid <= kMaxViews)
+    for (uint32_t c = seg; c < p.chunkStride; c += gridDim.x) p.chunkCountsNext[(size_t)tid * p.chunkStride + c] = 0u;
+  SC_STAMP(4);
+}
+
+struct ResolveParams
+{
+  const uint32_t* perm;                  // rank -> slot
+  const uint32_t* entity;                // slot -> handle
+  const uint32_t* totals;                // frame totals written by k_compact
+  uint32_t* outEntity[kMaxViews];
+  uint32_t* outSlot[kMaxViews];          // in: ranks, out: slots
+  uint32_t* culledEntity[kMaxViews];     // in: ranks, out: entity handles
+  uint32_t nViews, culled;
+};
+
+// rank -> (slot, entity handle) for every entry of every list, grid-stride: one independent chain of two loads per entry
+__global__ void __launch_bounds__(kBlock) k_resolve_lists(const __grid_constant__ ResolveParams p)
+{
+  pdl_wait();
+  const uint32_t stride = gridDim.x * kBlock;
+  const uint32_t cand = p.totals[p.nViews];
+  for (uint32_t v = 0; v < p.nViews; ++v)
+  {
+    const uint32_t nVis = p.totals[v];
+    uint32_t* __restrict__ outS = p.outSlot[v];
+    uint32_t* __restrict__ outE = p.outEntity[v];
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nVis; i += stride)
+    {
+      const uint32_t slot = __ldg(p.perm + outS[i]);
+      outS[i] = slot;
+      outE[i] = __ldg(p.entity + slot);
+    }
+    if (p.culled)
+    {
+      const uint32_t nCul = cand - nVis;
+      uint32_t* __restrict__ outC = p.culledEntity[v];
+      for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nCul; i += stride)
+        outC[i] = __ldg(p.entity + __ldg(p.perm + outC[i]));
     }
   }
 }

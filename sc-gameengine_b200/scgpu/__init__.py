@@ -47,6 +47,8 @@ class Counts(C.Structure):
         ("visible", C.c_uint32 * MAX_VIEWS),
         ("culled", C.c_uint32 * MAX_VIEWS),
         ("recomputed", C.c_uint32),
+        ("slowWindows", C.c_uint32),
+        ("extent", C.c_uint32),
     ]
 
 
@@ -472,8 +474,9 @@ class Scene:
     def launches(self) -> int:
         return int(self.lib.scgpuKernelLaunchCount(self.ctx))
 
-    def enable_timings(self, on=True):
-        self._ck(self.lib.scgpuEnableTimings(self.ctx, 1 if on else 0), "scgpuEnableTimings")
+    def enable_timings(self, on=True, every=1):
+        """every = n > 1: only every n-th update carries the event pairs (they cut the dependent-launch chain)"""
+        self._ck(self.lib.scgpuEnableTimings(self.ctx, (max(1, int(every)) if on else 0)), "scgpuEnableTimings")
 
     def last_timings(self):
         k = C.c_float(0)
