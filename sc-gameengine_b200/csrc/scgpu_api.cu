@@ -1622,7 +1622,7 @@ int scgpuBuildSortedDraws(ScGpuScene* c, uint32_t view, uint32_t maxDraws, const
   c->hSortCounters[0] = c->hSortCounters[1] = 0;
   if (emitted)
   {
-    // pipeline ids are < 63 by contract; find how many key bits are in use so the radix sort skips the rest
+    // the key holds exactly the bits the asset tables need: mesh | material | pipeline (+ 1 bit: dropped)
     uint32_t maxPipe = 0;
     for (uint32_t m = 0; m < nMaterials; ++m)
     {
@@ -1631,47 +1631,45 @@ int scgpuBuildSortedDraws(ScGpuScene* c, uint32_t view, uint32_t maxDraws, const
       if (pid >= 63u) return (int)fail(c, "scgpuBuildSortedDraws: pipeline id %u of material %u is >= 63", pid, m);
       maxPipe = std::max(maxPipe, pid);
     }
+    auto bitsFor = [](uint32_t count) { uint32_t b = 1; while (b < 31u && (1u << b) < count) ++b; return b; };  // bits for ids 0 .. count-1, at least one
+    DrawKeyLayout lay{};
+    lay.meshBits = bitsFor(meshCount);        // ids 0 .. meshCount-1
+    lay.matBits = bitsFor(nMaterials);
+    lay.pipeBits = bitsFor(maxPipe + 1u);
+    const uint32_t keyBits = lay.total() + 1u;
     if (!ensure(c, c->matPipe, std::max<size_t>((size_t)nMaterials * 4, 4))) return 0;
     if (nMaterials) SC_CUDA(c, cudaMemcpyAsync(c->matPipe.ptr, materialPipeline, (size_t)nMaterials * 4, cudaMemcpyHostToDevice, c->stream));
-    size_t tempSort = 0, tempScan = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tempSort, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)emitted, 0, 64, c->stream);
-    cub::DeviceScan::InclusiveSum(nullptr, tempScan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)emitted, c->stream);
+    const uint32_t nTiles = (emitted + kSortTile - 1u) / kSortTile;
     const size_t e8 = ((size_t)emitted * 8 + 255) & ~(size_t)255, e4 = ((size_t)emitted * 4 + 255) & ~(size_t)255;
-    const size_t temp = (std::max(tempSort, tempScan) + 255) & ~(size_t)255;
-    if (!ensure(c, c->sortWork, 2 * e8 + 4 * e4 + temp)) return 0;
+    const size_t hBytes = ((size_t)kRadix * nTiles * 4 + 255) & ~(size_t)255, tBytes = ((size_t)(nTiles + 1) * 4 + 255) & ~(size_t)255;
+    if (!ensure(c, c->sortWork, 2 * e8 + 2 * e4 + 2 * hBytes + 2 * tBytes + 256)) return 0;
     char* w = (char*)c->sortWork.ptr;
-    uint64_t* keysIn = (uint64_t*)w; uint64_t* keysOut = (uint64_t*)(w + e8);
-    uint32_t* posIn = (uint32_t*)(w + 2 * e8); uint32_t* posOut = (uint32_t*)(w + 2 * e8 + e4);
-    uint32_t* flags = (uint32_t*)(w + 2 * e8 + 2 * e4); uint32_t* runIncl = (uint32_t*)(w + 2 * e8 + 3 * e4);
-    void* dTemp = w + 2 * e8 + 4 * e4;
+    uint64_t* keysA = (uint64_t*)w; uint64_t* keysB = (uint64_t*)(w + e8);
+    uint32_t* posA = (uint32_t*)(w + 2 * e8); uint32_t* posB = (uint32_t*)(w + 2 * e8 + e4);
+    uint32_t* hist = (uint32_t*)(w + 2 * e8 + 2 * e4); uint32_t* histScan = (uint32_t*)(w + 2 * e8 + 2 * e4 + hBytes);
+    uint32_t* tileHeads = (uint32_t*)(w + 2 * e8 + 2 * e4 + 2 * hBytes); uint32_t* tileBase = (uint32_t*)(w + 2 * e8 + 2 * e4 + 2 * hBytes + tBytes);
+    uint32_t* dummyTotal = (uint32_t*)(w + 2 * e8 + 2 * e4 + 2 * hBytes + 2 * tBytes);
     if (!ensure(c, c->sortedDraws, (size_t)emitted * sizeof(ScGpuDrawItem))) return 0;
     if (!ensure(c, c->drawRuns, (size_t)emitted * sizeof(ScGpuDrawRun))) return 0;
     k_draw_keys<<<blocksFor(emitted), kBlock, 0, c->stream>>>(c->visSlot[view], c->a.meshMat, (const uint32_t*)c->matPipe.ptr,
-                                                                nMaterials, meshCount, emitted, keysIn, posIn, c->dSortCounters);
-    // key bits in use: mesh [0,29), material [29,58), pipeline [58, 58+bits(maxPipe)); the all-ones invalid key needs
-    // the full width only when it can occur, i.e. always be safe and sort up to bit 64 if any draw was dropped: the
-    // dropped draws are not known on the host yet, so the top bits are always included (2 extra passes at most).
-    int bitsMesh = 1, bitsMat = 1;
-    while (bitsMesh < (int)kDrawIdBits && (meshCount >> bitsMesh)) ++bitsMesh;
-    while (bitsMat < (int)kDrawIdBits && (nMaterials >> bitsMat)) ++bitsMat;
-    (void)maxPipe;
-    size_t tb = temp;
-    // pass 1: mesh bits, pass 2: material bits, pass 3: pipeline + invalid marker bits (stable LSD passes compose)
-    cub::DeviceRadixSort::SortPairs(dTemp, tb, keysIn, keysOut, posIn, posOut, (int)emitted, 0, bitsMesh, c->stream);
-    tb = temp;
-    cub::DeviceRadixSort::SortPairs(dTemp, tb, keysOut, keysIn, posOut, posIn, (int)emitted, (int)kDrawIdBits,
-                                    (int)kDrawIdBits + bitsMat, c->stream);
-    tb = temp;
-    cub::DeviceRadixSort::SortPairs(dTemp, tb, keysIn, keysOut, posIn, posOut, (int)emitted, 2 * (int)kDrawIdBits, 64, c->stream);
-    k_draw_run_flags<<<blocksFor(emitted), kBlock, 0, c->stream>>>(keysOut, c->dSortCounters, emitted, flags);
-    tb = temp;
-    cub::DeviceScan::InclusiveSum(dTemp, tb, flags, runIncl, (int)emitted, c->stream);
-    k_draw_runs<<<blocksFor(emitted), kBlock, 0, c->stream>>>(keysOut, runIncl, c->dSortCounters, (DrawRun*)c->drawRuns.ptr,
-                                                                c->dSortCounters + 1);
+                                                                nMaterials, meshCount, emitted, lay, keysA, posA, c->dSortCounters);
+    ++c->launches;
+    // stable LSD passes, 8 bits each, over the bits in use only
+    for (uint32_t shift = 0; shift < keyBits; shift += kRadixBits)
+    {
+      k_radix_hist<<<nTiles, kBlock, 0, c->stream>>>(keysA, emitted, shift, hist, nTiles);
+      k_scan_tiles<<<1, 1024, 0, c->stream>>>(hist, histScan, dummyTotal, kRadix * nTiles);
+      k_radix_scatter<<<nTiles, kBlock, 0, c->stream>>>(keysA, posA, keysB, posB, emitted, shift, histScan, nTiles);
+      std::swap(keysA, keysB);
+      std::swap(posA, posB);
+      c->launches += 3;
+    }
+    k_draw_heads<<<nTiles, kBlock, 0, c->stream>>>(keysA, c->dSortCounters, tileHeads);
+    k_scan_tiles<<<1, 1024, 0, c->stream>>>(tileHeads, tileBase, dummyTotal, nTiles);
+    k_draw_runs<<<nTiles, kBlock, 0, c->stream>>>(keysA, c->dSortCounters, tileBase, lay, (DrawRun*)c->drawRuns.ptr, c->dSortCounters + 1);
     k_draw_run_counts<<<blocksFor(emitted), kBlock, 0, c->stream>>>((DrawRun*)c->drawRuns.ptr, c->dSortCounters + 1);
     k_gather_sorted_draws<<<blocksFor((uint64_t)emitted * 5ull), kBlock, 0, c->stream>>>(
-      c->visSlot[view], posOut, c->dSortCounters, c->a.entity, c->a.meshMat, c->a.world[0], c->a.world[1], c->a.world[2],
+      c->visSlot[view], posA, c->dSortCounters, c->a.entity, c->a.meshMat, c->a.world[0], c->a.world[1], c->a.world[2],
       c->a.world[3], (float4*)c->sortedDraws.ptr);
     c->launches += 5;
     SC_CUDA(c, cudaGetLastError());

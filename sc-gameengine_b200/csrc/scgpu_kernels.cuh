@@ -1070,8 +1070,12 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   pdl_trigger();
   const uint32_t total = *totalWindows;
 
+  // "this slot must be recomputed" as ONE masked compare of its flags word: the stamp equals this update's id; with every
+  // instance forced dirty: the LIVE bit is set (a hole is never dirty); in a cull-only update: never (0 != 1 under mask 0)
   const bool skip = (p.flags & kUpdSkipTransform) != 0;
   const bool force = (p.flags & kUpdForceDirty) != 0;
+  const uint32_t dirtyMask = skip ? 0u : (force ? kFlagLive : 0xFFFFFF00u);
+  const uint32_t dirtyWant = skip ? 1u : (force ? kFlagLive : (p.stamp << kStampShift));
   uint32_t order = 0;  // favourite plane per view, see cull_views_warp
   uint32_t nRecomputed = 0, accCand = 0;
   const uint32_t warpBase = sBase + warp * kWwSize;
@@ -1125,7 +1129,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     cp_async_wait<0>();
     __syncwarp();  // the staged list words were copied by other lanes
     const uint32_t recAddr = laneBase + bufOff;
-    bool live, nodeDirty = false, fast;
+    bool live, nodeDirty = false, fast, partial = false;
     uint32_t info;
     Mat4 W;  // assigned on every path that reads it
     {
@@ -1148,7 +1152,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         r0 = lds128(recAddr); r1 = lds128(recAddr + 512); sclZ = __uint_as_float(lds32(recAddr + 1024));
         fl = lds32(recAddr + 1536 + 12);
       }
-      nodeDirty = live && !skip && ((force && (fl & kFlagLive)) || ((fl >> kStampShift) == p.stamp));
+      nodeDirty = live && ((fl & dirtyMask) == dirtyWant);
       parentLane = (info >> kInfoParentShift) & 31u;
       // ---- 1. children inherit dirtiness level by level ----
       liveMask = __ballot_sync(0xffffffffu, live);
@@ -1162,22 +1166,34 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         }
       }
       // ---- 2. local matrices of everything that is recomputed; stored world matrices of the rest ----
-      const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, sclZ);
-      float sx, cx, sy, cy, sz, cz;
-      sincos3_warp(nodeDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
-      // every lane builds a matrix (lanes beyond the window from all-zero records, clean lanes one that is replaced
-      // right below): no per-lane branch around sixteen live registers. Roots: world == local.
-      W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);
-      bool ok = tame || !nodeDirty;
-      if (dirtyM != liveMask)  // warp-uniform: a fully dirty window loads no stored matrix at all
+      // A window that keeps some stored matrices (warp-uniform test; a fully dirty window loads none) copies them
+      // global -> shared straight into this warp's matrix area, asynchronously: the DRAM round trip runs under the
+      // sincos / TRS arithmetic of the dirty lanes and costs no register. They are read back - and checked - with
+      // everybody else's matrix after the level loop.
+      partial = dirtyM != liveMask;
+      if (partial)
       {
         if (live && !nodeDirty)
         {
-          W = load_world(p, (lds32(listAddr) & kWinSlotMask) + lane);
-          ok = mat4_is_affine(W);
+          const uint32_t q = (lds32(listAddr) & kWinSlotMask) + lane;
+          const uint32_t own = laneBase + kWwMat;
+          cp_async16s(own, p.w0 + q); cp_async16s(own + kMatC1, p.w1 + q);
+          cp_async16s(own + kMatC2, p.w2 + q); cp_async16s(own + kMatC3, p.w3 + q);
         }
+        cp_async_commit();
       }
-      fast = __all_sync(0xffffffffu, ok);
+      if (dirtyM != 0u)  // warp-uniform: a window of static props (nothing dirty) builds no matrix at all
+      {
+        const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, sclZ);
+        float sx, cx, sy, cy, sz, cz;
+        sincos3_warp(nodeDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
+        // every lane builds a matrix (lanes beyond the window from all-zero records, clean lanes one that is never
+        // used): no per-lane branch around sixteen live registers. Roots: world == local.
+        W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);
+        fast = __all_sync(0xffffffffu, tame || !nodeDirty);
+      }
+      else
+        W = mat4_identity();  // replaced by the stored matrices below (lanes beyond the window never use theirs)
     }
     // ---- what comes next for this warp: the next window of the chunk, or the first one of the staged next chunk ----
     const uint32_t a = lds32(listAddr) & kWinSlotMask;  // this window's start: the list slot may be recycled below
@@ -1204,10 +1220,15 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     if (fast)
     {
       // ---- 3. parent.world * local level by level, one lane PAIR per child ----
-      if (maxL != 0u && dirtyM != 0u)
+      const bool compose = maxL != 0u && dirtyM != 0u;
+      if (compose || partial)
       {
         const uint32_t own = laneBase + kWwMat;
-        sts128(own, W.c0); sts128(own + kMatC1, W.c1); sts128(own + kMatC2, W.c2); sts128(own + kMatC3, W.c3);
+        if (!partial || nodeDirty)  // (the slots of the clean lanes are being filled by the copy engine)
+        {
+          sts128(own, W.c0); sts128(own + kMatC1, W.c1); sts128(own + kMatC2, W.c2); sts128(own + kMatC3, W.c3);
+        }
+        if (partial) cp_async_wait<1>();  // the stored matrices have landed; the next window's records may still fly
         __syncwarp();
         // one product: this lane computes columns 2h, 2h+1 (h = lane & 1) of child = parent * child, in place
         auto level_item = [&](uint32_t child, uint32_t par)
@@ -1240,7 +1261,11 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
           sts128(cAddr + kWwMat, oa);
           sts128(cAddr + kWwMat + 512, ob);
         };
-        if (dirtyM == liveMask && (lds32(listAddr) & kWinNoStatic) == 0u)
+        if (!compose)
+        {
+          // nothing to multiply (no hierarchy in this window, or nothing dirty): the matrices only pass through
+        }
+        else if (dirtyM == liveMask && (lds32(listAddr) & kWinNoStatic) == 0u)
         {
           // every node is recomputed: who multiplies what is a function of the topology alone and was laid down by
           // k_build_windows in the slotInfo words (6 bits per level)
@@ -1287,8 +1312,9 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         W.c0 = lds128(own); W.c1 = lds128(own + kMatC1); W.c2 = lds128(own + kMatC2); W.c3 = lds128(own + kMatC3);
         // the structured products are value-exact iff every parent translation was finite; a non-finite one
         // propagates into the translation of all its descendants, so one test of the results covers all levels
+        // (a stored matrix that is kept must be affine for the structured sphere and products to be exact)
         const float mag = fabsf(W.c3.x) + fabsf(W.c3.y) + fabsf(W.c3.z);
-        fast = __all_sync(0xffffffffu, !nodeDirty || mag < __int_as_float(0x7f800000));
+        fast = __all_sync(0xffffffffu, nodeDirty ? mag < __int_as_float(0x7f800000) : (!live || !partial || mat4_is_affine(W)));
       }
     }
     if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed, accCand);

@@ -161,6 +161,8 @@ def ref_lib():
             getattr(L, name).argtypes = [C.c_float]
         L.screfAtan2f.restype = C.c_float
         L.screfAtan2f.argtypes = [C.c_float, C.c_float]
+        L.screfRendererSubmit.restype = C.c_uint32
+        L.screfRendererSubmit.argtypes = [_vp, C.c_uint32, _vp, C.c_uint32, C.c_uint32, _vp, _vp]
         _ref = L
     return _ref
 
@@ -423,6 +425,37 @@ def renderer_sorted_draws(draws, material_pipeline, mesh_count):
         else:
             runs.append([k[0], k[1], k[2], pos, 1])
     return order, [tuple(r) for r in runs]
+
+
+def ref_renderer_submit(draws, material_pipeline, mesh_count):
+    """The reference's OWN draw submission block (src/engine/src/sc_vk.cpp:1841-1912, compiled into oracle/_ref by
+    ref_shim/scref_renderer.cpp) run over `draws` (DRAW_ITEM_DTYPE records). Returns (order, binds): order[k] = index of
+    the k-th vkCmdDrawIndexed'ed item, binds[k] = what the loop bound right before it (1 pipeline | 2 material | 4 mesh)."""
+    d = np.ascontiguousarray(draws, DRAW_ITEM_DTYPE)
+    mp = np.ascontiguousarray(material_pipeline, np.uint32)
+    order = np.zeros(len(d), np.uint32)
+    binds = np.zeros(len(d), np.uint8)
+    n = ref_lib().screfRendererSubmit(_p(d), len(d), _p(mp), len(mp), int(mesh_count), _p(order), _p(binds))
+    return order[:n], binds[:n]
+
+
+def check_against_renderer(draws, material_pipeline, mesh_count, order, runs, what=""):
+    """(order, runs) — ours, or the numpy restatement's — against what the reference's loop submitted: the same set of
+    draws, the same (pipeline, material, mesh) key at every position, a run starting exactly where the loop bound
+    something. std::sort is unstable: WHICH of several equal-key items stands at a position is not defined by the
+    reference, so inside a run only the multiset of items is compared."""
+    ro, rb = ref_renderer_submit(draws, material_pipeline, mesh_count)
+    assert len(ro) == len(order), (what, len(ro), len(order))
+    mesh, mat = np.asarray(draws["meshId"], np.int64), np.asarray(draws["materialId"], np.int64)
+    mp = np.asarray(material_pipeline, np.int64)
+    key = lambda idx: (mp[mat[idx]] << 58) | (mat[idx] << 29) | mesh[idx]
+    assert np.array_equal(key(ro), key(np.asarray(order))), what + ": key sequence differs from the reference's submission order"
+    starts = np.flatnonzero(rb != 0)
+    assert [int(r[3]) for r in runs] == [int(x) for x in starts], what + ": run starts != the loop's bind points"
+    assert np.array_equal(np.sort(ro), np.sort(np.asarray(order))), what + ": kept set differs"
+    for r in runs:
+        a, b = int(r[3]), int(r[3]) + int(r[4])
+        assert np.array_equal(np.sort(ro[a:b]), np.sort(np.asarray(order)[a:b])), what + ": items of a run differ"
 
 
 # ---- SURVEY.md 8(f) N4: traffic on rails -----------------------------------------------------------------------

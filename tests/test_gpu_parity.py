@@ -321,23 +321,26 @@ def test_random_forest_large(max_back, p_child, seed):
     g.close()
 
 
-@pytest.mark.parametrize("max_draws", [0, 700])
-def test_sorted_draws_and_runs_match_renderer_sort(max_draws):
-    """scgpuBuildSortedDraws against the restated renderer loop (sc_vk.cpp:1843-1905): same kept
-    set, same (pipeline, material, mesh) order, same runs; ties in visible order; models bit-identical."""
-    from oracle_bind import renderer_sorted_draws
+@pytest.mark.parametrize("max_draws,n_mesh,n_mat", [(0, 10, 37), (700, 10, 37), (0, 300, 1500), (0, 1, 1)])
+def test_sorted_draws_and_runs_match_renderer_sort(max_draws, n_mesh, n_mat):
+    """scgpuBuildSortedDraws (hand-written counting sort, one to three 8-bit passes depending on the
+    size of the asset tables) against the restated renderer loop AND, when oracle/_ref is there, against the reference's
+    own block of sc_vk.cpp (:1841-1912): same kept set, same (pipeline, material, mesh) order, runs exactly at the
+    loop's bind points; ties in visible order; models bit-identical."""
+    from oracle_bind import check_against_renderer, renderer_sorted_draws
     rng = np.random.default_rng(77)
     n = 30_000
     sc = scenes.city_flat(n, seed=9)
-    mm = np.stack([rng.integers(0, 12, n), rng.integers(0, 40, n)], axis=1).astype(np.uint32)  # meshId, materialId
+    mm = np.stack([rng.integers(0, n_mesh + 2, n), rng.integers(0, n_mat + 3, n)], axis=1).astype(np.uint32)  # meshId, materialId
     e = np.arange(n, dtype=np.uint32)
     g = GpuAdapter(n, max_views=2)
     vps = scenes.standard_views(2)
     g.spawn(e, sc["trs9"], None, sc["aabb6"], mm, sc["flags"])
     g.update(vps, freeze=True)  # every candidate visible: a long draw list
-    mesh_count = 10                                   # meshIds 10, 11 are out of range -> dropped
-    mat_pipe = rng.integers(0, 2, 37).astype(np.uint32)  # materials 37..39 unknown (beyond the table)
-    mat_pipe[[3, 17]] = 0xFFFFFFFF                    # getMaterial() == nullptr
+    mesh_count = n_mesh                                  # the two largest meshIds are out of range -> dropped
+    mat_pipe = rng.integers(0, 2, n_mat).astype(np.uint32)  # the three largest materialIds are beyond the table
+    if n_mat > 20:
+        mat_pipe[[3, 17]] = 0xFFFFFFFF                   # getMaterial() == nullptr
     draws, emitted, dropped = g.read_draw_items(0, max_draws)
     order, runs = renderer_sorted_draws(draws, mat_pipe, mesh_count)
     items, gruns = g.s.sorted_draws(0, mat_pipe, mesh_count, max_draws)
@@ -348,6 +351,11 @@ def test_sorted_draws_and_runs_match_renderer_sort(max_draws):
     assert_same_bits(items["model"], want["model"], "sorted draw models")
     assert [tuple(int(x) for x in r) for r in gruns] == runs
     assert sum(r[4] for r in runs) == len(items)
+    if oracle_bind.ref_available():
+        # ours -> positions in `draws` through the entity handle (unique per draw), then against the reference's loop
+        where = {int(h): i for i, h in enumerate(draws["entity"])}
+        mine = np.array([where[int(h)] for h in items["entity"]], np.int64)
+        check_against_renderer(draws, mat_pipe, mesh_count, mine, [tuple(int(x) for x in r) for r in gruns], "gpu vs sc_vk.cpp")
     # an empty table drops everything
     items0, runs0 = g.s.sorted_draws(0, np.zeros(0, np.uint32), mesh_count, max_draws)
     assert len(items0) == 0 and len(runs0) == 0

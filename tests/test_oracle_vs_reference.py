@@ -179,3 +179,23 @@ def test_long_streaming_churn_port_equals_reference():
             ph = r.read_parents(dense)
             far_seen = sum(1 for i, h in enumerate(ph) if int(h) in slot and abs(slot[int(h)] - i) >= 32)
     assert far_seen > n // 20, "the scene did not get scrambled: the test does not reach the regime it is about"
+
+
+def test_renderer_sort_restatement_equals_the_reference_loop():
+    """SURVEY 8(f) N1 oracle pinned: the numpy restatement of the renderer's filter + sort + bind-on-change loop
+    (oracle_bind.renderer_sorted_draws) against the reference's own block of sc_vk.cpp (:1841-1912) compiled into
+    oracle/_ref: kept set, key order, bind points. Unknown materials, null materials, out-of-range meshes, empty input."""
+    from oracle_bind import DRAW_ITEM_DTYPE, check_against_renderer, ref_renderer_submit, renderer_sorted_draws
+    rng = np.random.default_rng(5)
+    for n, n_mat, n_mesh in ((0, 4, 3), (1, 1, 1), (257, 9, 5), (20_000, 41, 12), (3000, 300, 70)):
+        d = np.zeros(n, DRAW_ITEM_DTYPE)
+        d["entity"] = np.arange(n)
+        d["meshId"] = rng.integers(0, n_mesh + 3, n)       # some out of range
+        d["materialId"] = rng.integers(0, n_mat + 2, n)    # some beyond the table
+        d["model"] = rng.normal(size=(n, 16))
+        mp = rng.integers(0, 2, n_mat).astype(np.uint32)   # PipelineId::UnlitColor / ::Textured
+        mp[rng.integers(0, n_mat, max(1, n_mat // 8))] = 0xFFFFFFFF  # getMaterial() == nullptr
+        order, runs = renderer_sorted_draws(d, mp, n_mesh)
+        check_against_renderer(d, mp, n_mesh, order, runs, f"n={n}")
+        ro, rb = ref_renderer_submit(d, mp, n_mesh)
+        assert len(ro) == 0 or rb[0] == 7  # the first draw binds pipeline, material and mesh
