@@ -10,8 +10,10 @@
 #include "sc_gpu_systems.h"
 #include "sc_jobs.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -33,8 +35,118 @@ namespace
   uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
 }
 
-int main()
+namespace
 {
+  double nowMs()
+  {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+
+  // --bench N: the three adapter systems against the reference's own three on ONE World of N entities in groups of
+  // five (root + four parented children, all with RenderMesh + Bounds), 10 % of the Transforms dirtied per frame
+  // through sc::setLocal. Prints one JSON object: host milliseconds per frame of each system.
+  int bench(uint32_t n, uint32_t frames)
+  {
+    ScRefWorld* w = screfCreate(0);
+    sc::World& world = w->world;
+    world.reserveEntities(n);
+    std::vector<sc::Entity> all;
+    all.reserve(n);
+    uint32_t rng = 99u;
+    sc::Entity root{};
+    for (uint32_t i = 0; i < n; ++i)
+    {
+      const sc::Entity e = world.create();
+      sc::Transform& t = world.add<sc::Transform>(e);
+      const bool isRoot = (i % 5u) == 0u;
+      const float p[3] = { isRoot ? (float)(lcg(rng) % 8192u) - 4096.0f : 0.5f, isRoot ? 0.0f : 0.25f, isRoot ? (float)(lcg(rng) % 8192u) - 4096.0f : -0.5f };
+      const float r[3] = { 0.0f, (float)(lcg(rng) % 628u) * 0.01f, 0.0f }, sc3[3] = { 1.0f, 1.0f, 1.0f };
+      sc::setLocal(t, p, r, sc3);
+      if (isRoot) root = e; else sc::setParent(t, root);
+      sc::RenderMesh& rm = world.add<sc::RenderMesh>(e);
+      rm.meshId = 1 + i % 3; rm.materialId = 1 + i % 4;
+      world.add<sc::Bounds>(e).localAabb = { { -0.5f, -0.5f, -0.5f }, { 0.5f, 0.5f, 0.5f } };
+      all.push_back(e);
+    }
+    const sc::Entity cam = world.create();
+    {
+      sc::Transform& t = world.add<sc::Transform>(cam);
+      const float p[3] = { 32.0f, 6.0f, 44.0f }, r[3] = { 0.0f, 3.14159265f, 0.0f }, s3[3] = { 1.0f, 1.0f, 1.0f };
+      sc::setLocal(t, p, r, s3);
+      sc::Camera& c = world.add<sc::Camera>(cam);
+      c.active = true;
+    }
+    sc::gpu::GpuSceneState gs{};
+    gs.maxInstances = n + 16;
+    gs.leaveDirtyFlags = true;
+    if (!sc::gpu::init(gs)) { std::printf("gpu init failed: %s\n", gs.lastError); return 2; }
+    sc::RenderFrameData gpuFrame{};
+    sc::CullingState gpuCull{};
+    gpuCull.frame = &gpuFrame;
+    sc::RenderPrepStreamingState gpuPrep{};
+    gpuPrep.frame = &gpuFrame;
+    gpuPrep.culling = &gpuCull;
+    gpuPrep.streaming = w->streaming;
+    sc::gpu::GpuCullingState gc{ &gs, &gpuCull, false, true };
+    sc::gpu::GpuRenderPrepState gp{ &gs, &gpuPrep };
+    double tGpuT = 0, tGpuC = 0, tGpuP = 0, tRefT = 0, tRefC = 0, tRefP = 0;
+    uint32_t timed = 0, visible = 0;
+    bool same = true;
+    for (uint32_t f = 0; f < frames + 2; ++f)
+    {
+      if (f > 0)
+        for (uint32_t k = 0; k < n / 10u; ++k)
+        {
+          sc::Transform* t = world.get<sc::Transform>(all[lcg(rng) % n]);
+          const float p[3] = { t->localPos[0] + 0.25f, t->localPos[1], t->localPos[2] }, r[3] = { 0.0f, t->localRot[1] + 0.1f, 0.0f };
+          sc::setLocal(*t, p, r, t->localScale);
+        }
+      const double a0 = nowMs();
+      sc::gpu::TransformSystem(world, 1.0f / 60.0f, &gs);
+      const double a1 = nowMs();
+      sc::jobs().beginFrame();
+      sc::TransformSystem(world, 1.0f / 60.0f, nullptr);
+      const double a2 = nowMs();
+      sc::CameraSystem(world, 1.0f / 60.0f, &w->camera);
+      const double a3 = nowMs();
+      sc::CullingSystem(world, 1.0f / 60.0f, &w->culling);
+      const double a4 = nowMs();
+      sc::RenderPrepStreamingSystem(world, 1.0f / 60.0f, &w->renderPrep);
+      const double a5 = nowMs();
+      sc::jobs().publishFrameTelemetry();
+      gpuFrame.viewProj = world.renderFrame().viewProj;
+      const double b0 = nowMs();
+      sc::gpu::CullingSystem(world, 1.0f / 60.0f, &gc);
+      const double b1 = nowMs();
+      sc::gpu::RenderPrepStreamingSystem(world, 1.0f / 60.0f, &gp);
+      const double b2 = nowMs();
+      same = same && w->culling.visible.size() == gpuCull.visible.size() &&
+             std::memcmp(w->culling.visible.data(), gpuCull.visible.data(), gpuCull.visible.size() * 4) == 0 &&
+             w->culling.candidates.size() == gpuCull.candidates.size() && world.renderFrame().draws.size() == gpuFrame.draws.size();
+      visible = gpuCull.stats.visible;
+      if (f >= 2)
+      {
+        tGpuT += a1 - a0; tRefT += a2 - a1; tRefC += a4 - a3; tRefP += a5 - a4; tGpuC += b1 - b0; tGpuP += b2 - b1;
+        ++timed;
+      }
+    }
+    const double k = 1.0 / timed;
+    std::printf("{\"entities\": %u, \"frames\": %u, \"dirty_fraction\": 0.1, \"visible\": %u, \"outputs_equal\": %s, \"resyncs\": %llu, "
+                "\"adapter_ms\": {\"TransformSystem\": %.3f, \"CullingSystem\": %.3f, \"RenderPrepStreamingSystem\": %.3f}, "
+                "\"reference_ms\": {\"TransformSystem\": %.3f, \"CullingSystem\": %.3f, \"RenderPrepStreamingSystem\": %.3f}, "
+                "\"reference_threads\": %u}\n",
+                n, timed, visible, same ? "true" : "false", (unsigned long long)gs.resyncs, tGpuT * k, tGpuC * k, tGpuP * k, tRefT * k,
+                tRefC * k, tRefP * k, screfJobWorkers() + 1u);
+    sc::gpu::shutdown(gs);
+    screfDestroy(w);
+    return same ? 0 : 1;
+  }
+}
+
+int main(int argc, char** argv)
+{
+  if (argc >= 3 && std::strcmp(argv[1], "--bench") == 0)
+    return bench((uint32_t)std::strtoul(argv[2], nullptr, 10), argc >= 4 ? (uint32_t)std::strtoul(argv[3], nullptr, 10) : 8u);
   ScRefWorld* w = screfCreate(0);
   if (!w) { std::printf("screfCreate failed\n"); return 2; }
   const uint32_t sectors = screfBuildDefaultScene(w, 60);
@@ -55,12 +167,13 @@ int main()
   gpuPrep.culling = &gpuCull;
   gpuPrep.streaming = w->streaming;
   gpuPrep.assets = nullptr;
-  sc::gpu::GpuCullingState gc{ &gs, &gpuCull, true, false };
+  sc::gpu::GpuCullingState gc{ &gs, &gpuCull, true, true };
   sc::gpu::GpuRenderPrepState gp{ &gs, &gpuPrep };
 
   uint32_t rng = 12345u;
   std::vector<sc::Entity> dense;
-  const uint32_t kFrames = 8;
+  std::vector<sc::Entity> lateOnes;  // Transform-only entities that get RenderMesh / Bounds later (sc_traffic_lod.cpp:47-70)
+  const uint32_t kFrames = 12;
   for (uint32_t frame = 0; frame < kFrames; ++frame)
   {
     dense.clear();
@@ -98,6 +211,37 @@ int main()
     }
     if (frame == 4)
       for (int k = 0; k < 25; ++k) world.destroy(dense[dense.size() - 1 - (3 * k) % dense.size()]);  // arbitrary order
+    if (frame == 8)
+      for (int k = 0; k < 9; ++k)   // Transform now, render components later
+      {
+        const sc::Entity e = world.create();
+        sc::Transform& t = world.add<sc::Transform>(e);
+        const float p[3] = { 30.0f + k, 1.0f, 40.0f - k }, r[3] = { 0.0f, 0.2f * k, 0.0f }, s[3] = { 1.0f, 1.0f, 1.0f };
+        sc::setLocal(t, p, r, s);
+        lateOnes.push_back(e);
+      }
+    if (frame == 9)
+      for (size_t k = 0; k < lateOnes.size(); ++k)   // late World::add<RenderMesh / Bounds> on a live Transform
+      {
+        sc::RenderMesh& rm = world.add<sc::RenderMesh>(lateOnes[k]);
+        rm.meshId = 2; rm.materialId = 3 + (uint32_t)k;
+        if (k % 2 == 0) world.add<sc::Bounds>(lateOnes[k]).localAabb = { { -2, -1, -2 }, { 2, 1, 2 } };
+      }
+    if (frame == 10)
+    {
+      for (size_t k = 0; k < lateOnes.size(); ++k)   // LOD swap: mesh / material ids change, a Bounds box grows
+      {
+        sc::RenderMesh* rm = world.get<sc::RenderMesh>(lateOnes[k]);
+        rm->meshId = 4; rm->materialId += 10;
+        if (sc::Bounds* b = world.get<sc::Bounds>(lateOnes[k])) b->localAabb.max.y = 3.0f;
+      }
+      world.get<sc::RenderMesh>(w->spawner.cube)->materialId = 9;   // sc_imgui.cpp:720
+    }
+    if (frame == 11)
+    {
+      world.remove<sc::RenderMesh>(lateOnes[1]);   // no longer a candidate
+      world.remove<sc::Bounds>(lateOnes[0]);       // always visible from now on
+    }
     w->culling.freezeCulling = gpuCull.freezeCulling = (frame == 6);
     w->streaming->budgets.maxDrawsBudget = (frame == 7) ? 50u : 6000u;
 
@@ -122,6 +266,8 @@ int main()
           std::memcmp(a.visible.data(), gpuCull.visible.data(), a.visible.size() * 4) == 0, "CullingState::visible (ordered)", frame);
     check(a.culled.size() == gpuCull.culled.size() &&
           std::memcmp(a.culled.data(), gpuCull.culled.data(), a.culled.size() * 4) == 0, "CullingState::culled (ordered)", frame);
+    check(a.candidates.size() == gpuCull.candidates.size() &&
+          std::memcmp(a.candidates.data(), gpuCull.candidates.data(), a.candidates.size() * 4) == 0, "CullingState::candidates (ordered)", frame);
     if (!a.freezeCulling)
       check(std::memcmp(a.frustum.planes, gpuCull.frustum.planes, sizeof(a.frustum.planes)) == 0, "CullingState::frustum", frame);
     const std::vector<sc::DrawItem>& da = world.renderFrame().draws;
@@ -151,6 +297,33 @@ int main()
     std::printf("frame %u: %zu transforms, visible %u culled %u draws %zu dropped %u resyncs %llu %s\n", frame, dense.size(),
                 gpuCull.stats.visible, gpuCull.stats.culled, db.size(), gpuPrep.stats.drawsDroppedByBudget,
                 (unsigned long long)gs.resyncs, g_fail ? "FAIL" : "ok");
+  }
+  {
+    // RenderPrepStreamingSystem without a culling stage (state->culling == nullptr, .cpp:1330-1346): every Transform +
+    // RenderMesh entity in pool order, budget applied
+    sc::RenderFrameData refFrame{};
+    sc::RenderPrepStreamingState refPrep = w->renderPrep;
+    refPrep.frame = &refFrame;
+    refPrep.culling = nullptr;
+    refPrep.assets = nullptr;
+    gpuPrep.culling = nullptr;
+    for (const uint32_t budget : { 0u, 100u })
+    {
+      w->streaming->budgets.maxDrawsBudget = budget;
+      sc::RenderPrepStreamingSystem(world, 1.0f / 60.0f, &refPrep);
+      sc::gpu::RenderPrepStreamingSystem(world, 1.0f / 60.0f, &gp);
+      bool ok = refFrame.draws.size() == gpuFrame.draws.size() && refPrep.stats.drawsEmitted == gpuPrep.stats.drawsEmitted &&
+                refPrep.stats.drawsDroppedByBudget == gpuPrep.stats.drawsDroppedByBudget;
+      for (size_t i = 0; ok && i < refFrame.draws.size(); ++i)
+      {
+        ok = refFrame.draws[i].entity == gpuFrame.draws[i].entity && refFrame.draws[i].meshId == gpuFrame.draws[i].meshId &&
+             refFrame.draws[i].materialId == gpuFrame.draws[i].materialId;
+        for (int k = 0; ok && k < 16; ++k) ok = sameValue(refFrame.draws[i].model.m[k], gpuFrame.draws[i].model.m[k]);
+      }
+      check(ok, "RenderPrepStreamingSystem without a culling stage", 100u + budget);
+      std::printf("no culling stage, budget %u: %zu draws, dropped %u %s\n", budget, gpuFrame.draws.size(), gpuPrep.stats.drawsDroppedByBudget,
+                  g_fail ? "FAIL" : "ok");
+    }
   }
   sc::gpu::shutdown(gs);
   screfDestroy(w);

@@ -9,9 +9,9 @@
 #include "sc_log.h"
 #include "sc_math.h"
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
-#include <unordered_set>
 
 namespace sc::gpu
 {
@@ -20,40 +20,54 @@ namespace sc::gpu
 
   namespace
   {
+    constexpr uint32_t kNoEntity = 0xFFFFFFFFu;
+
     void noteError(GpuSceneState& s, const char* where)
     {
       std::snprintf(s.lastError, sizeof(s.lastError), "%s: %s", where, scgpuLastError(s.ctx));
       sc::log(sc::LogLevel::Error, "scgpu %s", s.lastError);
     }
 
+    EntityShadow& shadowOf(GpuSceneState& s, uint32_t handle)
+    {
+      const uint32_t idx = handle & Entity::INDEX_MASK;
+      if (idx >= s.shadow.size()) s.shadow.resize((size_t)idx + 1u + s.shadow.size() / 2u);
+      return s.shadow[idx];
+    }
+
     struct SpawnBatch
     {
       std::vector<uint32_t> entity, parent, meshMat, flags;
       std::vector<float> trs, aabb;
-      void push(World& world, Entity e, Transform& t)
+      // reads the components the entity owns right now and records them in the shadow
+      void push(GpuSceneState& s, World& world, Entity e, Transform& t, uint32_t pos)
       {
+        EntityShadow& sh = shadowOf(s, e.value);
+        sh = EntityShadow{};
+        sh.handle = e.value;
+        sh.parent = t.parent.value;
+        sh.pos = pos;
+        sh.seen = s.stamp;
         entity.push_back(e.value);
         parent.push_back(t.parent.value);
         trs.insert(trs.end(), t.localPos, t.localPos + 3);
         trs.insert(trs.end(), t.localRot, t.localRot + 3);
         trs.insert(trs.end(), t.localScale, t.localScale + 3);
-        uint32_t f = 0;
-        float bb[6] = { -0.5f, -0.5f, -0.5f, 0.5f, 0.5f, 0.5f };
         if (const Bounds* b = world.get<Bounds>(e))
         {
-          f |= SCGPU_HAS_BOUNDS;
-          bb[0] = b->localAabb.min.x; bb[1] = b->localAabb.min.y; bb[2] = b->localAabb.min.z;
-          bb[3] = b->localAabb.max.x; bb[4] = b->localAabb.max.y; bb[5] = b->localAabb.max.z;
+          sh.flags |= SCGPU_HAS_BOUNDS;
+          sh.aabb[0] = b->localAabb.min.x; sh.aabb[1] = b->localAabb.min.y; sh.aabb[2] = b->localAabb.min.z;
+          sh.aabb[3] = b->localAabb.max.x; sh.aabb[4] = b->localAabb.max.y; sh.aabb[5] = b->localAabb.max.z;
         }
-        aabb.insert(aabb.end(), bb, bb + 6);
-        uint32_t mm[2] = { 0u, 0u };
+        aabb.insert(aabb.end(), sh.aabb, sh.aabb + 6);
         if (const RenderMesh* rm = world.get<RenderMesh>(e))
         {
-          f |= SCGPU_HAS_MESH;
-          mm[0] = rm->meshId; mm[1] = rm->materialId;
+          sh.flags |= SCGPU_HAS_MESH;
+          sh.meshId = rm->meshId; sh.materialId = rm->materialId;
         }
-        meshMat.insert(meshMat.end(), mm, mm + 2);
-        flags.push_back(f);
+        meshMat.push_back(sh.meshId);
+        meshMat.push_back(sh.materialId);
+        flags.push_back(sh.flags);
       }
       bool submit(GpuSceneState& s)
       {
@@ -87,6 +101,57 @@ namespace sc::gpu
         }
       }
     }
+
+    // ComponentPool::remove (sc_ecs.h:240-262) on the shadow of the pool
+    void shadowRemove(GpuSceneState& s, uint32_t handle)
+    {
+      EntityShadow& sh = shadowOf(s, handle);
+      const uint32_t pos = sh.pos, last = (uint32_t)s.dense.size() - 1u;
+      if (pos != last)
+      {
+        const uint32_t moved = s.dense[last];
+        s.dense[pos] = moved;
+        shadowOf(s, moved).pos = pos;
+      }
+      s.dense.pop_back();
+      sh = EntityShadow{};
+    }
+
+    // RenderMesh / Bounds added to, removed from or edited on an entity whose Transform is already on the GPU: compared
+    // with what was last uploaded, queued for this frame's scgpuSetRender batch when different
+    void checkRenderComponents(GpuSceneState& s, World& world, Entity e, EntityShadow& sh)
+    {
+      const RenderMesh* rm = world.get<RenderMesh>(e);
+      const Bounds* b = world.get<Bounds>(e);
+      uint32_t flags = 0;
+      bool changed = false;
+      if (rm)
+      {
+        flags |= SCGPU_HAS_MESH;
+        if (sh.meshId != rm->meshId || sh.materialId != rm->materialId) { sh.meshId = rm->meshId; sh.materialId = rm->materialId; changed = true; }
+      }
+      if (b)
+      {
+        flags |= SCGPU_HAS_BOUNDS;
+        const float bb[6] = { b->localAabb.min.x, b->localAabb.min.y, b->localAabb.min.z, b->localAabb.max.x, b->localAabb.max.y, b->localAabb.max.z };
+        if (std::memcmp(bb, sh.aabb, sizeof(bb)) != 0) { std::memcpy(sh.aabb, bb, sizeof(bb)); changed = true; }
+      }
+      if (flags == sh.flags && !changed) return;
+      sh.flags = flags;
+      s.renderE.push_back(sh.handle);
+      s.renderMM.push_back(sh.meshId); s.renderMM.push_back(sh.materialId);
+      s.renderBB.insert(s.renderBB.end(), sh.aabb, sh.aabb + 6);
+      s.renderF.push_back(flags);
+    }
+
+    // A parent is valid iff it is another entity that is alive and owns a Transform (sc_ecs.cpp:151-164) - i.e. iff the
+    // mirror of the Transform pool holds exactly that handle. No World look-up.
+    bool parentInMirror(const GpuSceneState& s, uint32_t self, uint32_t parent)
+    {
+      if (parent == self) return false;
+      const uint32_t idx = parent & Entity::INDEX_MASK;
+      return idx < s.shadow.size() && s.shadow[idx].handle == parent;
+    }
   }
 
   bool init(GpuSceneState& s)
@@ -112,87 +177,117 @@ namespace sc::gpu
     scgpuDestroy(s.ctx);
     s.ctx = nullptr;
     s.dense.clear();
-    s.parentOf.clear();
+    s.shadow.clear();
   }
 
+  // One sequential walk of the Transform pool per frame, like the reference's own TransformSystem (sc_ecs.cpp:118-211
+  // walks it twice), against a dense shadow table indexed by Entity::index(): no hash set, no map, no allocation in
+  // steady state. What it finds goes to the GPU as delta batches.
   void TransformSystem(World& world, float dt, void* user)
   {
     (void)dt;
     GpuSceneState* s = static_cast<GpuSceneState*>(user);
     if (!s || !s->ctx)
       return;
+    const auto t0 = std::chrono::steady_clock::now();
     s->transformPassDone = false;
+    if (++s->stamp == 0u) ++s->stamp;
 
-    // ---- 1. pool membership: what appeared / disappeared since the last frame ----
-    std::vector<Entity> cur;
-    cur.reserve(s->dense.size() + 64);
-    world.ForEach<Transform>([&](Entity e, Transform&) { cur.push_back(e); });
-
-    std::unordered_set<uint32_t> curSet;
-    curSet.reserve(cur.size() * 2);
-    for (const Entity e : cur) curSet.insert(e.value);
-
-    std::vector<uint32_t> removed;
-    for (const Entity e : s->dense)
-      if (!curSet.count(e.value)) removed.push_back(e.value);
-    if (!removed.empty())
+    // ---- 1. the pool as it stands: membership (new / known), component edits of the known ones ----
+    s->cur.clear(); s->fresh.clear(); s->dirtyE.clear(); s->dirtyTrs.clear(); s->reparentE.clear(); s->reparentP.clear();
+    s->renderE.clear(); s->renderMM.clear(); s->renderF.clear(); s->renderBB.clear();
+    uint32_t known = 0;
+    world.ForEach<Transform>([&](Entity e, Transform& t)
     {
-      if (!scgpuDespawn(s->ctx, (uint32_t)removed.size(), removed.data())) noteError(*s, "scgpuDespawn");
-      // replay ComponentPool::remove (sc_ecs.h:240-262) on the shadow to predict the GPU's pool order
-      std::unordered_map<uint32_t, uint32_t> slotOf;
-      slotOf.reserve(s->dense.size() * 2);
-      for (uint32_t i = 0; i < s->dense.size(); ++i) slotOf[s->dense[i].value] = i;
-      for (const uint32_t h : removed)
+      const uint32_t i = (uint32_t)s->cur.size();
+      s->cur.push_back(e.value);
+      EntityShadow& sh = shadowOf(*s, e.value);
+      if (sh.handle != e.value) { s->fresh.push_back(i); return; }  // appeared since the last frame
+      sh.seen = s->stamp;
+      ++known;
+      // TransformSystem's fix-ups (sc_ecs.cpp:143-164). The parent is re-validated against the World only when the
+      // handle changed; a parent that merely DIED shows up as a removal below and is dealt with there.
+      if (t.localScale[0] == 0.0f && t.localScale[1] == 0.0f && t.localScale[2] == 0.0f)
       {
-        const uint32_t slot = slotOf[h], last = (uint32_t)s->dense.size() - 1u;
-        if (slot != last)
-        {
-          s->dense[slot] = s->dense[last];
-          slotOf[s->dense[slot].value] = slot;
-        }
-        s->dense.pop_back();
-        slotOf.erase(h);
-        s->parentOf.erase(h);
+        t.localScale[0] = t.localScale[1] = t.localScale[2] = 1.0f;
+        t.dirty = true;
+      }
+      if (sh.parent != t.parent.value)
+      {
+        fixUp(world, e, t);
+        s->reparentE.push_back(e.value);
+        s->reparentP.push_back(t.parent.value);
+        sh.parent = t.parent.value;
+      }
+      if (t.dirty)
+      {
+        s->dirtyE.push_back(e.value);
+        s->dirtyTrs.insert(s->dirtyTrs.end(), t.localPos, t.localPos + 3);
+        s->dirtyTrs.insert(s->dirtyTrs.end(), t.localRot, t.localRot + 3);
+        s->dirtyTrs.insert(s->dirtyTrs.end(), t.localScale, t.localScale + 3);
+        if (!s->leaveDirtyFlags) t.dirty = false;
+      }
+      if (s->trackRenderComponents) checkRenderComponents(*s, world, e, sh);
+    });
+
+    // ---- 2. what disappeared: shadow entries the walk did not meet, in (old) pool order; then the pool shadow
+    //         replays ComponentPool::remove for them, which is the order scgpuDespawn produces on the GPU ----
+    if (known != s->dense.size())
+    {
+      s->removed.clear();
+      for (const uint32_t h : s->dense)
+        if (s->shadow[h & Entity::INDEX_MASK].seen != s->stamp) s->removed.push_back(h);
+      if (!scgpuDespawn(s->ctx, (uint32_t)s->removed.size(), s->removed.data())) noteError(*s, "scgpuDespawn");
+      for (const uint32_t h : s->removed) shadowRemove(*s, h);
+      // children of what just died: the reference detaches them and marks them dirty (sc_ecs.cpp:151-164); the device
+      // does the same on its own copy (k_resolve_parents), the host component is patched here
+      for (const uint32_t h : s->dense)
+      {
+        EntityShadow& sh = s->shadow[h & Entity::INDEX_MASK];
+        if (sh.parent == kNoEntity || parentInMirror(*s, h, sh.parent)) continue;
+        // (a parent spawned THIS frame is not in the mirror yet: ask the World before cutting the link)
+        Entity e{};
+        e.value = h;
+        Transform* t = world.get<Transform>(e);
+        if (!t) continue;
+        fixUp(world, e, *t);
+        sh.parent = t->parent.value;
       }
     }
 
-    std::unordered_set<uint32_t> known;
-    known.reserve(s->dense.size() * 2);
-    for (const Entity e : s->dense) known.insert(e.value);
-
+    // ---- 3. new Transforms, appended in pool order ----
     SpawnBatch spawn;
-    for (const Entity e : cur)
+    for (const uint32_t i : s->fresh)
     {
-      if (known.count(e.value)) continue;
+      Entity e{};
+      e.value = s->cur[i];
       Transform& t = *world.get<Transform>(e);
       fixUp(world, e, t);
-      spawn.push(world, e, t);
-      s->dense.push_back(e);
-      s->parentOf[e.value] = t.parent.value;
+      spawn.push(*s, world, e, t, (uint32_t)s->dense.size());
+      s->dense.push_back(e.value);
       if (!s->leaveDirtyFlags) t.dirty = false;
     }
     spawn.submit(*s);
 
     // The engine destroyed entities in an order we cannot see; if replaying them in pool order did not end in
     // the engine's pool order, rebuild the mirror (rare: orders agree when a batch is destroyed oldest-first).
-    bool same = s->dense.size() == cur.size();
-    for (size_t i = 0; same && i < cur.size(); ++i) same = s->dense[i] == cur[i];
-    const size_t firstNew = s->dense.size() - spawn.entity.size();
+    const bool same = s->dense.size() == s->cur.size() &&
+                      (s->cur.empty() || std::memcmp(s->dense.data(), s->cur.data(), s->cur.size() * sizeof(uint32_t)) == 0);
     if (!same)
     {
       ++s->resyncs;
-      std::vector<uint32_t> all;
-      for (const Entity e : s->dense) all.push_back(e.value);
-      if (!all.empty() && !scgpuDespawn(s->ctx, (uint32_t)all.size(), all.data())) noteError(*s, "scgpuDespawn(resync)");
-      s->dense = cur;
-      s->parentOf.clear();
+      if (!s->dense.empty() && !scgpuDespawn(s->ctx, (uint32_t)s->dense.size(), s->dense.data())) noteError(*s, "scgpuDespawn(resync)");
+      for (const uint32_t h : s->dense) s->shadow[h & Entity::INDEX_MASK] = EntityShadow{};
+      s->dense.clear();
       SpawnBatch rebuild;
-      for (const Entity e : cur)
+      for (const uint32_t h : s->cur)
       {
+        Entity e{};
+        e.value = h;
         Transform& t = *world.get<Transform>(e);
         fixUp(world, e, t);
-        rebuild.push(world, e, t);
-        s->parentOf[e.value] = t.parent.value;
+        rebuild.push(*s, world, e, t, (uint32_t)s->dense.size());
+        s->dense.push_back(h);
         if (!s->leaveDirtyFlags) t.dirty = false;
       }
       rebuild.submit(*s);
@@ -201,66 +296,44 @@ namespace sc::gpu
     }
     else
     {
-      // ---- 2. component edits: the engine writes Transform fields and sets dirty (sc_ecs.h:73-96) ----
-      std::vector<uint32_t> dirtyE, reparentE, reparentP;
-      std::vector<float> dirtyTrs;
-      for (size_t i = 0; i < firstNew; ++i)
-      {
-        const Entity e = s->dense[i];
-        Transform& t = *world.get<Transform>(e);
-        fixUp(world, e, t);
-        uint32_t& shadowParent = s->parentOf[e.value];
-        if (shadowParent != t.parent.value)
-        {
-          reparentE.push_back(e.value);
-          reparentP.push_back(t.parent.value);
-          shadowParent = t.parent.value;
-        }
-        if (t.dirty)
-        {
-          dirtyE.push_back(e.value);
-          dirtyTrs.insert(dirtyTrs.end(), t.localPos, t.localPos + 3);
-          dirtyTrs.insert(dirtyTrs.end(), t.localRot, t.localRot + 3);
-          dirtyTrs.insert(dirtyTrs.end(), t.localScale, t.localScale + 3);
-          if (!s->leaveDirtyFlags) t.dirty = false;
-        }
-      }
-      if (!reparentE.empty() && !scgpuSetParent(s->ctx, (uint32_t)reparentE.size(), reparentE.data(), reparentP.data()))
+      // ---- 4. component edits: the engine writes Transform fields and sets dirty (sc_ecs.h:73-96) ----
+      if (!s->reparentE.empty() &&
+          !scgpuSetParent(s->ctx, (uint32_t)s->reparentE.size(), s->reparentE.data(), s->reparentP.data()))
         noteError(*s, "scgpuSetParent");
-      if (!dirtyE.empty() && !scgpuSetLocal(s->ctx, (uint32_t)dirtyE.size(), dirtyE.data(), dirtyTrs.data()))
+      if (!s->dirtyE.empty() && !scgpuSetLocal(s->ctx, (uint32_t)s->dirtyE.size(), s->dirtyE.data(), s->dirtyTrs.data()))
         noteError(*s, "scgpuSetLocal");
+      if (!s->renderE.empty() &&
+          !scgpuSetRender(s->ctx, (uint32_t)s->renderE.size(), s->renderE.data(), s->renderMM.data(), s->renderBB.data(), s->renderF.data()))
+        noteError(*s, "scgpuSetRender");
     }
 
-    // ---- 3. matrices the host itself consumes before culling: cameras (CameraSystem, sc_ecs.cpp:268) ----
-    std::vector<uint32_t> needWorld;
+    // ---- 5. matrices the host itself consumes before culling: cameras (CameraSystem, sc_ecs.cpp:268) ----
+    s->needWorld.clear();
     world.ForEach<Camera, Transform>([&](Entity e, Camera&, Transform& t)
     {
       if (!isValidEntity(t.parent))
         t.worldMatrix = mat4_trs(t.localPos, t.localRot, t.localScale);  // a root: world == local, O(1) on the host
       else
-        needWorld.push_back(e.value);
+        s->needWorld.push_back(e.value);
     });
-    if (s->readBackAllWorldMatrices)
-    {
-      needWorld.clear();
-      for (const Entity e : s->dense) needWorld.push_back(e.value);
-    }
-    if (!needWorld.empty())
+    if (s->readBackAllWorldMatrices) s->needWorld = s->dense;
+    if (!s->needWorld.empty())
     {
       // parented camera (or full read-back requested): run the transform pass now, cull again once the view is known
       const float identity[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
       scgpuSetViews(s->ctx, 1, identity);
       if (!scgpuUpdate(s->ctx, 0)) noteError(*s, "scgpuUpdate(transform)");
       s->transformPassDone = true;
-      std::vector<float> m(needWorld.size() * 16);
-      if (!scgpuReadWorld(s->ctx, (uint32_t)needWorld.size(), needWorld.data(), m.data())) noteError(*s, "scgpuReadWorld");
-      for (size_t i = 0; i < needWorld.size(); ++i)
+      s->worldOut.resize(s->needWorld.size() * 16);
+      if (!scgpuReadWorld(s->ctx, (uint32_t)s->needWorld.size(), s->needWorld.data(), s->worldOut.data())) noteError(*s, "scgpuReadWorld");
+      for (size_t i = 0; i < s->needWorld.size(); ++i)
       {
         Entity e{};
-        e.value = needWorld[i];
-        if (Transform* t = world.get<Transform>(e)) std::memcpy(t->worldMatrix.m, m.data() + i * 16, 64);
+        e.value = s->needWorld[i];
+        if (Transform* t = world.get<Transform>(e)) std::memcpy(t->worldMatrix.m, s->worldOut.data() + i * 16, 64);
       }
     }
+    s->lastHostMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
 
   void CullingSystem(World& world, float dt, void* user)
@@ -300,8 +373,15 @@ namespace sc::gpu
     }
     if (st->fillCandidates)
     {
-      for (const Entity e : s.dense)
-        if (world.has<RenderMesh>(e)) cs.candidates.push_back(e);
+      // ForEach<Transform, RenderMesh> (.cpp:1206-1210): Transform-pool order, filtered by RenderMesh ownership
+      cs.candidates.reserve(c.renderablesTotal);
+      for (const uint32_t h : s.dense)
+        if (s.shadow[h & Entity::INDEX_MASK].flags & SCGPU_HAS_MESH)
+        {
+          Entity e{};
+          e.value = h;
+          cs.candidates.push_back(e);
+        }
     }
     if (c.renderablesTotal != 0 && !cs.freezeCulling)
     {
@@ -329,6 +409,17 @@ namespace sc::gpu
     RenderPrepStreamingState& rp = *st->prep;
     RenderFrameData& frame = *rp.frame;
     frame.clear();
+    if (!rp.culling)
+    {
+      // no culling stage registered (.cpp:1330-1346): every Transform + RenderMesh entity is drawn, in Transform-pool
+      // order — on the GPU that is the list a frozen culling pass yields; nobody has run the frame's update yet
+      GpuSceneState& gs = *st->scene;
+      const float identity[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+      if (!scgpuSetViews(gs.ctx, 1, identity)) noteError(gs, "scgpuSetViews");
+      if (!scgpuUpdate(gs.ctx, SCGPU_UPDATE_FREEZE_CULLING | (gs.transformPassDone ? SCGPU_UPDATE_SKIP_TRANSFORM : 0u)))
+        noteError(gs, "scgpuUpdate");
+      gs.transformPassDone = false;
+    }
 
     const uint32_t maxDraws = rp.streaming ? rp.streaming->budgets.maxDrawsBudget : 0u;
     if (rp.assets && rp.streaming)

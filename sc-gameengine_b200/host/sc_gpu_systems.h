@@ -17,11 +17,23 @@
 #include "scgpu.h"
 
 #include <cstdint>
-#include <unordered_map>
 #include <vector>
 
 namespace sc::gpu
 {
+  // What the GPU side was last told about the owner of one entity INDEX (Entity::index(), 24 bits): a dense table, no
+  // hashing anywhere in the per-frame path.
+  struct EntityShadow
+  {
+    uint32_t handle = kInvalidEntity.value;  // the Transform owner uploaded for this index, or invalid
+    uint32_t parent = kInvalidEntity.value;  // parent handle last uploaded
+    uint32_t pos = 0;                        // position in GpuSceneState::dense
+    uint32_t seen = 0;                       // frame stamp of the last Transform pass that met it
+    uint32_t meshId = 0, materialId = 0;     // RenderMesh last uploaded
+    float aabb[6] = { -0.5f, -0.5f, -0.5f, 0.5f, 0.5f, 0.5f };  // Bounds last uploaded
+    uint32_t flags = 0;                      // SCGPU_HAS_* last uploaded
+  };
+
   // One per World. Owns the scgpu context and the host-side shadow needed to turn the engine's "write the
   // component, set dirty" convention (sc_ecs.h:73-96) into delta batches.
   struct GpuSceneState
@@ -35,13 +47,22 @@ namespace sc::gpu
     bool leaveDirtyFlags = false;
     // write every world matrix back into Transform::worldMatrix (cameras are always written back)
     bool readBackAllWorldMatrices = false;
+    // follow World::add / remove of RenderMesh and Bounds and edits of their fields on entities that already own a
+    // Transform (sc_traffic_lod.cpp:47-70, sc_imgui.cpp:720): two more component look-ups per entity and frame
+    bool trackRenderComponents = true;
 
     // shadow of the Transform pool as the GPU knows it
-    std::vector<Entity> dense;                       // pool order
-    std::unordered_map<uint32_t, uint32_t> parentOf; // entity -> parent handle last uploaded
-    bool transformPassDone = false;                  // a transform-only update already ran this frame
-    uint64_t resyncs = 0;                            // full rebuilds (pool order could not be replayed)
+    std::vector<uint32_t> dense;          // entity handles in pool order
+    std::vector<EntityShadow> shadow;     // by Entity::index()
+    uint32_t stamp = 0;                   // frame counter of the passes
+    bool transformPassDone = false;       // a transform-only update already ran this frame
+    uint64_t resyncs = 0;                 // full rebuilds (pool order could not be replayed)
+    double lastHostMs = 0.0;              // wall time of the last TransformSystem call (host bookkeeping + enqueues)
     char lastError[256] = {};
+
+    // per-frame work arrays (kept: no allocation in steady state)
+    std::vector<uint32_t> cur, removed, fresh, dirtyE, reparentE, reparentP, renderE, renderMM, renderF, needWorld;
+    std::vector<float> dirtyTrs, renderBB, worldOut;
   };
 
   struct GpuCullingState
@@ -49,7 +70,7 @@ namespace sc::gpu
     GpuSceneState* scene = nullptr;
     CullingState* culling = nullptr;   // the reference's own state struct, filled identically
     bool fillCulledList = true;        // CullingState::culled (only DebugDraw reads it, sc_debug_draw_system.cpp:136-137)
-    bool fillCandidates = false;       // CullingState::candidates (nobody reads it outside CullingSystem)
+    bool fillCandidates = true;        // CullingState::candidates (.cpp:1206-1210; nobody reads it outside CullingSystem)
   };
 
   struct GpuRenderPrepState

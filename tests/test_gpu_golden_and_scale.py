@@ -128,6 +128,25 @@ def test_dropin_adapter_systems_against_reference_systems():
     assert "DROPIN OK" in r.stdout
 
 
+def test_dropin_adapter_at_scale_outputs_equal_and_host_cost():
+    """sc_dropin_test --bench: the three adapter systems and the reference's three on one World of 200 k entities (groups of
+    five), 10 % dirtied per frame through sc::setLocal: ordered visible lists, candidates and draw counts equal every
+    frame, no resync, and the adapter's per-frame host cost (one pool walk against a dense shadow table, no hashing)
+    below the reference's own TransformSystem."""
+    import json
+    exe = ROOT / "oracle" / "_ref" / "sc_dropin_test"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/sc_dropin_test not built (needs /root/reference)")
+    env = dict(os.environ, GLIBC_TUNABLES="glibc.cpu.hwcaps=-FMA,-AVX2")
+    r = subprocess.run([str(exe), "--bench", "200000", "6"], capture_output=True, text=True, timeout=600, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert r.returncode == 0 and line, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(line[-1])
+    print(res)
+    assert res["outputs_equal"] and res["resyncs"] == 0
+    assert res["adapter_ms"]["TransformSystem"] < res["reference_ms"]["TransformSystem"]
+
+
 def _default_scene_sectors(g):
     """(coords in activation order, rows of each sector) of the reference's default scene: every streamed sector
     starts with its ground plane (scale 64 x 0.1 x 64 at the sector centre)."""

@@ -51,10 +51,15 @@ def main():
                                           C.byref(runs)), "sort")
     n1()
     out["N1_sorted_draws"] = {"draws": n, "runs": runs.value, "ms": med(n1),
-                              "what": "scgpuBuildSortedDraws: keys + 3 radix passes + runs + gather of 80-byte items, device-resident"}
-    # the renderer's own loop is not compiled headless (sc_vk.cpp needs Vulkan): numpy restatement for scale only
-    from oracle_bind import renderer_sorted_draws
+                              "what": "scgpuBuildSortedDraws: keys + stable 8-bit counting-sort passes over the key bits in use (15 here: 2 passes) + runs + gather of 80-byte items, device-resident; hand-written, no library sort"}
+    from oracle_bind import ref_available, ref_renderer_submit
     draws, _, _ = s.read_draw_items(0, 0)
+    if ref_available():
+        # the reference's own block of sc_vk.cpp (:1841-1912: filter, std::sort, bind-on-change loop) compiled into oracle/_ref
+        t0 = time.perf_counter()
+        ro, rb = ref_renderer_submit(draws, mat_pipe, 64)
+        out["N1_sorted_draws"]["reference_loop_ms"] = (time.perf_counter() - t0) * 1e3
+        out["N1_sorted_draws"]["reference_loop_bind_points"] = int((rb != 0).sum())
     t0 = time.perf_counter()
     order = np.lexsort((draws["meshId"], draws["materialId"], mat_pipe[draws["materialId"]]))
     out["N1_sorted_draws"]["numpy_lexsort_ms"] = (time.perf_counter() - t0) * 1e3
