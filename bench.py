@@ -46,16 +46,22 @@ REF_WORLD_MAX = 8_000_000  # the reference's job system is safe up to ~11 M enti
 CHURN_INSTANCES = 8 * 1024 * 1024
 
 
-def build_scene(n, rank, seed=424242):
+def block_shift(rank, world, side):
+    """x offset of rank r's block of world cells: the blocks stand side by side along x and the camera sits over the middle
+    of the whole world, i.e. (for N > 1) on the seam between two ranks' blocks — the visible lists come from more than one
+    GPU and none of them need be the submitting rank's. N = 1: no shift."""
+    from scgpu import scenes
+    return np.float32((rank - (world - 1) / 2.0) * side * scenes.SECTOR_SIZE)
+
+
+def build_scene(n, rank, seed=424242, world=1):
     from scgpu import scenes
     if os.environ.get("SCGPU_BENCH_WORKLOAD", "hier") == "flat":  # diagnostic only; the reported workload is "hier"
         sc = scenes.city_flat(n, seed=seed + 7919 * rank)
         return sc
     sc = scenes.city_hier(n, seed=seed + 7919 * rank)
-    # rank r owns the block of world cells shifted by r grid sides along +x: contiguous cell blocks of one world
-    shift = np.float32(rank * sc["side"] * scenes.SECTOR_SIZE)
     roots = sc["parent"] < 0
-    sc["trs9"][roots, 0] += shift
+    sc["trs9"][roots, 0] += block_shift(rank, world, sc["side"])
     return sc
 
 
@@ -263,7 +269,8 @@ def workload_config(args, n_per_gpu, sample=False):
         "workload": "synthetic city, depth-4 groups (vehicles+wheels, peds+attachments), main view + 4 shadow "
                     "cascades, all instances dirty every step (BASELINE.json configs[2]; x8 GPUs = configs[3])",
         "instances_per_gpu": int(n_per_gpu), "views": args.views, "dirty_fraction": 1.0,
-        "sharding": ("world cell blocks, one process per GPU; visible lists gathered to rank 0 through "
+        "sharding": ("world cell blocks side by side, one process per GPU, the camera over the seam in the middle of the "
+                     "world; visible lists gathered to rank 0 through "
                      + ("NVLink peer memory" if os.environ.get("SCGPU_GATHER", "peer") == "peer" else "NCCL send/recv"))
         if args.gpus > 1 else "single GPU",
         "l2": "inputs (>= 2 GB per step) exceed the 126 MB L2; no explicit flush" if not sample else "cpu run",
@@ -414,8 +421,7 @@ def churn_leg(args, D, rank, local_rank, torch):
     frames, warm = args.churn_frames, 4
     cohorts = 10
     sc = scenes.city_hier(n, seed=99 + 7919 * rank)
-    if rank:
-        sc["trs9"][sc["parent"] < 0, 0] += np.float32(rank * sc["side"] * scenes.SECTOR_SIZE)
+    sc["trs9"][sc["parent"] < 0, 0] += block_shift(rank, D.world, sc["side"])
     rng = np.random.default_rng(5 + rank)
     roots = np.nonzero(sc["parent"] < 0)[0]
     glen = np.diff(np.append(roots, n))
@@ -553,7 +559,7 @@ def main():
     D = Dist(world, local_rank)
 
     n = args.instances
-    sc = build_scene(n, rank)
+    sc = build_scene(n, rank, world=world)
     vps = views_for(sc, args.views)
     scene = scgpu.Scene(n, max_views=args.views, device=local_rank, max_entity_index=n)
     entity = np.arange(n, dtype=np.uint32)
@@ -729,5 +735,23 @@ def main():
     D.close()
 
 
+def _guarded_main():
+    """one rank that dies must not leave the others waiting in a collective until the driver's limit: any exception ends
+    the process at once, and a watchdog ends a run that exceeds SCGPU_BENCH_LIMIT_S (default 20 min)"""
+    limit = float(os.environ.get("SCGPU_BENCH_LIMIT_S", "1200"))
+    watchdog = threading.Timer(limit, lambda: (sys.stderr.write("bench.py: time limit exceeded\n"), os._exit(3)))
+    watchdog.daemon = True
+    watchdog.start()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+
+
 if __name__ == "__main__":
-    main()
+    _guarded_main()

@@ -179,6 +179,7 @@ struct ScGpuScene
   cudaEvent_t upEv[kUpSlots] = {};
   bool upPending[kUpSlots] = {};
   uint32_t hostThreads = 1;       // host threads for the pool replay and for staged uploads (SCGPU_HOST_THREADS)
+  HostWorkers* workers = nullptr; // hostThreads - 1 helper threads that live as long as the context
 
   uint64_t launches = 0;
   std::string err;
@@ -369,6 +370,7 @@ void freeAll(ScGpuScene* c)
     if (c->evU1[i]) cudaEventDestroy(c->evU1[i]);
   }
   if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+  delete c->workers;
   delete c;
 }
 
@@ -504,7 +506,7 @@ int uploadSegs(ScGpuScene* c, const UpSeg* segs, uint32_t nSegs)
   if (pieces.empty()) return 1;
 
   const uint32_t nPieces = (uint32_t)pieces.size();
-  const uint32_t T = std::min(std::min(c->hostThreads, ScGpuScene::kUpSlots / 2u), nPieces);
+  const uint32_t T = std::min(std::min(c->hostThreads, ScGpuScene::kUpSlots / 2u), nPieces);  // one share (two ring chunks) per thread
   if (!ensureUploadRing(c)) return 0;
   std::atomic<int> err{(int)cudaSuccess};
   const Piece* const pc = pieces.data();
@@ -522,17 +524,9 @@ int uploadSegs(ScGpuScene* c, const UpSeg* segs, uint32_t nSegs)
     }
     if (e != cudaSuccess) err.store((int)e);
   };
-  std::vector<std::thread> th;
-  th.reserve(T - 1u);
-  uint32_t started = 1;
-  for (; started < T; ++started)
-  {
-    try { th.emplace_back(work, started); }
-    catch (...) { break; }  // thread limit reached: the calling thread takes the remaining shares (no exception across the ABI)
-  }
-  work(0u);
-  for (uint32_t t = started; t < T; ++t) work(t);
-  for (std::thread& t : th) t.join();
+  if (c->workers) c->workers->run(T, work);
+  else
+    for (uint32_t t = 0; t < T; ++t) work(t);
   if (err.load() != (int)cudaSuccess)
     return (int)fail(c, "staged upload failed: %s", cudaGetErrorString((cudaError_t)err.load()));
   return 1;
@@ -573,11 +567,17 @@ ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc)
   if (!c) { fail(nullptr, "out of host memory"); return nullptr; }
   if (const char* pl = getenv("SCGPU_PDL")) g_pdlLevel = atoi(pl);
   {
-    // host threads for the pool bookkeeping of large despawn batches: SCGPU_HOST_THREADS, else half the cores up to 4 (the sequential middle pass bounds the gain)
+    // host threads for the pool bookkeeping of large despawn batches and staged uploads: SCGPU_HOST_THREADS, else half
+    // the cores up to 8 (the sequential middle pass of the pool replay bounds the gain). The helpers are created once.
     const char* ht = getenv("SCGPU_HOST_THREADS");
     const unsigned hw = std::thread::hardware_concurrency();
-    long want = ht ? strtol(ht, nullptr, 10) : (long)std::min(4u, std::max(1u, hw / 2u));
+    long want = ht ? strtol(ht, nullptr, 10) : (long)std::min(8u, std::max(1u, hw / 2u));
     c->hostThreads = (uint32_t)std::min(64l, std::max(1l, want));
+    if (c->hostThreads > 1u)
+    {
+      c->workers = new (std::nothrow) HostWorkers(c->hostThreads - 1u);
+      c->hostThreads = c->workers ? c->workers->helpers() + 1u : 1u;
+    }
   }
   if (!createImpl(c, desc) || (c->hostThreads > 1u && !ensureUploadRing(c)))  // ring up front: no first-upload hiccup
   {
@@ -689,7 +689,13 @@ static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, cons
     if (c->hSlotScratch.size() < n) c->hSlotScratch.resize(n + n / 4);
     uint32_t* const sl = c->hSlotScratch.data();
     c->layout.placeBatch(n, entity, parent, sl);  // cannot fail: holes + tail room >= capacity - count >= n
-    for (uint32_t j = 0; j < n; ++j) so[entity[j] & 0xFFFFFFu] = sl[j];
+    poolParallelFor(c->hostThreads, n, [=](uint32_t, uint32_t b, uint32_t e) {
+      for (uint32_t j = b; j < e; ++j)
+      {
+        if (j + 16u < e) __builtin_prefetch(so + (entity[j + 16u] & 0xFFFFFFu), 1);
+        so[entity[j] & 0xFFFFFFu] = sl[j];
+      }
+    }, c->workers);
     *slot0 = 0;
     *slotOf = sl;
   }
@@ -1131,7 +1137,7 @@ int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
   static_assert(sizeof(PoolMove) == sizeof(uint2), "k_despawn_apply reads the moves as uint2");
   std::vector<PoolMove>& moves = c->hMoves;
   std::vector<uint32_t>& removedIdx = c->hRemoved;
-  poolReplayDespawn(c->hEntity, c->hSparse, c->count, n, entity, moves, removedIdx, c->hPoolScratch, c->hostThreads);
+  poolReplayDespawn(c->hEntity, c->hSparse, c->count, n, entity, moves, removedIdx, c->hPoolScratch, c->hostThreads, c->workers);
 
   const uint32_t nMoves = (uint32_t)moves.size(), nRem = (uint32_t)removedIdx.size();
   if (nRem > 0)
@@ -1140,11 +1146,14 @@ int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
     if (c->hSlotScratch.size() < nRem) c->hSlotScratch.resize(nRem + nRem / 4);
     uint32_t* const sl = c->hSlotScratch.data();
     const uint32_t* const so = c->hSlotOf.data();
-    for (uint32_t v = 0; v < nRem; ++v)
-    {
-      if (v + 16u < nRem) __builtin_prefetch(so + removedIdx[v + 16u], 0);
-      sl[v] = so[removedIdx[v]];
-    }
+    const uint32_t* const ri = removedIdx.data();
+    poolParallelFor(c->hostThreads, nRem, [=](uint32_t, uint32_t b, uint32_t e) {
+      for (uint32_t v = b; v < e; ++v)
+      {
+        if (v + 16u < e) __builtin_prefetch(so + ri[v + 16u], 0);
+        sl[v] = so[ri[v]];
+      }
+    }, c->workers);
     c->layout.release(nRem, sl);
     char* s = (char*)c->staging.ptr;
     const UpSeg segs[2] = {{s, moves.data(), (size_t)nMoves * 8}, {s + (size_t)nMoves * 8, sl, (size_t)nRem * 4}};
@@ -1385,6 +1394,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.chunkStride = c->chunkStride;
     p.acc = c->acc;
     p.count = extent;
+    p.live = c->count;
     p.bitWords = c->bitWords;
     p.stamp = stamp;
     p.nViews = c->nViews;
@@ -1432,6 +1442,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     q.bitWords = c->bitWords;
     q.nViews = c->nViews;
     q.culled = wantCulled ? 1u : 0u;
+    q.listCap = c->capacityPad;
     switch (c->nViews)
     {
 #define SC_LAUNCH_COMPACT(V) case V: SC_CUDA(c, launchPdl(k_compact<V>, grid, kCompactThreads, c->stream, q)); break;
@@ -1445,6 +1456,8 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     for (uint32_t v = 0; v < kMaxViews; ++v) { rp.outEntity[v] = c->visEntity[v]; rp.outSlot[v] = c->visSlot[v]; rp.culledEntity[v] = c->culledEntity[v]; }
     rp.nViews = c->nViews;
     rp.culled = q.culled;
+    rp.live = c->count;
+    rp.extent = extent;
     SC_CUDA(c, launchPdl(k_resolve_lists, c->numSMs * 2u, kBlock, c->stream, rp));
     c->launches += 2;
   }

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(kBlock) k_radix_scatter(const uint64_t* __rest
       if (have)
       {
         const uint32_t dst = sNext[d] + sWarpCnt[warp][d] + before;
+        SC_ASSERT(dst < n);
         keysOut[dst] = key;
         posOut[dst] = p;
       }

@@ -28,6 +28,17 @@
 #pragma once
 #include "scgpu_math.cuh"
 
+// Checked build (make libscgpu_checked.so, -DSCGPU_CHECKED): every index the kernels derive from data — ranks, slots,
+// chunk numbers, output positions, window geometry — is asserted against the bounds of the array it goes into. A
+// violated assertion traps the kernel and the next API call fails. compute-sanitizer is closed on the GPU pool; the
+// parity suite runs against this build instead (SCGPU_LIB=.../libscgpu_checked.so).
+#ifdef SCGPU_CHECKED
+#include <cassert>
+#define SC_ASSERT(cond) assert(cond)
+#else
+#define SC_ASSERT(cond) ((void)0)
+#endif
+
 namespace scgpu
 {
 
@@ -66,6 +77,7 @@ struct UpdateParams
   uint32_t chunkStride;
   uint32_t* acc;         // kAcc* counters
   uint32_t count;        // slots in use (extent): live Transforms + holes
+  uint32_t live;         // live Transforms: every rank is below it
   uint32_t bitWords;     // words per bitmap plane
   uint32_t stamp;
   uint32_t nViews;
@@ -170,6 +182,7 @@ __device__ __noinline__ uint32_t walk_up(const UpdateParams& p, uint32_t ps, boo
     int steps = 0, power = 1, lam = 0;
     for (;;)
     {
+      SC_ASSERT(cur < p.count);
       if (slot_dirty(p, cur)) lastDirty = steps;
       const uint32_t nxt = p.parentSlot[cur];
       if (nxt == kNone) break;
@@ -386,7 +399,10 @@ __device__ __forceinline__ void emit_visible_warp(const UpdateParams& p, uint32_
   const bool need = mask != 0u || (wantCand && cand);
   const uint32_t needM = __ballot_sync(0xffffffffu, need);
   if (needM == 0u) return;
+  SC_ASSERT(!need || s < p.count);
   const uint32_t r = need ? p.rank[s] : 0u;
+  SC_ASSERT(r < p.live || !need);
+  SC_ASSERT((r >> 5) < p.bitWords && (r >> kChunkShift) < p.chunkStride);
   const uint32_t first = __ffs(needM) - 1u;
   const uint32_t rFirst = __shfl_sync(0xffffffffu, r, first);
   const uint32_t base = rFirst - first;  // rank lane 0 would have
@@ -1135,6 +1151,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     {
       const uint32_t e0 = lds32(listAddr);
       const uint32_t len = (lds32(listAddr + 4) & kWinSlotMask) - (e0 & kWinSlotMask);
+      SC_ASSERT(len <= 32u && (e0 & kWinSlotMask) + len <= p.count);
       live = lane < len;
       fast = (e0 & kWinSlow) == 0u;
       info = live ? lds32(recAddr + 2048 - lane * 12) : 0u;
@@ -1323,6 +1340,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
       // redone by k_update_win_slow (generic path), which also culls and counts it
       uint32_t slot = 0;
       if (lane == 0) slot = atomicAdd(queue + 1, 1u);
+      SC_ASSERT(slot < total);
       if (lane == 0) slowList[slot] = a | (((lds32(listAddr + 4) & kWinSlotMask) - a) << 24);
     }
     listAddr = nextList;
@@ -1538,6 +1556,7 @@ struct CompactParams
   uint32_t bitWords, chunkStride;        // words per plane / counts per row
   uint32_t nWords;                       // words that can hold a set bit: ceil(live count / 32), rounded up to 4
   uint32_t nViews, culled;
+  uint32_t listCap;                      // entries every output list can hold
 };
 
 __device__ __forceinline__ uint32_t popc4(uint4 w) { return __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w); }
@@ -1572,8 +1591,9 @@ __device__ __forceinline__ uint64_t block_exclusive_scan_u64(uint64_t v, uint64_
 
 // the set bits of one plane row held by this warp (4 words per lane, consecutive lanes = consecutive words) as ranks at
 // out[first position of the word + rank order inside the word]; one warp step per non-empty word
-__device__ __forceinline__ void emit_ranks_warp(uint32_t* __restrict__ out, uint4 b, uint32_t pos, uint32_t w, uint32_t lane)
+__device__ __forceinline__ void emit_ranks_warp(uint32_t* __restrict__ out, uint4 b, uint32_t pos, uint32_t w, uint32_t lane, uint32_t cap)
 {
+  (void)cap;
   const uint32_t word[4] = { b.x, b.y, b.z, b.w };
   const uint32_t ltMask = (1u << lane) - 1u;
 #pragma unroll
@@ -1587,6 +1607,7 @@ __device__ __forceinline__ void emit_ranks_warp(uint32_t* __restrict__ out, uint
       const uint32_t wv = __shfl_sync(0xffffffffu, word[k], src);
       const uint32_t wp = __shfl_sync(0xffffffffu, pos, src);
       const uint32_t wr = (__shfl_sync(0xffffffffu, w, src) + k) * 32u;
+      SC_ASSERT(wp + __popc(wv) <= cap);
       if ((wv >> lane) & 1u) out[wp + __popc(wv & ltMask)] = wr + lane;
     }
     pos += __popc(word[k]);
@@ -1672,6 +1693,25 @@ __global__ void __launch_bounds__(kCompactThreads, 4) k_compact(const __grid_con
   }
   __syncthreads();
   SC_STAMP(2);
+#ifdef SCGPU_CHECKED
+  {
+    // the per-chunk counts of the frame kernels must be the popcounts of their bits
+    __shared__ uint32_t sPop[2 * V];
+    if (tid < 2u * V) sPop[tid] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t v = 0; v < V; ++v)
+    {
+      const uint32_t c = __reduce_add_sync(0xffffffffu, popc4(vis[v]));
+      if (lane == 0 && c) atomicAdd(&sPop[v], c);
+      const uint32_t d = __reduce_add_sync(0xffffffffu, culled ? popc4(andn4(cand, vis[v])) : 0u);
+      if (lane == 0 && d) atomicAdd(&sPop[V + v], d);
+    }
+    __syncthreads();
+    if (tid < nRows) SC_ASSERT(sPop[tid] == sCount[tid]);
+    __syncthreads();
+  }
+#endif
   if (seg == gridDim.x - 1u)
   {
     // frame totals; accumulators and the window queue are left zeroed for the next frame
@@ -1717,7 +1757,7 @@ __global__ void __launch_bounds__(kCompactThreads, 4) k_compact(const __grid_con
       if (r < nRows && ((total >> (21u * j)) & 0x1FFFFFu) != 0u)  // warp-uniform (block-uniform)
       {
         uint32_t* out = r < V ? p.outSlot[r < V ? r : 0] : p.culledEntity[r >= V && r < 2u * V ? r - V : 0];
-        emit_ranks_warp(out, bitsOf[j], sBase[r] + (uint32_t)((excl >> (21u * j)) & 0x1FFFFFu), w, lane);
+        emit_ranks_warp(out, bitsOf[j], sBase[r] + (uint32_t)((excl >> (21u * j)) & 0x1FFFFFu), w, lane, p.listCap);
       }
     }
   }
@@ -1750,6 +1790,7 @@ struct ResolveParams
   uint32_t* outSlot[kMaxViews];          // in: ranks, out: slots
   uint32_t* culledEntity[kMaxViews];     // in: ranks, out: entity handles
   uint32_t nViews, culled;
+  uint32_t live, extent;                 // checked build: bounds of ranks and slots
 };
 
 // rank -> (slot, entity handle) for every entry of every list, grid-stride: one independent chain of two loads per entry
@@ -1765,7 +1806,9 @@ __global__ void __launch_bounds__(kBlock) k_resolve_lists(const __grid_constant_
     uint32_t* __restrict__ outE = p.outEntity[v];
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nVis; i += stride)
     {
+      SC_ASSERT(outS[i] < p.live);
       const uint32_t slot = __ldg(p.perm + outS[i]);
+      SC_ASSERT(slot < p.extent);
       outS[i] = slot;
       outE[i] = __ldg(p.entity + slot);
     }
@@ -1838,6 +1881,7 @@ __global__ void __launch_bounds__(kBlock) k_spawn(SceneArrays a, uint32_t slot0,
   const uint32_t j = blockIdx.x * kBlock + threadIdx.x;
   if (j >= n) return;
   const uint32_t s = spawn_slot(slot0, slotOf, j);
+  SC_ASSERT(a.entity[s] == kNone || a.entity[s] == 0u);  // a hole or a never-used slot
   a.rank[s] = rank0 + j;
   a.perm[rank0 + j] = s;
   const float* t = trs9 + (size_t)j * 9;
@@ -2137,7 +2181,9 @@ __global__ void __launch_bounds__(kBlock) k_despawn_apply(SceneArrays a, uint32_
   if (j < nMoves)
   {
     const uint32_t dst = moves[j].x, src = moves[j].y;
+    SC_ASSERT(dst < src);
     const uint32_t s = a.perm[src];
+    SC_ASSERT(a.rank[s] == src && a.entity[s] != kNone);
     a.perm[dst] = s;
     a.rank[s] = dst;
   }
@@ -2145,6 +2191,7 @@ __global__ void __launch_bounds__(kBlock) k_despawn_apply(SceneArrays a, uint32_
   {
     const uint32_t s = removedSlot[j - nMoves];
     const uint32_t e = a.entity[s];
+    SC_ASSERT(e != kNone && a.sparse[e & 0xFFFFFFu] == s + 1u);
     a.sparse[e & 0xFFFFFFu] = 0u;
     a.entity[s] = kNone;
     a.parent[s] = kNone;

@@ -27,9 +27,12 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -54,12 +57,114 @@ struct PoolScratch
   std::vector<uint32_t> chunkMoves, partCount;
 };
 
-// Runs fn(part, begin, end) over [0, n) cut into `parts` contiguous ranges, part 0 on the calling thread.
+// Helper threads that live as long as their owner (one set per scgpu context): run(parts, fn) executes fn(part) for
+// every part in [0, parts), the caller taking parts like any helper, and returns when all are done. Creating and
+// joining std::threads per call cost 50-100 us a time, several times per frame; these sleep on a condition variable
+// between calls. No exception leaves run(); a helper that could not be created is simply absent.
+class HostWorkers
+{
+public:
+  explicit HostWorkers(uint32_t helpers)
+  {
+    m_threads.reserve(helpers);
+    for (uint32_t i = 0; i < helpers; ++i)
+    {
+      try { m_threads.emplace_back([this] { loop(); }); }
+      catch (...) { break; }  // thread limit reached: fewer helpers
+    }
+  }
+  ~HostWorkers()
+  {
+    {
+      std::lock_guard<std::mutex> lk(m_mutex);
+      m_quit = true;
+      ++m_generation;
+    }
+    m_wake.notify_all();
+    for (std::thread& t : m_threads) t.join();
+  }
+  HostWorkers(const HostWorkers&) = delete;
+  HostWorkers& operator=(const HostWorkers&) = delete;
+  uint32_t helpers() const { return (uint32_t)m_threads.size(); }
+
+  void run(uint32_t parts, const std::function<void(uint32_t)>& fn)
+  {
+    if (parts == 0) return;
+    if (parts == 1 || m_threads.empty()) { for (uint32_t p = 0; p < parts; ++p) fn(p); return; }
+    {
+      std::lock_guard<std::mutex> lk(m_mutex);
+      m_fn = &fn;
+      m_parts = parts;
+      m_next.store(0, std::memory_order_relaxed);
+      m_done = 0;
+      ++m_generation;
+    }
+    m_wake.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_mutex);
+    m_finished.wait(lk, [&] { return m_done == m_parts; });
+    m_fn = nullptr;
+  }
+
+private:
+  void work()
+  {
+    uint32_t mine = 0;
+    for (;;)
+    {
+      const uint32_t p = m_next.fetch_add(1, std::memory_order_relaxed);
+      if (p >= m_parts) break;
+      (*m_fn)(p);
+      ++mine;
+    }
+    if (mine)
+    {
+      std::lock_guard<std::mutex> lk(m_mutex);
+      m_done += mine;
+      if (m_done == m_parts) m_finished.notify_all();
+    }
+  }
+  void loop()
+  {
+    uint64_t seen = 0;
+    for (;;)
+    {
+      {
+        std::unique_lock<std::mutex> lk(m_mutex);
+        m_wake.wait(lk, [&] { return m_generation != seen; });
+        seen = m_generation;
+        if (m_quit) return;
+        if (!m_fn) continue;  // woke up after the job was already finished by the others
+      }
+      work();
+    }
+  }
+
+  std::vector<std::thread> m_threads;
+  std::mutex m_mutex;
+  std::condition_variable m_wake, m_finished;
+  const std::function<void(uint32_t)>* m_fn = nullptr;
+  std::atomic<uint32_t> m_next{0};
+  uint32_t m_parts = 0, m_done = 0;
+  uint64_t m_generation = 0;
+  bool m_quit = false;
+};
+
+// Runs fn(part, begin, end) over [0, n) cut into `parts` contiguous ranges: on the owner's helper threads when it has
+// some, else on short-lived threads (tests/hostsim), part 0 on the calling thread.
 template <class Fn>
-inline void poolParallelFor(uint32_t parts, uint32_t n, Fn fn)
+inline void poolParallelFor(uint32_t parts, uint32_t n, Fn fn, HostWorkers* workers = nullptr)
 {
   if (parts <= 1u || n < 32768u) { fn(0u, 0u, n); return; }
   const uint32_t per = (n + parts - 1u) / parts;
+  if (workers)
+  {
+    workers->run(parts, [&](uint32_t p) {
+      const uint32_t b = std::min(n, p * per), e = std::min(n, b + per);
+      fn(p, b, e);
+    });
+    return;
+  }
   std::vector<std::thread> th;
   th.reserve(parts - 1u);
   uint32_t started = 1;  // ranges [0, started) have an owner; a thread that cannot be created leaves its range to the caller
@@ -90,7 +195,7 @@ inline void poolParallelFor(uint32_t parts, uint32_t n, Fn fn)
 // Stale, unknown, repeated and invalid handles are skipped, like World::destroy returning false.
 inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t>& sparse, uint32_t& count, uint32_t n,
                               const uint32_t* entity, std::vector<PoolMove>& moves, std::vector<uint32_t>& removed,
-                              PoolScratch& scratch, uint32_t threads = 1)
+                              PoolScratch& scratch, uint32_t threads = 1, HostWorkers* workers = nullptr)
 {
   moves.clear();
   removed.clear();
@@ -153,7 +258,7 @@ inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t
     }
     partCount[part + 1u] = valid;
     if (again) repeats.fetch_add(again, std::memory_order_relaxed);
-  });
+  }, workers);
 
   // ---- A2: the victims in batch order (slot0) and their entity indices (removed)
   std::vector<uint32_t>& slot0 = scratch.slot0;
@@ -175,7 +280,7 @@ inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t
         rm[w] = entity[j] & kPoolIndexMask;
         ++w;
       }
-    });
+    }, workers);
   }
   else
   {
@@ -258,7 +363,7 @@ inline void poolReplayDespawn(std::vector<uint32_t>& dense, std::vector<uint32_t
       mv[m++] = PoolMove{dst, base + t};
     }
     chunkMoves[part] = m - b;
-  });
+  }, workers);
   // close the gaps between the ranges' move lists
   uint32_t total = chunkMoves[0];
   if (parts > 1u)

@@ -517,10 +517,11 @@ class Scene:
         self._ck(self.lib.scgpuGetGatheredCounts(self.ctx, _ptr(out), self.n_ranks), "scgpuGetGatheredCounts")
         return out
 
-    def read_gathered_visible(self, view=0):
+    def read_gathered_visible(self, view=0, out=None):
         n = C.c_uint32(0)
         self._ck(self.lib.scgpuReadGatheredVisible(self.ctx, view, None, 0, C.byref(n)), "scgpuReadGatheredVisible")
-        out = np.empty(n.value, np.uint32)
+        if out is None:
+            out = np.empty(n.value, np.uint32)
         self._ck(self.lib.scgpuReadGatheredVisible(self.ctx, view, _ptr(out), out.shape[0], C.byref(n)),
                  "scgpuReadGatheredVisible")
-        return out
+        return out[: n.value]

@@ -77,6 +77,39 @@ def main():
             pass
     dist.barrier()
     s.close()
+
+    # ---- a frame whose lists overflow the mailbox fails THAT frame only: the error word is per gather ----
+    t = scgpu.Scene(len(mine) + 16, max_views=views, device=local, max_entity_index=n)
+    t.spawn(e[mine], sc["trs9"][mine], par[mine], sc["aabb6"][mine], sc["mesh_mat"][mine], sc["flags"][mine])
+    uid = [scgpu.Scene.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    t.comm_init(world, rank, uid[0])
+    t.enable_peer_gather(0, cap_entries=64)          # far too small for the standard views
+    t.set_views(vps)
+    t.update()
+    t.gather_visible(0)
+    if rank == 0:
+        try:
+            t.gathered_counts()
+            raise AssertionError("an overflowing frame must be reported")
+        except scgpu.ScGpuError as ex:
+            assert "exceed the mailbox capacity" in str(ex), str(ex)
+    t.synchronize()
+    dist.barrier()
+    away = scenes.standard_views(views, center=(1.0e6, 6.0, 1.0e6))   # nothing of the city is near these frusta
+    t.set_views(away)
+    for frame in range(3):
+        t.update()
+        t.gather_visible(0)
+    if rank == 0:
+        pc = t.gathered_counts()                         # the earlier overflow must not fail this frame
+        assert pc.sum() <= 64 * world, pc
+        for v in range(views):
+            assert len(t.read_gathered_visible(v)) == pc[:, v].sum()
+        print("MULTIGPU PEER RECOVERY OK", flush=True)
+    t.synchronize()
+    dist.barrier()
+    t.close()
     dist.destroy_process_group()
 
 

@@ -110,7 +110,7 @@ def test_nccl_gather_across_gpus():
            "127.0.0.1", "--master-port", "29611", str(ROOT / "tests" / "multigpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "MULTIGPU OK" in r.stdout and "MULTIGPU PEER OK" in r.stdout
+    assert "MULTIGPU OK" in r.stdout and "MULTIGPU PEER OK" in r.stdout and "MULTIGPU PEER RECOVERY OK" in r.stdout
 
 
 def test_dropin_adapter_systems_against_reference_systems():
