@@ -423,24 +423,35 @@ def churn_leg(args, D, rank, local_rank, torch):
     sc = scenes.city_hier(n, seed=99 + 7919 * rank)
     sc["trs9"][sc["parent"] < 0, 0] += block_shift(rank, D.world, sc["side"])
     rng = np.random.default_rng(5 + rank)
-    roots = np.nonzero(sc["parent"] < 0)[0]
-    glen = np.diff(np.append(roots, n))
-    gco = rng.integers(0, cohorts, size=len(roots))           # every group belongs to one of ten cohorts, at random
-    cohort_of = np.repeat(gco, glen).astype(np.uint8)
+    # The unit of streaming is the world SECTOR (64 m cell), as in the reference's WorldPartition (pumpUnloadQueue destroys a
+    # sector's entities, pumpCompletedLoads creates one's, sc_world_partition.cpp:839-1034): every sector belongs to one of
+    # ten cohorts, at random; frame f unloads cohort f % 10 and loads it again — the same content, but the sectors arrive
+    # in a fresh random order, so a new sector lands in whatever holes an old one left, not in its own.
+    sec_key = sc["sector"][:, 0].astype(np.int64) * (1 << 20) + sc["sector"][:, 1].astype(np.int64)
+    sec_start = np.concatenate([[0], np.nonzero(np.diff(sec_key))[0] + 1])   # the scene is laid out sector by sector
+    sec_len = np.diff(np.append(sec_start, n))
+    sco = rng.integers(0, cohorts, size=len(sec_start))
+    cohort_of = np.repeat(sco, sec_len).astype(np.uint8)
     index = np.arange(n, dtype=np.uint32)                     # entity index == initial position, reused by every generation
     gen = np.zeros(cohorts, np.uint32)
-    members = [np.nonzero(cohort_of == c)[0].astype(np.uint32) for c in range(cohorts)]   # group order kept
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     tmpl = []
     for c in range(cohorts):
-        ix = members[c]
+        secs = np.nonzero(sco == c)[0]
+        tmpl.append(dict(secs=secs, ix=np.nonzero(cohort_of == c)[0].astype(np.uint32)))
+    moved_pat = [np.sort(rng.choice(n, (3 * n) // 10, replace=False)).astype(np.uint32) for _ in range(4)]
+    moved_trs = [pin(sc["trs9"][p] + np.float32(0.25)) for p in moved_pat]
+
+    def spawn_batch(c):
+        """cohort c's sectors in a fresh random order: handles, parents, components (host prep, outside the timed calls)"""
+        secs = rng.permutation(tmpl[c]["secs"])
+        ix = np.concatenate([np.arange(sec_start[k], sec_start[k] + sec_len[k], dtype=np.int64) for k in secs])
         pos = np.full(n, -1, np.int64)
         pos[ix] = np.arange(len(ix))
         lp = np.where(sc["parent"][ix] >= 0, pos[np.maximum(sc["parent"][ix], 0)], -1)
-        tmpl.append(dict(ix=ix, parent=lp, trs=pin(sc["trs9"][ix]), aabb=pin(sc["aabb6"][ix]), mm=pin(sc["mesh_mat"][ix]),
-                         flags=pin(sc["flags"][ix])))
-    moved_pat = [np.sort(rng.choice(n, (3 * n) // 10, replace=False)).astype(np.uint32) for _ in range(4)]
-    moved_trs = [pin(sc["trs9"][p] + np.float32(0.25)) for p in moved_pat]
+        fresh = pin(ix.astype(np.uint32) | (gen[c] << np.uint32(24)))
+        return (fresh, pin(scenes.parent_handles(lp, fresh)), pin(sc["trs9"][ix]), pin(sc["aabb6"][ix]), pin(sc["mesh_mat"][ix]),
+                pin(sc["flags"][ix]))
 
     scene = scgpu.Scene(n + n // 8, max_views=args.views, device=local_rank, max_entity_index=n)
     scene.spawn(index, sc["trs9"], scenes.parent_handles(sc["parent"], index), sc["aabb6"], sc["mesh_mat"], sc["flags"])
@@ -454,11 +465,9 @@ def churn_leg(args, D, rank, local_rank, torch):
     rec = 0
     for f in range(warm + frames):
         c = f % cohorts
-        t = tmpl[c]
-        dead = pin(t["ix"] | (gen[c] << np.uint32(24)))
+        dead = pin(tmpl[c]["ix"] | (gen[c] << np.uint32(24)))
         gen[c] = (gen[c] + 1) & 0xFF
-        fresh = pin(t["ix"] | (gen[c] << np.uint32(24)))
-        fpar = pin(scenes.parent_handles(t["parent"], fresh))
+        fresh, fpar, f_trs, f_aabb, f_mm, f_flags = spawn_batch(c)
         mp = moved_pat[f % 4]
         keep = cohort_of[mp] != c                               # the cohort that was just replaced keeps its spawn TRS
         moved = pin(mp[keep] | (gen[cohort_of[mp[keep]]] << np.uint32(24)))
@@ -467,7 +476,7 @@ def churn_leg(args, D, rank, local_rank, torch):
         t0 = time.perf_counter()
         scene.despawn(dead)
         t1 = time.perf_counter()
-        scene.spawn(fresh, t["trs"], fpar, t["aabb"], t["mm"], t["flags"])
+        scene.spawn(fresh, f_trs, fpar, f_aabb, f_mm, f_flags)
         t2 = time.perf_counter()
         scene.set_local(moved, mtrs)
         t3 = time.perf_counter()
@@ -494,8 +503,8 @@ def churn_leg(args, D, rank, local_rank, torch):
     alg = ALG_BYTES_DIRTY * rec + ALG_BYTES_CLEAN * (live - rec)
     out = {
         "workload": "BASELINE.json configs[4], per-GPU share: %d instances in depth-4 groups, %d views; per frame ~10 %% despawn "
-                    "(whole groups, chosen at random at start-up) + as many spawn + 30 %% setLocal, through the C ABI from "
-                    "pinned host buffers" % (n, args.views),
+                    "(whole world sectors, a random tenth of them) + as many spawn (the same sectors in a fresh random order) "
+                    "+ 30 %% setLocal (random instances), through the C ABI from pinned host buffers" % (n, args.views),
         "frames": frames, "n_gpus": D.world, "instances_per_gpu": live, "slots_walked": extent,
         "e2e_frame_ms_median": frame_ms, "e2e_value": live * D.world / (frame_ms * 1e-3), "unit": UNIT,
         "calls_ms_median": {k_: float(np.median(v)) for k_, v in calls.items()},
@@ -623,9 +632,8 @@ def main():
         pin_t = torch.from_numpy(sc["trs9"]).pin_memory()
         pin_pr = torch.from_numpy(np.ascontiguousarray(sc["trs9"][:, 0:6])).pin_memory()
         pe, pt, ppr = pin_e.numpy(), pin_t.numpy(), pin_pr.numpy()
-        cap = n * (world if rank == 0 else 1)
-        out_lists = [torch.empty(min(cap, 1 << 26), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-                     for _ in range(args.views)]
+        cap = min(n * (world if rank == 0 else 1), 8 << 20)   # per view; the lists are ~1 % of the scene
+        out_lists = [torch.empty(cap, dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(args.views)]
 
         def read_back():
             scene.counts()

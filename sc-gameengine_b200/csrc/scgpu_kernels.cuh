@@ -436,22 +436,27 @@ __device__ __forceinline__ void emit_visible_warp(const UpdateParams& p, uint32_
       }
     }
   }
-  else if (need)
+  else
   {
-    const uint32_t bit = 1u << (r & 31u);
-    uint32_t* w = p.visBits + (r >> 5);
-    uint32_t* cnt = p.chunkCounts + (r >> kChunkShift);
+    // Ranks scattered (a window whose groups were spawned at different times, after churn): still one reduction per
+    // bitmap word and per chunk, by the lanes that share it — a warp near the camera would otherwise send up to 64
+    // single-bit reductions per view at a handful of addresses, and those serialise in the L2.
 #pragma unroll
-    for (int v = 0; v < kViews; ++v)
-      if ((mask >> v) & 1u)
-      {
-        red_global_or(w + (size_t)v * p.bitWords, bit);
-        red_global_add_u32(cnt + (size_t)v * p.chunkStride, 1u);
-      }
-    if (wantCand && cand)
+    for (int v = 0; v <= kViews; ++v)
     {
-      red_global_or(w + (size_t)kViews * p.bitWords, bit);
-      red_global_add_u32(cnt + (size_t)kViews * p.chunkStride, 1u);
+      if (v == kViews && !wantCand) break;
+      const bool bit = v < kViews ? ((mask >> v) & 1u) != 0u : cand;
+      const uint32_t m = __ballot_sync(0xffffffffu, bit);
+      if (m == 0u) continue;
+      if (bit)
+      {
+        const uint32_t sameWord = __match_any_sync(m, r >> 5);
+        const uint32_t bits = __reduce_or_sync(sameWord, 1u << (r & 31u));
+        if (lane == __ffs(sameWord) - 1u) red_global_or(p.visBits + (size_t)v * p.bitWords + (r >> 5), bits);
+        const uint32_t sameChunk = __match_any_sync(m, r >> kChunkShift);
+        if (lane == __ffs(sameChunk) - 1u)
+          red_global_add_u32(p.chunkCounts + (size_t)v * p.chunkStride + (r >> kChunkShift), __popc(sameChunk));
+      }
     }
   }
 }

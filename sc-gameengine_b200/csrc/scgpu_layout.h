@@ -9,9 +9,16 @@
 // So a Transform gets a device SLOT when it is spawned and keeps it until it is despawned; only its rank changes
 // (rank[slot], perm[rank] on the device, maintained by the same `dst <- src` moves the pool mirror derives). Slots are
 // handed out per hierarchy GROUP — a run of a spawn batch in which every element's parent is an earlier element of the
-// same run — so that parent and children stay inside one window for as long as they live, and the holes that whole-group
-// despawns leave are reused by later groups of the same size. The visible lists are put back into rank order by the
-// compaction kernel (a bitmap indexed by rank), which is ~1 % of the scene.
+// same run — so that parent and children stay inside one window for as long as they live. The visible lists are put
+// back into rank order by the compaction kernel (a bitmap indexed by rank), which is ~1 % of the scene.
+//
+// The allocator is a free-slot BITMAP walked by a roving cursor (next fit): a spawn batch takes the free runs it meets
+// in address order, each group the first run from the cursor on that holds it. What spawns together therefore lands
+// close together — a world sector that streams in fills the holes a sector that streamed out left, one after the other
+// — and that SPATIAL coherence of neighbouring slots is what the warp-wide early-outs of the culling code live on (a
+// warp whose 32 instances come from all over the city has somebody near a frustum most of the time). Adjacent holes
+// coalesce by construction (they are adjacent bits), fragments too small for a group are passed over and taken by a
+// smaller group or a later lap.
 //
 // Pure host C++ (no CUDA types): compiled into libscgpu.so and, for the CPU suite, into tests/hostsim.
 #pragma once
@@ -33,8 +40,11 @@ public:
     m_capacity = capacity;
     m_extent = 0;
     m_freeSlots = 0;
-    for (auto& b : m_bucket) b.clear();
-    m_big.clear();
+    for (uint32_t& c : m_cursor) c = 0;
+    m_free.assign(((size_t)capacity + 63u) / 64u + 1u, 0ull);
+    for (uint32_t& f : m_noRunSince) f = 0;
+    for (uint32_t& f : m_noExactSince) f = 0;
+    m_epoch = 1;
   }
   uint32_t extent() const { return m_extent; }        // slots [0, extent) are in use or free holes
   uint32_t freeSlots() const { return m_freeSlots; }  // holes below the extent
@@ -50,37 +60,35 @@ public:
     return s;
   }
 
-  // g <= kLayoutMaxGroup consecutive slots: a hole of exactly that size, else the front of the smallest larger hole,
-  // else fresh slots at the end. UINT32_MAX when nothing contiguous of that size is left.
+  // g <= kLayoutMaxGroup consecutive slots. Every group size has its own roving cursor and sweeps the bitmap forward
+  // (one lap around the extent at most), first for a run of EXACTLY g slots or a long run (>= a window: a sector-sized
+  // hole, carved group after group), then — when a whole lap holds no such run — for any run that is large enough;
+  // else fresh slots at the end. Preferring the exact fit matters when holes and groups come in a few sizes (vehicles
+  // of 10, peds of 4): plain first fit lets the small groups eat the large holes and leaves the large groups crumbs.
+  // A hole is looked at once per lap and size class, so a batch costs O(holes it passes), not O(groups x look-ahead).
+  // UINT32_MAX when nothing contiguous of that size is left.
   uint32_t allocGroup(uint32_t g)
   {
     if (g == 0 || g > kLayoutMaxGroup) return 0xFFFFFFFFu;
-    for (uint32_t len = g; len <= kLayoutMaxGroup; ++len)
+    if (m_freeSlots >= g)
     {
-      std::vector<uint32_t>& b = m_bucket[len];
-      if (b.empty()) continue;
-      const uint32_t s = b.back();
-      b.pop_back();
-      m_freeSlots -= g;
-      if (len > g) m_bucket[len - g].push_back(s + g);
-      return s;
-    }
-    if (!m_big.empty())
-    {
-      std::pair<uint32_t, uint32_t>& r = m_big.back();
-      const uint32_t s = r.first;
-      r.first += g;
-      r.second -= g;
-      m_freeSlots -= g;
-      if (r.second <= kLayoutMaxGroup)
+      if (m_noExactSince[g] != m_epoch)
       {
-        const std::pair<uint32_t, uint32_t> rest = r;
-        m_big.pop_back();
-        if (rest.second) m_bucket[rest.second].push_back(rest.first);
+        const uint32_t s = sweep(g, true);
+        if (s != 0xFFFFFFFFu) return s;
+        m_noExactSince[g] = m_epoch;
       }
-      return s;
+      if (m_noRunSince[g] != m_epoch)
+      {
+        const uint32_t s = sweep(g, false);
+        if (s != 0xFFFFFFFFu) return s;
+        // no run of g anywhere: do not lap again for this size (or a larger one) until something is released
+        for (uint32_t k = g; k <= kLayoutMaxGroup; ++k) m_noRunSince[k] = m_epoch;
+      }
     }
-    return appendRun(g);
+    const uint32_t s = appendRun(g);
+    if (s != 0xFFFFFFFFu) m_cursor[g] = m_extent;
+    return s;
   }
 
   // Assigns a slot to every element of a spawn batch. entity / parent: the batch as scgpuSpawn receives it (parent may
@@ -124,41 +132,149 @@ public:
     return true;
   }
 
-  // Slots of despawned Transforms, in batch order. Consecutive ascending slots (a group destroyed as a whole) become one
-  // hole; a run that ends at the extent shrinks the extent instead.
+  // Slots of despawned Transforms, in batch order. Free slots at the very end of the extent give it back.
   void release(uint32_t n, const uint32_t* slot)
   {
-    uint32_t j = 0;
-    while (j < n)
+    if (n == 0) return;
+    for (uint32_t j = 0; j < n; ++j)
     {
-      uint32_t end = j + 1;
-      while (end < n && slot[end] == slot[end - 1] + 1u) ++end;
-      addHole(slot[j], end - j);
-      j = end;
+      const uint32_t s = slot[j];
+      m_free[s >> 6] |= 1ull << (s & 63u);
+    }
+    m_freeSlots += n;
+    ++m_epoch;
+    if (m_epoch == 0) { ++m_epoch; for (uint32_t& f : m_noRunSince) f = 0; for (uint32_t& f : m_noExactSince) f = 0; }
+    while (m_extent > 0u && ((m_free[(m_extent - 1u) >> 6] >> ((m_extent - 1u) & 63u)) & 1ull))
+    {
+      // whole trailing words at once where possible
+      const uint32_t last = m_extent - 1u;
+      if ((last & 63u) == 63u && m_free[last >> 6] == ~0ull) { m_free[last >> 6] = 0ull; m_extent -= 64u; m_freeSlots -= 64u; continue; }
+      m_free[last >> 6] &= ~(1ull << (last & 63u));
+      --m_extent;
+      --m_freeSlots;
     }
   }
 
-  // every hole as (start, length), unordered (tests)
+  // every hole as (start, length), ascending (tests)
   void holes(std::vector<std::pair<uint32_t, uint32_t>>& out) const
   {
     out.clear();
-    for (uint32_t len = 1; len <= kLayoutMaxGroup; ++len)
-      for (uint32_t s : m_bucket[len]) out.emplace_back(s, len);
-    for (const auto& r : m_big) out.push_back(r);
+    uint32_t pos = 0;
+    for (;;)
+    {
+      const uint32_t f = nextFree(pos, m_extent);
+      if (f >= m_extent) break;
+      uint32_t e = f;
+      while (e < m_extent && ((m_free[e >> 6] >> (e & 63u)) & 1ull)) ++e;
+      out.emplace_back(f, e - f);
+      pos = e;
+    }
   }
 
 private:
-  void addHole(uint32_t start, uint32_t len)
+  void take(uint32_t f, uint32_t g)
   {
-    if (start + len == m_extent) { m_extent = start; return; }
-    m_freeSlots += len;
-    if (len <= kLayoutMaxGroup) m_bucket[len].push_back(start);
-    else m_big.emplace_back(start, len);
+    clearBits(f, g);
+    m_freeSlots -= g;
+  }
+
+  // one lap from this size's cursor: the first run that qualifies, or UINT32_MAX
+  uint32_t sweep(uint32_t g, bool exactOrLong)
+  {
+    uint32_t pos = m_cursor[g] < m_extent ? m_cursor[g] : 0u;
+    const uint32_t startedAt = pos;
+    bool wrapped = false;
+    for (;;)
+    {
+      const uint32_t limit = wrapped ? startedAt : m_extent;  // the second half of the lap ends where the first began
+      ++m_steps;
+      const uint32_t f = nextFree(pos, limit);
+      if (f >= limit)
+      {
+        if (wrapped || startedAt == 0u) return 0xFFFFFFFFu;
+        wrapped = true;
+        pos = 0u;
+        continue;
+      }
+      const uint32_t len = runLength(f, 64u);  // free slots from f on, counted up to 64 (a run may reach across `limit`: fine)
+      if (f + g <= m_extent && (exactOrLong ? (len == g || len >= kLayoutMaxGroup) : len >= g))
+      {
+        take(f, g);
+        m_cursor[g] = f + g;
+        return f;
+      }
+      pos = len < 64u ? f + len : runEnd(f + 64u, limit);  // on to the end of this run
+    }
+  }
+
+  // first free slot in [from, limit), or limit
+  uint32_t nextFree(uint32_t from, uint32_t limit) const
+  {
+    if (from >= limit) return limit;
+    size_t w = from >> 6;
+    uint64_t bits = m_free[w] & (~0ull << (from & 63u));
+    const size_t lastWord = (limit - 1u) >> 6;
+    for (;;)
+    {
+      if (bits)
+      {
+        const uint32_t f = (uint32_t)(w << 6) + (uint32_t)__builtin_ctzll(bits);
+        return f < limit ? f : limit;
+      }
+      if (++w > lastWord) return limit;
+      bits = m_free[w];
+    }
+  }
+
+  // first slot in [from, limit) that is NOT free, or limit
+  uint32_t runEnd(uint32_t from, uint32_t limit) const
+  {
+    if (from >= limit) return limit;
+    size_t w = from >> 6;
+    uint64_t bits = ~m_free[w] & (~0ull << (from & 63u));
+    const size_t lastWord = (limit - 1u) >> 6;
+    for (;;)
+    {
+      if (bits)
+      {
+        const uint32_t e = (uint32_t)(w << 6) + (uint32_t)__builtin_ctzll(bits);
+        return e < limit ? e : limit;
+      }
+      if (++w > lastWord) return limit;
+      bits = ~m_free[w];
+    }
+  }
+
+  // number of consecutive free slots starting at f, counted up to `cap` (<= 64)
+  uint32_t runLength(uint32_t f, uint32_t cap) const
+  {
+    // 64 bits starting at f, from two words
+    const size_t w = f >> 6;
+    const uint32_t sh = f & 63u;
+    uint64_t bits = m_free[w] >> sh;
+    if (sh) bits |= m_free[w + 1] << (64u - sh);
+    const uint64_t inv = ~bits;
+    const uint32_t len = inv ? (uint32_t)__builtin_ctzll(inv) : 64u;
+    return len < cap ? len : cap;
+  }
+
+  void clearBits(uint32_t f, uint32_t g)  // g <= 32: at most two words
+  {
+    const size_t w = f >> 6;
+    const uint32_t sh = f & 63u;
+    const uint64_t mask = g >= 64u ? ~0ull : ((1ull << g) - 1ull);
+    m_free[w] &= ~(mask << sh);
+    if (sh + g > 64u) m_free[w + 1] &= ~(mask >> (64u - sh));
   }
 
   uint32_t m_capacity = 0, m_extent = 0, m_freeSlots = 0;
-  std::vector<uint32_t> m_bucket[kLayoutMaxGroup + 1];   // [len]: starts of the holes of exactly that length
-  std::vector<std::pair<uint32_t, uint32_t>> m_big;      // holes longer than a window
+  uint32_t m_cursor[kLayoutMaxGroup + 1] = {};        // per group size: where its next sweep starts
+  std::vector<uint64_t> m_free;                       // one bit per slot: set = a hole below the extent
+  uint32_t m_noExactSince[kLayoutMaxGroup + 1] = {};  // epoch in which a full lap found no exact or long run for that size
+  uint32_t m_noRunSince[kLayoutMaxGroup + 1] = {};    // epoch in which a full lap found no run of that size at all
+  uint32_t m_epoch = 1;                               // advanced by every release
+public:
+  uint64_t m_steps = 0;                               // diagnostics: free runs examined so far
 };
 
 }  // namespace scgpu
