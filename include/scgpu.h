@@ -328,12 +328,15 @@ SCGPU_API int scgpuCommInit(ScGpuScene* ctx, uint32_t nRanks, uint32_t rank, con
 /* After scgpuUpdate: gathers every rank's counts to all ranks and every rank's visible lists to `root`,
  * concatenated in rank order (shard-major stable order). Enqueued on the context stream. */
 SCGPU_API int scgpuGatherVisible(ScGpuScene* ctx, uint32_t root);
-/* Optional, collective (every rank calls it with the same arguments, once): from now on scgpuGatherVisible(root)
- * moves the lists through NVLink PEER MEMORY instead of NCCL — every rank's pack kernel stores its lists straight
- * into a mailbox in the root's HBM (cudaIpc mapping, handle carried by one ncclBroadcast here) and raises a flag;
- * the root waits for the flags on the device. No host synchronisation and no NCCL call per frame. capEntries =
- * mailbox capacity per rank in list entries (0 => min(max_instances * max_views, 4 Mi)); a frame whose lists exceed
- * it fails in the read-back calls. With the peer gather the counts and lists exist on the root only. */
+/* Optional, collective (every rank calls it with the same arguments, once): from now on the lists travel through
+ * NVLink PEER MEMORY instead of NCCL. Every scgpuUpdate's last kernel stores the entity handles it resolves straight
+ * into a mailbox in the root's HBM as well (cudaIpc mapping, handle carried by one ncclBroadcast here) and raises a
+ * flag — compute and peer store in one kernel; scgpuGatherVisible(root) is then one small kernel on the root that waits
+ * for the flags, and nothing at all on the other ranks. No host synchronisation and no NCCL call per frame. All ranks
+ * must issue the same number of scgpuUpdate calls per frame (a producer may run one update ahead of the root, not two).
+ * capEntries = mailbox capacity per rank in list entries (0 => min(max_instances * max_views, 4 Mi)); a frame whose
+ * lists exceed it fails in the read-back calls — that frame only. With the peer gather the counts and lists exist on
+ * the root only. */
 SCGPU_API int scgpuCommEnablePeerGather(ScGpuScene* ctx, uint32_t root, uint32_t capEntries);
 /* counts[rank][view] for all ranks (NCCL gather: valid on every rank; peer gather: on the root) */
 SCGPU_API int scgpuGetGatheredCounts(ScGpuScene* ctx, uint32_t* outCounts, uint32_t capRanks);

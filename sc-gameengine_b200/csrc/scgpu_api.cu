@@ -195,8 +195,9 @@ struct ScGpuScene
   bool peerEnabled = false;
   bool peerMapped = false;      // base is a cudaIpc mapping (not the root)
   uint32_t peerRoot = 0, peerSeq = 0;
-  uint32_t* dPeerState = nullptr;  // [0] ticket counter, [1] error word
+  uint32_t* dPeerState = nullptr;  // [0] ticket counter, [1], [2] error word of the gathers with even / odd sequence number
   bool lastGatherPeer = false;
+  bool peerPublished = false;   // the last update stored its lists into the root's mailbox (peer gather enabled before it)
   size_t gatheredCap = 0;
   bool gatheredValid = false;
 };
@@ -643,7 +644,7 @@ int scgpuSynchronize(ScGpuScene* ctx)
   {
     // a producer that could not deliver learns it here (the root learns it from its read-back calls)
     uint32_t err = 0;
-    SC_CUDA(ctx, cudaMemcpy(&err, ctx->dPeerState + 1, 4, cudaMemcpyDeviceToHost));
+    SC_CUDA(ctx, cudaMemcpy(&err, ctx->dPeerState + 1 + (ctx->peerSeq & 1u), 4, cudaMemcpyDeviceToHost));
     if (err & 1u) return (int)fail(ctx, "peer gather: the root did not release this rank's mailbox within the time limit; the last frame's lists were not delivered");
   }
   return 1;
@@ -1458,6 +1459,18 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     rp.culled = q.culled;
     rp.live = c->count;
     rp.extent = extent;
+    if (c->peerEnabled)
+    {
+      // every update is also the producer side of the gather: lists into the root's mailbox, flag by the last CTA
+      rp.box = c->peerBox;
+      rp.peer = 1u;
+      rp.seq = ++c->peerSeq;
+      rp.rank = c->rank;
+      rp.isRoot = c->rank == c->peerRoot ? 1u : 0u;
+      rp.done = c->dPeerState;
+      rp.error = c->dPeerState + 1;
+      c->peerPublished = true;
+    }
     SC_CUDA(c, launchPdl(k_resolve_lists, c->numSMs * 2u, kBlock, c->stream, rp));
     c->launches += 2;
   }
@@ -1822,7 +1835,7 @@ int scgpuCommEnablePeerGather(ScGpuScene* c, uint32_t root, uint32_t capEntries)
   if (root >= c->nRanks) return (int)fail(c, "scgpuCommEnablePeerGather: root %u >= %u ranks", root, c->nRanks);
   if (c->peerEnabled) return (int)fail(c, "scgpuCommEnablePeerGather: already enabled (root %u)", c->peerRoot);
   if (capEntries == 0) capEntries = std::min<uint64_t>((uint64_t)c->capacityPad * c->maxViews, 4u << 20);
-  if (!c->dPeerState && !devAlloc(c, &c->dPeerState, 2, true)) return 0;
+  if (!c->dPeerState && !devAlloc(c, &c->dPeerState, 4, true)) return 0;
   // the root allocates the mailbox and publishes its IPC handle through NCCL (the bootstrap channel we have)
   cudaIpcMemHandle_t handle{};
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1862,24 +1875,13 @@ int scgpuGatherVisible(ScGpuScene* c, uint32_t root)
   const size_t row = kMaxViews + 2;
   if (c->peerEnabled && root == c->peerRoot)
   {
-    // peer-memory path: pack straight into the root's mailbox over NVLink, flag, root waits on the device
-    PeerPackParams q{};
-    q.box = c->peerBox;
-    q.totals = c->totals;
-    for (uint32_t v = 0; v < kMaxViews; ++v) q.visEntity[v] = c->visEntity[v];
-    q.done = c->dPeerState;
-    q.error = c->dPeerState + 1;
-    q.seq = ++c->peerSeq;
-    q.rank = c->rank;
-    q.nViews = c->nViews;
-    q.isRoot = (c->rank == root) ? 1u : 0u;
-    // the error word describes ONE gather: a slow or overflowing frame must not fail every later one
-    SC_CUDA(c, cudaMemsetAsync(c->dPeerState + 1, 0, 4, c->stream));
-    k_peer_pack<<<32, kBlock, 0, c->stream>>>(q);
-    ++c->launches;
+    // peer-memory path: the update's last kernel (k_resolve_lists) has already stored this rank's lists into the root's
+    // mailbox over NVLink and raised its flag; the root waits for all flags on the device, nobody else does anything
+    if (!c->peerPublished)
+      return (int)fail(c, "scgpuGatherVisible: scgpuCommEnablePeerGather must precede the scgpuUpdate whose lists are gathered");
     if (c->rank == root)
     {
-      k_peer_wait<<<1, 64, 0, c->stream>>>(c->peerBox, q.seq, c->dAllCounts, c->dPeerState + 1);
+      SC_CUDA(c, launchPdl(k_peer_wait, 1u, 64u, c->stream, c->peerBox, c->peerSeq, c->dAllCounts, c->dPeerState + 1 + (c->peerSeq & 1u)));
       ++c->launches;
     }
     SC_CUDA(c, cudaGetLastError());
@@ -1952,7 +1954,7 @@ static int peerFetchCounts(ScGpuScene* c)
   if (c->rank != c->peerRoot) return (int)fail(c, "peer gather: counts and lists exist on the root (rank %u) only", c->peerRoot);
   uint32_t err = 0;
   SC_CUDA(c, cudaMemcpyAsync(c->hAllCounts, c->dAllCounts, (size_t)c->nRanks * (kMaxViews + 2) * 4, cudaMemcpyDeviceToHost, c->stream));
-  SC_CUDA(c, cudaMemcpyAsync(&err, c->dPeerState + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+  SC_CUDA(c, cudaMemcpyAsync(&err, c->dPeerState + 1 + (c->peerSeq & 1u), 4, cudaMemcpyDeviceToHost, c->stream));
   SC_CUDA(c, cudaStreamSynchronize(c->stream));
   if (err & 2u) return (int)fail(c, "peer gather: a rank did not deliver within the time limit");
   if (err & 4u) return (int)fail(c, "peer gather: a rank's visible lists exceed the mailbox capacity (scgpuCommEnablePeerGather capEntries)");

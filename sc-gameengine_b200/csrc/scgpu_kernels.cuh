@@ -1786,6 +1786,43 @@ __global__ void __launch_bounds__(kCompactThreads, 4) k_compact(const __grid_con
   SC_STAMP(4);
 }
 
+// Mailbox in the gather root's HBM (scgpu_peer.cuh documents the protocol; the struct lives here because the last
+// kernel of the frame writes into it).
+constexpr uint32_t kPeerHeaderWords = 16;  // 64 B
+constexpr uint32_t kPeerFlag = 0, kPeerCounts = 1, kPeerOverflow = kPeerCounts + kMaxViews + 2;
+constexpr long long kPeerSpinClocks = 4000000000ll;  // ~2 s at 1.9 GHz: a dead peer must not hang the box
+
+struct PeerBox
+{
+  uint32_t* base;      // mailbox in the root's memory (local pointer on the root, IPC mapping elsewhere)
+  uint32_t nRanks;
+  uint32_t cap;        // payload entries per (rank, parity)
+  __host__ __device__ uint32_t* progress() const { return base; }
+  __host__ __device__ uint32_t* header(uint32_t rank, uint32_t parity) const
+  {
+    return base + kPeerHeaderWords * (1u + rank * 2u + parity);
+  }
+  __host__ __device__ uint32_t* payload(uint32_t rank, uint32_t parity) const
+  {
+    return base + kPeerHeaderWords * (1u + 2u * nRanks) + (size_t)(rank * 2u + parity) * cap;
+  }
+  static size_t bytes(uint32_t nRanks, uint32_t cap)
+  {
+    return ((size_t)kPeerHeaderWords * (1u + 2u * nRanks) + (size_t)nRanks * 2u * cap) * 4u;
+  }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 struct ResolveParams
 {
   const uint32_t* perm;                  // rank -> slot
@@ -1796,26 +1833,73 @@ struct ResolveParams
   uint32_t* culledEntity[kMaxViews];     // in: ranks, out: entity handles
   uint32_t nViews, culled;
   uint32_t live, extent;                 // checked build: bounds of ranks and slots
+  // multi-GPU, peer gather enabled: the entity handles go straight into this rank's slot of the ROOT's mailbox too
+  // (NVLink stores from the kernel that produces them), and the last CTA publishes counts + flag
+  PeerBox box;
+  uint32_t peer, seq, rank, isRoot;
+  uint32_t* done;                        // local ticket counter (zero between launches)
+  uint32_t* error;                       // local error words, one per gather parity
 };
 
-// rank -> (slot, entity handle) for every entry of every list, grid-stride: one independent chain of two loads per entry
+// rank -> (slot, entity handle) for every entry of every list, grid-stride: one independent chain of two loads per
+// entry. With the peer gather enabled this is also the producer side of the gather — compute and peer store in one
+// kernel: every handle is stored locally AND into the root's mailbox the moment it is known.
 __global__ void __launch_bounds__(kBlock) k_resolve_lists(const __grid_constant__ ResolveParams p)
 {
+  __shared__ uint32_t sOff[kMaxViews + 1];
+  __shared__ uint32_t sLast, sStale;
+  pdl_trigger();  // (the root's k_peer_wait only polls the mailbox: it may take its place already)
   pdl_wait();
   const uint32_t stride = gridDim.x * kBlock;
   const uint32_t cand = p.totals[p.nViews];
+  const uint32_t parity = p.seq & 1u;
+  bool remote = false;
+  uint32_t* mail = nullptr;
+  if (p.peer)
+  {
+    if (threadIdx.x == 0)
+    {
+      sStale = 0u;
+      if (blockIdx.x == 0) p.error[parity ^ 1u] = 0u;  // the error word describes ONE gather: clear the next one's
+      if (p.isRoot)
+      {
+        // everything the root enqueued before this frame's kernels (the readers of gather seq-1 included) has completed
+        if (blockIdx.x == 0) st_release_sys(p.box.progress(), p.seq);
+      }
+      else
+      {
+        // the buffer of this parity was last used by gather seq-2: wait until the root is past gather seq-1's start
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys(p.box.progress()) - (p.seq - 1u)) < 0)
+        {
+          // the root may still be reading this buffer: write NOTHING into it, report the frame as failed instead
+          if (clock64() - t0 > kPeerSpinClocks) { atomicOr(p.error + parity, 1u); sStale = 1u; break; }
+          __nanosleep(200);
+        }
+      }
+      uint32_t off = 0;
+      for (uint32_t v = 0; v < p.nViews; ++v) { sOff[v] = off; off += p.totals[v]; }
+      sOff[p.nViews] = off;
+    }
+    __syncthreads();
+    remote = sStale == 0u && sOff[p.nViews] <= p.box.cap;
+    mail = p.box.payload(p.rank, parity);
+  }
   for (uint32_t v = 0; v < p.nViews; ++v)
   {
     const uint32_t nVis = p.totals[v];
     uint32_t* __restrict__ outS = p.outSlot[v];
     uint32_t* __restrict__ outE = p.outEntity[v];
+    uint32_t* __restrict__ outM = remote ? mail + sOff[v] : nullptr;
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nVis; i += stride)
     {
       SC_ASSERT(outS[i] < p.live);
       const uint32_t slot = __ldg(p.perm + outS[i]);
       SC_ASSERT(slot < p.extent);
       outS[i] = slot;
-      outE[i] = __ldg(p.entity + slot);
+      const uint32_t e = __ldg(p.entity + slot);
+      outE[i] = e;
+      if (outM) outM[i] = e;
     }
     if (p.culled)
     {
@@ -1823,6 +1907,27 @@ __global__ void __launch_bounds__(kBlock) k_resolve_lists(const __grid_constant_
       uint32_t* __restrict__ outC = p.culledEntity[v];
       for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nCul; i += stride)
         outC[i] = __ldg(p.entity + __ldg(p.perm + outC[i]));
+    }
+  }
+  if (p.peer)
+  {
+    __threadfence_system();  // this thread's remote stores are visible system-wide before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0) sLast = (atomicAdd(p.done, 1u) == gridDim.x - 1u) ? 1u : 0u;
+    __syncthreads();
+    if (sLast)
+    {
+      // (the header is 64 B that the root reads only after the flag: safe to write even when the payload was not)
+      uint32_t* h = p.box.header(p.rank, parity);
+      if (threadIdx.x < kMaxViews + 2) h[kPeerCounts + threadIdx.x] = p.totals[threadIdx.x];
+      if (threadIdx.x == 0) h[kPeerOverflow] = sStale ? 2u : (sOff[p.nViews] > p.box.cap ? 1u : 0u);
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+        *p.done = 0u;
+        st_release_sys(h + kPeerFlag, p.seq);
+      }
     }
   }
 }
