@@ -1150,7 +1150,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     cp_async_wait<0>();
     __syncwarp();  // the staged list words were copied by other lanes
     const uint32_t recAddr = laneBase + bufOff;
-    bool live, nodeDirty = false, fast, partial = false;
+    bool live, nodeDirty = false, fast;
     uint32_t info;
     Mat4 W;  // assigned on every path that reads it
     {
@@ -1188,14 +1188,18 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         }
       }
       // ---- 2. local matrices of everything that is recomputed; stored world matrices of the rest ----
-      // A window that keeps some stored matrices (warp-uniform test; a fully dirty window loads none) copies them
-      // global -> shared straight into this warp's matrix area, asynchronously: the DRAM round trip runs under the
-      // sincos / TRS arithmetic of the dirty lanes and costs no register. They are read back - and checked - with
-      // everybody else's matrix after the level loop.
-      partial = dirtyM != liveMask;
-      if (partial)
+      // A window with NOTHING dirty (static props; every window of a cull-only update) keeps its stored matrices: they
+      // are copied global -> shared straight into this warp's matrix area, asynchronously, and read back - and
+      // checked - below. A window that is PARTLY dirty is computed like a fully dirty one: every mutation of a
+      // Transform (setLocal*, setParent, spawn, the fix-ups) stamps it dirty and dirtiness is inherited, so a clean
+      // node's stored matrix IS what its record and its (clean) ancestors yield - recomputing it reproduces the same
+      // value (up to the sign of a zero, see DESIGN.md "Parity"), costs no 64-byte read of the stored matrix and lets
+      // the window use the static schedule of its level loop. Only the dirty lanes are written back and counted.
+      const bool loadStored = dirtyM == 0u;
+      const bool compute = loadStored ? false : live;  // this lane builds its matrix
+      if (loadStored)
       {
-        if (live && !nodeDirty)
+        if (live)
         {
           const uint32_t q = (lds32(listAddr) & kWinSlotMask) + lane;
           const uint32_t own = laneBase + kWwMat;
@@ -1204,15 +1208,15 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         }
         cp_async_commit();
       }
-      if (dirtyM != 0u)  // warp-uniform: a window of static props (nothing dirty) builds no matrix at all
+      if (dirtyM != 0u)  // warp-uniform
       {
         const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, sclZ);
         float sx, cx, sy, cy, sz, cz;
-        sincos3_warp(nodeDirty && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
-        // every lane builds a matrix (lanes beyond the window from all-zero records, clean lanes one that is never
-        // used): no per-lane branch around sixteen live registers. Roots: world == local.
+        sincos3_warp(compute && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
+        // every lane builds a matrix (lanes beyond the window from all-zero records): no per-lane branch around sixteen
+        // live registers. Roots: world == local.
         W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);
-        fast = __all_sync(0xffffffffu, tame || !nodeDirty);
+        fast = __all_sync(0xffffffffu, tame || !compute);
       }
       else
         W = mat4_identity();  // replaced by the stored matrices below (lanes beyond the window never use theirs)
@@ -1243,14 +1247,16 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     {
       // ---- 3. parent.world * local level by level, one lane PAIR per child ----
       const bool compose = maxL != 0u && dirtyM != 0u;
-      if (compose || partial)
+      const bool loadStored = dirtyM == 0u;
+      if (compose || loadStored)
       {
         const uint32_t own = laneBase + kWwMat;
-        if (!partial || nodeDirty)  // (the slots of the clean lanes are being filled by the copy engine)
+        if (!loadStored)
         {
           sts128(own, W.c0); sts128(own + kMatC1, W.c1); sts128(own + kMatC2, W.c2); sts128(own + kMatC3, W.c3);
         }
-        if (partial) cp_async_wait<1>();  // the stored matrices have landed; the next window's records may still fly
+        else
+          cp_async_wait<1>();  // the stored matrices have landed; the next window's records may still fly
         __syncwarp();
         // one product: this lane computes columns 2h, 2h+1 (h = lane & 1) of child = parent * child, in place
         auto level_item = [&](uint32_t child, uint32_t par)
@@ -1287,9 +1293,9 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         {
           // nothing to multiply (no hierarchy in this window, or nothing dirty): the matrices only pass through
         }
-        else if (dirtyM == liveMask && (lds32(listAddr) & kWinNoStatic) == 0u)
+        else if ((lds32(listAddr) & kWinNoStatic) == 0u)
         {
-          // every node is recomputed: who multiplies what is a function of the topology alone and was laid down by
+          // every node is computed: who multiplies what is a function of the topology alone and was laid down by
           // k_build_windows in the slotInfo words (6 bits per level)
 #pragma unroll
           for (uint32_t l = 0; l < 3u; ++l)
@@ -1309,11 +1315,11 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         }
         else
         {
-          // general case: the nodes of each level that are actually recomputed are compacted into a schedule at run
-          // time, 16 per round
+          // windows without a static schedule (deeper than three levels, or a level wider than half the window): the
+          // nodes of each level are compacted into a schedule at run time, 16 per round
           for (uint32_t l = 1; l <= maxL; ++l)
           {
-            const bool mine = nodeDirty && wl == l;
+            const bool mine = live && wl == l;
             const uint32_t m = __ballot_sync(0xffffffffu, mine);
             if (m == 0u) continue;
             const uint32_t cnt = __popc(m);
@@ -1336,7 +1342,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         // propagates into the translation of all its descendants, so one test of the results covers all levels
         // (a stored matrix that is kept must be affine for the structured sphere and products to be exact)
         const float mag = fabsf(W.c3.x) + fabsf(W.c3.y) + fabsf(W.c3.z);
-        fast = __all_sync(0xffffffffu, nodeDirty ? mag < __int_as_float(0x7f800000) : (!live || !partial || mat4_is_affine(W)));
+        fast = __all_sync(0xffffffffu, !live || (loadStored ? mat4_is_affine(W) : mag < __int_as_float(0x7f800000)));
       }
     }
     if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed, accCand);
@@ -2306,7 +2312,9 @@ __global__ void __launch_bounds__(kBlock) k_despawn_apply(SceneArrays a, uint32_
     a.entity[s] = kNone;
     a.parent[s] = kNone;
     a.parentSlot[s] = kNone;
-    a.rec[3][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // an all-zero record: no LIVE bit, never dirty, no RenderMesh; and tame, should its window be computed as a whole
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.rec[0][s] = z; a.rec[1][s] = z; a.rec[2][s] = z; a.rec[3][s] = z;
   }
 }
 
