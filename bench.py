@@ -11,6 +11,7 @@ it = configs[3], 128 Mi instances sharded by world cell). Weak scaling: every ra
 world cells; the only exchange is the gather of the compacted lists to rank 0 (inside the timed step for N>1).
 
 Beside the headline numbers the same line carries
+  "clean_frame"    the same scene with nothing dirty (static city, the camera moves): the cull-only kernel, 96 B per instance;
   "partial_dirty"  the same scene with 30 % of the instances dirty per frame (TransformSystem only recomputes
                    t.dirty || parentDirty, sc_ecs.cpp:178-210): device time and the mixed 132 / 96-byte roofline;
   "churn"          BASELINE.json configs[4], the per-GPU share: 8 Mi instances, per frame 10 % despawn + 10 % spawn +
@@ -411,6 +412,41 @@ def partial_dirty_leg(scene, sc, n, args, D, stream, torch):
                     "includes the device-side setLocal of the 30 % (k_set_local), kernel_ms is the fused kernel alone"}
 
 
+def clean_leg(scene, n, args, D, stream, torch):
+    """Frames in which nothing is dirty (a static city under a moving camera): the library sees that no delta call came
+    since the last transforming update and runs the cull-only kernel: 96 B per instance (AABB + flags + stored matrix)."""
+    steps = max(5, min(args.steps, 20))
+
+    def step():
+        scene.update(0)
+        if D.world > 1:
+            scene.gather_visible(0)
+
+    for _ in range(3):
+        step()
+    D.barrier()
+    scene.enable_timings(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    ev1.record(stream)
+    D.barrier()
+    ms = D.max(ev0.elapsed_time(ev1) / steps)
+    k_ms, u_ms = scene.read_timings(steps)
+    c = scene.counts()
+    assert int(c.recomputed) == 0
+    peak, _ = measured_peak()
+    k = float(np.mean(k_ms))
+    alg = ALG_BYTES_CLEAN * n
+    return {"dirty_fraction": 0.0, "steps": steps, "ms_per_step": ms, "value": n * D.world / (ms * 1e-3), "unit": UNIT,
+            "kernel": "k_cull_only<V>", "kernel_ms_avg": k, "update_ms_avg": float(np.mean(u_ms)),
+            "visible_per_view": [int(c.visible[v]) for v in range(args.views)],
+            "roofline": {"bound": "hbm", "achieved": alg / (k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": int(alg),
+                         "formula": "96 B x instances (SURVEY.md 8d: flags 4 + parent 4 + world 64 + AABB 24)"}}
+
+
 def churn_leg(args, D, rank, local_rank, torch):
     """BASELINE.json configs[4], per-GPU share: 8 Mi instances in depth-4 groups, 5 views; per frame ~10 % of the instances
     despawn as whole groups, as many spawn (same entity indices, next generation, like the reference's LIFO index
@@ -684,8 +720,9 @@ def main():
                        ("scgpuGatherVisible + scgpuReadGatheredVisible x views on rank 0" if world > 1 else "scgpuReadVisible x views"),
                "variants": variants}
 
-    partial = None
+    partial = clean = None
     if not args.no_partial:
+        clean = clean_leg(scene, n, args, D, stream, torch)
         partial = partial_dirty_leg(scene, sc, n, args, D, stream, torch)
     scene.close()
     del scene
@@ -720,6 +757,8 @@ def main():
         }
         if gather:
             line["gather"] = gather
+        if clean:
+            line["clean_frame"] = clean
         if partial:
             line["partial_dirty"] = partial
         if churn:

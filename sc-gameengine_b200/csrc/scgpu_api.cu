@@ -104,6 +104,7 @@ struct ScGpuScene
   bool topologyDirty = false;
   bool anyParentEver = false;
   bool forceAllDirty = false;
+  bool anyDirty = false;     // some call since the last transforming update may have dirtied a Transform
   bool updatedOnce = false;
   bool poisoned = false;     // a device step failed after the host mirror was committed: the two no longer agree
   uint32_t lastUpdateFlags = 0;
@@ -677,6 +678,7 @@ static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, cons
     case 2: return (int)fail(c, "%s: entity index %u >= max_entity_index %u", who, entity[at] & 0xFFFFFFu, c->sparseSize);
     default: return (int)fail(c, "%s: entity index %u already owns a Transform", who, entity[at] & 0xFFFFFFu);
   }
+  c->anyDirty = true;  // new Transforms are dirty
   uint32_t* const so = c->hSlotOf.data();
   if (!c->layout.hasHoles())
   {
@@ -1073,6 +1075,7 @@ int scgpuTrafficAdvance(ScGpuScene* c, const ScGpuTrafficStep* st, uint32_t* out
   SC_CUDA(c, cudaMemsetAsync(c->dTrafficMoved, 0, 4, c->stream));
   k_traffic_advance<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, g, p, n, (uint4*)c->trafficAgents.ptr, (float*)c->trafficLook.ptr, dBrake,
                                                             dSkip, stampOf(c->frame), c->dTrafficMoved);
+  c->anyDirty = true;
   ++c->launches;
   SC_CUDA(c, cudaGetLastError());
   if (outMoved)
@@ -1164,6 +1167,7 @@ int scgpuDespawn(ScGpuScene* c, uint32_t n, const uint32_t* entity)
     ++c->launches;
     SC_CUDA_P(c, cudaGetLastError());
     if (c->anyParentEver) c->topologyDirty = true;
+    c->anyDirty = true;  // children of a destroyed parent become dirty roots (k_resolve_parents)
   }
   return 1;
 }
@@ -1205,6 +1209,7 @@ static int setLocalImpl(ScGpuScene* c, const char* who, uint32_t n, const uint32
     dT = c->staging.ptr;
   }
   k_set_local<kFloats><<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, firstDense, (const float*)dT, stampOf(c->frame));
+  c->anyDirty = true;
   ++c->launches;
   SC_CUDA(c, cudaGetLastError());
   return 1;
@@ -1272,6 +1277,7 @@ int scgpuSetLocalDevice(ScGpuScene* c, uint32_t n, const uint32_t* d_entity, con
   if (n == 0) return 1;
   if (!d_entity || !d_trs9) return (int)fail(c, "scgpuSetLocalDevice: NULL argument");
   k_set_local<9><<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, d_entity, 0u, d_trs9, stampOf(c->frame));
+  c->anyDirty = true;
   ++c->launches;
   SC_CUDA(c, cudaGetLastError());
   return 1;
@@ -1285,6 +1291,7 @@ int scgpuSetParent(ScGpuScene* c, uint32_t n, const uint32_t* entity, const uint
   const uint32_t* dE; const void* dP;
   if (!uploadEntityBatch(c, n, entity, parent, 4, &dE, &dP)) return 0;
   k_set_parent<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, (const uint32_t*)dP, stampOf(c->frame));
+  c->anyDirty = true;
   ++c->launches;
   SC_CUDA(c, cudaGetLastError());
   c->anyParentEver = true;
@@ -1300,6 +1307,7 @@ int scgpuMarkDirty(ScGpuScene* c, uint32_t n, const uint32_t* entity)
   const uint32_t* dE;
   if (!uploadEntityBatch(c, n, entity, nullptr, 0, &dE, nullptr)) return 0;
   k_mark_dirty<<<blocksFor(n), kBlock, 0, c->stream>>>(c->a, n, dE, stampOf(c->frame));
+  c->anyDirty = true;
   ++c->launches;
   SC_CUDA(c, cudaGetLastError());
   return 1;
@@ -1402,9 +1410,14 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     p.flags = (c->forceAllDirty ? kUpdForceDirty : 0u) | ((flags & SCGPU_UPDATE_FREEZE_CULLING) ? kUpdFreeze : 0u) |
               (skipTransform ? kUpdSkipTransform : 0u) | (wantCulled ? kUpdCandBits : 0u);
     if (timed) SC_CUDA(c, cudaEventRecord(c->evK0[tslot], c->stream));
+    // nothing to transform (a cull-only update, or no delta call since the last transforming update): the stored world
+    // matrices are valid as they are and neither records nor hierarchy are needed - pure streaming cull
+    const bool cullOnly = skipTransform || (!c->forceAllDirty && !c->anyDirty);
 #define SC_LAUNCH_UPDATE(V)                                                                                              \
   case V:                                                                                                                \
-    if (c->anyParentEver)                                                                                                \
+    if (cullOnly)                                                                                                        \
+      k_cull_only<V><<<(numTiles * kSubTiles + kCullSubTiles - 1u) / kCullSubTiles, kBlock, 0, c->stream>>>(p, c->planes); \
+    else if (c->anyParentEver)                                                                                           \
     {                                                                                                                    \
       k_update_win<V><<<c->numSMs * SCGPU_WIN_MINBLOCKS, kWinBlock, 0, c->stream>>>(                                     \
         p, c->planes, c->slotInfo, c->winList, c->tileWinBase + numTiles, c->acc + kAccQueueNext, c->slowList);          \
@@ -1490,6 +1503,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     // A cull-only update consumes no dirty stamp: whatever was dirtied before it is still recomputed by the next
     // transforming update, like the reference's t.dirty, which stays set until TransformSystem has seen the node.
     c->forceAllDirty = false;
+    c->anyDirty = false;
     ++c->frame;
     if (stampOf(c->frame) == 0u)
     {

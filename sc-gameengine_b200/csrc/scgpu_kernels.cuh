@@ -585,6 +585,53 @@ __global__ void __launch_bounds__(kBlock, 4) k_update_flat(const __grid_constant
   if (tid < 2 && sCounts[tid]) atomicAdd(p.acc + (tid == 0 ? kAccCand : kAccRecomputed), sCounts[tid]);
 }
 
+// ---- cull-only frames: nothing to transform -----------------------------------------------------------------------------
+// A frame in which no Transform is dirty (a static city under a moving camera; every SCGPU_UPDATE_SKIP_TRANSFORM update)
+// needs neither the TRS records nor the hierarchy: the stored world matrices are valid, whatever their parents are. Pure
+// streaming over the slots: AABB + flags (32 B) and world matrix (64 B) per instance = the 96 algorithmic bytes of a
+// clean instance, six independent 128-bit loads per thread in flight at once, sphere + plane tests in
+// registers, visible bits out. A CTA walks kCullSubTiles consecutive sub-tiles so that the favourite-plane memory of
+// its warps (see cull_views_warp) carries over.
+constexpr uint32_t kCullSubTiles = 8;
+
+template <int kViews>
+__global__ void __launch_bounds__(kBlock, 6) k_cull_only(const __grid_constant__ UpdateParams p, const __grid_constant__ ViewPlanes vp)
+{
+  __shared__ uint32_t sCand;
+  constexpr uint32_t allMask = (1u << kViews) - 1u;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u;
+  const bool freeze = (p.flags & kUpdFreeze) != 0;
+  if (tid == 0) sCand = 0u;
+  __syncthreads();
+  uint32_t order = 0, nCand = 0;
+#pragma unroll 1
+  for (uint32_t sub = 0; sub < kCullSubTiles; ++sub)
+  {
+    const uint32_t s = (blockIdx.x * kCullSubTiles + sub) * kBlock + tid;
+    if (s - tid >= p.count) break;  // block-uniform
+    const bool live = s < p.count;
+    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f), r3 = r2;
+    Mat4 W = mat4_identity();
+    if (live)
+    {
+      r3 = ld_stream(p.rec3 + s); r2 = ld_stream(p.rec2 + s);
+      W.c0 = ld_stream(p.w0 + s); W.c1 = ld_stream(p.w1 + s); W.c2 = ld_stream(p.w2 + s); W.c3 = ld_stream(p.w3 + s);
+    }
+    const uint32_t fl = __float_as_uint(r3.w);
+    const bool cand = live && (fl & kFlagMesh);
+    const bool test = cand && !freeze && (fl & kFlagBounds);
+    uint32_t mask = 0;
+    if (__any_sync(0xffffffffu, test)) mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
+    if (cand && !test) mask = allMask;  // frozen culling or no Bounds component: always visible
+    emit_visible_warp<kViews>(p, s, lane, mask, cand);
+    nCand += cand ? 1u : 0u;
+  }
+  const uint32_t r = __reduce_add_sync(0xffffffffu, nCand);
+  if (lane == 0 && r) atomicAdd(&sCand, r);
+  __syncthreads();
+  if (tid == 0 && sCand) atomicAdd(p.acc + kAccCand, sCand);
+}
+
 // ---- hierarchy windows ------------------------------------------------------------------------------------------
 // A window is a run of <= 32 consecutive slots owned by one warp. k_build_windows (topology changes only) cuts the
 // slot range into windows at positions that NO parent link crosses, so a hierarchy group never straddles two warps
