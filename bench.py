@@ -42,8 +42,10 @@ DEFAULT_INSTANCES = 16 * 1024 * 1024 - 4096  # per GPU; < 2^24 entity indices pe
 ALG_BYTES_DIRTY = 132   # read TRS 36 + parent 4 + flags 4 + AABB 24, write world 64
 ALG_BYTES_CLEAN = 96    # read flags 4 + parent 4 + world 64 + AABB 24, no write
 REF_SAMPLE = 2_000_000  # instances per step of the bounded cpu_baseline sample (N = 1 line of our arm)
-REF_WORLD_MAX = 8_000_000  # the reference's job system is safe up to ~11 M entities per World: larger
-                           # scenes run as consecutive Worlds of at most this many instances, times summed
+REF_WORLD_MAX = 2_000_000  # The reference's job-payload arena holds ~11.18 M culling jobs' worth per frame (BASELINE.md §2:
+                           # beyond it CullingSystem never returns) and the baseline culls 5 views per frame, so a World
+                           # may hold at most ~2.2 M instances here. Larger scenes run as consecutive Worlds of at most
+                           # this many instances, times summed.
 CHURN_INSTANCES = 8 * 1024 * 1024
 
 
@@ -240,7 +242,7 @@ def run_cpu_worker(sample, views, steps, warmup, timeout=900):
 
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation on OUR arm's config: the whole per-GPU instance set (16.77 M), as
-    consecutive Worlds of <= 8 M. --quick falls back to the bounded 2 M sample."""
+    consecutive Worlds of <= 2 M (5 views per frame). --quick falls back to the bounded 2 M sample."""
     if rank != 0:
         return
     sample = args.ref_sample if args.quick else args.instances
