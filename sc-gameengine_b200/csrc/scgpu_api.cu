@@ -568,6 +568,8 @@ ScGpuScene* scgpuCreate(const ScGpuSceneDesc* desc)
   ScGpuScene* c = new (std::nothrow) ScGpuScene();
   if (!c) { fail(nullptr, "out of host memory"); return nullptr; }
   if (const char* pl = getenv("SCGPU_PDL")) g_pdlLevel = atoi(pl);
+  // test hook: id of the first update, to reach the wrap of the 24-bit dirty stamp without 16.7 M frames
+  if (const char* ff = getenv("SCGPU_TEST_FIRST_FRAME")) c->frame = std::max(1ul, strtoul(ff, nullptr, 0));
   {
     // host threads for the pool bookkeeping of large despawn batches and staged uploads: SCGPU_HOST_THREADS, else half
     // the cores up to 8 (the sequential middle pass of the pool replay bounds the gain). The helpers are created once.

@@ -79,3 +79,32 @@ def test_sorted_draws_repeat_bit_for_bit():
         items, runs = s.sorted_draws(0, mp, 200)
         assert np.array_equal(items["entity"], items0["entity"]) and np.array_equal(runs, runs0), f"sort {f} differs"
     s.close()
+
+
+def test_dirty_stamp_wrap_keeps_clean_nodes_clean(monkeypatch):
+    """The dirty stamp is the 24-bit id of the update that must recompute an instance. Across the wrap of that id every
+    stored stamp is reset once (k_clear_stamps), so that no stamp of 16.7 M updates ago resurrects as 'dirty now':
+    the recomputed count must stay what the oracle's dirty flags give, frame by frame, through the wrap."""
+    from oracle_bind import PortScene
+    from scenarios import GpuAdapter, compare_frame
+    monkeypatch.setenv("SCGPU_TEST_FIRST_FRAME", str(0xFFFFFF - 6))
+    n = 30_000
+    rng = np.random.default_rng(8)
+    sc = scenes.city_hier(n, seed=15)
+    e = np.arange(n, dtype=np.uint32)
+    par = scenes.parent_handles(sc["parent"], e)
+    g, p = GpuAdapter(n, max_views=3), PortScene()
+    vps = scenes.standard_views(3)
+    for s in (g, p):
+        s.spawn(e, sc["trs9"], par, sc["aabb6"], sc["mesh_mat"], sc["flags"])
+        s.update(vps)
+    for frame in range(16):   # ids 0xFFFFFA .. wrap .. 0x00000A
+        idx = rng.choice(n, 500 + 37 * frame, replace=False)
+        trs = sc["trs9"][idx].copy()
+        trs[:, 0] += np.float32(0.5 + frame)
+        for s in (g, p):
+            s.set_local(e[idx], trs)
+            s.update(vps)
+        assert g.recomputed == p.recomputed, (frame, g.recomputed, p.recomputed)
+        compare_frame(g, p, e, 3, f"wrap frame {frame}")
+    g.close()
