@@ -132,7 +132,7 @@ def test_math_kats_port_equals_reference(ref, port):
 
 
 def test_long_streaming_churn_port_equals_reference():
-    """30 frames of group-wise churn on a depth-4 city (the pattern of tools/bench_churn.py in miniature): whole groups
+    """30 frames of group-wise churn on a depth-4 city (the pattern of bench.py's churn leg in miniature): whole groups
     despawn, fresh groups spawn, a fifth of the live instances get a new local TRS. Swap-with-last scrambles the pool
     frame by frame (tools/model_churn_order.py: after 30 frames a quarter of the children sit 32 or more slots from their
     parent, a third of the parents FOLLOW their children) — the regime the GPU path's window builder and generic path

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Host-only timing of the Transform-pool mirror (sc-gameengine_b200/csrc/scgpu_pool.h through tests/hostsim; no GPU):
-an 8 Mi pool under the bench_churn.py pattern — 4 % of the instances despawn per frame as whole groups, as many spawn —
+an 8 Mi pool under the churn pattern of round 1 — 4 % of the instances despawn per frame as whole groups, as many spawn —
 for 1, 4 and 8 host threads.  python tools/bench_pool_host.py [instances]
 
 The numbers in DESIGN.md §8c (9.3 ms on one thread, 5.8 ms inside scgpuDespawn with four) were taken on the GPU box's

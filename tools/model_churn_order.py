@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""CPU model of what streaming churn does to the Transform-pool ORDER (no GPU needed): the bench_churn.py pattern (4 % of
+"""CPU model of what streaming churn does to the Transform-pool ORDER (no GPU needed): the churn pattern of round 1 (4 % of
 the instances despawn per frame as whole groups, as many spawn) replayed on the real pool mirror (scgpu_pool.h through
 tests/hostsim, i.e. the reference's swap-with-last order), reporting per frame how many instances end up 32 or more slots away from their parent (a
 link no hierarchy window can hold: k_update_win hands those windows to the generic path) and how many have their parent
