@@ -1379,7 +1379,7 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
 
   if (c->topologyDirty && extent)
   {
-    k_resolve_parents<<<blocksFor(extent), kBlock, 0, c->stream>>>(c->a, extent, stamp);
+    k_resolve_parents<<<blocksFor((extent + 3u) / 4u), kBlock, 0, c->stream>>>(c->a, extent, stamp);
     ++c->launches;
     SC_CUDA(c, cudaGetLastError());
     if (c->anyParentEver)

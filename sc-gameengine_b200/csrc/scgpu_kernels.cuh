@@ -754,19 +754,18 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
     while (start < end && nw < kMaxWin)
     {
       if (lane == 0) sStart[nw] = (uint16_t)(start - tileBase);
-      ++nw;
       const uint32_t c = start + 1 + lane;  // candidate end
       const bool ok = c <= end && (c == end || sCross[c - origin] == 0);
       const uint32_t m = __ballot_sync(0xffffffffu, ok);
-      start = m ? start + 32u - __clz(m) : min(start + 32u, end);
+      const uint32_t next = m ? start + 32u - __clz(m) : min(start + 32u, end);
+      if (start + lane < next) sWinOf[start + lane - tileBase] = (uint16_t)nw;  // the window's slots learn their window here
+      start = next;
+      ++nw;
     }
     if (lane == 0) { sStart[nw] = (uint16_t)(end - tileBase); sNumWin = nw; }
   }
   __syncthreads();
   const uint32_t nw = sNumWin;
-  for (uint32_t w = warp; w < nw; w += kBlock / 32)
-    for (uint32_t k = sStart[w] + lane; k < sStart[w + 1]; k += 32) sWinOf[k] = (uint16_t)w;
-  __syncthreads();
   // per owned slot: depth and parent lane inside the window
   for (uint32_t k = (beg - tileBase) + tid; k < end - tileBase; k += kBlock)
   {
@@ -2387,21 +2386,42 @@ __global__ void __launch_bounds__(kBlock) k_gather_dense(SceneArrays a, uint32_t
 // Transform); otherwise the node becomes a root and, if it had a parent handle, dirty.
 __global__ void __launch_bounds__(kBlock) k_resolve_parents(SceneArrays a, uint32_t count, uint32_t stamp)
 {
-  const uint32_t s = blockIdx.x * kBlock + threadIdx.x;
-  if (s >= count) return;
-  const uint32_t ph = a.parent[s];
-  uint32_t ps = kNone;
-  if (ph != kNone)
+  // four consecutive slots per thread: two 128-bit loads, then four independent neighbour look-ups in flight at once
+  // (the kernel is bound by the latency of those gathers, not by bytes); count is padded to a multiple of four slots
+  const uint32_t s0 = (blockIdx.x * kBlock + threadIdx.x) * 4u;
+  if (s0 >= count) return;
+  const uint4 ph4 = reinterpret_cast<const uint4*>(a.parent)[s0 >> 2];
+  const uint4 old4 = reinterpret_cast<const uint4*>(a.parentSlot)[s0 >> 2];
+  const uint32_t ph_[4] = { ph4.x, ph4.y, ph4.z, ph4.w }, old_[4] = { old4.x, old4.y, old4.z, old4.w };
+  uint32_t held[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4u; ++k)
   {
-    if (ph != a.entity[s]) ps = find_slot(a, ph);
-    if (ps == kNone)
-    {
-      a.parent[s] = kNone;
-      uint32_t* fw = reinterpret_cast<uint32_t*>(a.rec[3] + s) + 3;
-      *fw = (*fw & 0xFFu) | (stamp << kStampShift);
-    }
+    // A link resolved earlier stays valid for as long as that slot holds that very handle (index AND generation: the
+    // parent is alive and owns its Transform) - a look at a neighbouring slot instead of the random walk through the
+    // sparse table; a slot never moves. Only new or broken links go the long way.
+    const bool look = s0 + k < count && ph_[k] != kNone && old_[k] != kNone && old_[k] != s0 + k && old_[k] < count;
+    held[k] = look ? a.entity[old_[k]] : kNone;
   }
-  a.parentSlot[s] = ps;
+#pragma unroll
+  for (uint32_t k = 0; k < 4u; ++k)
+  {
+    const uint32_t s = s0 + k, ph = ph_[k];
+    if (s >= count) break;
+    uint32_t ps = kNone;
+    if (ph != kNone)
+    {
+      if (held[k] == ph) continue;  // (ph != kNone, so a skipped look-up never matches)
+      if (ph != a.entity[s]) ps = find_slot(a, ph);
+      if (ps == kNone)
+      {
+        a.parent[s] = kNone;
+        uint32_t* fw = reinterpret_cast<uint32_t*>(a.rec[3] + s) + 3;
+        *fw = (*fw & 0xFFu) | (stamp << kStampShift);
+      }
+    }
+    if (old_[k] != ps) a.parentSlot[s] = ps;
+  }
 }
 
 // gathers for read-back by entity handle
