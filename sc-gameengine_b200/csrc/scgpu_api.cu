@@ -673,7 +673,31 @@ static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, cons
   if (c->hSparse.size() < c->sparseSize) c->hSparse.resize(c->sparseSize, 0u);
   if (c->hSlotOf.size() < c->sparseSize) c->hSlotOf.resize(c->sparseSize, 0u);
   uint32_t at = 0;
-  switch (poolRegisterSpawn(c->hEntity, c->hSparse, c->count, n, entity, &at))
+  int why = 0;
+  const bool holes = c->layout.hasHoles();
+  uint32_t* sl = nullptr;
+  if (holes)
+  {
+    if (c->hSlotScratch.size() < n) c->hSlotScratch.resize(n + n / 4);
+    sl = c->hSlotScratch.data();
+  }
+  if (holes && c->workers && n >= 65536u)
+  {
+    // pool registration (random writes into the sparse table) and slot placement (a walk of the free-slot bitmap) touch
+    // disjoint state: side by side on two threads. Placement cannot fail (holes + tail room >= capacity - count >= n);
+    // if the registration refuses the batch the slots are simply handed back.
+    c->workers->run(2u, [&](uint32_t part) {
+      if (part == 0u) why = poolRegisterSpawn(c->hEntity, c->hSparse, c->count, n, entity, &at);
+      else c->layout.placeBatch(n, entity, parent, sl);
+    });
+    if (why) c->layout.release(n, sl);
+  }
+  else
+  {
+    why = poolRegisterSpawn(c->hEntity, c->hSparse, c->count, n, entity, &at);
+    if (!why && holes) c->layout.placeBatch(n, entity, parent, sl);
+  }
+  switch (why)
   {
     case 0: break;
     case 1: return (int)fail(c, "%s: entity[%u] is the invalid handle", who, at);
@@ -682,7 +706,7 @@ static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, cons
   }
   c->anyDirty = true;  // new Transforms are dirty
   uint32_t* const so = c->hSlotOf.data();
-  if (!c->layout.hasHoles())
+  if (!holes)
   {
     const uint32_t s0 = c->layout.appendRun(n);  // cannot fail: without holes the extent is the pool size
     for (uint32_t j = 0; j < n; ++j) so[entity[j] & 0xFFFFFFu] = s0 + j;
@@ -691,9 +715,6 @@ static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, cons
   }
   else
   {
-    if (c->hSlotScratch.size() < n) c->hSlotScratch.resize(n + n / 4);
-    uint32_t* const sl = c->hSlotScratch.data();
-    c->layout.placeBatch(n, entity, parent, sl);  // cannot fail: holes + tail room >= capacity - count >= n
     poolParallelFor(c->hostThreads, n, [=](uint32_t, uint32_t b, uint32_t e) {
       for (uint32_t j = b; j < e; ++j)
       {
