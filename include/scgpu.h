@@ -18,9 +18,13 @@
  * once. PINNED or registered memory (cudaHostAlloc / cudaHostRegister) is read by the copy engine asynchronously and
  * without an intermediate copy: it must stay untouched until the next call that waits for the stream — any result
  * call, or scgpuSynchronize — has returned. Large pageable arrays are copied through a pinned ring inside the library
- * by up to SCGPU_HOST_THREADS (environment, default min(4, cores / 2)) short-lived host threads, which also share the
- * pool bookkeeping of large scgpuDespawn batches; SCGPU_HOST_THREADS=1 keeps every call on the calling thread.
- * Results never depend on the thread count.
+ * by the context's helper threads — SCGPU_HOST_THREADS - 1 of them (environment, default min(8, cores / 2)), created
+ * with the context and asleep between calls — which also share the pool bookkeeping of large scgpuSpawn / scgpuDespawn
+ * batches; SCGPU_HOST_THREADS=1 keeps every call on the calling thread. Results never depend on the thread count.
+ *
+ * A device failure AFTER a call has already updated the host mirror of the Transform pool (an upload or launch error
+ * inside scgpuSpawn* / scgpuDespawn) leaves host and device out of step for good: the context is poisoned, every later
+ * call fails and scgpuLastError() keeps the message of the failure that did it.
  *
  * There is no CPU fallback: without a CUDA device scgpuCreate() fails.
  */
