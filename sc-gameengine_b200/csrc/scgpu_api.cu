@@ -334,6 +334,24 @@ void planesFromViewProj(const float* m, float4* out)
   }
 }
 
+// ViewPlanes::slackK: 2^-19 x the largest magnitude of any normal component in use. The window kernel's fused
+// pre-test needs an upper bound of |n . o| from |o|_1 alone; +Inf / NaN planes give +Inf / NaN, which switches the
+// pre-test off (every comparison fails) and leaves the exact tests.
+void refreshPlaneSlack(ViewPlanes& vp, uint32_t nViews)
+{
+  float m = 0.f;
+  for (uint32_t v = 0; v < nViews; ++v)
+    for (int p = 0; p < 6; ++p)
+    {
+      const float4 pl = vp.planes[v][p];
+      const float a = fabsf(pl.x), b = fabsf(pl.y), cc = fabsf(pl.z);
+      if (!(a <= m)) m = a;  // written so that NaN sticks
+      if (!(b <= m)) m = b;
+      if (!(cc <= m)) m = cc;
+    }
+  vp.slackK = m * 0x1p-19f;
+}
+
 void freeAll(ScGpuScene* c)
 {
   if (!c) return;
@@ -1351,6 +1369,7 @@ int scgpuSetViews(ScGpuScene* c, uint32_t nViews, const float* viewProj16)
   if (nViews == 0 || nViews > c->maxViews) return (int)fail(c, "scgpuSetViews: nViews %u not in 1..%u", nViews, c->maxViews);
   if (!viewProj16) return (int)fail(c, "scgpuSetViews: NULL matrix");
   for (uint32_t v = 0; v < nViews; ++v) planesFromViewProj(viewProj16 + (size_t)v * 16, c->planes.planes[v]);
+  refreshPlaneSlack(c->planes, nViews);
   c->nViews = nViews;
   return 1;
 }
@@ -1366,6 +1385,7 @@ int scgpuSetViewPlanes(ScGpuScene* c, uint32_t nViews, const float* planes24)
       const float* s = planes24 + (size_t)v * 24 + p * 4;
       c->planes.planes[v][p] = make_float4(s[0], s[1], s[2], s[3]);
     }
+  refreshPlaneSlack(c->planes, nViews);
   c->nViews = nViews;
   return 1;
 }

@@ -58,6 +58,10 @@ constexpr uint32_t kAccCand = 0, kAccRecomputed = 1, kAccQueueNext = 2, kAccQueu
 struct ViewPlanes
 {
   float4 planes[kMaxViews][6];
+  // 2^-19 * the largest |normal component| of any plane in use (host, scgpuSetViews / scgpuSetViewPlanes): scale of
+  // the rounding slack of the fused favourite-plane pre-test, see sphere_cull_warp_fav
+  float slackK;
+  float pad_[3];
 };
 
 struct UpdateParams
@@ -291,10 +295,23 @@ __device__ __forceinline__ float plane_dist(const float4 pl, float cx, float cy,
 __device__ __forceinline__ void sincos3_warp(bool active, float rx, float ry, float rz, float& sx, float& cx, float& sy,
                                              float& cy, float& sz, float& cz)
 {
+  const bool nx = active && !sincos_is_trivial(rx), ny = active && !sincos_is_trivial(ry), nz = active && !sincos_is_trivial(rz);
   sx = rx; cx = 1.0f; sy = ry; cy = 1.0f; sz = rz; cz = 1.0f;
-  uint32_t need = 0;
-  if (active)
-    need = (sincos_is_trivial(rx) ? 0u : 1u) | (sincos_is_trivial(ry) ? 0u : 2u) | (sincos_is_trivial(rz) ? 0u : 4u);
+  if (!__any_sync(0xffffffffu, nx || ny || nz)) return;
+  // First round without a per-lane branch: EVERY lane evaluates one angle - its first non-trivial one; a lane that has
+  // none evaluates 0 and drops the result - and the results are put in place with selects. (The loop form below costs
+  // ~25 more instructions per round in divergence bookkeeping: BSSY / BSYNC, the three-way assignment as branches.)
+  {
+    const float y = nx ? rx : (ny ? ry : (nz ? rz : 0.0f));
+    float sn, cs;
+    sincosf_glibc_nt(y, sn, cs);
+    const bool ay = !nx && ny, az = !nx && !ny && nz;
+    sx = nx ? sn : sx; cx = nx ? cs : cx;
+    sy = ay ? sn : sy; cy = ay ? cs : cy;
+    sz = az ? sn : sz; cz = az ? cs : cz;
+  }
+  // lanes with a second / third non-trivial angle (none in a city of wheels, props and roots)
+  uint32_t need = ((nx && ny) ? 2u : 0u) | (((nx || ny) && nz) ? 4u : 0u);
   while (__any_sync(0xffffffffu, need != 0u))
   {
     if (need)
@@ -375,6 +392,85 @@ __device__ __forceinline__ uint32_t sphere_cull_warp(const ViewPlanes& vp, bool 
   }
   if (__all_sync(0xffffffffu, certain || !test)) return 0u;
   return cull_views_warp<kViews>(vp, test, ox, oy, oz, -world_bounds_radius(W, ex, ey, ez), order);
+}
+
+// The same for the window kernel, whose issue slots are the bound: the pre-test costs ~24 instructions per warp
+// instead of ~68 for five views.
+//  * The favourite plane of every view is kept in a per-warp shared-memory cache (rewritten when `order` changes:
+//    only in warps near a frustum), two views side by side: { nx_a nx_b ny_a ny_b } { nz_a nz_b d'_a d'_b } - two
+//    broadcast LDS.128 per pair of views, no index arithmetic on `order`, no constant-bank loads.
+//  * Two views per instruction: three fma.rn.f32x2 give n . o + d' for a pair of views.
+//  * FUSED multiply-adds are allowed here although the reference's distance is ((n0*o0 + n1*o1) + n2*o2) + d with every
+//    operation rounded: the pre-test only PROVES "culled", and it does so with a margin that covers the difference.
+//    Both evaluations approximate the real number X = n . o + d; the reference's D with |D - X| <= 4u(1+e) S, the fused
+//    chain D' with |D' - X| <= 3u(1+e) S, where u = 2^-24 and S = |n0 o0| + |n1 o1| + |n2 o2| + |d| <= K |o|_1 + |d|,
+//    K = the largest |normal component| of any plane (ViewPlanes::slackK = 2^-19 K, from the host). The chain starts
+//    from d' = d + 2^-19 |d| (rounded up) and is compared with negBound - 2^-19 K |o|_1: a slack of
+//    2^-19 S >= 4 x the 7u S the two roundings can differ by. (Underflow adds at most a few 2^-149, the bound's
+//    absolute 1e-30 covers that; rounding negBound - slack moves it by u |negBound|, the bound's factor 1.0001 covers
+//    that.) So "D' + slack < negBound" implies D < negBound <= -radius: exactly the instances the reference culls by
+//    that plane. NaN / Inf anywhere make a comparison false and the warp takes the exact path.
+__device__ __forceinline__ float2 ffma2_rn(float ax, float ay, float b, float2 c)
+{
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(ax), "f"(ay));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a);
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v);
+
+// (re)writes the warp's cache of favourite planes from `order`; lane i writes float i of the layout above
+template <int kViews>
+__device__ __forceinline__ void fav_refresh(const ViewPlanes& vp, uint32_t favAddr, uint32_t lane, uint32_t order)
+{
+  constexpr uint32_t nC = kViews < 6 ? kViews : 6;
+  __syncwarp();
+  if (lane < ((nC + 1u) / 2u) * 8u)
+  {
+    const uint32_t c = (lane >> 1) & 3u;
+    const uint32_t v = min(2u * (lane >> 3) + (lane & 1u), nC - 1u);  // an odd view count: the last view twice
+    const float4 pl = vp.planes[v][(order >> (3u * v)) & 7u];
+    const float val = c == 0u ? pl.x : (c == 1u ? pl.y : (c == 2u ? pl.z : __fmaf_ru(fabsf(pl.w), 0x1p-19f, pl.w)));
+    sts32(favAddr + lane * 4u, __float_as_uint(val));
+  }
+  __syncwarp();
+}
+
+template <int kViews>
+__device__ __forceinline__ uint32_t sphere_cull_warp_fav(const ViewPlanes& vp, uint32_t favAddr, uint32_t lane, bool test,
+                                                         const Mat4& W, float4 r2, float4 r3, uint32_t& order)
+{
+  constexpr int nC = kViews < 6 ? kViews : 6;
+  float ox, oy, oz, ex, ey, ez;
+  world_bounds_centre(W, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, ox, oy, oz, ex, ey, ez);
+  const float negBound = -world_bounds_radius_bound(W, ex, ey, ez);
+  const float nb = __fmaf_rn(-vp.slackK, fabsf(ox) + fabsf(oy) + fabsf(oz), negBound);
+  bool certain = true;
+#pragma unroll
+  for (int j = 0; j < (nC + 1) / 2; ++j)
+  {
+    const float4 A = lds128(favAddr + 32u * j), B = lds128(favAddr + 32u * j + 16u);
+    float2 t = ffma2_rn(B.x, B.y, oz, make_float2(B.z, B.w));
+    t = ffma2_rn(A.z, A.w, oy, t);
+    t = ffma2_rn(A.x, A.y, ox, t);
+    certain = certain & (t.x < nb) & (t.y < nb);
+  }
+#pragma unroll
+  for (int v = nC; v < kViews; ++v)  // a seventh and eighth view: the plain form
+  {
+    const uint32_t k0 = (order >> (3 * v)) & 7u;
+    certain = certain & (plane_dist(vp.planes[v][k0], ox, oy, oz) < negBound);
+  }
+  if (__all_sync(0xffffffffu, certain || !test)) return 0u;
+  const uint32_t before = order;
+  const uint32_t alive = cull_views_warp<kViews>(vp, test, ox, oy, oz, -world_bounds_radius(W, ex, ey, ez), order);
+  if (order != before) fav_refresh<kViews>(vp, favAddr, lane, order);  // warp-uniform
+  return alive;
 }
 
 // ---- visible bits -> the per-view bitmaps, indexed by POOL RANK (the reference's order) ------------------------------
@@ -1025,9 +1121,13 @@ constexpr uint32_t kWwMat = 2 * kWsBuf;                 // [4][32] float4: matri
 // which work on consecutive children, cover 128 distinct bytes.
 constexpr uint32_t kMatC1 = 512, kMatC2 = 1024 + 64, kMatC3 = 1536 + 64;
 constexpr uint32_t kWwSched = kWwMat + 4 * 512 + 64;    // [32] u16: children of the current level
-constexpr uint32_t kWwList = kWwSched + 64;             // 2 x [kWinChunk+1] u32 (64 B each): window starts of the current
-                                                        // and of the next claimed chunk
-constexpr uint32_t kWwSize = kWwList + 128;             // per-warp block
+constexpr uint32_t kWwListSlot = 48;                    // bytes per list slot (kWinChunk + 1 words, rounded up to 16)
+constexpr uint32_t kWwList = kWwSched + 64;             // 2 x [kWinChunk+1] u32: window starts of the current and of the
+                                                        // next claimed chunk
+constexpr uint32_t kWwFav = kWwList + 2 * kWwListSlot;  // 3 x 32 B: favourite planes of up to 6 views, two views per
+                                                        // f32x2 lane pair (sphere_cull_warp_fav)
+constexpr uint32_t kWwSize = kWwFav + 96;               // per-warp block
+static_assert((kWinChunk + 1) * 4 <= kWwListSlot && kWwFav % 16 == 0 && kWwSize % 16 == 0, "per-warp block layout");
 constexpr uint32_t kWsRecomputed = kWinWarps * kWwSize; // u32: world matrices rewritten by this CTA; +4: its candidates
 constexpr uint32_t kUpdateSmemWin = kWsRecomputed + 16;
 // device-side work queue of k_update_win: acc[kAccQueueNext] = next unclaimed chunk, acc[kAccQueueSlow] = number of
@@ -1076,26 +1176,28 @@ __device__ __forceinline__ uint32_t queue_claim_result(uint32_t old)
 
 // store + bounding sphere + plane tests of one resolved window (records in shared memory at recAddr); visible lanes set
 // their bits in the rank-indexed bitmaps, candidates are counted warp-uniformly and flushed once per warp
-template <int kViews>
+// favAddr: the warp's favourite-plane cache (k_update_win), 0 = none (k_update_win_slow)
+template <int kViews, bool kFav>
 __device__ __forceinline__ void finish_window(const UpdateParams& p, const ViewPlanes& vp, uint32_t a, uint32_t lane, uint32_t recAddr,
                                               bool live, bool nodeDirty, const Mat4& W, uint32_t& order, uint32_t& nRecomputed,
-                                              uint32_t& accCand)
+                                              uint32_t& accCand, uint32_t favAddr)
 {
   constexpr uint32_t allMask = (1u << kViews) - 1u;
   const bool freeze = (p.flags & kUpdFreeze) != 0;
   if (nodeDirty) store_world(p, a + lane, W);
   nRecomputed += __popc(__ballot_sync(0xffffffffu, nodeDirty));  // warp-uniform running count, flushed once per warp
-  float4 r3 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (live) r3 = lds128(recAddr + 1536);
+  // lanes beyond the window read whatever their part of the buffer holds (their own shared memory; `live` masks
+  // everything derived from it): no branch around the loads
+  const float4 r3 = lds128(recAddr + 1536);
   const uint32_t fl = __float_as_uint(r3.w);
   const bool cand = live && (fl & kFlagMesh);
   const bool test = cand && !freeze && (fl & kFlagBounds);
   uint32_t mask = 0;
   if (__any_sync(0xffffffffu, test))
   {
-    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) r2 = lds128(recAddr + 1024);
-    mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
+    const float4 r2 = lds128(recAddr + 1024);
+    if (kFav) mask = sphere_cull_warp_fav<kViews>(vp, favAddr, lane, test, W, r2, r3, order);
+    else mask = sphere_cull_warp<kViews>(vp, test, W, r2, r3, order);
   }
   if (cand && !test) mask = allMask;
   accCand += __popc(__ballot_sync(0xffffffffu, cand));
@@ -1151,7 +1253,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
   // window starts of chunk [cs, cs + kWinChunk] -> list slot `slot` (0/1) of this warp, asynchronously
   auto stage_list = [&](uint32_t cs, uint32_t slot)
   {
-    if (lane <= kWinChunk) cp_async4s(warpBase + kWwList + slot * 64u + lane * 4u, winList + min(cs + lane, total));
+    if (lane <= kWinChunk) cp_async4s(warpBase + kWwList + slot * kWwListSlot + lane * 4u, winList + min(cs + lane, total));
   };
   // records + slotInfo words of the window whose list entry sits at listAddr -> prefetch buffer at byte offset off
   auto fetch = [&](uint32_t listAddr, uint32_t off)
@@ -1169,6 +1271,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     }
   };
 
+  fav_refresh<kViews>(vp, warpBase + kWwFav, lane, order);
   // ---- prologue: first chunk (its list is waited for), second chunk claimed and staged, third claim in flight ----
   uint32_t claimOld;
   queue_claim_issue(queue, claimOld);
@@ -1212,14 +1315,10 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
     uint32_t dirtyM = 0, liveMask = 0, parentLane = 0;
     if (fast)
     {
-      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-      float sclZ = 0.f;
-      uint32_t fl = 0;
-      if (live)
-      {
-        r0 = lds128(recAddr); r1 = lds128(recAddr + 512); sclZ = __uint_as_float(lds32(recAddr + 1024));
-        fl = lds32(recAddr + 1536 + 12);
-      }
+      // (lanes beyond the window read stale bytes of their own buffer part; `live` masks everything derived from them)
+      const float4 r0 = lds128(recAddr), r1 = lds128(recAddr + 512);
+      const float sclZ = __uint_as_float(lds32(recAddr + 1024));
+      const uint32_t fl = lds32(recAddr + 1536 + 12);
       nodeDirty = live && ((fl & dirtyMask) == dirtyWant);
       parentLane = (info >> kInfoParentShift) & 31u;
       // ---- 1. children inherit dirtiness level by level ----
@@ -1259,7 +1358,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         const bool tame = trs_inputs_tame(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, sclZ);
         float sx, cx, sy, cy, sz, cz;
         sincos3_warp(compute && tame, r0.w, r1.x, r1.y, sx, cx, sy, cy, sz, cz);
-        // every lane builds a matrix (lanes beyond the window from all-zero records): no per-lane branch around sixteen
+        // every lane builds a matrix (lanes beyond the window from stale bytes, never used): no per-lane branch around sixteen
         // live registers. Roots: world == local.
         W = mat4_trs_from_sincos(r0.x, r0.y, r0.z, sx, cx, sy, cy, sz, cz, r1.z, r1.w, sclZ);
         fast = __all_sync(0xffffffffu, tame || !compute);
@@ -1276,13 +1375,13 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
       // in flight for a whole chunk, stage that chunk's window starts there, and put the next claim in flight
       uint32_t csNext;
       claim_to_chunk(queue_claim_result(claimOld), total, k1, csNext, cntNext);
-      if (cntNext) stage_list(csNext, ((listAddr - warpBase - kWwList) < 64u) ? 1u : 0u);
+      if (cntNext) stage_list(csNext, ((listAddr - warpBase - kWwList) < kWwListSlot) ? 1u : 0u);
       queue_claim_issue(queue, claimOld);
     }
     ++pos;
     if (pos == cnt)
     {
-      nextList = warpBase + kWwList + (((listAddr - warpBase - kWwList) < 64u) ? 64u : 0u);
+      nextList = warpBase + kWwList + (((listAddr - warpBase - kWwList) < kWwListSlot) ? kWwListSlot : 0u);
       cnt = cntNext;
       cntNext = 0u;
       pos = 0u;
@@ -1348,13 +1447,12 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
           {
             if (l < maxL)
             {
+              // the child's parent lane comes from the child lane's register (one SHFL by the whole warp instead of
+              // address + LDS + shift + mask by the scheduled lanes)
               const uint32_t sch = info >> (kInfoSchedShift + 6u * l);
-              if (sch & 32u)
-              {
-                const uint32_t child = sch & 31u;
-                const uint32_t pinfo = lds32(warpBase + bufOff + 2048 + child * 4u);
-                level_item(child, (pinfo >> kInfoParentShift) & 31u);
-              }
+              const uint32_t child = sch & 31u;
+              const uint32_t par = __shfl_sync(0xffffffffu, parentLane, child);
+              if (sch & 32u) level_item(child, par);
               __syncwarp();
             }
           }
@@ -1391,7 +1489,7 @@ __global__ void __launch_bounds__(kWinBlock, SCGPU_WIN_MINBLOCKS) k_update_win(c
         fast = __all_sync(0xffffffffu, !live || (loadStored ? mat4_is_affine(W) : mag < __int_as_float(0x7f800000)));
       }
     }
-    if (fast) finish_window<kViews>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed, accCand);
+    if (fast) finish_window<kViews, true>(p, vp, a, lane, recAddr, live, nodeDirty, W, order, nRecomputed, accCand, warpBase + kWwFav);
     else
     {
       // redone by k_update_win_slow (generic path), which also culls and counts it
@@ -1448,7 +1546,7 @@ __global__ void __launch_bounds__(kWinBlock) k_update_win_slow(const __grid_cons
     const uint32_t info = live ? slotInfo[a + lane] : 0u;
     float4 wb[4];
     const bool nodeDirty = window_slow(p, a, len, info, wb) != 0u;
-    finish_window<kViews>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, nRecomputed, accCand);
+    finish_window<kViews, false>(p, vp, a, lane, laneBase, live, nodeDirty, xs_load(wb), order, nRecomputed, accCand, 0u);
   }
   if (nRecomputed) warp_reds_add(sBase + kWsRecomputed, nRecomputed);
   if (accCand) warp_reds_add(sBase + kWsRecomputed + 4, accCand);
