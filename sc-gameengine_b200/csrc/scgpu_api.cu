@@ -692,7 +692,9 @@ static int registerSpawn(ScGpuScene* c, uint32_t n, const uint32_t* entity, cons
   if (c->hSlotOf.size() < c->sparseSize) c->hSlotOf.resize(c->sparseSize, 0u);
   uint32_t at = 0;
   int why = 0;
-  const bool holes = c->layout.hasHoles();
+  // slots are assigned one by one when there are holes to fill or hierarchy groups to keep together and to pack into
+  // windows (scgpu_layout.h); a flat batch into a pool without holes simply takes the next n slots
+  const bool holes = c->layout.hasHoles() || SlotLayout::batchHasHierarchy(n, parent);
   uint32_t* sl = nullptr;
   if (holes)
   {

@@ -36,7 +36,7 @@ int hs_scene_spawn(HsScene* s, uint32_t n, const uint32_t* entity, const uint32_
   uint32_t at = 0;
   const int r = poolRegisterSpawn(s->dense, s->sparse, s->count, n, entity, &at);
   if (r) return r;
-  if (!s->layout.hasHoles())
+  if (!s->layout.hasHoles() && !SlotLayout::batchHasHierarchy(n, parent))
   {
     const uint32_t s0 = s->layout.appendRun(n);
     if (s0 == 0xFFFFFFFFu) return 8;

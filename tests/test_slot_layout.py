@@ -166,7 +166,8 @@ def test_pool_order_survives_group_churn(hs):
     nxt, gcount = 1, 0
     e, par, gid, nxt = _mk_groups(rng, 3000, nxt, 0)
     rc, slot = d.spawn(e, par, gid + gcount)
-    assert rc == 0 and np.array_equal(slot, np.arange(len(e)))  # no holes yet: one run of fresh slots
+    # no holes yet: the batch takes exactly the next len(e) slots (a permutation of them: groups are packed into windows)
+    assert rc == 0 and np.array_equal(np.sort(slot), np.arange(len(e)))
     gcount += 3000
     for h in e:
         naive.add(int(h))
@@ -255,3 +256,45 @@ def test_tail_despawn_shrinks_the_extent(hs):
     assert rc == 0 and np.array_equal(slot, np.arange(100, 140))
     d.check_invariants()
     d.close()
+
+
+def _window_fill(group_of_slot):
+    """the greedy cut of k_build_windows over consecutive slots: a window takes whole groups while they fit in 32 slots"""
+    bounds = np.flatnonzero(np.diff(group_of_slot) != 0) + 1  # positions no parent link crosses
+    bounds = np.concatenate([bounds, [len(group_of_slot)]])
+    windows, start = 0, 0
+    i = 0
+    while start < len(group_of_slot):
+        j = np.searchsorted(bounds, start + 32, side="right") - 1
+        nxt = bounds[j] if j >= 0 and bounds[j] > start else start + 32
+        start = int(nxt)
+        windows += 1
+    return len(group_of_slot) / windows
+
+
+def test_groups_are_packed_into_full_windows(hs):
+    """vehicles of 10 and peds of 4 in random order: arrival order fills a window to 28.6 of 32 slots, the packed
+    layout to > 31; nobody is placed far from its neighbours in the batch; flat batches keep their order"""
+    rng = np.random.default_rng(11)
+    d = DeviceModel(hs, 400_000, 1 << 20)
+    e, par, gid, nxt = _mk_groups(rng, 40_000, 1, 0, sizes=(10, 4))
+    rc, slot = d.spawn(e, par, gid)
+    assert rc == 0 and np.array_equal(np.sort(slot), np.arange(len(e)))
+    d.check_invariants()
+    by_slot = np.empty(len(e), np.int64)
+    by_slot[slot] = gid
+    arrival = _window_fill(gid)
+    packed = _window_fill(by_slot)
+    assert arrival < 29.0 and packed > 31.0, (arrival, packed)
+    # every group in consecutive slots, members in spawn order
+    first = np.flatnonzero(np.r_[True, np.diff(gid) != 0])
+    size = np.diff(np.r_[first, len(e)])
+    assert np.array_equal(slot, np.repeat(slot[first], size) + (np.arange(len(e)) - np.repeat(first, size)))
+    # bounded look-ahead (128 slots' worth of waiting groups): a group lands close to where arrival order would have put it
+    assert np.abs(slot[first].astype(np.int64) - first).max() < 512
+    # the pool order (rank) is still arrival order
+    assert np.array_equal(d.dense_in_rank_order(), e)
+    # a flat batch behind it: one run of fresh slots, in order
+    e2 = np.arange(nxt, nxt + 5000, dtype=np.uint32)
+    rc, slot2 = d.spawn(e2, np.full(5000, INVALID, np.uint32), np.arange(5000) + 100_000)
+    assert rc == 0 and np.array_equal(slot2, len(e) + np.arange(5000))
