@@ -458,7 +458,7 @@ def churn_leg(args, D, rank, local_rank, torch):
     from scgpu import scenes
     n = args.churn_instances
     frames, warm = args.churn_frames, 4
-    cohorts = 10
+    cohorts = int(os.environ.get("SCGPU_CHURN_COHORTS", "10"))  # 1 / cohorts of the sectors stream out and in per frame
     sc = scenes.city_hier(n, seed=99 + 7919 * rank)
     sc["trs9"][sc["parent"] < 0, 0] += block_shift(rank, D.world, sc["side"])
     rng = np.random.default_rng(5 + rank)

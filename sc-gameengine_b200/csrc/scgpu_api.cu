@@ -102,6 +102,7 @@ struct ScGpuScene
   uint32_t count = 0;        // live Transforms (size of the reference's pool)
   uint32_t frame = 1;        // id of the NEXT update; instances dirtied now carry this stamp
   bool topologyDirty = false;
+  uint32_t builtExtent = 0;  // the extent k_build_windows last saw
   bool anyParentEver = false;
   bool forceAllDirty = false;
   bool anyDirty = false;     // some call since the last transforming update may have dirtied a Transform
@@ -361,7 +362,7 @@ void freeAll(ScGpuScene* c)
   for (int k = 0; k < 4; ++k) { cudaFree(c->a.rec[k]); cudaFree(c->a.world[k]); }
   cudaFree(c->a.parent); cudaFree(c->a.parentSlot); cudaFree(c->a.entity); cudaFree(c->a.meshMat); cudaFree(c->a.sparse);
   cudaFree(c->slotInfo); cudaFree(c->winLocal); cudaFree(c->tileWinCount); cudaFree(c->tileWinBase); cudaFree(c->winList); cudaFree(c->slowList); cudaFree(c->visBits); cudaFree(c->acc); cudaFree(c->chunkCounts); cudaFree(c->totals);
-  cudaFree(c->a.rank); cudaFree(c->a.perm);
+  cudaFree(c->a.rank); cudaFree(c->a.perm); cudaFree(c->a.tileDirty);
   for (uint32_t v = 0; v < kMaxViews; ++v)
   {
     cudaFree(c->visEntity[v]); cudaFree(c->visSlot[v]); cudaFree(c->culledEntity[v]); cudaFree(c->gathered[v]);
@@ -450,6 +451,9 @@ int createImpl(ScGpuScene* c, const ScGpuSceneDesc* d)
   c->chunkStride = c->bitWords / kCompactChunkWords + 1u;
   if (!devAlloc(c, &c->chunkCounts, (size_t)2 * (kMaxViews + 1) * c->chunkStride, true)) return 0;
   if (!devAlloc(c, &c->slotInfo, n, true)) return 0;
+  // every tile starts out "to be cut" (k_build_windows is incremental): byte t + 1 belongs to tile t
+  if (!devAlloc(c, &c->a.tileDirty, ((size_t)c->maxTiles + 2) * 4, false)) return 0;
+  SC_CUDA(c, cudaMemsetAsync(c->a.tileDirty, 1, ((size_t)c->maxTiles + 2) * 4, c->stream));
   if (!devAlloc(c, &c->winLocal, (size_t)c->maxTiles * (kMaxWin + 1), true)) return 0;
   if (!devAlloc(c, &c->tileWinCount, (size_t)c->maxTiles, true)) return 0;
   if (!devAlloc(c, &c->tileWinBase, (size_t)c->maxTiles + 1, true)) return 0;
@@ -1427,9 +1431,20 @@ int scgpuUpdate(ScGpuScene* c, uint32_t flags)
     SC_CUDA(c, cudaGetLastError());
     if (c->anyParentEver)
     {
-      k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winLocal, c->tileWinCount, extent);
+      if (extent != c->builtExtent)
+      {
+        // the cut depends on the extent near its end: the tiles between the old and the new end (and the one before:
+        // kHalo) are cut again; tiles that fall off the end are marked for the day the pool grows back
+        const uint32_t lo = std::min(extent, c->builtExtent), hi = std::max(extent, c->builtExtent);
+        const uint32_t t0 = lo / kTile > 0u ? lo / kTile - 1u : 0u, t1 = std::min(c->maxTiles, hi / kTile + 1u);
+        SC_CUDA(c, cudaMemsetAsync(c->a.tileDirty + ((size_t)1 + t0) * 4, 1, (size_t)(t1 - t0) * 4, c->stream));
+        c->builtExtent = extent;
+      }
+      k_build_windows<<<numTiles, kBlock, 0, c->stream>>>(c->a.parentSlot, c->slotInfo, c->winLocal, c->tileWinCount, extent,
+                                                          c->a.tileDirty);
       k_scan_tiles<<<1, 1024, 0, c->stream>>>(c->tileWinCount, c->tileWinBase, c->tileWinBase + numTiles, numTiles);
-      k_flatten_windows<<<numTiles, 128, 0, c->stream>>>(c->winLocal, c->tileWinCount, c->tileWinBase, c->winList, numTiles, extent);
+      k_flatten_windows<<<numTiles, 128, 0, c->stream>>>(c->winLocal, c->tileWinCount, c->tileWinBase, c->winList, numTiles, extent,
+                                                          c->a.tileDirty);
       c->launches += 3;
       SC_CUDA(c, cudaGetLastError());
     }

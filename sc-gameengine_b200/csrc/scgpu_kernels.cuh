@@ -759,10 +759,18 @@ __device__ __forceinline__ uint32_t first_uncrossed(const int* sCross, uint32_t 
   return from;
 }
 
+// INCREMENTAL: the cut of a tile depends on the parentSlot words of [tileBase - kHalo, tileBase + kTile + 2 kHalo) and on
+// `count` alone, slots never move, and the per-tile results (slotInfo, winLocal, tileWinCount) stay in place between
+// calls. So a tile is cut again only if a link changed in it, in the last kHalo slots of the tile before it or in the
+// first 2 kHalo slots of the tile behind it (tileDirty, see SceneArrays; the host marks the tiles around a changed
+// `count`); every other CTA returns at once. The cost of a topology change is
+// proportional to what changed, not to the size of the scene.
 __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __restrict__ parentSlot, uint32_t* __restrict__ slotInfo,
                                                           uint16_t* __restrict__ winLocal, uint32_t* __restrict__ tileWinCount,
-                                                          uint32_t count)
+                                                          uint32_t count, const uint8_t* __restrict__ tileDirty)
 {
+  static_assert(kHalo == 32, "mark_tile's edge zones");
+  if (!(tileDirty[blockIdx.x * 4u + 2u] | tileDirty[(blockIdx.x + 1u) * 4u] | tileDirty[(blockIdx.x + 2u) * 4u + 1u])) return;
   constexpr uint32_t kSpan = kTile + 3 * kHalo;  // slots [tileBase - kHalo, tileBase + kTile + 2*kHalo)
   __shared__ int sCross[kSpan + 8];              // sCross[c - origin]: number of short links crossing position c
   __shared__ uint16_t sStart[kMaxWin + 1];       // window starts relative to tileBase (<= kTile + kHalo)
@@ -938,9 +946,10 @@ __global__ void __launch_bounds__(kBlock) k_build_windows(const uint32_t* __rest
 // per-tile window lists -> one list of absolute start slots (bit 31: generic path), winList[total] = count
 __global__ void __launch_bounds__(128) k_flatten_windows(const uint16_t* __restrict__ winLocal, const uint32_t* __restrict__ tileWinCount,
                                                          const uint32_t* __restrict__ tileWinBase, uint32_t* __restrict__ winList,
-                                                         uint32_t numTiles, uint32_t count)
+                                                         uint32_t numTiles, uint32_t count, uint8_t* __restrict__ tileDirty)
 {
   const uint32_t tile = blockIdx.x, nw = tileWinCount[tile], base = tileWinBase[tile];
+  if (threadIdx.x < 4) tileDirty[(tile + 1u) * 4u + threadIdx.x] = 0;  // every k_build_windows CTA of this rebuild has finished (stream order)
   for (uint32_t k = threadIdx.x; k < nw; k += 128)
   {
     const uint32_t e = winLocal[(size_t)tile * (kMaxWin + 1) + k];
@@ -2123,7 +2132,19 @@ struct SceneArrays
   uint32_t sparseSize;
   uint32_t* rank;        // slot -> dense index in the reference's Transform pool (ComponentPool::m_denseEntities)
   uint32_t* perm;        // dense index -> slot
+  uint8_t* tileDirty;    // [1 + tiles + 1][4] bytes, tile t at [t + 1]: since k_build_windows last cut the tile into windows
+                         // a parentSlot changed (or a slot was spawned) [0] anywhere in it, [1] in its first 2 kHalo slots,
+                         // [2] in its last kHalo slots; set by whoever writes parentSlot, cleared by k_flatten_windows
 };
+// marks the tile of slot s for the next window cut (benign races: everybody stores the same bytes)
+__device__ __forceinline__ void mark_tile(const SceneArrays& a, uint32_t s)
+{
+  uint8_t* d = a.tileDirty + ((size_t)(s / kTile) + 1u) * 4u;
+  const uint32_t off = s % kTile;
+  d[0] = 1;
+  if (off < 64u) d[1] = 1;          // 2 * kHalo: what the tile before this one looks at
+  if (off >= kTile - 32u) d[2] = 1;  // kHalo: what the tile behind this one looks at
+}
 
 // slot of the j-th element of a spawn batch: a run of fresh slots, or wherever the host's layout put it (scgpu_layout.h)
 __device__ __forceinline__ uint32_t spawn_slot(uint32_t slot0, const uint32_t* __restrict__ slotOf, uint32_t j)
@@ -2167,6 +2188,7 @@ __global__ void __launch_bounds__(kBlock) k_spawn(SceneArrays a, uint32_t slot0,
   a.entity[s] = e;
   a.parent[s] = parent ? parent[j] : kNone;
   a.parentSlot[s] = kNone;
+  mark_tile(a, s);
   a.meshMat[s] = meshMat2 ? make_uint2(meshMat2[(size_t)j * 2], meshMat2[(size_t)j * 2 + 1]) : make_uint2(0u, 0u);
   const uint32_t idx = e & 0xFFFFFFu;
   if (idx < a.sparseSize) a.sparse[idx] = s + 1u;
@@ -2262,6 +2284,7 @@ __global__ void __launch_bounds__(64) k_spawn_sectors(SceneArrays a, SectorGen g
     a.entity[s] = e;
     a.parent[s] = kNone;
     a.parentSlot[s] = kNone;
+    mark_tile(a, s);
     a.meshMat[s] = make_uint2(mesh, mat);
     const uint32_t idx = e & 0xFFFFFFu;
     if (idx < a.sparseSize) a.sparse[idx] = s + 1u;
@@ -2320,6 +2343,7 @@ __global__ void __launch_bounds__(kBlock) k_spawn_sector_file(SceneArrays a, uin
   a.entity[s] = e;
   a.parent[s] = kNone;
   a.parentSlot[s] = kNone;
+  mark_tile(a, s);
   a.meshMat[s] = make_uint2(mesh, mat);
   const uint32_t idx = e & 0xFFFFFFu;
   if (idx < a.sparseSize) a.sparse[idx] = s + 1u;
@@ -2455,6 +2479,7 @@ __global__ void __launch_bounds__(kBlock) k_despawn_apply(SceneArrays a, uint32_
     a.sparse[e & 0xFFFFFFu] = 0u;
     a.entity[s] = kNone;
     a.parent[s] = kNone;
+    if (a.parentSlot[s] != kNone) mark_tile(a, s);  // a link that goes away changes the window cut; a dead root does not
     a.parentSlot[s] = kNone;
     // an all-zero record: no LIVE bit, never dirty, no RenderMesh; and tame, should its window be computed as a whole
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -2518,7 +2543,11 @@ __global__ void __launch_bounds__(kBlock) k_resolve_parents(SceneArrays a, uint3
         *fw = (*fw & 0xFFu) | (stamp << kStampShift);
       }
     }
-    if (old_[k] != ps) a.parentSlot[s] = ps;
+    if (old_[k] != ps)
+    {
+      a.parentSlot[s] = ps;
+      mark_tile(a, s);
+    }
   }
 }
 

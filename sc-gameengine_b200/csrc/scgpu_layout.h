@@ -138,6 +138,7 @@ public:
     m_gTaken.clear();
     for (auto& q : m_queue) { q.clear(); }
     for (uint32_t& h : m_qHead) h = 0;
+    m_sizeMask = 0;
     m_oldest = 0;
     m_pendingSlots = 0;
     beginRuns();
@@ -157,6 +158,7 @@ public:
       }
       const uint32_t g = end - j;
       m_queue[g].push_back((uint32_t)m_gStart.size());
+      m_sizeMask |= 1ull << g;
       m_gStart.push_back(j);
       m_gSize.push_back((uint8_t)g);
       m_gTaken.push_back(0);
@@ -225,7 +227,7 @@ private:
   uint32_t popQueue(uint32_t g)
   {
     const uint32_t gi = m_queue[g][m_qHead[g]++];
-    if (m_qHead[g] == m_queue[g].size()) { m_queue[g].clear(); m_qHead[g] = 0; }
+    if (m_qHead[g] == m_queue[g].size()) { m_queue[g].clear(); m_qHead[g] = 0; m_sizeMask &= ~(1ull << g); }
     m_gTaken[gi] = 1;
     m_pendingSlots -= g;
     return gi;
@@ -273,8 +275,9 @@ private:
   uint64_t reachable(uint32_t less) const
   {
     uint64_t reach = 1ull;
-    for (uint32_t g = 1; g <= kLayoutMaxGroup; ++g)
+    for (uint64_t m = m_sizeMask; m; m &= m - 1ull)  // the sizes that wait, ascending
     {
+      const uint32_t g = (uint32_t)__builtin_ctzll(m);
       uint32_t c = waiting(g);
       if (g == less && c) --c;
       if (c > 63u / g) c = 63u / g;
@@ -292,10 +295,10 @@ private:
     uint64_t reachBefore[160];
     uint32_t copies = 0;
     uint64_t reach = 1ull;
-    for (uint32_t g = 1; g <= cap; ++g)
+    for (uint64_t m = m_sizeMask & ((2ull << cap) - 1ull); m; m &= m - 1ull)  // the sizes that wait and fit, ascending
     {
+      const uint32_t g = (uint32_t)__builtin_ctzll(m);
       const uint32_t w = waiting(g);
-      if (w == 0u) continue;
       const uint32_t c = w < cap / g ? w : cap / g;
       for (uint32_t k = 0; k < c && copies < 160u; ++k)
       {
@@ -483,6 +486,7 @@ private:
   uint32_t m_qHead[kLayoutMaxGroup + 1] = {};
   size_t m_oldest = 0;
   uint32_t m_pendingSlots = 0;
+  uint64_t m_sizeMask = 0;                             // bit g: groups of size g are waiting
   uint32_t m_binCursor = 0;                            // where the previous batch stopped carving
   uint32_t m_runPos = 0, m_lapStart = 0, m_runAt = 0, m_runLeft = 0;
   bool m_wrapped = false, m_tailMode = false;
