@@ -333,7 +333,8 @@ private:
       if (!final && m_pendingSlots < kPackKeep) break;
       if (m_runLeft == 0u && !nextRun())
       {
-        // no contiguous room anywhere (a pool that is all but full): group by group, then slot by slot
+        // no contiguous room anywhere (a pool that is all but full): group by group, then slot by slot. (Only in tail
+        // mode, i.e. when this walk holds no hole of its own: allocGroup takes its slots from the bitmap directly.)
         placeGroup(popQueue(m_gSize[m_oldest]), slotOut);
         continue;
       }
@@ -359,7 +360,11 @@ private:
       used += fillFromWaiting(cap - used, bin, nb);
       if (used == 0u)
       {
-        m_runLeft = 0u;  // nothing that waits fits what is left of this run: it stays a hole
+        // nothing that waits fits what is left of this run: a hole stays a hole (for a later batch); at the END of the
+        // pool (the tail has less room than the smallest waiting group, the walk of the holes is over) the oldest group
+        // is placed on its own - into any hole that holds it, else slot by slot - and the tail is looked at afresh
+        if (m_tailMode) placeGroup(popQueue(g0), slotOut);
+        m_runLeft = 0u;
         continue;
       }
       const uint32_t at0 = m_runAt;

@@ -298,3 +298,62 @@ def test_groups_are_packed_into_full_windows(hs):
     e2 = np.arange(nxt, nxt + 5000, dtype=np.uint32)
     rc, slot2 = d.spawn(e2, np.full(5000, INVALID, np.uint32), np.arange(5000) + 100_000)
     assert rc == 0 and np.array_equal(slot2, len(e) + np.arange(5000))
+
+
+def test_packing_random_group_sizes_and_nearly_full_pool(hs):
+    """any mix of group sizes 1..32 (chains longer than a window are cut), churn of single groups and of long runs, a pool
+    that is filled to the last slot: every element gets its own slot, groups stay consecutive, the pool order is the
+    reference's, and placement always terminates"""
+    rng = np.random.default_rng(23)
+    cap = 6000
+    d = DeviceModel(hs, cap, 1 << 18)
+    naive = NaivePool()
+    nxt, gcount = 1, 0
+    groups = {}
+
+    def spawn(n_groups, sizes, gen):
+        nonlocal nxt, gcount
+        room = cap - d.count
+        e, par, gid = [], [], []
+        for g in range(n_groups):
+            k = int(rng.choice(sizes))
+            if len(e) + k > room:
+                break
+            hs_ = [(gen << 24) | (nxt + i) for i in range(k)]
+            nxt += k
+            for i, h in enumerate(hs_):
+                e.append(h)
+                par.append(INVALID if i == 0 else hs_[i - 1 if k > 32 else int(rng.integers(0, i))])
+                gid.append(g)
+        if not e:
+            return
+        e, par, gid = np.array(e, np.uint32), np.array(par, np.uint32), np.array(gid)
+        rc, slot = d.spawn(e, par, gid + gcount)
+        assert rc == 0
+        assert len(np.unique(slot)) == len(slot)
+        for h, g in zip(e, gid):
+            naive.add(int(h))
+            groups.setdefault(int(g) + gcount, []).append(int(h))
+        gcount += n_groups
+
+    sizes_all = list(range(1, 33)) + [40, 70]   # 40, 70: chains longer than a window
+    spawn(400, sizes_all, 0)
+    for frame in range(60):
+        keys = list(groups.keys())
+        if frame % 3 == 0:   # a long run of neighbours in spawn order
+            a = int(rng.integers(0, max(1, len(keys) - 30)))
+            victims = keys[a:a + 30]
+        else:
+            victims = list(rng.choice(keys, max(1, len(keys) // 8), replace=False))
+        dead = [h for g in victims for h in groups.pop(int(g))]
+        d.despawn(np.array(dead, np.uint32))
+        for h in dead:
+            naive.remove(h)
+        # refill to the brim every few frames, with whatever sizes
+        sizes = sizes_all if frame % 2 else [1, 2, 3, 7, 32]
+        spawn(10_000 if frame % 4 == 0 else len(victims), sizes, 1 + frame % 100)
+        assert np.array_equal(d.dense_in_rank_order(), np.array(naive.dense, np.uint32)), f"frame {frame}"
+        d.check_invariants()
+        assert d.count <= cap and d.extent <= cap
+    assert d.count > cap - 40   # the pool did get full
+    d.close()
