@@ -39,6 +39,66 @@ int hs_in_frustum(const float* planes24, const float* c, float r)
 {
   return sphere_in_frustum((const float4*)planes24, c[0], c[1], c[2], r) ? 1 : 0;
 }
+// The favourite-plane PRE-TEST of k_update_win (sphere_cull_warp_fav, csrc/scgpu_kernels.cuh) restated with the same
+// operations - fmaf is the per-lane semantics of fma.rn.f32x2 - on top of the REAL header functions for the sphere
+// centre, the radius bound and the exact radius. Fuzzes the claim the kernel relies on: whenever the fused chain with
+// its slack says "certainly culled by this plane", the reference's own predicate (every operation rounded, exact
+// radius) culls too. cityLike != 0 keeps the magnitudes to those of a city scene. out[0] = cases, out[1] = "certain" verdicts, out[2] = cases the reference culls by that plane,
+// out[3] = VIOLATIONS (must be 0), out[4] = culled by the old pre-test (rounded distance < -bound) but not certain now.
+void hs_fav_pretest_fuzz(uint64_t seed, uint64_t n, int cityLike, uint64_t* out)
+{
+  uint64_t st = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto next = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+  auto uni = [&]() { return (float)((next() >> 40) * (1.0 / 16777216.0)); };                  // [0, 1)
+  auto sym = [&]() { return uni() * 2.0f - 1.0f; };
+  auto mag = [&](float lo, float hi) { return std::pow(10.0f, lo + (hi - lo) * uni()); };  // log-uniform
+  for (int k = 0; k < 5; ++k) out[k] = 0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    // an affine world matrix (rotation-ish 3x3 with scales over four decades, translation up to 1e5 m), an AABB
+    Mat4 W;
+    // cityLike: scales 0.1 .. 10, positions up to 10 km, half extents 0.1 .. 5 m; else four decades more of everything
+    const float sc = cityLike ? mag(-1.f, 1.f) : mag(-2.f, 2.f), tr = cityLike ? mag(0.f, 4.f) : mag(-1.f, 5.f);
+    W.c0 = make_float4(sym() * sc, sym() * sc, sym() * sc, 0.f);
+    W.c1 = make_float4(sym() * sc, sym() * sc, sym() * sc, 0.f);
+    W.c2 = make_float4(sym() * sc, sym() * sc, sym() * sc, 0.f);
+    W.c3 = make_float4(sym() * tr, sym() * tr, sym() * tr, 1.f);
+    const float he = cityLike ? mag(-1.f, 0.7f) : mag(-2.f, 1.f);
+    const float cxl = sym(), cyl = sym(), czl = sym();
+    float ox, oy, oz, ex, ey, ez;
+    world_bounds_centre(W, cxl - he * uni(), cyl - he * uni(), czl - he * uni(), cxl + he * uni(), cyl + he * uni(), czl + he * uni(),
+                        ox, oy, oz, ex, ey, ez);
+    const float bound = world_bounds_radius_bound(W, ex, ey, ez), radius = world_bounds_radius(W, ex, ey, ez);
+    // a plane: normalised like frustumFromViewProj does it (a * invLen), or left tiny / unnormalised now and then
+    float a = sym(), b = sym(), c = sym();
+    const float lenSq = a * a + b * b + c * c;
+    const uint64_t kind = next() % 16;
+    if (kind == 0) { a *= 1e-5f; b *= 1e-5f; c *= 1e-5f; }
+    else if (kind == 1) { a *= 3.f; b *= 3.f; c *= 3.f; }  // scgpuSetViewPlanes takes whatever it is given
+    else if (lenSq > 1e-8f) { const float inv = 1.0f / std::sqrt(lenSq); a *= inv; b *= inv; c *= inv; }
+    // d so that the sphere sits at a chosen signed distance in units of its radius bound: mostly around the threshold
+    const float want = (kind < 12 ? -(0.9f + 0.3f * uni()) : -mag(0.f, 3.f) * (next() & 1 ? 1.f : -0.1f)) * bound;
+    const float d = want - (a * ox + b * oy + c * oz);
+    const float K = std::fmax(std::fabs(a), std::fmax(std::fabs(b), std::fabs(c)));  // refreshPlaneSlack, one plane
+    const float slackK = K * 0x1p-19f;
+    // reference predicate: sphereInFrustum's distance, every operation rounded (plane_dist)
+    const float D = (((a * ox) + (b * oy)) + (c * oz)) + d;
+    const bool refCulls = D < -radius;
+    // the kernel's pre-test
+    const float negBound = -bound;
+    const float nb = fmaf(-slackK, std::fabs(ox) + std::fabs(oy) + std::fabs(oz), negBound);
+    // the device starts the chain from __fmaf_ru(|d|, 2^-19, d); the round-to-nearest value used here is never larger,
+    // the chain is monotone in its start value, so a "certain" here is a superset of the device's: the weaker claim is checked
+    const float dStart = fmaf(std::fabs(d), 0x1p-19f, d);
+    float t = fmaf(c, oz, dStart); t = fmaf(b, oy, t); t = fmaf(a, ox, t);
+    const bool certain = t < nb;
+    out[0] += 1;
+    out[1] += certain ? 1 : 0;
+    out[2] += refCulls ? 1 : 0;
+    out[3] += (certain && !refCulls) ? 1 : 0;
+    out[4] += (D < negBound && !certain) ? 1 : 0;
+  }
+}
 // exhaustive-capable sweep: counts bit mismatches of device sincos vs reference fns over [first, first+count)
 uint64_t hs_sincos_sweep(uint32_t first, uint64_t count, uint32_t stride, float (*rs)(float), float (*rc)(float))
 {

@@ -97,3 +97,25 @@ def test_sphere_and_plane_tests_are_bit_exact(hs, port):
         c = (rng.normal(size=3) * 3).astype(np.float32)
         r = np.float32(abs(rng.normal()))
         assert hs.hs_in_frustum(f(pl), f(c), C.c_float(float(r))) == port.sco_sphere_in_frustum(f(pl), f(c), C.c_float(float(r)))
+
+
+def test_fused_favourite_plane_pretest_never_culls_what_the_reference_keeps(hs):
+    """k_update_win decides "this plane culls the whole warp" with three fused multiply-adds per view and a slack
+    (csrc/scgpu_kernels.cuh: sphere_cull_warp_fav) although the reference's distance rounds
+    every operation. 30 M random (matrix, AABB, plane) cases over nine decades of magnitudes plus 10 M of city-like ones,
+    most of them within +-15 % of the threshold d = -radius: a "certain" verdict without the reference culling too never
+    happens; the verdict is not vacuous; and for city-like magnitudes it gives up fewer than 2 % of the cases - three
+    quarters of which sit within 15 % of the threshold - that the plain pre-test (rounded distance against the same
+    radius bound) accepts: the slack is centimetres at 10 km."""
+    hs.hs_fav_pretest_fuzz.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    out = np.zeros(5, np.uint64)
+    for city, seeds in ((0, range(1, 7)), (1, range(7, 9))):
+        tot = np.zeros(5, np.uint64)
+        for seed in seeds:
+            hs.hs_fav_pretest_fuzz(seed, 5_000_000, city, f(out))
+            tot += out
+        cases, certain, ref_culls, violations, lost = (int(x) for x in tot)
+        assert violations == 0, (city, tot)
+        assert certain > cases // 4 and ref_culls >= certain, (city, tot)
+        if city:
+            assert lost * 50 < cases, (city, tot)
