@@ -1,3 +1,4 @@
+# the round-end artefact call: full bench line at N = 1 and the ncu launch list that profiles/make_summaries_r02.py reads
 timeout 400 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; echo "bench rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --churn-frames 4 > gpurun_out/ncu_l.log 2>&1; echo "ncu list rc=$?"
 python - <<PY

@@ -1,3 +1,4 @@
+# what a `gpurun -- bash tools/gpurun_check.sh` call of round 2 ran after a kernel change: GPU parity suite, one bench line, (optionally) an ncu metric pass
 T=${TAG:-a}
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/t_$T.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/t_$T.log
 timeout 300 python bench.py --no-cpu-baseline --no-e2e --churn-frames 30 > gpurun_out/b_$T.json 2> gpurun_out/b_$T.err; echo "bench rc=$?"
